@@ -1,0 +1,601 @@
+// oracle.cpp -- CPU restatement of the ALPS/looper loop update.  TEST INFRASTRUCTURE ONLY:
+// see oracle.h for the rules (never linked, imported or called by the product path) and for the
+// golden vectors that pin it.  Citations are file:line under the reference root.
+//
+// Build: see oracle/Makefile (g++ -O2 -shared -fPIC; also the `oracle_loop` CLI that prints the
+// text of standalone/loop.op).
+
+#include "oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// standalone/union_find.h:41-54 (node), :69-72 (add), :74-77 (root_index), :103-125
+// (update_link, unify_weight).  parent_ < 0 : root holding -weight.
+// ---------------------------------------------------------------------------------------------
+struct sa_node {
+  int parent = -1;
+  int id = 0;
+  bool is_root() const { return parent < 0; }
+  int weight() const { return -parent; }
+};
+
+inline int sa_add(std::vector<sa_node>& v) {
+  v.push_back(sa_node());
+  return int(v.size()) - 1;
+}
+inline int sa_root_index(std::vector<sa_node> const& v, int g) {
+  while (!v[g].is_root()) g = v[g].parent;
+  return g;
+}
+inline void sa_update_link(std::vector<sa_node>& v, int g, int r) {
+  while (g != r) {
+    int p = v[g].parent;
+    v[g].parent = r;
+    g = p;
+  }
+}
+// standalone/union_find.h:112-125: heavier root wins, ties keep r0.
+inline int sa_unify(std::vector<sa_node>& v, int g0, int g1) {
+  int r0 = sa_root_index(v, g0);
+  int r1 = sa_root_index(v, g1);
+  if (r0 != r1) {
+    if (v[r0].weight() < v[r1].weight()) std::swap(r0, r1);
+    v[r0].parent += v[r1].parent;
+    v[r1].parent = r0;
+  }
+  sa_update_link(v, g0, r0);
+  sa_update_link(v, g1, r0);
+  return r0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// looper/union_find.h:57-82 (node: parent_ <= 0 root with -weight, else parent+1),
+// :111-136 (node_noweight), :158-172 (root_index_ph), :242-284 (unify_pathhalving, serial branch)
+// ---------------------------------------------------------------------------------------------
+struct lp_node {
+  int parent_ = -1;
+  bool is_root() const { return parent_ <= 0; }
+  void set_parent(int p) { parent_ = p + 1; }
+  int parent() const { return parent_ - 1; }
+  void set_weight(int w) { parent_ = -w; }
+  int weight() const { return -parent_; }
+};
+struct lp_node_noweight {
+  int parent_ = -1;  // id_mask: root with id 0
+  bool is_root() const { return parent_ <= 0; }
+  void set_parent(int p) { parent_ = p + 1; }
+  int parent() const { return parent_ - 1; }
+  void set_weight(int) { parent_ = 0 ^ -1; }
+  int weight() const { return 0; }
+};
+template <class T>
+int lp_root_index(std::vector<T> const& v, int g) {
+  while (!v[g].is_root()) g = v[g].parent();
+  return g;
+}
+template <class T>
+int lp_root_index_ph(std::vector<T>& v, int g) {
+  if (v[g].is_root()) return g;
+  while (true) {
+    int p = v[g].parent();
+    if (v[p].is_root()) return p;
+    v[g].set_parent(v[p].parent());
+    g = p;
+  }
+}
+template <class T>
+int lp_unify(std::vector<T>& v, int g0, int g1) {
+  int r0 = lp_root_index_ph(v, g0);
+  int r1 = lp_root_index_ph(v, g1);
+  if (r0 != r1) {
+    if (v[r0].weight() < v[r1].weight()) std::swap(r0, r1);
+    v[r0].set_weight(v[r0].weight() + v[r1].weight());
+    v[r1].set_parent(r0);
+  }
+  return r0;
+}
+
+// standalone/observable.h:29-41
+struct observable {
+  double sum = 0, esq = 0;
+  unsigned count = 0;
+  void operator<<(double x) { sum += x; esq += x * x; ++count; }
+  double mean() const { return count > 0 ? sum / count : 0.; }
+  double error() const {
+    return count > 1 ? std::sqrt((esq / count - mean() * mean()) / (count - 1)) : 0.;
+  }
+};
+
+inline double power2(double x) { return x * x; }
+inline double power4(double x) { return power2(power2(x)); }
+
+// looper/susceptibility.h:97-105 estimate (8 doubles)
+struct lp_estimate {
+  double usize0 = 0, umag0 = 0, usize = 0, umag = 0;
+  double ssize0 = 0, smag0 = 0, ssize = 0, smag = 0;
+  // susceptibility.h:126-132 end_s ; :117-119 begin_s = end_s(-t)
+  void end_s(double gg, double t, int c) {
+    usize += t * 0.5;
+    umag += t * (0.5 - c);
+    ssize += gg * t * 0.5;
+    smag += gg * t * (0.5 - c);
+  }
+  void begin_s(double gg, double t, int c) { end_s(gg, -t, c); }
+  // susceptibility.h:139-146 start_bottom
+  void start_bottom(double gg, double t, int c) {
+    begin_s(gg, t, c);
+    usize0 += 0.5;
+    umag0 += (0.5 - c);
+    ssize0 += gg * 0.5;
+    smag0 += gg * (0.5 - c);
+  }
+};
+
+// susceptibility.h:182-198 collector += estimate ; standalone/common.h:67-72
+inline void collect(orc_collector& c, lp_estimate const& e) {
+  c.umag0 += e.umag0;
+  c.usize2 += power2(e.usize0);
+  c.umag2 += power2(e.umag0);
+  c.usize4 += power4(e.usize0);
+  c.umag4 += power4(e.umag0);
+  c.usize += power2(e.usize);
+  c.umag += power2(e.umag);
+  c.smag0 += e.smag0;
+  c.ssize2 += power2(e.ssize0);
+  c.smag2 += power2(e.smag0);
+  c.ssize4 += power4(e.ssize0);
+  c.smag4 += power4(e.smag0);
+  c.ssize += power2(e.ssize);
+  c.smag += power2(e.smag);
+}
+
+struct sa_estimate {  // standalone/common.h:44-56
+  double mag = 0, size = 0, length = 0;
+};
+
+struct op_t {  // standalone/common.h:29-37
+  int type;    // 0 diagonal, 1 offdiagonal (bit0) | graph<<2
+  int bond;
+  int upper_cluster, lower_cluster;
+  double time;
+};
+
+}  // namespace
+
+struct orc_sim {
+  int nsites, nbonds;
+  std::vector<int> src, dst;
+  std::vector<double> gauge;
+  double beta;
+  std::mt19937 eng;
+  std::uniform_real_distribution<> d_uniform;
+  std::exponential_distribution<> d_time;
+  std::vector<op_t> operators, operators_p;
+  std::vector<int> spins, current, spins_before;
+  std::vector<sa_node> fragments;
+  std::vector<char> to_flip;
+  std::vector<int> built_type;  // operator types as built (pre flip)
+  int nc = 0;
+  orc_sim(int ns, int nb, const int32_t* s, const int32_t* d, const double* g, double b,
+          uint32_t seed)
+      : nsites(ns), nbonds(nb), src(s, s + nb), dst(d, d + nb), gauge(ns, 0.0), beta(b),
+        eng(seed), d_time(b * nb / 2), spins(ns, 0), current(ns) {
+    if (g) gauge.assign(g, g + ns);
+  }
+};
+
+extern "C" {
+
+orc_sim* orc_create(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                    const double* gauge, double beta, uint32_t seed) {
+  return new orc_sim(nsites, nbonds, src, dst, gauge, beta, seed);
+}
+void orc_destroy(orc_sim* s) { delete s; }
+
+// standalone/loop.C:87-167, with left()/right() (common.h:92-93) read from the bond table.
+void orc_sweep(orc_sim* S, orc_collector* out) {
+  const int nsites = S->nsites, nbonds = S->nbonds;
+  std::vector<op_t>&operators = S->operators, &operators_p = S->operators_p;
+  std::vector<int>&spins = S->spins, &current = S->current;
+  std::vector<sa_node>& fragments = S->fragments;
+  S->spins_before = spins;
+
+  // loop.C:87
+  std::swap(operators, operators_p);
+  operators.resize(0);
+  // loop.C:90-91
+  fragments.resize(0);
+  fragments.resize(nsites);
+  for (int s = 0; s < nsites; ++s) current[s] = s;
+
+  // loop.C:93-126
+  double t = S->d_time(S->eng);
+  for (std::vector<op_t>::iterator opi = operators_p.begin();
+       t < 1 || opi != operators_p.end();) {
+    if (opi == operators_p.end() || t < opi->time) {
+      const int b = static_cast<int>(nbonds * S->d_uniform(S->eng));
+      if (spins[S->src[b]] != spins[S->dst[b]]) {
+        op_t o;
+        o.type = 0;
+        o.bond = b;
+        o.time = t;
+        operators.push_back(o);
+        t += S->d_time(S->eng);
+      } else {
+        t += S->d_time(S->eng);
+        continue;
+      }
+    } else {
+      if (opi->type == 0) {
+        ++opi;
+        continue;
+      } else {
+        operators.push_back(*opi);
+        ++opi;
+      }
+    }
+    op_t& oi = operators.back();
+    const int s0 = S->src[oi.bond];
+    const int s1 = S->dst[oi.bond];
+    if (oi.type == 1) {
+      spins[s0] ^= 1;
+      spins[s1] ^= 1;
+    }
+    oi.lower_cluster = sa_unify(fragments, current[s0], current[s1]);
+    oi.upper_cluster = current[s0] = current[s1] = sa_add(fragments);
+  }
+  // loop.C:128
+  for (int s = 0; s < nsites; ++s) sa_unify(fragments, s, current[s]);
+
+  // loop.C:135-137
+  int nc = 0;
+  for (auto& f : fragments)
+    if (f.is_root()) f.id = nc++;
+  for (auto& f : fragments) f.id = fragments[sa_root_index(fragments, int(&f - &fragments[0]))].id;
+  S->nc = nc;
+  S->to_flip.assign(nc, 0);
+  std::vector<sa_estimate> estimates(nc);
+  std::vector<lp_estimate> lest(nc);
+
+  // loop.C:141-151
+  for (auto& op : operators) {
+    const double tt = op.time;
+    estimates[fragments[op.lower_cluster].id].length += 2 * tt;
+    estimates[fragments[op.upper_cluster].id].length -= 2 * tt;
+  }
+  for (int s = 0; s < nsites; ++s) {
+    const int id = fragments[s].id;
+    estimates[id].mag += 1 - 2 * spins[s];
+    estimates[id].size += 1;
+    estimates[id].length += 1;
+  }
+  // looper estimator on the same graph: path_integral.C:682-734 (accum_i), HAF graph 0:
+  // loop_l0 = loop_l1 = loop0, loop_u0 = loop_u1 = loop1 (graph_impl.h:489-494)
+  {
+    std::vector<int> sc(spins);  // spins at tau = 0 (== spins after the walk, periodic)
+    for (int s = 0; s < nsites; ++s)
+      lest[fragments[s].id].start_bottom(S->gauge[s], 0.0, sc[s]);
+    for (auto& op : operators) {
+      const int s0 = S->src[op.bond], s1 = S->dst[op.bond];
+      lp_estimate& lo = lest[fragments[op.lower_cluster].id];
+      lo.end_s(S->gauge[s0], op.time, sc[s0]);
+      lo.end_s(S->gauge[s1], op.time, sc[s1]);
+      if (op.type & 1) {
+        sc[s0] ^= 1;
+        sc[s1] ^= 1;
+      }
+      lp_estimate& up = lest[fragments[op.upper_cluster].id];
+      up.begin_s(S->gauge[s0], op.time, sc[s0]);
+      up.begin_s(S->gauge[s1], op.time, sc[s1]);
+    }
+    for (int s = 0; s < nsites; ++s)
+      lest[fragments[current[s]].id].end_s(S->gauge[s], 1.0, sc[s]);
+  }
+
+  // loop.C:154-157 and path_integral.C:774-777
+  orc_collector coll;
+  std::memset(&coll, 0, sizeof(coll));
+  coll.nop = double(operators.size());
+  coll.nc = nc;
+  for (auto& est : estimates) {
+    coll.sa_usus += est.mag * est.mag;
+    coll.sa_smag += est.size * est.size;
+    coll.sa_ssus += est.length * est.length;
+  }
+  for (auto& e : lest) collect(coll, e);
+  // path_integral.C:850-851 with energy_offset = sum of bond offsets = nbonds/4 (weight_impl.h:187)
+  coll.ene = 0.25 * nbonds - coll.nop / S->beta;
+
+  S->built_type.resize(operators.size());
+  for (size_t i = 0; i < operators.size(); ++i) S->built_type[i] = operators[i].type;
+
+  // loop.C:160
+  for (int c = 0; c < nc; ++c) S->to_flip[c] = (S->d_uniform(S->eng) < 0.5);
+  // loop.C:163-167
+  for (auto& op : operators)
+    if (S->to_flip[fragments[op.lower_cluster].id] ^ S->to_flip[fragments[op.upper_cluster].id])
+      op.type ^= 1;
+  for (int s = 0; s < nsites; ++s)
+    if (S->to_flip[fragments[s].id]) spins[s] ^= 1;
+
+  if (out) *out = coll;
+}
+
+int64_t orc_num_ops(const orc_sim* S) { return int64_t(S->operators.size()); }
+
+void orc_get_state(const orc_sim* S, int32_t* spins, orc_op* ops) {
+  for (int s = 0; s < S->nsites; ++s) spins[s] = S->spins[s];
+  for (size_t i = 0; i < S->operators.size(); ++i) {
+    ops[i].time = S->operators[i].time;
+    ops[i].loc = (S->operators[i].bond << 1) | 1;
+    ops[i].type = S->operators[i].type;
+  }
+}
+
+void orc_set_state(orc_sim* S, const int32_t* spins, const orc_op* ops, int64_t n) {
+  for (int s = 0; s < S->nsites; ++s) S->spins[s] = spins[s];
+  S->operators.resize(size_t(n));
+  for (int64_t i = 0; i < n; ++i) {
+    S->operators[i].time = ops[i].time;
+    S->operators[i].bond = ops[i].loc >> 1;
+    S->operators[i].type = ops[i].type & 1;
+    S->operators[i].lower_cluster = S->operators[i].upper_cluster = 0;
+  }
+}
+
+void orc_get_last_graph(const orc_sim* S, int32_t* spins_before, orc_op* ops_built,
+                        int32_t* lower_id, int32_t* upper_id, int32_t* site_id, int32_t* nc,
+                        int32_t* flip) {
+  for (int s = 0; s < S->nsites; ++s) {
+    if (spins_before) spins_before[s] = S->spins_before[s];
+    if (site_id) site_id[s] = S->fragments[s].id;
+  }
+  for (size_t i = 0; i < S->operators.size(); ++i) {
+    if (ops_built) {
+      ops_built[i].time = S->operators[i].time;
+      ops_built[i].loc = (S->operators[i].bond << 1) | 1;
+      ops_built[i].type = S->built_type[i];
+    }
+    if (lower_id) lower_id[i] = S->fragments[S->operators[i].lower_cluster].id;
+    if (upper_id) upper_id[i] = S->fragments[S->operators[i].upper_cluster].id;
+  }
+  if (nc) *nc = S->nc;
+  if (flip)
+    for (int c = 0; c < S->nc; ++c) flip[c] = S->to_flip[c];
+}
+
+// path_integral.C:539-566 (walk) + graph_impl.h:277-295 (xxz reconnect; g=0 is the HAF case
+// :168-177) + path_integral.C:584-588 (close) + union_find.h:325-343 (set_id/copy_id) +
+// path_integral.C:666-734 (improved accumulators) + :774-777 (collect).
+int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                       const double* gauge, const int32_t* spins, const orc_op* ops, int64_t n,
+                       int32_t* labels_out, int64_t* nc_out, orc_collector* coll_out) {
+  std::vector<lp_node> fragments(nsites);
+  fragments.reserve(size_t(nsites) + size_t(n));
+  std::vector<int> current(nsites), sc(spins, spins + nsites);
+  for (int s = 0; s < nsites; ++s) current[s] = s;
+  // per operator: fragment index of the four legs
+  std::vector<int> l0(n), l1(n), u0(n), u1(n);
+  double tprev = -1;
+  for (int64_t k = 0; k < n; ++k) {
+    if (!(ops[k].loc & 1)) return -2;  // site operators are not handled by this routine
+    const int b = ops[k].loc >> 1;
+    if (b < 0 || b >= nbonds) return -3;
+    if (ops[k].time < tprev) return -4;
+    tprev = ops[k].time;
+    const int s0 = src[b], s1 = dst[b];
+    const int g = ops[k].type >> 2;
+    // graph_impl.h:257 is_compatible(g, c0, c1) = (g & 1) ^ c0 ^ c1, evaluated BELOW the operator
+    if (!((g & 1) ^ sc[s0] ^ sc[s1])) return -1;
+    if (ops[k].type & 1) {
+      sc[s0] ^= 1;
+      sc[s1] ^= 1;
+    }
+    int loop0, loop1;
+    if ((g & 2) == 2) {  // frozen: graph_impl.h:281-282
+      loop0 = loop1 = current[s0] = current[s1] = lp_unify(fragments, current[s0], current[s1]);
+    } else if (g == 0) {  // graph_impl.h:283-287
+      fragments.push_back(lp_node());
+      loop0 = lp_unify(fragments, current[s0], current[s1]);
+      loop1 = current[s0] = current[s1] = int(fragments.size()) - 1;
+    } else {  // cross: graph_impl.h:288-292
+      loop0 = current[s0];
+      loop1 = current[s1];
+      std::swap(current[s0], current[s1]);
+    }
+    // graph_impl.h:489-494
+    l0[k] = loop0;
+    l1[k] = (g == 0) ? loop0 : loop1;
+    u0[k] = loop1;
+    u1[k] = (g == 0) ? loop1 : loop0;
+  }
+  for (int s = 0; s < nsites; ++s)
+    if (sc[s] != spins[s]) return -1;  // not periodic in imaginary time
+  for (int s = 0; s < nsites; ++s) lp_unify(fragments, s, current[s]);
+
+  // union_find.h:325-343
+  const int nf = int(fragments.size());
+  std::vector<int> id(nf, -1);
+  int nc = 0;
+  for (int i = 0; i < nf; ++i)
+    if (fragments[i].is_root()) id[i] = nc++;
+  for (int i = 0; i < nf; ++i) id[i] = id[lp_root_index(fragments, i)];
+
+  // canonical min-index labels over leg nodes: site s -> s, upper legs of op k -> N+2k, N+2k+1
+  if (labels_out) {
+    std::vector<int> minidx(nc, -1);
+    auto touch = [&](int cid, int idx) {
+      if (minidx[cid] < 0) minidx[cid] = idx;  // visited in increasing idx order
+    };
+    for (int s = 0; s < nsites; ++s) touch(id[s], s);
+    for (int64_t k = 0; k < n; ++k) {
+      touch(id[u0[k]], int(nsites + 2 * k));
+      touch(id[u1[k]], int(nsites + 2 * k + 1));
+    }
+    for (int s = 0; s < nsites; ++s) labels_out[s] = minidx[id[s]];
+    for (int64_t k = 0; k < n; ++k) {
+      labels_out[nsites + 2 * k] = minidx[id[u0[k]]];
+      labels_out[nsites + 2 * k + 1] = minidx[id[u1[k]]];
+    }
+  }
+  if (nc_out) *nc_out = nc;
+
+  if (coll_out) {
+    std::vector<lp_estimate> lest(nc);
+    std::vector<sa_estimate> est(nc);
+    std::vector<double> gg(nsites, 0.0);
+    if (gauge) gg.assign(gauge, gauge + nsites);
+    sc.assign(spins, spins + nsites);
+    for (int s = 0; s < nsites; ++s) {
+      lest[id[s]].start_bottom(gg[s], 0.0, sc[s]);
+      est[id[s]].mag += 1 - 2 * sc[s];
+      est[id[s]].size += 1;
+      est[id[s]].length += 1;
+    }
+    for (int64_t k = 0; k < n; ++k) {
+      const int b = ops[k].loc >> 1;
+      const int s0 = src[b], s1 = dst[b];
+      const int g = ops[k].type >> 2;
+      const double t = ops[k].time;
+      if ((g & 2) == 2) {  // frozen graphs are skipped by the accumulators (path_integral.C:692)
+        if (ops[k].type & 1) { sc[s0] ^= 1; sc[s1] ^= 1; }
+        continue;
+      }
+      lest[id[l0[k]]].end_s(gg[s0], t, sc[s0]);
+      lest[id[l1[k]]].end_s(gg[s1], t, sc[s1]);
+      est[id[l0[k]]].length += t;
+      est[id[l1[k]]].length += t;
+      if (ops[k].type & 1) { sc[s0] ^= 1; sc[s1] ^= 1; }
+      lest[id[u0[k]]].begin_s(gg[s0], t, sc[s0]);
+      lest[id[u1[k]]].begin_s(gg[s1], t, sc[s1]);
+      est[id[u0[k]]].length -= t;
+      est[id[u1[k]]].length -= t;
+    }
+    for (int s = 0; s < nsites; ++s) lest[id[current[s]]].end_s(gg[s], 1.0, sc[s]);
+    orc_collector coll;
+    std::memset(&coll, 0, sizeof(coll));
+    coll.nop = double(n);
+    coll.nc = nc;
+    for (auto& e : lest) collect(coll, e);
+    for (auto& e : est) {
+      coll.sa_usus += e.mag * e.mag;
+      coll.sa_smag += e.size * e.size;
+      coll.sa_ssus += e.length * e.length;
+    }
+    *coll_out = coll;
+  }
+  return 0;
+}
+
+// test/union_find.C:40-74 with boost::mt19937(29833u) == std::mt19937(29833) and
+// boost::uniform_real<>()(eng) == eng() / 2^32.
+int orc_union_find_replay(char* buf, int buflen) {
+  const int n = 100;
+  std::mt19937 eng(29833u);
+  auto rng = [&]() { return eng() / 4294967296.0; };
+  std::string out;
+  char line[256];
+  out += "[[union find test]]\n";
+  std::vector<lp_node> nodes(n);
+  std::vector<lp_node_noweight> nodes_noweight(n);
+  out += "\n[making tree]\n";
+  for (int i = 0; i < n; i++) {
+    int i0 = static_cast<int>(n * rng());
+    int i1 = static_cast<int>(n * rng());
+    std::snprintf(line, sizeof line, "connecting node %d to node %d\n", i0, i1);
+    out += line;
+    lp_unify(nodes, i0, i1);
+    lp_unify(nodes_noweight, i0, i1);
+  }
+  out += "\n[results]\n";
+  for (int i = 0; i < n; i++) {
+    if (nodes[i].is_root())
+      std::snprintf(line, sizeof line, "node %d is root and tree size is %d\n", i,
+                    nodes[i].weight());
+    else
+      std::snprintf(line, sizeof line, "node %d's parent is %d and its root is %d\n", i,
+                    nodes[i].parent(), lp_root_index(nodes, i));
+    out += line;
+  }
+  for (int i = 0; i < n; i++) {  // test/union_find.C:68-74 prints `nodes` again
+    if (nodes[i].is_root())
+      std::snprintf(line, sizeof line, "node %d is root\n", i);
+    else
+      std::snprintf(line, sizeof line, "node %d's parent is %d and its root is %d\n", i,
+                    nodes[i].parent(), lp_root_index(nodes, i));
+    out += line;
+  }
+  if (buf && buflen > 0) {
+    int m = std::min<int>(buflen - 1, int(out.size()));
+    std::memcpy(buf, out.data(), m);
+    buf[m] = 0;
+  }
+  return int(out.size());
+}
+
+// looper/weight_impl.h:165-188; crop_0/crop_01 from looper/crop.h.
+void orc_xxz_weights(double jxy_in, double jz, double a, double v[4], double* offset, int* sign) {
+  auto crop_0 = [](double x) { return x > 0 ? x : 0.0; };
+  a = a < 0 ? 0 : (a > 1 ? 1 : a);
+  if (sign) *sign = (jxy_in <= 0 ? 1 : -1);
+  double jxy = std::abs(jxy_in);
+  if (jxy + std::abs(jz) > 1e-10) {
+    if (jxy - jz > 2 * a * jxy) {
+      v[0] = crop_0(std::min(jxy / 2, (jxy + jz) / 4));
+      v[1] = crop_0(std::min(jxy / 2, (jxy - jz) / 4));
+      v[2] = crop_0(-(jxy - jz) / 2.0);
+      v[3] = crop_0(-(jxy + jz) / 2);
+    } else {
+      v[0] = (1 - a) * jxy / 2;
+      v[1] = a * jxy / 2;
+      v[2] = -((1 - 2 * a) * jxy - jz) / 2;
+      v[3] = 0;
+    }
+  } else {
+    v[0] = v[1] = v[2] = v[3] = 0;
+  }
+  if (offset) *offset = (v[0] + v[1] + v[2] + v[3]) / 2;
+}
+
+// standalone/loop.C:39-195 end to end.
+void orc_run_chain(int length, double temperature, unsigned sweeps, unsigned therm,
+                   double out[10]) {
+  std::vector<int32_t> src(length), dst(length);
+  std::vector<double> gauge(length);
+  for (int b = 0; b < length; ++b) {
+    src[b] = b;                            // common.h:92
+    dst[b] = (b == length - 1) ? 0 : b + 1;  // common.h:93
+    gauge[b] = (b & 1) ? -1 : 1;
+  }
+  const double beta = 1 / temperature;
+  orc_sim* S = orc_create(length, length, src.data(), dst.data(), gauge.data(), beta, 29833);
+  observable num_clusters, energy, usus, smag, ssus;
+  for (unsigned mcs = 0; mcs < therm + sweeps; ++mcs) {
+    orc_collector coll;
+    orc_sweep(S, &coll);
+    if (mcs >= therm) {  // loop.C:173-179
+      num_clusters << coll.nc;
+      energy << (0.25 * length - coll.nop / beta) / length;
+      usus << 0.25 * beta * coll.sa_usus / length;
+      smag << 0.25 * coll.sa_smag;
+      ssus << 0.25 * beta * coll.sa_ssus / length;
+    }
+  }
+  orc_destroy(S);
+  out[0] = num_clusters.mean(); out[1] = num_clusters.error();
+  out[2] = energy.mean();       out[3] = energy.error();
+  out[4] = usus.mean();         out[5] = usus.error();
+  out[6] = smag.mean();         out[7] = smag.error();
+  out[8] = ssus.mean();         out[9] = ssus.error();
+}
+
+}  // extern "C"
