@@ -1,0 +1,197 @@
+// lq_device.cuh -- device-side data layout, Philox, lock-free union-find, block primitives.
+//
+// Layout in HBM (see DESIGN.md "Data layout"):
+//   space is cut into T tiles of neighbouring sites, imaginary time into W windows; the operators
+//   of the bonds owned by tile t inside window w form one PAGE p = t*Wl + wl of fixed capacity
+//   `cap`, stored SoA (time f64, info u32), grouped by bond and time-sorted inside each
+//   (bond, window) BUCKET; boff[p*(nbmax+1) + lb] are the bucket offsets inside the page.
+//   Node ids of the world-line graph: site s -> s, upper leg(s) of operator #idx -> N + NPO*idx(+side)
+//   with idx = nbase[p] + j dense over the occupied slots.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lq {
+
+typedef uint32_t node_t;
+static const node_t NODE_NONE = 0xffffffffu;
+
+// info word of an operator (mirrors looper/operator.h type_ in the low bits)
+//   bit 0      offdiagonal            (local_operator_type::offdiagonal, operator.h:44)
+//   bits 2..3  graph type g           (type_ >> 2, operator.h:76; graph_impl.h:93-103)
+//   bit 4, 5   spin below the operator on source / target site (filled by k_link)
+//   bits 8..   local bond index inside the owning tile
+#define LQ_INFO_OFFDIAG 1u
+#define LQ_INFO_GSHIFT 2
+#define LQ_INFO_C0 16u
+#define LQ_INFO_C1 32u
+#define LQ_INFO_LBSHIFT 8
+
+// error bits raised by kernels (sticky, read back by the host after a sweep)
+#define LQ_ERR_PAGE_FULL 1
+#define LQ_ERR_CAND_FULL 2
+#define LQ_ERR_NODE_FULL 4
+#define LQ_ERR_CLUSTER_FULL 8
+#define LQ_ERR_NEIGH_FULL 16
+
+// fixed-point scale of imaginary time in the cluster sums (order-independent integer atomics)
+#define LQ_FX 1099511627776.0 /* 2^40 */
+
+struct Dev {
+  // ---- lattice, internal (tile-contiguous) numbering ----
+  int N, B, T, nbmax;
+  int W;            // global number of windows
+  int w0, Wl;       // this rank owns windows [w0, w0+Wl)
+  int cap;          // page capacity (operators)
+  int npo;          // nodes per operator (1: graphs {0,2,3}; 2: cross graph present)
+  int rank, nranks;
+  const int* bond_s0;    // [B] source site
+  const int* bond_s1;    // [B] target site
+  const int* bond_tile;  // [B] owning tile
+  const int* bond_base;  // [T+1] first bond of tile
+  const int* adj_off;    // [N+1]
+  const int* adj;        // [2B] (bond << 1 | side)
+  const double* bond_rate;  // [B] sum_g v_g  (candidate rate / beta, graph_impl.h:694)
+  const float4* bond_p;     // [B] {P(g=0|anti), P(accept|anti), P(g=1|par), P(accept|par)}
+  const float* bond_q;      // [B] P(g=0 | offdiagonal)  (graph_impl.h:311-313)
+  const signed char* gauge;  // [N] +1/-1/0
+  // ---- pages (double buffered) ----
+  double* time[2];
+  uint32_t* info[2];
+  uint16_t* boff[2];
+  int* pcount[2];
+  int* nbase;  // [P+1] exclusive scan of pcount (dense operator index base)
+  // ---- per (window, site) carries ----
+  uint8_t* spinW;  // [(Wl+1)*N] spin at the start of local window wl
+  node_t* curW;    // [(Wl+1)*N] node of the world-line segment crossing the start of window wl
+  // ---- union-find / labels ----
+  node_t* parent;  // [N + npo*ncap]; after k_relabel holds the cluster id
+  node_t* low0;    // [ncap] node below the operator on the source side
+  node_t* low1;    // [ncap] (npo == 2 only) node below on the target side
+  uint32_t* bitmap;  // root flags, one bit per node
+  uint32_t* wcount;  // roots per bitmap word -> exclusive scan in wbase
+  uint32_t* wbase;
+  // ---- clusters ----
+  long long* est;  // [4][nccap] usize, umag, ssize, smag in half units of LQ_FX
+  int* est0;       // [4][N]     usize0, umag0, ssize0, smag0 in half units
+  uint8_t* flipb;  // [nccap]
+  long long ncap;   // operator arena (= P*cap)
+  long long nccap;  // cluster arena
+  // ---- scalars on device ----
+  int* d_ntotal;     // total operators after the update (nbase[P])
+  uint32_t* d_nc;    // [0] number of clusters, [1] clusters rooted at a site node
+  int* d_err;
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) -- counter-based, so every (bond, window, draw) and every
+// cluster gets its own stream without any state in memory.
+// ------------------------------------------------------------------------------------------
+struct philox_t { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ philox_t philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                           uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+#else
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  philox_t r; r.x = c0; r.y = c1; r.z = c2; r.w = c3;
+  return r;
+}
+
+// uniform in (0,1] with 53 bits
+__host__ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  uint64_t v = (((uint64_t)a << 32) | b) >> 11;
+  return (double)(v + 1) * (1.0 / 9007199254740992.0);
+}
+// uniform in [0,1) with 24 bits (graph choice)
+__host__ __device__ __forceinline__ float u24(uint32_t a) { return (float)(a >> 8) * (1.0f / 16777216.0f); }
+
+// RNG stream ids (counter word 3)
+#define LQ_STREAM_CAND 0x10000000u
+#define LQ_STREAM_OFFD 0x20000000u
+#define LQ_STREAM_FLIP 0x30000000u
+
+// ------------------------------------------------------------------------------------------
+// Lock-free union-find (replaces looper/union_find.h:242-284 + atomic.h CAS lock).
+// Invariant: parent[x] <= x; a root has parent[x] == x; hooking always puts the LARGER root under
+// the SMALLER one with one atomicCAS, so the final root of a cluster is its minimum node index --
+// the reference's LOOPER_USE_DETERMINISTIC_UNIFY rule (union_find.h:229-233, 260-264) -- and the
+// partition is independent of the order in which threads win.
+// Reads go through L2 (ld.cg): stale L1 lines would still be valid ancestors, but L2 keeps the
+// retry loops short.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ node_t uf_load(const node_t* p) { return __ldcg(p); }
+
+__device__ __forceinline__ node_t uf_find(node_t* parent, node_t x) {
+  node_t p = uf_load(parent + x);
+  while (p != x) {
+    node_t gp = uf_load(parent + p);
+    if (gp != p) parent[x] = gp;  // path halving: only non-roots are written, always to an ancestor
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(node_t* parent, node_t a, node_t b) {
+  node_t ra = uf_find(parent, a);
+  node_t rb = uf_find(parent, b);
+  while (ra != rb) {
+    if (ra < rb) { node_t t = ra; ra = rb; rb = t; }  // ra > rb: hook ra under rb
+    node_t old = atomicCAS(parent + ra, ra, rb);
+    if (old == ra) return;
+    ra = uf_find(parent, old);  // somebody else hooked ra first; continue from its new ancestor
+    rb = uf_find(parent, rb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one int per thread (warp shuffles + one smem hop)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_exscan(int v, int* total, int* smem /* >= 33 ints */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) smem[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = (lane < nw) ? smem[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += n;
+    }
+    smem[lane] = winc - w;
+    if (lane == 31) smem[32] = winc;
+  }
+  __syncthreads();
+  int res = smem[wid] + inc - v;
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+// time window bounds; identical arithmetic on host (bucketing in lq_set_state) and device
+__host__ __device__ __forceinline__ double window_lo(int w, int W) { return (double)w / (double)W; }
+__host__ __device__ __forceinline__ double window_hi(int w, int W) {
+  return (w + 1 >= W) ? 1.0 : (double)(w + 1) / (double)W;
+}
+
+}  // namespace lq

@@ -1,0 +1,827 @@
+// lq_engine.cu -- host side of the engine behind include/lq.h: spatial tiling, arenas, the
+// per-step kernel schedule, state import/export, and the extern "C" entry points.
+//
+// Build: alps-looper_b200/csrc/Makefile  (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)
+// There is deliberately no CPU path in this file: every entry point that computes needs a CUDA
+// device and fails with LQ_E_CUDA otherwise.
+#include "../../include/lq.h"
+#include "lq_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+struct cuda_error { cudaError_t e; const char* what; const char* file; int line; };
+#define CK(call)                                                              \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) throw cuda_error{e__, #call, __FILE__, __LINE__}; \
+  } while (0)
+
+struct lq_error { int code; std::string msg; };
+[[noreturn]] void fail(int code, const std::string& m) { throw lq_error{code, m}; }
+
+template <class T>
+struct DBuf {  // device array
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count, size_t* total) {
+    release();
+    n = count;
+    if (count) {
+      CK(cudaMalloc((void**)&p, count * sizeof(T)));
+      if (total) *total += count * sizeof(T);
+    }
+  }
+  void upload(const std::vector<T>& v, size_t* total) {
+    alloc(v.size(), total);
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DBuf() { release(); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Spatial tiling: sites are renumbered so that every tile is a contiguous range, bonds so that
+// the bonds owned by a tile (those whose source site lies in it) are contiguous.
+// ---------------------------------------------------------------------------------------------
+struct Partition {
+  int N = 0, B = 0, T = 0, nbmax = 0;
+  std::vector<int> site_e2i, site_i2e, bond_e2i, bond_i2e;
+  std::vector<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj;
+};
+
+void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
+  const int N = L.num_sites, B = L.num_bonds;
+  P.N = N;
+  P.B = B;
+  std::vector<int> tile_of(N);
+  long long prod = 1;
+  int nd = 0;
+  for (int k = 0; k < 3; ++k)
+    if (L.dims[k] > 0) { prod *= L.dims[k]; ++nd; }
+  int T = 0;
+  if (nd > 0 && prod == N) {
+    int dim[3] = {std::max(1, L.dims[0]), std::max(1, L.dims[1]), std::max(1, L.dims[2])};
+    int e[3] = {1, 1, 1};
+    // distribute the factors of two of tile_sites round-robin over the extended directions
+    int budget = std::max(1, tile_sites);
+    bool grew = true;
+    while (budget > 1 && grew) {
+      grew = false;
+      for (int k = 0; k < 3 && budget > 1; ++k)
+        if (e[k] * 2 <= dim[k]) { e[k] *= 2; budget /= 2; grew = true; }
+    }
+    int nt[3];
+    for (int k = 0; k < 3; ++k) nt[k] = (dim[k] + e[k] - 1) / e[k];
+    T = nt[0] * nt[1] * nt[2];
+    for (int s = 0; s < N; ++s) {
+      int x = s % dim[0], y = (s / dim[0]) % dim[1], z = s / (dim[0] * dim[1]);
+      tile_of[s] = (x / e[0]) + nt[0] * ((y / e[1]) + nt[1] * (z / e[2]));
+    }
+  } else {
+    const int S = std::max(1, tile_sites);
+    T = (N + S - 1) / S;
+    for (int s = 0; s < N; ++s) tile_of[s] = s / S;
+  }
+  // sites
+  P.site_i2e.resize(N);
+  std::iota(P.site_i2e.begin(), P.site_i2e.end(), 0);
+  std::stable_sort(P.site_i2e.begin(), P.site_i2e.end(),
+                   [&](int a, int b) { return tile_of[a] < tile_of[b]; });
+  P.site_e2i.resize(N);
+  for (int i = 0; i < N; ++i) P.site_e2i[P.site_i2e[i]] = i;
+  // drop empty tiles (ragged shapes) by compacting tile ids
+  std::vector<int> tmap(T, -1);
+  int Tc = 0;
+  for (int i = 0; i < N; ++i) {
+    int t = tile_of[P.site_i2e[i]];
+    if (tmap[t] < 0) tmap[t] = Tc++;
+  }
+  for (int s = 0; s < N; ++s) tile_of[s] = tmap[tile_of[s]];
+  P.T = T = Tc;
+  // bonds
+  P.bond_i2e.resize(B);
+  std::iota(P.bond_i2e.begin(), P.bond_i2e.end(), 0);
+  std::stable_sort(P.bond_i2e.begin(), P.bond_i2e.end(),
+                   [&](int a, int b) { return tile_of[L.src[a]] < tile_of[L.src[b]]; });
+  P.bond_e2i.resize(B);
+  P.bond_s0.resize(B);
+  P.bond_s1.resize(B);
+  P.bond_tile.resize(B);
+  P.bond_base.assign(T + 1, 0);
+  for (int i = 0; i < B; ++i) {
+    const int e = P.bond_i2e[i];
+    P.bond_e2i[e] = i;
+    P.bond_s0[i] = P.site_e2i[L.src[e]];
+    P.bond_s1[i] = P.site_e2i[L.dst[e]];
+    P.bond_tile[i] = tile_of[L.src[e]];
+    P.bond_base[P.bond_tile[i] + 1]++;
+  }
+  P.nbmax = 0;
+  for (int t = 0; t < T; ++t) {
+    P.nbmax = std::max(P.nbmax, P.bond_base[t + 1]);
+    P.bond_base[t + 1] += P.bond_base[t];
+  }
+  // adjacency
+  P.adj_off.assign(N + 1, 0);
+  for (int i = 0; i < B; ++i) { P.adj_off[P.bond_s0[i] + 1]++; P.adj_off[P.bond_s1[i] + 1]++; }
+  for (int s = 0; s < N; ++s) P.adj_off[s + 1] += P.adj_off[s];
+  P.adj.resize(2 * (size_t)B);
+  std::vector<int> fill(P.adj_off.begin(), P.adj_off.end() - 1);
+  for (int i = 0; i < B; ++i) {
+    P.adj[fill[P.bond_s0[i]]++] = (i << 1) | 0;
+    P.adj[fill[P.bond_s1[i]]++] = (i << 1) | 1;
+  }
+}
+
+inline int window_of(double t, int W) {
+  int w = (int)(t * W);
+  if (w >= W) w = W - 1;
+  if (w < 0) w = 0;
+  while (w > 0 && lq::window_lo(w, W) > t) --w;
+  while (w + 1 < W && lq::window_hi(w, W) <= t) ++w;
+  return w;
+}
+
+const char* kTimerLabels[17] = {"", "", "", "dispatch", "init", "fill_times(K1 rng)", "init_fragments",
+                                "insert/remove+reconnect", "", "close in tau", "", "assign ids",
+                                "accumulate", "collect", "flip decision", "flip", "measurement"};
+
+}  // namespace
+
+struct lq_engine {
+  // configuration
+  Partition part;
+  std::vector<double> weights;  // [B][4] external bond order
+  std::vector<signed char> gauge_e;
+  double energy_offset = 0, beta = 1;
+  lq_options opt{};
+  int W = 1, Wl = 1, w0 = 0, cap = 0, tpb = 32, npo = 1;
+  size_t P = 0;
+  long long ncap = 0, nccap = 0;
+  size_t nwords_cap = 0, device_bytes = 0;
+  int sm_count = 0;
+  uint32_t mcs = 0;
+  int cur = 0;  // live page buffer
+  int64_t launches = 0;
+  bool timers_on = false;
+  // device
+  lq::Dev d{};
+  cudaStream_t stream = nullptr;
+  DBuf<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
+  DBuf<double> bond_rate, time_[2], partial, d_out;
+  DBuf<float4> bond_p;
+  DBuf<float> bond_q;
+  DBuf<signed char> gauge;
+  DBuf<uint32_t> info[2], parent, low0, low1, bitmap, wcount, wbase, scan_tmp, d_nc, curW, labels;
+  DBuf<uint16_t> boff[2];
+  DBuf<uint8_t> spinW, flipb;
+  DBuf<long long> est;
+  DBuf<int> est0;
+  double* h_out = nullptr;  // pinned
+  size_t h_out_n = 0;
+  size_t nblk_collect = 0;
+  lq_comm comm{};
+  bool has_comm = false;
+  // timers
+  struct TimerAcc { double sec = 0; int count = 0; } tacc[17];
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tpending;
+
+  ~lq_engine() {
+    if (h_out) cudaFreeHost(h_out);
+    for (auto& t : tpending) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // -------------------------------------------------------------------------------------------
+  void setup(const lq_lattice& L, const lq_model& M, double beta_, const lq_options& o) {
+    if (L.num_sites <= 0 || L.num_bonds < 0 || !L.src || !L.dst) fail(LQ_E_INVALID, "empty lattice");
+    if (!(beta_ > 0)) fail(LQ_E_INVALID, "beta must be positive");
+    for (int b = 0; b < L.num_bonds; ++b) {
+      if (L.src[b] < 0 || L.src[b] >= L.num_sites || L.dst[b] < 0 || L.dst[b] >= L.num_sites)
+        fail(LQ_E_INVALID, "bond endpoint out of range");
+      if (L.src[b] == L.dst[b]) fail(LQ_E_INVALID, "self-loop bond");
+    }
+    opt = o;
+    if (opt.tile_sites <= 0) opt.tile_sites = 64;
+    if (!(opt.window_ops > 0)) opt.window_ops = 2.0;
+    if (!(opt.reserve > 0)) opt.reserve = 1.7;
+    if (!(opt.cluster_reserve > 0)) opt.cluster_reserve = 0.75;
+    if (opt.nranks < 1) { opt.nranks = 1; opt.rank = 0; }
+    if (opt.rank < 0 || opt.rank >= opt.nranks) fail(LQ_E_INVALID, "rank out of range");
+    timers_on = (opt.flags & 1) != 0;
+    beta = beta_;
+    energy_offset = M.energy_offset;
+    weights.resize(4 * (size_t)L.num_bonds);
+    for (int b = 0; b < L.num_bonds; ++b)
+      for (int g = 0; g < 4; ++g) {
+        double v = M.bond_weights ? M.bond_weights[4 * (size_t)b + g] : M.uniform_weights[g];
+        if (!(v >= 0)) fail(LQ_E_INVALID, "negative graph weight");
+        weights[4 * (size_t)b + g] = v;
+      }
+    gauge_e.assign(L.num_sites, 0);
+    if (L.gauge)
+      for (int s = 0; s < L.num_sites; ++s) gauge_e[s] = (signed char)(L.gauge[s] > 0 ? 1 : (L.gauge[s] < 0 ? -1 : 0));
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      fail(LQ_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                          " (this engine has no CPU fallback)");
+    CK(cudaSetDevice(opt.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, opt.device));
+    sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+
+    make_partition(L, opt.tile_sites, part);
+    if (part.nbmax + 1 > 1024)
+      fail(LQ_E_INVALID, "tile owns more than 1023 bonds: lower lq_options.tile_sites");
+    tpb = ((part.nbmax + 1 + 31) / 32) * 32;
+
+    // static tables
+    const int N = part.N, B = part.B;
+    std::vector<double> rate(B);
+    std::vector<float4> bp(B);
+    std::vector<float> bq(B);
+    npo = 1;
+    for (int i = 0; i < B; ++i) {
+      const double* v = &weights[4 * (size_t)part.bond_i2e[i]];
+      const double sum = v[0] + v[1] + v[2] + v[3];
+      rate[i] = sum;
+      if (v[1] > 0) npo = 2;
+      if (sum > 0) bp[i] = make_float4((float)(v[0] / sum), (float)((v[0] + v[2]) / sum),
+                                       (float)(v[1] / sum), (float)((v[1] + v[3]) / sum));
+      else bp[i] = make_float4(0, 0, 0, 0);
+      bq[i] = (v[0] + v[1] > 0) ? (float)(v[0] / (v[0] + v[1])) : 1.0f;
+      if (v[1] == 0) bq[i] = 1.0f;
+    }
+    std::vector<signed char> gi(N);
+    for (int i = 0; i < N; ++i) gi[i] = gauge_e[part.site_i2e[i]];
+    bond_s0.upload(part.bond_s0, &device_bytes);
+    bond_s1.upload(part.bond_s1, &device_bytes);
+    bond_tile.upload(part.bond_tile, &device_bytes);
+    bond_base.upload(part.bond_base, &device_bytes);
+    adj_off.upload(part.adj_off, &device_bytes);
+    adj.upload(part.adj, &device_bytes);
+    bond_rate.upload(rate, &device_bytes);
+    bond_p.upload(bp, &device_bytes);
+    bond_q.upload(bq, &device_bytes);
+    gauge.upload(gi, &device_bytes);
+    d_ntotal.alloc(1, &device_bytes);
+    d_err.alloc(1, &device_bytes);
+    d_nc.alloc(2, &device_bytes);
+    CK(cudaMemset(d_err.p, 0, sizeof(int)));
+    CK(cudaMemset(d_ntotal.p, 0, sizeof(int)));
+    CK(cudaMemset(d_nc.p, 0, 2 * sizeof(uint32_t)));
+    size_arenas();
+    // initial state: all up, no operators (path_integral.C:225)
+    clear_state();
+  }
+
+  // (re)size everything that depends on beta
+  void size_arenas() {
+    const int N = part.N, B = part.B, T = part.T;
+    double maxrate = 0;
+    std::vector<double> tile_rate(T, 0.0);
+    for (int i = 0; i < B; ++i) {
+      const double* v = &weights[4 * (size_t)part.bond_i2e[i]];
+      const double sum = v[0] + v[1] + v[2] + v[3];
+      maxrate = std::max(maxrate, sum);
+      tile_rate[part.bond_tile[i]] += sum;
+    }
+    W = (int)std::ceil(beta * maxrate / opt.window_ops);
+    if (W < 1) W = 1;
+    W = ((W + opt.nranks - 1) / opt.nranks) * opt.nranks;
+    Wl = W / opt.nranks;
+    w0 = opt.rank * Wl;
+    double mu = 0;
+    for (int t = 0; t < T; ++t) mu = std::max(mu, tile_rate[t] * beta / W);
+    const double m = opt.reserve * mu;
+    long long c = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
+    if (c > 65535) fail(LQ_E_INVALID, "page capacity exceeds 65535 operators: lower tile_sites or window_ops");
+    cap = (int)c;
+    P = (size_t)T * Wl;
+    ncap = (long long)P * cap;
+    const long long nodes_cap = (long long)N + (long long)npo * ncap;
+    if (nodes_cap >= 0xfffffff0ll) fail(LQ_E_INVALID, "more than 2^32 graph nodes: split the run over more GPUs");
+    nccap = std::min<long long>(nodes_cap, (long long)N + (long long)std::ceil(opt.cluster_reserve * (double)(npo * ncap)));
+    nwords_cap = (size_t)((nodes_cap + 31) / 32);
+
+    size_t* tb = &device_bytes;
+    for (int k = 0; k < 2; ++k) {
+      time_[k].alloc((size_t)ncap, tb);
+      info[k].alloc((size_t)ncap, tb);
+      boff[k].alloc(P * (size_t)(part.nbmax + 1), tb);
+      pcount[k].alloc(P, tb);
+    }
+    nbase.alloc(P + 1, tb);
+    spinW.alloc((size_t)(Wl + 1) * N, tb);
+    curW.alloc((size_t)(Wl + 1) * N, tb);
+    parent.alloc((size_t)nodes_cap, tb);
+    low0.alloc((size_t)ncap, tb);
+    if (npo == 2) low1.alloc((size_t)ncap, tb); else low1.release();
+    bitmap.alloc(nwords_cap + 1, tb);
+    wcount.alloc(nwords_cap + 1, tb);
+    wbase.alloc(nwords_cap + 1, tb);
+    const size_t scan_n = std::max(nwords_cap, P) + 1;
+    scan_tmp.alloc((scan_n + LQ_SCAN_CHUNK - 1) / LQ_SCAN_CHUNK + 1, tb);
+    est.alloc(4 * (size_t)nccap, tb);
+    est0.alloc(4 * (size_t)N, tb);
+    flipb.alloc((size_t)nccap, tb);
+    nblk_collect = ((size_t)nccap + 255) / 256;
+    partial.alloc(nblk_collect * LQ_NSUM, tb);
+    CK(cudaMemset(est.p, 0, est.n * sizeof(long long)));
+    CK(cudaMemset(est0.p, 0, est0.n * sizeof(int)));
+    CK(cudaMemset(bitmap.p, 0, bitmap.n * sizeof(uint32_t)));
+    CK(cudaMemset(wcount.p, 0, wcount.n * sizeof(uint32_t)));
+    fill_dev();
+  }
+
+  void fill_dev() {
+    d.N = part.N; d.B = part.B; d.T = part.T; d.nbmax = part.nbmax;
+    d.W = W; d.w0 = w0; d.Wl = Wl; d.cap = cap; d.npo = npo;
+    d.rank = opt.rank; d.nranks = opt.nranks;
+    d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_tile = bond_tile.p; d.bond_base = bond_base.p;
+    d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
+    d.bond_q = bond_q.p; d.gauge = gauge.p;
+    for (int k = 0; k < 2; ++k) {
+      d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
+    }
+    d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
+    d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
+    d.est = est.p; d.est0 = est0.p; d.flipb = flipb.p; d.ncap = ncap; d.nccap = nccap;
+    d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
+  }
+
+  void clear_state() {
+    for (int k = 0; k < 2; ++k) {
+      CK(cudaMemset(boff[k].p, 0, boff[k].n * sizeof(uint16_t)));
+      CK(cudaMemset(pcount[k].p, 0, pcount[k].n * sizeof(int)));
+    }
+    CK(cudaMemset(nbase.p, 0, nbase.n * sizeof(int)));
+    CK(cudaMemset(spinW.p, 0, spinW.n));
+    CK(cudaMemset(d_ntotal.p, 0, sizeof(int)));
+    cur = 0;
+  }
+
+  // -------------------------------------------------------------------------------------------
+  // timers (ids of path_integral.C:284-299); device time between two events on the stream
+  struct Section {
+    lq_engine* e; int id; cudaEvent_t a = nullptr, b = nullptr;
+    Section(lq_engine* e_, int id_) : e(e_), id(id_) {
+      if (e->timers_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, e->stream); }
+    }
+    ~Section() {
+      if (e->timers_on) { cudaEventRecord(b, e->stream); e->tpending.push_back({id, {a, b}}); }
+    }
+  };
+  void drain_timers() {
+    for (auto& t : tpending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, t.second.first, t.second.second) == cudaSuccess) {
+        tacc[t.first].sec += 1e-3 * ms;
+        tacc[t.first].count++;
+      }
+      cudaEventDestroy(t.second.first);
+      cudaEventDestroy(t.second.second);
+    }
+    tpending.clear();
+  }
+
+  // -------------------------------------------------------------------------------------------
+  void scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_out, int* total_out2) {
+    const size_t nblk = (n + LQ_SCAN_CHUNK - 1) / LQ_SCAN_CHUNK;
+    lq::k_scan_blocksum<<<(unsigned)nblk, LQ_SCAN_THREADS, 0, stream>>>(in, n, scan_tmp.p);
+    lq::k_scan_top<<<1, LQ_SCAN_THREADS, 0, stream>>>(scan_tmp.p, nblk, total_out, total_out2);
+    lq::k_scan_final<<<(unsigned)nblk, LQ_SCAN_THREADS, 0, stream>>>(in, out, n, scan_tmp.p);
+    launches += 3;
+  }
+
+  static unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+  // K2 + K3 on the live buffer (+ K4/K5 sums); used by the step and by lq_build_clusters
+  void label_clusters(double* out_slot, uint32_t step_id) {
+    const int N = part.N;
+    const size_t nodes_cap = (size_t)N + (size_t)npo * (size_t)ncap;
+    const uint32_t key0 = (uint32_t)opt.seed, key1 = (uint32_t)(opt.seed >> 32);
+    {
+      Section s(this, 6);
+      scan_u32((const uint32_t*)pcount[cur].p, (uint32_t*)nbase.p, P, (uint32_t*)(nbase.p + P), d_ntotal.p);
+      lq::k_init_nodes<<<grid_for(nodes_cap, 256), 256, 0, stream>>>(d);
+      lq::k_carry<<<grid_for(N, 128), 128, 0, stream>>>(d, cur);
+      launches += 2;
+    }
+    {
+      Section s(this, 7);
+      lq::k_link<<<(unsigned)P, tpb, 0, stream>>>(d, cur);
+      launches += 1;
+    }
+    {
+      Section s(this, 9);
+      if (opt.nranks == 1) { lq::k_close<<<grid_for(N, 128), 128, 0, stream>>>(d); launches += 1; }
+    }
+    {
+      Section s(this, 11);
+      lq::k_compress<<<grid_for(nwords_cap * 32, 256), 256, 0, stream>>>(d, nwords_cap);
+      scan_u32(wcount.p, wbase.p, nwords_cap, wbase.p + nwords_cap, (int*)d_nc.p);
+      lq::k_relabel<<<grid_for(nodes_cap, 256), 256, 0, stream>>>(d);
+      launches += 2;
+    }
+    {
+      Section s(this, 12);
+      lq::k_estimate<<<(unsigned)P, 256, sizeof(lq::EstHash), stream>>>(d, cur);
+      lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
+      launches += 2;
+    }
+    {
+      Section s(this, 13);
+      lq::k_collect<<<(unsigned)nblk_collect, 256, 0, stream>>>(d, partial.p, key0, key1, step_id);
+      lq::k_collect_final<<<1, 256, 0, stream>>>(d, partial.p, nblk_collect, out_slot);
+      launches += 2;
+    }
+  }
+
+  void ensure_out(size_t slots) {
+    if (d_out.n < slots * 32) d_out.alloc(slots * 32, &device_bytes);
+    if (h_out_n < slots * 32) {
+      if (h_out) cudaFreeHost(h_out);
+      CK(cudaMallocHost((void**)&h_out, slots * 32 * sizeof(double)));
+      h_out_n = slots * 32;
+    }
+  }
+
+  void enqueue_step(double* out_slot) {
+    const uint32_t key0 = (uint32_t)opt.seed, key1 = (uint32_t)(opt.seed >> 32);
+    {
+      Section s(this, 5);
+      lq::k_diag_update<<<(unsigned)P, tpb, 0, stream>>>(d, cur, beta, key0, key1, mcs);
+      launches += 1;
+      cur ^= 1;
+    }
+    label_clusters(out_slot, mcs);
+    {
+      Section s(this, 15);
+      lq::k_flip<<<(unsigned)P, 256, 0, stream>>>(d, cur);
+      lq::k_flip_spins<<<grid_for((size_t)(Wl + 1) * part.N, 256), 256, 0, stream>>>(d);
+      launches += 2;
+    }
+    ++mcs;
+  }
+
+  void to_collector(const double* o, lq_collector* c) const {
+    c->umag0 = o[0]; c->usize2 = o[1]; c->umag2 = o[2]; c->usize4 = o[3]; c->umag4 = o[4];
+    c->usize = o[5]; c->umag = o[6];
+    c->smag0 = o[7]; c->ssize2 = o[8]; c->smag2 = o[9]; c->ssize4 = o[10]; c->smag4 = o[11];
+    c->ssize = o[12]; c->smag = o[13];
+    c->nc = o[14]; c->nop = o[15]; c->noc = 0;
+    c->ene = energy_offset - c->nop / beta;  // path_integral.C:851
+  }
+
+  void check_err(int err) {
+    if (!err) return;
+    CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
+    std::string m = "arena overflow:";
+    if (err & LQ_ERR_PAGE_FULL) m += " page full (raise lq_options.reserve);";
+    if (err & LQ_ERR_CAND_FULL) m += " >32 accepted candidates in one bucket (lower window_ops);";
+    if (err & LQ_ERR_NEIGH_FULL) m += " >64 off-diagonal neighbour legs in one window (lower window_ops);";
+    if (err & LQ_ERR_CLUSTER_FULL) m += " cluster arena full (raise cluster_reserve);";
+    if (err & LQ_ERR_NODE_FULL) m += " node arena full;";
+    fail(LQ_E_OVERFLOW, m);
+  }
+
+  void sweep_many(int count, lq_collector* out) {
+    if (count <= 0) return;
+    if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
+    ensure_out((size_t)count);
+    for (int i = 0; i < count; ++i) enqueue_step(d_out.p + (size_t)i * 32);
+    CK(cudaMemcpyAsync(h_out, d_out.p, (size_t)count * 32 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    drain_timers();
+    int err = 0;
+    for (int i = 0; i < count; ++i) {
+      if (out) to_collector(h_out + (size_t)i * 32, out + i);
+      err |= (int)h_out[(size_t)i * 32 + 16];
+    }
+    check_err(err);
+  }
+
+  // -------------------------------------------------------------------------------------------
+  // state import / export (host side, test and checkpoint path)
+  // -------------------------------------------------------------------------------------------
+  void set_state(const int32_t* spins, const lq_op* ops, int64_t n) {
+    const int N = part.N, B = part.B;
+    std::vector<std::vector<std::pair<double, uint32_t>>> buckets;  // per (page, lb) for local windows
+    const size_t nbk = P * (size_t)part.nbmax;
+    buckets.resize(nbk);
+    // spin at the start of every global window
+    std::vector<uint8_t> par((size_t)(W + 1) * N, 0);
+    double tprev = -1;
+    for (int64_t k = 0; k < n; ++k) {
+      if (!(ops[k].loc & 1)) fail(LQ_E_UNSUPPORTED, "site operators are not supported yet");
+      const int be = ops[k].loc >> 1;
+      if (be < 0 || be >= B) fail(LQ_E_INVALID, "operator bond out of range");
+      const double t = ops[k].time;
+      if (!(t >= 0 && t < 1)) fail(LQ_E_INVALID, "operator time outside [0,1)");
+      if (t < tprev) fail(LQ_E_INVALID, "operators must be sorted by time");
+      tprev = t;
+      const int g = (ops[k].type >> 2) & 3;
+      if (g == 1 && npo != 2) fail(LQ_E_INVALID, "cross graph on a model without v[1] weight");
+      const int bi = part.bond_e2i[be];
+      const int w = window_of(t, W);
+      if (ops[k].type & 1) {
+        par[(size_t)(w + 1) * N + part.bond_s0[bi]] ^= 1;
+        par[(size_t)(w + 1) * N + part.bond_s1[bi]] ^= 1;
+      }
+      if (w < w0 || w >= w0 + Wl) continue;
+      const int tl = part.bond_tile[bi];
+      const int lb = bi - part.bond_base[tl];
+      const size_t p = (size_t)tl * Wl + (w - w0);
+      const uint32_t inf = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)g << LQ_INFO_GSHIFT) | (uint32_t)(ops[k].type & 1);
+      buckets[p * part.nbmax + lb].push_back({t, inf});
+    }
+    std::vector<uint8_t> sw((size_t)(Wl + 1) * N);
+    {
+      std::vector<uint8_t> c(N);
+      for (int i = 0; i < N; ++i) c[i] = (uint8_t)(spins[part.site_i2e[i]] & 1);
+      for (int w = 0; w <= W; ++w) {
+        for (int i = 0; i < N; ++i) c[i] ^= par[(size_t)w * N + i];
+        if (w >= w0 && w <= w0 + Wl)
+          std::memcpy(&sw[(size_t)(w - w0) * N], c.data(), N);
+      }
+      for (int i = 0; i < N; ++i)
+        if (c[i] != (uint8_t)(spins[part.site_i2e[i]] & 1))
+          fail(LQ_E_INVALID, "operator string is not periodic in imaginary time");
+    }
+    std::vector<double> ht((size_t)ncap, 0.0);
+    std::vector<uint32_t> hi((size_t)ncap, 0u);
+    std::vector<uint16_t> hb(P * (size_t)(part.nbmax + 1), 0);
+    std::vector<int> hc(P, 0);
+    for (size_t p = 0; p < P; ++p) {
+      int off = 0;
+      for (int lb = 0; lb < part.nbmax; ++lb) {
+        auto& v = buckets[p * part.nbmax + lb];
+        hb[p * (part.nbmax + 1) + lb] = (uint16_t)off;
+        std::stable_sort(v.begin(), v.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        if (off + (int)v.size() > cap) fail(LQ_E_OVERFLOW, "page full while loading state (raise lq_options.reserve)");
+        for (auto& o : v) {
+          ht[p * (size_t)cap + off] = o.first;
+          hi[p * (size_t)cap + off] = o.second;
+          ++off;
+        }
+      }
+      hb[p * (part.nbmax + 1) + part.nbmax] = (uint16_t)off;
+      hc[p] = off;
+    }
+    CK(cudaStreamSynchronize(stream));
+    cur = 0;
+    CK(cudaMemcpy(time_[0].p, ht.data(), ht.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(info[0].p, hi.data(), hi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(boff[0].p, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pcount[0].p, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(spinW.p, sw.data(), sw.size(), cudaMemcpyHostToDevice));
+  }
+
+  struct HostOp { double time; int bi; uint32_t info; int idx; };
+
+  // all local operators sorted by (time, internal bond); idx = dense device index
+  void fetch_ops(std::vector<HostOp>& out) {
+    CK(cudaStreamSynchronize(stream));
+    std::vector<int> hc(P);
+    CK(cudaMemcpy(hc.data(), pcount[cur].p, P * sizeof(int), cudaMemcpyDeviceToHost));
+    out.clear();
+    std::vector<double> ht(cap);
+    std::vector<uint32_t> hi(cap);
+    int idx = 0;
+    for (size_t p = 0; p < P; ++p) {
+      const int n = hc[p];
+      if (n > 0) {
+        CK(cudaMemcpy(ht.data(), time_[cur].p + p * (size_t)cap, n * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hi.data(), info[cur].p + p * (size_t)cap, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      }
+      const int tl = (int)(p / Wl);
+      for (int j = 0; j < n; ++j)
+        out.push_back({ht[j], part.bond_base[tl] + (int)(hi[j] >> LQ_INFO_LBSHIFT), hi[j], idx + j});
+      idx += n;
+    }
+    std::sort(out.begin(), out.end(), [](const HostOp& a, const HostOp& b) {
+      return a.time < b.time || (a.time == b.time && a.bi < b.bi);
+    });
+  }
+
+  void get_state(int32_t* spins, lq_op* ops, int64_t* n) {
+    std::vector<HostOp> v;
+    fetch_ops(v);
+    if (n) *n = (int64_t)v.size();
+    if (ops)
+      for (size_t k = 0; k < v.size(); ++k) {
+        ops[k].time = v[k].time;
+        ops[k].loc = (part.bond_i2e[v[k].bi] << 1) | 1;
+        ops[k].type = (int32_t)(v[k].info & 0xf) & ~2;  // offdiag bit + graph bits
+      }
+    if (spins) {
+      std::vector<uint8_t> sw(part.N);
+      CK(cudaMemcpy(sw.data(), spinW.p, part.N, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < part.N; ++i) spins[part.site_i2e[i]] = sw[i];
+    }
+  }
+
+  void build_clusters(int32_t* labels_out, int64_t* nc_out, lq_collector* coll_out) {
+    if (opt.nranks > 1) fail(LQ_E_UNSUPPORTED, "lq_build_clusters is a single-engine call");
+    ensure_out(1);
+    label_clusters(d_out.p, 0xffffffffu);
+    labels.alloc(2 * (size_t)std::max<long long>(ncap, 1), nullptr);
+    lq::k_export_labels<<<(unsigned)P, 256, 0, stream>>>(d, cur, labels.p);
+    launches += 1;
+    CK(cudaMemcpyAsync(h_out, d_out.p, 32 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    drain_timers();
+    check_err((int)h_out[16]);
+    if (coll_out) to_collector(h_out, coll_out);
+    if (nc_out) *nc_out = (int64_t)h_out[14];
+    if (labels_out) {
+      std::vector<HostOp> v;
+      fetch_ops(v);
+      const int N = part.N;
+      const size_t n = v.size();
+      std::vector<uint32_t> sl(N), ol(2 * std::max<size_t>(n, 1));
+      CK(cudaMemcpy(sl.data(), parent.p, N * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      if (n) CK(cudaMemcpy(ol.data(), labels.p, 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      // canonical min-index labels over: site s (external) -> s ; legs of operator k -> N+2k, N+2k+1
+      const size_t ncl = (size_t)h_out[14];
+      std::vector<int32_t> minidx(ncl + 1, -1);
+      auto touch = [&](uint32_t cid, int32_t idx) {
+        if (cid >= minidx.size()) fail(LQ_E_INVALID, "cluster id out of range (internal error)");
+        if (minidx[cid] < 0) minidx[cid] = idx;
+      };
+      for (int se = 0; se < N; ++se) touch(sl[part.site_e2i[se]], se);
+      for (size_t k = 0; k < n; ++k) {
+        touch(ol[2 * (size_t)v[k].idx], (int32_t)(N + 2 * k));
+        touch(ol[2 * (size_t)v[k].idx + 1], (int32_t)(N + 2 * k + 1));
+      }
+      for (int se = 0; se < N; ++se) labels_out[se] = minidx[sl[part.site_e2i[se]]];
+      for (size_t k = 0; k < n; ++k) {
+        labels_out[N + 2 * k] = minidx[ol[2 * (size_t)v[k].idx]];
+        labels_out[N + 2 * k + 1] = minidx[ol[2 * (size_t)v[k].idx + 1]];
+      }
+    }
+    labels.release();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------
+#define LQ_TRY(body)                                                                      \
+  try { body; return LQ_OK; }                                                             \
+  catch (const lq_error& e) { g_err = e.msg; return e.code; }                             \
+  catch (const cuda_error& e) {                                                           \
+    g_err = std::string(cudaGetErrorString(e.e)) + " in " + e.what + " at " + e.file + ":" + \
+            std::to_string(e.line);                                                       \
+    return LQ_E_CUDA;                                                                     \
+  }                                                                                       \
+  catch (const std::bad_alloc&) { g_err = "host out of memory"; return LQ_E_NOMEM; }      \
+  catch (const std::exception& e) { g_err = e.what(); return LQ_E_INVALID; }
+
+extern "C" {
+
+int lq_create(lq_handle* out, const lq_lattice* lat, const lq_model* model, double beta,
+              const lq_options* opt) {
+  if (!out || !lat || !model) { g_err = "null argument"; return LQ_E_INVALID; }
+  *out = nullptr;
+  lq_options o{};
+  if (opt) o = *opt;
+  lq_engine* e = nullptr;
+  try {
+    e = new lq_engine();
+    e->setup(*lat, *model, beta, o);
+    *out = e;
+    return LQ_OK;
+  } catch (const lq_error& x) { g_err = x.msg; delete e; return x.code; }
+  catch (const cuda_error& x) {
+    g_err = std::string(cudaGetErrorString(x.e)) + " in " + x.what + " at " + x.file + ":" + std::to_string(x.line);
+    delete e;
+    return (x.e == cudaErrorMemoryAllocation) ? LQ_E_NOMEM : LQ_E_CUDA;
+  } catch (const std::exception& x) { g_err = x.what(); delete e; return LQ_E_INVALID; }
+}
+
+int lq_destroy(lq_handle h) {
+  if (!h) return LQ_OK;
+  cudaSetDevice(h->opt.device);
+  delete h;
+  return LQ_OK;
+}
+
+int lq_set_beta(lq_handle h, double beta) {
+  if (!h) { g_err = "null handle"; return LQ_E_INVALID; }
+  LQ_TRY({
+    if (!(beta > 0)) fail(LQ_E_INVALID, "beta must be positive");
+    CK(cudaSetDevice(h->opt.device));
+    std::vector<lq_engine::HostOp> v;
+    if (h->opt.nranks > 1) fail(LQ_E_UNSUPPORTED, "lq_set_beta on a slab engine");
+    int64_t n = 0;
+    h->get_state(nullptr, nullptr, &n);
+    std::vector<int32_t> spins(h->part.N);
+    std::vector<lq_op> ops((size_t)n);
+    h->get_state(spins.data(), ops.data(), &n);
+    h->beta = beta;
+    h->size_arenas();
+    h->clear_state();
+    h->set_state(spins.data(), ops.data(), n);
+  })
+}
+
+int lq_set_state(lq_handle h, const int32_t* spins, const lq_op* ops, int64_t n) {
+  if (!h || !spins || (n > 0 && !ops) || n < 0) { g_err = "bad argument"; return LQ_E_INVALID; }
+  LQ_TRY({ CK(cudaSetDevice(h->opt.device)); h->set_state(spins, ops, n); })
+}
+
+int lq_get_state(lq_handle h, int32_t* spins, lq_op* ops, int64_t* n) {
+  if (!h) { g_err = "null handle"; return LQ_E_INVALID; }
+  LQ_TRY({ CK(cudaSetDevice(h->opt.device)); h->get_state(spins, ops, n); })
+}
+
+int lq_sweep(lq_handle h, lq_collector* out) {
+  if (!h) { g_err = "null handle"; return LQ_E_INVALID; }
+  LQ_TRY({ CK(cudaSetDevice(h->opt.device)); h->sweep_many(1, out); })
+}
+
+int lq_sweep_many(lq_handle h, int32_t count, lq_collector* out) {
+  if (!h || count < 0) { g_err = "bad argument"; return LQ_E_INVALID; }
+  LQ_TRY({
+    CK(cudaSetDevice(h->opt.device));
+    int done = 0;
+    while (done < count) {  // bounded batches keep the pinned result buffer small
+      const int m = std::min(count - done, 4096);
+      h->sweep_many(m, out ? out + done : nullptr);
+      done += m;
+    }
+  })
+}
+
+int lq_build_clusters(lq_handle h, int32_t* labels_out, int64_t* nc_out, lq_collector* coll_out) {
+  if (!h) { g_err = "null handle"; return LQ_E_INVALID; }
+  LQ_TRY({ CK(cudaSetDevice(h->opt.device)); h->build_clusters(labels_out, nc_out, coll_out); })
+}
+
+int lq_timers(lq_handle h, lq_timer* out, int32_t* count) {
+  if (!h || !count) { g_err = "bad argument"; return LQ_E_INVALID; }
+  int n = 0;
+  for (int id = 3; id <= 16; ++id) {
+    if (h->tacc[id].count == 0) continue;
+    if (out && n < *count) {
+      out[n].id = id;
+      out[n].count = h->tacc[id].count;
+      out[n].seconds = h->tacc[id].sec;
+      std::snprintf(out[n].label, sizeof out[n].label, "%s", kTimerLabels[id]);
+    }
+    ++n;
+  }
+  *count = n;
+  return LQ_OK;
+}
+
+int lq_get_info(lq_handle h, lq_info* out) {
+  if (!h || !out) { g_err = "bad argument"; return LQ_E_INVALID; }
+  out->num_tiles = h->part.T;
+  out->num_windows = h->W;
+  out->page_capacity = h->cap;
+  out->threads_per_page = h->tpb;
+  out->op_capacity = h->ncap;
+  out->cluster_capacity = h->nccap;
+  out->device_bytes = (int64_t)h->device_bytes;
+  out->sm_count = h->sm_count;
+  out->nodes_per_op = h->npo;
+  return LQ_OK;
+}
+
+int64_t lq_kernel_launches(lq_handle h) { return h ? h->launches : 0; }
+
+int lq_set_comm(lq_handle h, const lq_comm* comm) {
+  if (!h || !comm) { g_err = "bad argument"; return LQ_E_INVALID; }
+  h->comm = *comm;
+  h->has_comm = true;
+  return LQ_OK;
+}
+
+void* lq_stream(lq_handle h) { return h ? (void*)h->stream : nullptr; }
+
+const char* lq_last_error(void) { return g_err.c_str(); }
+const char* lq_version(void) { return "alps-looper_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

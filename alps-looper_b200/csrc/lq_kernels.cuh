@@ -1,0 +1,635 @@
+// lq_kernels.cuh -- the sm_100a kernels of one loop-update Monte Carlo step.
+//
+//   K1 k_diag_update   path_integral.C:403-425,484-537 / standalone/loop.C:93-115
+//   K2 k_carry, k_link path_integral.C:539-566,584-588; graph_impl.h:168-177,277-295; union_find.h:242-284
+//   K3 k_compress, k_relabel   union_find.h:325-343 (set_id / copy_id)
+//   K4 k_estimate, k_estimate_sites   path_integral.C:650-737; measurement.h:612-650; susceptibility.h:117-155
+//   K5 k_collect       path_integral.C:774-777,796-799; susceptibility.h:182-198
+//   K6 k_flip, k_flip_spins   path_integral.C:815-823
+//
+// All kernels are HBM-bound integer/byte work: no tensor-core path.  Pages are processed one CTA
+// per page; node- and cluster-indexed kernels are grid-stride free, sized for the arena capacity
+// with a device-side bound so that a whole step needs no host synchronisation.
+#pragma once
+#include "lq_device.cuh"
+
+namespace lq {
+
+#define LQ_MAXC 32  /* accepted candidates kept per (bond, window) bucket */
+#define LQ_MAXN 64  /* off-diagonal neighbour legs per bond and window    */
+
+struct BucketRef {
+  size_t base;  // first slot of the bucket in the page arrays
+  int n;        // operators in the bucket
+  int idx0;     // dense operator index of the first one
+};
+
+__device__ __forceinline__ BucketRef bucket_of(const Dev& d, int buf, int b, int wl) {
+  const int t = d.bond_tile[b];
+  const int lb = b - d.bond_base[t];
+  const size_t p = (size_t)t * d.Wl + wl;
+  const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1) + lb;
+  const int o0 = bo[0], o1 = bo[1];
+  BucketRef r;
+  r.base = p * (size_t)d.cap + o0;
+  r.n = o1 - o0;
+  r.idx0 = d.nbase[p] + o0;
+  return r;
+}
+
+__device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
+  return (node_t)d.N + (d.npo == 2 ? (node_t)(2 * (size_t)idx + side) : (node_t)idx);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: diagonal update.  One CTA per page, one thread per (bond, window) bucket.
+//  * old diagonal operators are dropped, off-diagonal ones kept (graph re-chosen, graph_impl.h:324)
+//  * candidates: Poisson process of rate beta * sum_g v_g on the bond, realised as exponential gaps
+//    (= Knuth's product method of poisson_distribution.h:60-75 with the arrival times kept)
+//  * acceptance needs only the RELATIVE orientation of the two spins: operators on this bond flip
+//    both, so only off-diagonal operators of the OTHER bonds at the two sites matter.
+//  * the new bucket sizes are scanned across the CTA and the page is rewritten compacted.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_diag_update(Dev d, int src, double beta, uint32_t key0, uint32_t key1, uint32_t mcs) {
+  __shared__ int s_scan[34];
+  const int dst = src ^ 1;
+  const size_t p = blockIdx.x;
+  const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl), wg = d.w0 + wl;
+  const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
+  const int lb = threadIdx.x;
+  const bool active = lb < nb;
+
+  double ctime[LQ_MAXC];
+  uint8_t cgraph[LQ_MAXC];
+  int nacc = 0, nkeep = 0;
+  size_t obase = 0;
+  int on = 0;
+  int b = 0;
+  if (active) {
+    b = b0 + lb;
+    const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
+    int rel = d.spinW[(size_t)wl * d.N + s0] ^ d.spinW[(size_t)wl * d.N + s1];
+    // off-diagonal legs of the other bonds at the two sites
+    double nt[LQ_MAXN];
+    int nn = 0;
+    for (int side = 0; side < 2; ++side) {
+      const int s = side ? s1 : s0;
+      for (int a = d.adj_off[s]; a < d.adj_off[s + 1]; ++a) {
+        const int b2 = d.adj[a] >> 1;
+        if (b2 == b) continue;
+        BucketRef r = bucket_of(d, src, b2, wl);
+        for (int j = 0; j < r.n; ++j) {
+          if (d.info[src][r.base + j] & LQ_INFO_OFFDIAG) {
+            if (nn < LQ_MAXN) nt[nn++] = d.time[src][r.base + j];
+            else atomicOr(d.d_err, LQ_ERR_NEIGH_FULL);
+          }
+        }
+      }
+    }
+    // own old bucket
+    BucketRef r = bucket_of(d, src, b, wl);
+    obase = r.base;
+    on = r.n;
+    for (int j = 0; j < on; ++j) nkeep += (d.info[src][obase + j] & LQ_INFO_OFFDIAG);
+    // candidates
+    const double rate = beta * d.bond_rate[b];
+    if (rate > 0) {
+      const float4 pr = d.bond_p[b];
+      const double tlo = window_lo(wg, d.W), thi = window_hi(wg, d.W);
+      const double inv = 1.0 / rate;
+      double tc = tlo;
+      for (uint32_t i = 0;; ++i) {
+        philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + i, key0, key1);
+        tc += -log(u53(x.x, x.y)) * inv;
+        if (!(tc < thi)) break;
+        int c = 0;
+        for (int k = 0; k < nn; ++k) c += (nt[k] < tc);
+        const int anti = rel ^ (c & 1);
+        const float u = u24(x.z);
+        int g = -1;
+        if (anti) { if (u < pr.x) g = 0; else if (u < pr.y) g = 2; }
+        else      { if (u < pr.z) g = 1; else if (u < pr.w) g = 3; }
+        if (g >= 0) {
+          if (nacc < LQ_MAXC) { ctime[nacc] = tc; cgraph[nacc] = (uint8_t)g; ++nacc; }
+          else atomicOr(d.d_err, LQ_ERR_CAND_FULL);
+        }
+      }
+    }
+  }
+  int total;
+  const int cnt = active ? (nkeep + nacc) : 0;
+  const int off = block_exscan(cnt, &total, s_scan);
+  uint16_t* bo = d.boff[dst] + p * (size_t)(d.nbmax + 1);
+  if (total > d.cap) {
+    if (threadIdx.x == 0) { atomicOr(d.d_err, LQ_ERR_PAGE_FULL); d.pcount[dst][p] = 0; }
+    if (lb <= nb) bo[lb] = 0;
+    return;
+  }
+  if (active) bo[lb] = (uint16_t)off;
+  if (lb == nb) { bo[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
+  if (active) {
+    // merge kept off-diagonal operators with the accepted candidates, both time-ordered
+    const size_t wbase = p * (size_t)d.cap + off;
+    const float q0 = d.bond_q[b];
+    int k = 0, ci = 0;
+    for (int j = 0; j < on; ++j) {
+      const uint32_t inf = d.info[src][obase + j];
+      if (!(inf & LQ_INFO_OFFDIAG)) continue;
+      const double tt = d.time[src][obase + j];
+      while (ci < nacc && ctime[ci] < tt) {
+        d.time[dst][wbase + k] = ctime[ci];
+        d.info[dst][wbase + k] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)cgraph[ci] << LQ_INFO_GSHIFT);
+        ++k; ++ci;
+      }
+      uint32_t g = 0;
+      if (q0 < 1.0f) {  // graph_impl.h:324-327 choose_offdiagonal
+        philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)j, key0, key1);
+        g = (u24(x.x) < q0) ? 0u : 1u;
+      }
+      d.time[dst][wbase + k] = tt;
+      d.info[dst][wbase + k] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG;
+      ++k;
+    }
+    while (ci < nacc) {
+      d.time[dst][wbase + k] = ctime[ci];
+      d.info[dst][wbase + k] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)cgraph[ci] << LQ_INFO_GSHIFT);
+      ++k; ++ci;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic exclusive scan of uint32 arrays (bucket bases, root ranks): 3 small kernels
+// ------------------------------------------------------------------------------------------
+#define LQ_SCAN_ITEMS 4
+#define LQ_SCAN_THREADS 1024
+#define LQ_SCAN_CHUNK (LQ_SCAN_ITEMS * LQ_SCAN_THREADS)
+
+__global__ void __launch_bounds__(LQ_SCAN_THREADS)
+k_scan_blocksum(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ bsum) {
+  __shared__ int s_scan[34];
+  const size_t base = (size_t)blockIdx.x * LQ_SCAN_CHUNK + (size_t)threadIdx.x * LQ_SCAN_ITEMS;
+  int v = 0;
+#pragma unroll
+  for (int i = 0; i < LQ_SCAN_ITEMS; ++i) if (base + i < n) v += (int)in[base + i];
+  int total;
+  block_exscan(v, &total, s_scan);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = (uint32_t)total;
+}
+
+// single CTA: exclusive scan of the block sums in place, total to *total_out (and total_out2)
+__global__ void __launch_bounds__(LQ_SCAN_THREADS)
+k_scan_top(uint32_t* bsum, size_t nblk, uint32_t* total_out, int* total_out2) {
+  __shared__ int s_scan[34];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (size_t start = 0; start < nblk; start += LQ_SCAN_THREADS) {
+    const size_t i = start + threadIdx.x;
+    const int v = (i < nblk) ? (int)bsum[i] : 0;
+    int total;
+    const int ex = block_exscan(v, &total, s_scan);
+    const uint32_t carry = s_carry;
+    if (i < nblk) bsum[i] = carry + (uint32_t)ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + (uint32_t)total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (total_out) *total_out = s_carry;
+    if (total_out2) *total_out2 = (int)s_carry;
+  }
+}
+
+__global__ void __launch_bounds__(LQ_SCAN_THREADS)
+k_scan_final(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n,
+             const uint32_t* __restrict__ bsum) {
+  __shared__ int s_scan[34];
+  const size_t base = (size_t)blockIdx.x * LQ_SCAN_CHUNK + (size_t)threadIdx.x * LQ_SCAN_ITEMS;
+  uint32_t x[LQ_SCAN_ITEMS];
+  int v = 0;
+#pragma unroll
+  for (int i = 0; i < LQ_SCAN_ITEMS; ++i) { x[i] = (base + i < n) ? in[base + i] : 0u; v += (int)x[i]; }
+  int total;
+  uint32_t run = bsum[blockIdx.x] + (uint32_t)block_exscan(v, &total, s_scan);
+#pragma unroll
+  for (int i = 0; i < LQ_SCAN_ITEMS; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += x[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a: parent[x] = x for every node of this step (sites + operator legs)
+// ------------------------------------------------------------------------------------------
+__global__ void k_init_nodes(Dev d) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
+  if (x < nn) d.parent[x] = (node_t)x;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: per site, the node of the world-line segment that crosses the start of every window
+// (the reference's current[s], path_integral.C:452, carried through imaginary time).
+// One thread per site, sequential over windows; neighbouring threads read neighbouring buckets.
+// ------------------------------------------------------------------------------------------
+__global__ void k_carry(Dev d, int buf) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  node_t cur = (node_t)s;
+  const int a0 = d.adj_off[s], a1 = d.adj_off[s + 1];
+  for (int wl = 0; wl < d.Wl; ++wl) {
+    d.curW[(size_t)wl * d.N + s] = cur;
+    double bt = -1.0;
+    int bb = -1;
+    for (int a = a0; a < a1; ++a) {
+      const int e = d.adj[a];
+      const int b2 = e >> 1;
+      BucketRef r = bucket_of(d, buf, b2, wl);
+      if (r.n > 0) {
+        const double tt = d.time[buf][r.base + r.n - 1];
+        if (tt > bt || (tt == bt && b2 > bb)) {
+          bt = tt; bb = b2;
+          cur = upper_node(d, r.idx0 + r.n - 1, e & 1);
+        }
+      }
+    }
+  }
+  d.curW[(size_t)d.Wl * d.N + s] = cur;
+}
+
+// node of the leg arriving from below at (site s, time tt of bond b) and the spin on it
+__device__ __forceinline__ node_t scan_below(const Dev& d, int buf, int s, int wl, double tt, int b,
+                                             int jself, int* spin_out) {
+  node_t best = d.curW[(size_t)wl * d.N + s];
+  int spin = d.spinW[(size_t)wl * d.N + s];
+  double bt = -1.0;
+  int bb = -1;
+  for (int a = d.adj_off[s]; a < d.adj_off[s + 1]; ++a) {
+    const int e = d.adj[a];
+    const int b2 = e >> 1;
+    BucketRef r = bucket_of(d, buf, b2, wl);
+    const int lim = (b2 == b) ? jself : r.n;
+    for (int j = 0; j < lim; ++j) {
+      const double t2 = d.time[buf][r.base + j];
+      if (b2 != b && !(t2 < tt || (t2 == tt && b2 < b))) break;
+      spin ^= (int)(d.info[buf][r.base + j] & LQ_INFO_OFFDIAG);
+      if (t2 > bt || (t2 == bt && b2 > bb)) {
+        bt = t2; bb = b2;
+        best = upper_node(d, r.idx0 + j, e & 1);
+      }
+    }
+  }
+  *spin_out = spin;
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2c: link.  One CTA per page, one thread per bucket: for every operator find the two nodes
+// arriving from below, record them, and apply the graph's unions (graph_impl.h:277-295):
+//   g = 0      unify(below0, below1); the upper legs are the operator's own new node
+//   g = 1      cross: upper0 ~ below1, upper1 ~ below0            (needs npo == 2)
+//   g = 2, 3   freeze: all four legs in one cluster
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_link(Dev d, int buf) {
+  const size_t p = blockIdx.x;
+  const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl);
+  const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
+  const int lb = threadIdx.x;
+  if (lb >= nb) return;
+  const int b = b0 + lb;
+  const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
+  BucketRef r = bucket_of(d, buf, b, wl);
+  for (int j = 0; j < r.n; ++j) {
+    const double tt = d.time[buf][r.base + j];
+    uint32_t inf = d.info[buf][r.base + j];
+    int c0, c1;
+    const node_t p0 = scan_below(d, buf, s0, wl, tt, b, j, &c0);
+    const node_t p1 = scan_below(d, buf, s1, wl, tt, b, j, &c1);
+    inf = (inf & ~(LQ_INFO_C0 | LQ_INFO_C1)) | (c0 ? LQ_INFO_C0 : 0u) | (c1 ? LQ_INFO_C1 : 0u);
+    d.info[buf][r.base + j] = inf;
+    const int idx = r.idx0 + j;
+    d.low0[idx] = p0;
+    const int g = (inf >> LQ_INFO_GSHIFT) & 3;
+    const node_t u0 = upper_node(d, idx, 0);
+    if (d.npo == 2) {
+      d.low1[idx] = p1;
+      const node_t u1 = upper_node(d, idx, 1);
+      if (g == 0) { uf_union(d.parent, p0, p1); uf_union(d.parent, u0, u1); }
+      else if (g == 1) { uf_union(d.parent, u0, p1); uf_union(d.parent, u1, p0); }
+      else { uf_union(d.parent, p0, p1); uf_union(d.parent, u0, p0); uf_union(d.parent, u1, p0); }
+    } else {
+      uf_union(d.parent, p0, p1);
+      if (g & 2) uf_union(d.parent, u0, p0);
+    }
+  }
+}
+
+// close the world lines in imaginary time (path_integral.C:584-588); serial engine only --
+// with several slabs the top boundary is merged by the exchange step instead.
+__global__ void k_close(Dev d) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  uf_union(d.parent, (node_t)s, d.curW[(size_t)d.Wl * d.N + s]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: cluster ids.  set_id numbers the roots in array order (union_find.h:325-330); here the root
+// flags of 32 consecutive nodes are one ballot word, ranks come from a scan over the words, and
+// copy_id (:338-343) becomes one gather per node.  parent[] ends up holding the cluster id.
+// ------------------------------------------------------------------------------------------
+__global__ void k_compress(Dev d, size_t nwords_cap) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
+  const size_t nwords = (nn + 31) >> 5;
+  if ((x >> 5) >= nwords_cap) return;
+  if ((x >> 5) >= nwords) {  // whole warp beyond the live nodes: keep the scan input clean
+    if ((threadIdx.x & 31) == 0) { d.bitmap[x >> 5] = 0u; d.wcount[x >> 5] = 0u; }
+    return;
+  }
+  bool isroot = false;
+  if (x < nn) {
+    node_t r = (node_t)x;
+    node_t pr = uf_load(d.parent + r);
+    while (pr != r) { r = pr; pr = uf_load(d.parent + r); }
+    d.parent[x] = r;
+    isroot = (r == (node_t)x);
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, isroot);
+  if ((threadIdx.x & 31) == 0) {
+    d.bitmap[x >> 5] = word;
+    d.wcount[x >> 5] = (uint32_t)__popc(word);
+  }
+}
+
+__device__ __forceinline__ uint32_t cid_of_root(const Dev& d, node_t r) {
+  return d.wbase[r >> 5] + (uint32_t)__popc(d.bitmap[r >> 5] & ((1u << (r & 31)) - 1u));
+}
+
+__global__ void k_relabel(Dev d) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
+  if (x == 0) {
+    // clusters rooted at a site node come first (site ids are the smallest node ids)
+    d.d_nc[1] = cid_of_root(d, (node_t)d.N);
+    if ((long long)d.d_nc[0] > d.nccap) atomicOr(d.d_err, LQ_ERR_CLUSTER_FULL);
+  }
+  if (x >= nn) return;
+  d.parent[x] = cid_of_root(d, d.parent[x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: per-cluster sums of the improved estimators (susceptibility.h:117-155).  Every leg that
+// ends (+t) or begins (-t) at an operator contributes to the cluster it belongs to:
+//   usize += t/2, umag += t(1/2-c), ssize += g t/2, smag += g t(1/2-c)
+// accumulated in integer half-units of 2^-40, so sums do not depend on the order of the atomics.
+// One CTA per page; contributions are first merged in a shared-memory hash keyed by cluster id
+// (at low temperature most legs of a page belong to a handful of long loops), then flushed with
+// one global atomic per distinct key and field.
+// ------------------------------------------------------------------------------------------
+#define LQ_HASH 1024
+struct EstHash {
+  uint32_t key[LQ_HASH];
+  unsigned long long val[4][LQ_HASH];
+};
+
+__device__ __forceinline__ void est_global_add(const Dev& d, uint32_t cid, long long a, long long b,
+                                               long long c, long long e) {
+  if ((long long)cid >= d.nccap) return;  // flagged by k_relabel
+  unsigned long long* est = (unsigned long long*)d.est;
+  if (a) atomicAdd(est + 0 * d.nccap + cid, (unsigned long long)a);
+  if (b) atomicAdd(est + 1 * d.nccap + cid, (unsigned long long)b);
+  if (c) atomicAdd(est + 2 * d.nccap + cid, (unsigned long long)c);
+  if (e) atomicAdd(est + 3 * d.nccap + cid, (unsigned long long)e);
+}
+
+__device__ __forceinline__ void est_hash_add(const Dev& d, EstHash* h, uint32_t cid, long long a,
+                                             long long b, long long c, long long e) {
+  uint32_t slot = (cid * 2654435761u) >> 22;  // 10 bits
+  for (int probe = 0; probe < 8; ++probe) {
+    const uint32_t k = atomicCAS(&h->key[slot], 0xffffffffu, cid);
+    if (k == 0xffffffffu || k == cid) {
+      if (a) atomicAdd(&h->val[0][slot], (unsigned long long)a);
+      if (b) atomicAdd(&h->val[1][slot], (unsigned long long)b);
+      if (c) atomicAdd(&h->val[2][slot], (unsigned long long)c);
+      if (e) atomicAdd(&h->val[3][slot], (unsigned long long)e);
+      return;
+    }
+    slot = (slot + 1) & (LQ_HASH - 1);
+  }
+  est_global_add(d, cid, a, b, c, e);  // table crowded: go straight to HBM
+}
+
+__global__ void __launch_bounds__(256)
+k_estimate(Dev d, int buf) {
+  extern __shared__ unsigned char s_raw[];
+  EstHash* h = (EstHash*)s_raw;
+  for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
+    h->key[i] = 0xffffffffu;
+    h->val[0][i] = h->val[1][i] = h->val[2][i] = h->val[3][i] = 0ull;
+  }
+  __syncthreads();
+  const size_t p = blockIdx.x;
+  const int t = (int)(p / d.Wl);
+  const int b0 = d.bond_base[t];
+  const int n = d.pcount[buf][p];
+  const int idx0 = d.nbase[p];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const uint32_t inf = d.info[buf][p * (size_t)d.cap + j];
+    const int g = (inf >> LQ_INFO_GSHIFT) & 3;
+    if (g & 2) continue;  // frozen graphs are skipped (path_integral.C:692)
+    const double tt = d.time[buf][p * (size_t)d.cap + j];
+    const long long q = (long long)llrint(tt * LQ_FX);
+    const int b = b0 + (int)(inf >> LQ_INFO_LBSHIFT);
+    const int g0 = d.gauge[d.bond_s0[b]], g1 = d.gauge[d.bond_s1[b]];
+    const int c0 = (inf & LQ_INFO_C0) ? 1 : 0, c1 = (inf & LQ_INFO_C1) ? 1 : 0;
+    const int off = (int)(inf & LQ_INFO_OFFDIAG);
+    const int m0 = 1 - 2 * c0, m1 = 1 - 2 * c1;              // 2(1/2-c) below
+    const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
+    const int idx = idx0 + j;
+    const uint32_t cl0 = d.parent[d.low0[idx]];
+    const uint32_t cu0 = d.parent[upper_node(d, idx, 0)];
+    if (d.npo == 1) {
+      // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
+      est_hash_add(d, h, cl0, 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
+      est_hash_add(d, h, cu0, -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
+    } else {
+      const uint32_t cl1 = d.parent[d.low1[idx]];
+      const uint32_t cu1 = d.parent[upper_node(d, idx, 1)];
+      est_hash_add(d, h, cl0, q, q * m0, q * g0, q * g0 * m0);
+      est_hash_add(d, h, cl1, q, q * m1, q * g1, q * g1 * m1);
+      est_hash_add(d, h, cu0, -q, -q * n0, -q * g0, -q * g0 * n0);
+      est_hash_add(d, h, cu1, -q, -q * n1, -q * g1, -q * g1 * n1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
+    const uint32_t k = h->key[i];
+    if (k != 0xffffffffu)
+      est_global_add(d, k, (long long)h->val[0][i], (long long)h->val[1][i],
+                     (long long)h->val[2][i], (long long)h->val[3][i]);
+  }
+}
+
+// start_bottom / stop_top of every world line (path_integral.C:666-669,729-733;
+// susceptibility.h:139-155); for a slab [tau0,tau1) they are start(tau0) / stop(tau1)
+// (path_integral_mpi.C), and only rank 0 owns the tau = 0 magnetisations.
+__global__ void k_estimate_sites(Dev d) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  const int g = d.gauge[s];
+  const int c = d.spinW[s];
+  const int m = 1 - 2 * c;
+  const uint32_t cb = d.parent[s];
+  const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  const long long qlo = (long long)llrint(window_lo(d.w0, d.W) * LQ_FX);
+  const long long qhi = (long long)llrint(window_hi(d.w0 + d.Wl - 1, d.W) * LQ_FX);
+  if (d.rank == 0) {
+    atomicAdd(d.est0 + 0 * (size_t)d.N + cb, 1);
+    atomicAdd(d.est0 + 1 * (size_t)d.N + cb, m);
+    atomicAdd(d.est0 + 2 * (size_t)d.N + cb, g);
+    atomicAdd(d.est0 + 3 * (size_t)d.N + cb, g * m);
+  }
+  if (qlo) est_global_add(d, cb, -qlo, -qlo * m, -qlo * g, -qlo * g * m);
+  // periodic in imaginary time: the spin at the top of the slab stack equals the one at tau = 0;
+  // inside a slab it is the spin at the start of the next slab = spinW[Wl]
+  const int ctop = d.spinW[(size_t)d.Wl * d.N + s];
+  const int mt = 1 - 2 * ctop;
+  est_global_add(d, ct, qhi, qhi * mt, qhi * g, qhi * g * mt);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: collector += estimate over clusters (susceptibility.h:182-198) and the Bernoulli(1/2) flip
+// decision per cluster (path_integral.C:796-799).  Deterministic two-stage reduction
+// (warp shuffles -> per-CTA partials -> one CTA).  The cluster arena is zeroed on the way.
+// ------------------------------------------------------------------------------------------
+#define LQ_NSUM 14
+__global__ void __launch_bounds__(256)
+k_collect(Dev d, double* partial, uint32_t key0, uint32_t key1, uint32_t mcs) {
+  __shared__ double s_red[8][LQ_NSUM];
+  const uint32_t nc = d.d_nc[0], ncs = d.d_nc[1];
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v[LQ_NSUM];
+#pragma unroll
+  for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;
+  if (c < nc && (long long)c < d.nccap) {
+    const double sc = 0.5 / LQ_FX;
+    const double usize = sc * (double)d.est[0 * d.nccap + c];
+    const double umag = sc * (double)d.est[1 * d.nccap + c];
+    const double ssize = sc * (double)d.est[2 * d.nccap + c];
+    const double smag = sc * (double)d.est[3 * d.nccap + c];
+    d.est[0 * d.nccap + c] = 0; d.est[1 * d.nccap + c] = 0;
+    d.est[2 * d.nccap + c] = 0; d.est[3 * d.nccap + c] = 0;
+    double usize0 = 0, umag0 = 0, ssize0 = 0, smag0 = 0;
+    if (c < ncs) {
+      usize0 = 0.5 * d.est0[0 * (size_t)d.N + c]; umag0 = 0.5 * d.est0[1 * (size_t)d.N + c];
+      ssize0 = 0.5 * d.est0[2 * (size_t)d.N + c]; smag0 = 0.5 * d.est0[3 * (size_t)d.N + c];
+      d.est0[0 * (size_t)d.N + c] = 0; d.est0[1 * (size_t)d.N + c] = 0;
+      d.est0[2 * (size_t)d.N + c] = 0; d.est0[3 * (size_t)d.N + c] = 0;
+    }
+    // order = lq_collector: umag0 usize2 umag2 usize4 umag4 usize umag | smag0 ssize2 smag2 ssize4 smag4 ssize smag
+    v[0] = umag0; v[1] = usize0 * usize0; v[2] = umag0 * umag0;
+    v[3] = v[1] * v[1]; v[4] = v[2] * v[2]; v[5] = usize * usize; v[6] = umag * umag;
+    v[7] = smag0; v[8] = ssize0 * ssize0; v[9] = smag0 * smag0;
+    v[10] = v[8] * v[8]; v[11] = v[9] * v[9]; v[12] = ssize * ssize; v[13] = smag * smag;
+    philox_t x = philox4x32_10((uint32_t)c, (uint32_t)d.rank, mcs, LQ_STREAM_FLIP, key0, key1);
+    d.flipb[c] = (uint8_t)(x.x & 1u);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < LQ_NSUM; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[wid][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < LQ_NSUM) {
+    double x = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += s_red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * LQ_NSUM + threadIdx.x] = x;
+  }
+}
+
+// one CTA: sum the per-CTA partials in a fixed order -> out[0..13]; out[14] = nc, out[15] = nop
+__global__ void __launch_bounds__(256)
+k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
+  __shared__ double s_red[8][LQ_NSUM];
+  const uint32_t nc = d.d_nc[0];
+  size_t nblk = ((size_t)nc + 255) / 256;
+  if (nblk > nblk_cap) nblk = nblk_cap;
+  double v[LQ_NSUM];
+#pragma unroll
+  for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;
+  for (size_t k = threadIdx.x; k < nblk; k += blockDim.x)
+#pragma unroll
+    for (int i = 0; i < LQ_NSUM; ++i) v[i] += partial[k * LQ_NSUM + i];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < LQ_NSUM; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[wid][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < LQ_NSUM) {
+    double x = 0;
+    for (int w = 0; w < 8; ++w) x += s_red[w][threadIdx.x];
+    out[threadIdx.x] = x;
+  }
+  if (threadIdx.x == 0) {
+    out[14] = (double)nc;
+    out[15] = (double)(*d.d_ntotal);
+    out[16] = (double)(*d.d_err);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: flip (path_integral.C:815-823).  An operator changes between diagonal and off-diagonal iff
+// the cluster arriving from below on the source side and the one leaving upwards there are
+// flipped differently (loop_0 / loop_1 of graph_impl.h:277-295 in leg form).  The spin carried
+// into every window flips with the cluster of the segment crossing the window start.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t flip_of(const Dev& d, uint32_t cid) {
+  return ((long long)cid < d.nccap) ? (uint32_t)d.flipb[cid] : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_flip(Dev d, int buf) {
+  const size_t p = blockIdx.x;
+  const int n = d.pcount[buf][p];
+  const int idx0 = d.nbase[p];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int idx = idx0 + j;
+    const uint32_t cl = d.parent[d.low0[idx]];
+    const uint32_t cu = d.parent[upper_node(d, idx, 0)];
+    const uint32_t f = (flip_of(d, cl) ^ flip_of(d, cu)) & 1u;
+    if (f) d.info[buf][p * (size_t)d.cap + j] ^= LQ_INFO_OFFDIAG;
+  }
+}
+
+__global__ void k_flip_spins(Dev d) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)(d.Wl + 1) * d.N) return;
+  const uint32_t c = d.parent[d.curW[i]];
+  d.spinW[i] ^= (uint8_t)flip_of(d, c);
+}
+
+// ------------------------------------------------------------------------------------------
+// parity-test helper: cluster ids of the upper legs of every operator in page order
+// ------------------------------------------------------------------------------------------
+__global__ void k_export_labels(Dev d, int buf, uint32_t* out /* [2*ncap-ish], by dense idx */) {
+  const size_t p = blockIdx.x;
+  const int n = d.pcount[buf][p];
+  const int idx0 = d.nbase[p];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int idx = idx0 + j;
+    out[2 * (size_t)idx] = d.parent[upper_node(d, idx, 0)];
+    out[2 * (size_t)idx + 1] = d.parent[upper_node(d, idx, 1)];
+  }
+}
+
+}  // namespace lq

@@ -1,0 +1,156 @@
+/*
+ * lq.h -- C ABI of the B200-native loop-update engine ("lq" = loop QMC).
+ *
+ * This is the drop-in boundary for ONE hot path of ALPS/looper: the body of
+ * loop_worker::dispatch<FIELD=false,SIGN=false,IMPROVE=true>() (path_integral.C:355-864,
+ * standalone/loop.C:80-180): diagonal update -> union-find cluster labelling -> cluster flip +
+ * improved estimators.  The reference has no FFI; its seam is the C++ worker class
+ * (path_integral.C:57-125).  Each entry point below names the reference code it replaces.
+ * The host-side mirror of that class (looper::loop_worker in alps-looper_b200/looper/) is a thin
+ * C++ layer over exactly these calls.
+ *
+ * Conventions: opaque handle; int return (0 = ok, negative = LQ_E_*; text via lq_last_error);
+ * no exceptions cross the ABI; all pointers are caller-owned HOST memory; one host thread per
+ * handle; one CUDA stream per handle.  There is NO CPU fallback: if no CUDA device / kernel image
+ * is usable, lq_create fails with LQ_E_CUDA.
+ */
+#ifndef LQ_H
+#define LQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQ_OK            0
+#define LQ_E_INVALID    -1   /* bad argument / inconsistent state                                */
+#define LQ_E_CUDA       -2   /* CUDA runtime error (message has the cudaError string)            */
+#define LQ_E_OVERFLOW   -3   /* a page / node / cluster arena is full: raise lq_options.reserve  */
+#define LQ_E_NOMEM      -4
+#define LQ_E_COMM       -5   /* multi-GPU exchange failed                                        */
+#define LQ_E_UNSUPPORTED -6
+
+typedef struct lq_engine* lq_handle;
+
+/* Lattice = the reference's virtual graph for S=1/2 (looper/lattice.h:576-675): bond b joins
+ * source(b)=src[b] and target(b)=dst[b] (lattice.h:49-62); gauge[s] = +1/-1 staggering sign
+ * (lattice.h:85, read at susceptibility.h:56,129), all 0 if not bipartite.  dims is an optional
+ * hint for the spatial tiling (site index = x + dims[0]*(y + dims[1]*z)); 0,0,0 = unknown. */
+typedef struct lq_lattice {
+  int32_t        num_sites;
+  int32_t        num_bonds;
+  const int32_t* src;
+  const int32_t* dst;
+  const double*  gauge;      /* may be NULL (= not bipartite)                                    */
+  int32_t        dims[3];
+} lq_lattice;
+
+/* Model = graph weights per bond, the output of weight_helper (looper/weight_impl.h:349-423):
+ * v[4*b + g] for the XXZ graphs g = 0..3 (graph_impl.h:93-103); S=1/2 HAF J=1 is {0.5,0,0,0}
+ * (test/weight.op "Jxy = 1, Jz = 1").  bond_weights == NULL means uniform_weights for all bonds.
+ * energy_offset = model.energy_offset() (model.h:84) = sum of bond offsets. */
+typedef struct lq_model {
+  const double* bond_weights;     /* 4 * num_bonds, or NULL                                      */
+  double        uniform_weights[4];
+  double        energy_offset;
+} lq_model;
+
+typedef struct lq_options {
+  uint64_t seed;             /* Philox key; the reference seeds mt19937 (loop.C:50)              */
+  int32_t  device;           /* CUDA device ordinal                                              */
+  int32_t  tile_sites;       /* spatial tile size in sites (0 = default 64)                      */
+  double   window_ops;       /* target mean candidate count per bond and time window (0 = 2.0)   */
+  double   reserve;          /* page capacity / mean candidate count (0 = default 1.7); the
+                                analogue of RESERVE_OPERATORS (path_integral.C:240-243)          */
+  double   cluster_reserve;  /* cluster arena / operator arena (0 = default 0.75)                */
+  int32_t  rank, nranks;     /* imaginary-time slab of this engine (path_integral_mpi.C:231-232);
+                                nranks <= 1 = serial                                             */
+  int32_t  flags;            /* reserved, 0                                                      */
+} lq_options;
+
+/* looper/operator.h:120-143: {time_, loc_, type_}; loc = pos<<1 | is_bond
+ * (location_impl.h:37); type bit0 = offdiagonal, bits >= 2 = graph type (operator.h:62,76). */
+typedef struct lq_op {
+  double  time;
+  int32_t loc;
+  int32_t type;
+} lq_op;
+
+/* basic_measurement::collector nop_/nc_/noc_ (looper/measurement.h:366-372), energy ene_
+ * (energy.h:56), susceptibility improved collector (susceptibility.h:158-160). */
+typedef struct lq_collector {
+  double nop, nc, noc;
+  double ene;
+  double umag0, usize2, umag2, usize4, umag4, usize, umag;
+  double smag0, ssize2, smag2, ssize4, smag4, ssize, smag;
+} lq_collector;
+
+/* Section timers; ids mirror path_integral.C:284-299 (4 init .. 16 measurement). */
+typedef struct lq_timer {
+  int32_t id;
+  int32_t count;
+  double  seconds;           /* device time (CUDA events)                                        */
+  char    label[40];
+} lq_timer;
+
+typedef struct lq_info {
+  int32_t num_tiles, num_windows, page_capacity, threads_per_page;
+  int64_t op_capacity, cluster_capacity;
+  int64_t device_bytes;
+  int32_t sm_count, nodes_per_op;
+} lq_info;
+
+/* Replaces loop_worker::loop_worker (path_integral.C:202-305): builds lattice tables, graph
+ * chooser tables, sizes the arenas.  Initial state: all spins up, no operators (:225). */
+int lq_create(lq_handle* out, const lq_lattice* lat, const lq_model* model, double beta,
+              const lq_options* opt);
+int lq_destroy(lq_handle h);
+
+/* set_beta (path_integral.C:98-105).  Re-tiles imaginary time; operators are kept. */
+int lq_set_beta(lq_handle h, double beta);
+
+/* load()/save() payload (path_integral.C:111-124): spins at tau=0 (0 up / 1 down) and the
+ * operator string sorted by time.  lq_get_state with ops == NULL only returns *n. */
+int lq_set_state(lq_handle h, const int32_t* spins, const lq_op* ops, int64_t n);
+int lq_get_state(lq_handle h, int32_t* spins, lq_op* ops, int64_t* n);
+
+/* One Monte Carlo step = the whole of dispatch() (path_integral.C:355-864).  The collector is
+ * that of THIS step's clusters; ene = energy_offset - nop/beta (:851). */
+int lq_sweep(lq_handle h, lq_collector* out);
+/* `count` steps back to back; out[i] for step i (out may be NULL). One device sync at the end. */
+int lq_sweep_many(lq_handle h, int32_t count, lq_collector* out);
+
+/* Cluster construction only (path_integral.C:539-588 + union_find.h:325-343) on the CURRENT
+ * state, no diagonal update, no flip.  Operators are numbered k = 0..n-1 in the order
+ * lq_get_state returns them.  labels_out has num_sites + 2n entries: cluster id of site s, then
+ * of the two legs leaving operator k upwards (source side, target side).  Ids are canonical
+ * min-index labels over that numbering (looper LOOPER_USE_DETERMINISTIC_UNIFY convention,
+ * union_find.h:229-233), so they compare bit-for-bit with the reference partition. */
+int lq_build_clusters(lq_handle h, int32_t* labels_out, int64_t* nc_out, lq_collector* coll_out);
+
+int lq_timers(lq_handle h, lq_timer* out, int32_t* count);   /* timer.summarize (timer.hpp:184) */
+int lq_get_info(lq_handle h, lq_info* out);
+/* number of kernel launches issued by this handle so far */
+int64_t lq_kernel_launches(lq_handle h);
+
+/* Multi-GPU (imaginary-time slabs, one engine per GPU; replaces
+ * parallel_cluster_unifier::unify, looper/parallel.h:1609-1809): the engine calls
+ * exchange(ctx, ...) between the local labelling and the flip.  See INTEGRATION.md. */
+typedef struct lq_comm {
+  void* ctx;
+  /* all-gather `bytes` bytes per rank (device pointers, on the engine's stream) */
+  int (*all_gather)(void* ctx, const void* send_dev, void* recv_dev, int64_t bytes, void* stream);
+  /* in-place sum all-reduce of `count` int64 values (device pointer) */
+  int (*all_reduce_i64)(void* ctx, void* buf_dev, int64_t count, void* stream);
+} lq_comm;
+int lq_set_comm(lq_handle h, const lq_comm* comm);
+void* lq_stream(lq_handle h);                                 /* cudaStream_t of the handle      */
+
+const char* lq_last_error(void);
+const char* lq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQ_H */

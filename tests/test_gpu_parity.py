@@ -1,0 +1,195 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/lq.h) against the oracle.
+
+Layer 1 (bit-exact): for an identical operator configuration the cluster partition must equal
+the reference union-find's, compared through canonical min-index labels.
+Layer 2 (statistical): observables of a full simulation against exact diagonalisation and the
+reference's own numbers.
+"""
+import numpy as np
+import pytest
+
+import oracle_util as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _lq():
+    import looper_b200 as lq
+    return lq
+
+
+def _thermalised_oracle(lat, beta, nsweeps, seed=29833):
+    sim = orc.OracleSim(lat, beta, seed)
+    for _ in range(nsweeps):
+        sim.sweep()
+    return sim
+
+
+CASES = [
+    ("chain16_T0.1", lambda lq: lq.chain_lattice(16), 10.0, 300),
+    ("chain8_T0.2", lambda lq: lq.chain_lattice(8), 5.0, 300),
+    ("chain64_b16", lambda lq: lq.chain_lattice(64), 16.0, 100),
+    ("square8_b4", lambda lq: lq.hypercubic_lattice((8, 8)), 4.0, 100),
+    ("square32_b8", lambda lq: lq.hypercubic_lattice((32, 32)), 8.0, 60),
+    ("square12x20_b6", lambda lq: lq.hypercubic_lattice((12, 20)), 6.0, 60),
+    ("cubic8_b2", lambda lq: lq.hypercubic_lattice((8, 8, 8)), 2.0, 40),
+    ("ladder2x16_b8", lambda lq: lq.hypercubic_lattice((16, 2)), 8.0, 100),
+]
+
+
+@pytest.mark.parametrize("name,latf,beta,therm", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("tile_sites", [0, 16])
+def test_partition_bit_exact(name, latf, beta, therm, tile_sites):
+    lq = _lq()
+    lat = latf(lq)
+    sim = _thermalised_oracle(lat, beta, therm)
+    for rep in range(3):
+        sim.sweep()
+        spins, ops = sim.get_state()
+        ref_labels, ref_nc, ref_coll = orc.build_clusters(lat, spins, ops)
+        eng = lq.Engine(lat, beta, tile_sites=tile_sites)
+        eng.set_state(spins, ops)
+        s2, o2 = eng.get_state()
+        assert np.array_equal(s2, spins)
+        assert len(o2) == len(ops)
+        # same multiset of operators; order may differ only between equal times (none here)
+        assert np.array_equal(o2["time"], ops["time"])
+        assert np.array_equal(o2["loc"], ops["loc"])
+        assert np.array_equal(o2["type"] & 1, ops["type"] & 1)
+        labels, nc, coll = eng.build_clusters()
+        assert nc == ref_nc
+        assert np.array_equal(labels, ref_labels), "cluster partition differs from the reference"
+        assert coll["nop"] == len(ops)
+        for f in ["umag0", "usize2", "umag2", "usize4", "umag4", "usize", "umag",
+                  "smag0", "ssize2", "smag2", "ssize4", "smag4", "ssize", "smag"]:
+            # cluster sums: the reference adds f64 in operator order, the GPU adds 2^-40 fixed point
+            assert coll[f] == pytest.approx(ref_coll[f], rel=1e-8, abs=1e-7), f
+        eng.close()
+
+
+def test_empty_and_trivial_states():
+    lq = _lq()
+    lat = lq.chain_lattice(8)
+    eng = lq.Engine(lat, 5.0)
+    labels, nc, coll = eng.build_clusters()
+    assert nc == 8 and np.array_equal(labels, np.arange(8))
+    assert coll["nop"] == 0
+    # all spins up: nothing can be inserted; every site is its own cluster (standalone/loop.C:58)
+    c = eng.sweep()
+    assert c["nop"] == 0 and c["nc"] == 8
+    assert c["usize2"] == pytest.approx(8 * 0.25)
+    eng.close()
+
+
+def test_sweep_keeps_configuration_valid():
+    """after every GPU step the state must be a legal world-line configuration: the oracle's
+    sequential walk accepts it (antiparallel spins under every operator, periodic in time)."""
+    lq = _lq()
+    for lat, beta in [(lq.chain_lattice(16), 10.0), (lq.hypercubic_lattice((8, 8)), 6.0)]:
+        eng = lq.Engine(lat, beta, seed=7, tile_sites=16)
+        nops = []
+        for step in range(40):
+            c = eng.sweep()
+            spins, ops = eng.get_state()
+            assert c["nop"] == len(ops)
+            assert np.all(np.diff(ops["time"]) >= 0)
+            labels, nc, coll = orc.build_clusters(lat, spins, ops)  # raises if illegal
+            nops.append(len(ops))
+        assert max(nops) > 0
+        eng.close()
+
+
+def test_step_matches_oracle_on_same_graph():
+    """one full GPU step, checked piecewise against the oracle on the SAME graph: after the GPU's
+    diagonal update + flip, undo nothing -- instead verify (a) collector of the step equals the
+    oracle's collector of the pre-flip configuration rebuilt from the GPU's post-flip state is not
+    possible, so: (b) the post-flip state has the same operator times/bonds and differs from a
+    legal configuration only by cluster flips -- checked via legality above -- and (c) the
+    collector's nop/nc/energy are self-consistent."""
+    lq = _lq()
+    lat = lq.hypercubic_lattice((8, 8))
+    eng = lq.Engine(lat, 4.0, seed=11)
+    for _ in range(30):
+        c = eng.sweep()
+    assert c["ene"] == pytest.approx(eng.energy_offset - c["nop"] / 4.0)
+    # cluster count of the step = cluster count of the same graph rebuilt (flip does not change it)
+    spins, ops = eng.get_state()
+    labels, nc, coll = eng.build_clusters()
+    assert nc == c["nc"]
+    assert coll["usize"] == pytest.approx(c["usize"], rel=1e-12)
+    assert coll["usize2"] == pytest.approx(c["usize2"], rel=1e-12)
+    assert coll["smag2"] == pytest.approx(c["smag2"], rel=1e-12)
+    eng.close()
+
+
+def test_deterministic_given_seed():
+    lq = _lq()
+    lat = lq.hypercubic_lattice((8, 8))
+    runs = []
+    for rep in range(2):
+        eng = lq.Engine(lat, 4.0, seed=1234)
+        out = eng.sweep_many(50)
+        spins, ops = eng.get_state()
+        runs.append((out.copy(), spins, ops))
+        eng.close()
+    assert np.array_equal(runs[0][1], runs[1][1])
+    assert np.array_equal(runs[0][2], runs[1][2])
+    for f in runs[0][0].dtype.names:
+        assert np.array_equal(runs[0][0][f], runs[1][0][f]), f
+
+
+def _blocked_error(x, nblocks=32):
+    x = np.asarray(x, dtype=np.float64)
+    m = len(x) // nblocks
+    b = x[: m * nblocks].reshape(nblocks, m).mean(axis=1)
+    return b.std(ddof=1) / np.sqrt(nblocks)
+
+
+# exact diagonalisation values: SURVEY Appendix B (numpy restatement of diag.C:376-468, which
+# reproduces loop.op:22,62,64,66) -- (E/N, chi_u/N, Ms^2 total, chi_s/N)
+ED = {
+    (8, 0.2): (-0.441438, 0.0804441, 6.59939, 2.40159),
+    (16, 0.1): (-0.4428968, 0.0732023, 16.59930, 5.332633),
+}
+
+
+@pytest.mark.parametrize("L,T,sweeps", [(8, 0.2, 20000), (16, 0.1, 20000)])
+def test_observables_vs_exact_diagonalisation(L, T, sweeps):
+    lq = _lq()
+    lat = lq.chain_lattice(L)
+    beta = 1 / T
+    eng = lq.Engine(lat, beta, seed=29833)
+    eng.sweep_many(sweeps // 8, collect=False)
+    out = eng.sweep_many(sweeps)
+    eng.close()
+    ene = (0.25 * L - out["nop"] / beta) / L          # standalone/loop.C:175
+    usus = beta * out["umag2"] / L                     # = 0.25 beta sum mag^2 / N (loop.C:176)
+    smag = out["usize2"]                               # = 0.25 sum size^2 (loop.C:177)
+    ssus = beta * out["usize"] / L                     # = 0.25 beta sum length^2 / N (loop.C:178)
+    exact = ED[(L, T)]
+    for name, series, ex in [("energy", ene, exact[0]), ("usus", usus, exact[1]),
+                             ("smag", smag, exact[2]), ("ssus", ssus, exact[3])]:
+        err = _blocked_error(series)
+        assert abs(series.mean() - ex) < 4.0 * err + 1e-12, (name, series.mean(), ex, err)
+    # the looper-named estimators agree with the standalone ones on a bipartite HAF
+    assert np.allclose(out["smag"], out["usize"], rtol=1e-9)
+    assert np.allclose(out["smag2"], out["usize2"], rtol=1e-12)
+
+
+def test_large_lattice_properties():
+    """config 2 shape at reduced beta: size-independent invariants of one step."""
+    lq = _lq()
+    lat = lq.hypercubic_lattice((64, 64))
+    beta = 8.0
+    eng = lq.Engine(lat, beta, seed=5)
+    out = eng.sweep_many(60)
+    n = out["nop"][-1]
+    N = 64 * 64
+    # <n> = beta (B/4 - E), E/N ~ -0.6 at this temperature: loose physical window
+    assert 0.9 * beta * N < n < 1.4 * beta * N
+    # sum over clusters of size0 = N/2 exactly: sum usize0 = N * 0.5 -> checked through usize2 >= ...
+    assert np.all(out["usize2"] >= N * 0.25)  # sum of squares >= sum of single-site squares
+    assert np.all(out["nc"] >= 1)
+    spins, ops = eng.get_state()
+    orc.build_clusters(lat, spins, ops)  # legal configuration
+    eng.close()
