@@ -85,7 +85,7 @@ class LqComm(C.Structure):
 
 # every symbol include/lq.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["lq_create", "lq_destroy", "lq_set_beta", "lq_set_state", "lq_get_state", "lq_sweep",
-           "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_get_info", "lq_kernel_launches",
+           "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_enable_timers", "lq_get_info", "lq_kernel_launches", "lq_h2d_bytes", "lq_d2h_bytes",
            "lq_set_comm", "lq_stream", "lq_last_error", "lq_version"]
 
 _h = C.c_void_p
@@ -99,9 +99,14 @@ lib.lq_sweep.argtypes = [_h, C.POINTER(LqCollector)]
 lib.lq_sweep_many.argtypes = [_h, C.c_int32, C.c_void_p]
 lib.lq_build_clusters.argtypes = [_h, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(LqCollector)]
 lib.lq_timers.argtypes = [_h, C.POINTER(LqTimer), C.POINTER(C.c_int32)]
+lib.lq_enable_timers.argtypes = [_h, C.c_int]
 lib.lq_get_info.argtypes = [_h, C.POINTER(LqInfo)]
 lib.lq_kernel_launches.argtypes = [_h]
 lib.lq_kernel_launches.restype = C.c_int64
+lib.lq_h2d_bytes.argtypes = [_h]
+lib.lq_h2d_bytes.restype = C.c_int64
+lib.lq_d2h_bytes.argtypes = [_h]
+lib.lq_d2h_bytes.restype = C.c_int64
 lib.lq_set_comm.argtypes = [_h, C.POINTER(LqComm)]
 lib.lq_stream.argtypes = [_h]
 lib.lq_stream.restype = C.c_void_p
@@ -294,8 +299,14 @@ class Engine:
         return [dict(id=arr[i].id, count=arr[i].count, seconds=arr[i].seconds,
                      label=arr[i].label.decode()) for i in range(min(cnt.value, 32))]
 
+    def enable_timers(self, on=True):
+        _check(lib.lq_enable_timers(self._h, 1 if on else 0))
+
     def kernel_launches(self):
         return int(lib.lq_kernel_launches(self._h))
+
+    def copied_bytes(self):
+        return int(lib.lq_h2d_bytes(self._h)), int(lib.lq_d2h_bytes(self._h))
 
     def stream(self):
         return lib.lq_stream(self._h)

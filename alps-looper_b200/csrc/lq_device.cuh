@@ -37,6 +37,14 @@ static const node_t NODE_NONE = 0xffffffffu;
 // fixed-point scale of imaginary time in the cluster sums (order-independent integer atomics)
 #define LQ_FX 1099511627776.0 /* 2^40 */
 
+// per-step inputs, copied host -> device from pinned memory before every step
+struct StepParams {
+  double beta;
+  uint32_t key0, key1;  // Philox key (seed)
+  uint32_t mcs;         // step counter = Philox counter word
+  uint32_t pad;
+};
+
 struct Dev {
   // ---- lattice, internal (tile-contiguous) numbering ----
   int N, B, T, nbmax;

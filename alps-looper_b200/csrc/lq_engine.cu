@@ -193,6 +193,10 @@ struct lq_engine {
   DBuf<int> est0;
   double* h_out = nullptr;  // pinned
   size_t h_out_n = 0;
+  lq::StepParams* h_params = nullptr;  // pinned ring of per-step inputs
+  DBuf<lq::StepParams> d_params;
+  size_t params_n = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
   size_t nblk_collect = 0;
   lq_comm comm{};
   bool has_comm = false;
@@ -202,6 +206,7 @@ struct lq_engine {
 
   ~lq_engine() {
     if (h_out) cudaFreeHost(h_out);
+    if (h_params) cudaFreeHost(h_params);
     for (auto& t : tpending) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     if (stream) cudaStreamDestroy(stream);
   }
@@ -414,10 +419,9 @@ struct lq_engine {
   static unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
   // K2 + K3 on the live buffer (+ K4/K5 sums); used by the step and by lq_build_clusters
-  void label_clusters(double* out_slot, uint32_t step_id) {
+  void label_clusters(double* out_slot, const lq::StepParams* sp) {
     const int N = part.N;
     const size_t nodes_cap = (size_t)N + (size_t)npo * (size_t)ncap;
-    const uint32_t key0 = (uint32_t)opt.seed, key1 = (uint32_t)(opt.seed >> 32);
     {
       Section s(this, 6);
       scan_u32((const uint32_t*)pcount[cur].p, (uint32_t*)nbase.p, P, (uint32_t*)(nbase.p + P), d_ntotal.p);
@@ -449,13 +453,19 @@ struct lq_engine {
     }
     {
       Section s(this, 13);
-      lq::k_collect<<<(unsigned)nblk_collect, 256, 0, stream>>>(d, partial.p, key0, key1, step_id);
+      lq::k_collect<<<(unsigned)nblk_collect, 256, 0, stream>>>(d, partial.p, sp);
       lq::k_collect_final<<<1, 256, 0, stream>>>(d, partial.p, nblk_collect, out_slot);
       launches += 2;
     }
   }
 
   void ensure_out(size_t slots) {
+    if (params_n < slots) {
+      if (h_params) cudaFreeHost(h_params);
+      CK(cudaMallocHost((void**)&h_params, slots * sizeof(lq::StepParams)));
+      d_params.alloc(slots, &device_bytes);
+      params_n = slots;
+    }
     if (d_out.n < slots * 32) d_out.alloc(slots * 32, &device_bytes);
     if (h_out_n < slots * 32) {
       if (h_out) cudaFreeHost(h_out);
@@ -464,15 +474,28 @@ struct lq_engine {
     }
   }
 
-  void enqueue_step(double* out_slot) {
-    const uint32_t key0 = (uint32_t)opt.seed, key1 = (uint32_t)(opt.seed >> 32);
+  // stage the inputs of `count` steps in pinned memory and copy them to the device
+  void stage_params(int count, bool advance) {
+    for (int i = 0; i < count; ++i) {
+      h_params[i].beta = beta;
+      h_params[i].key0 = (uint32_t)opt.seed;
+      h_params[i].key1 = (uint32_t)(opt.seed >> 32);
+      h_params[i].mcs = advance ? mcs + (uint32_t)i : 0xffffffffu;
+      h_params[i].pad = 0;
+    }
+    CK(cudaMemcpyAsync(d_params.p, h_params, (size_t)count * sizeof(lq::StepParams),
+                       cudaMemcpyHostToDevice, stream));
+    h2d_bytes += (int64_t)count * (int64_t)sizeof(lq::StepParams);
+  }
+
+  void enqueue_step(double* out_slot, const lq::StepParams* sp) {
     {
       Section s(this, 5);
-      lq::k_diag_update<<<(unsigned)P, tpb, 0, stream>>>(d, cur, beta, key0, key1, mcs);
+      lq::k_diag_update<<<(unsigned)P, tpb, 0, stream>>>(d, cur, sp);
       launches += 1;
       cur ^= 1;
     }
-    label_clusters(out_slot, mcs);
+    label_clusters(out_slot, sp);
     {
       Section s(this, 15);
       lq::k_flip<<<(unsigned)P, 256, 0, stream>>>(d, cur);
@@ -507,8 +530,10 @@ struct lq_engine {
     if (count <= 0) return;
     if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
     ensure_out((size_t)count);
-    for (int i = 0; i < count; ++i) enqueue_step(d_out.p + (size_t)i * 32);
+    stage_params(count, true);
+    for (int i = 0; i < count; ++i) enqueue_step(d_out.p + (size_t)i * 32, d_params.p + i);
     CK(cudaMemcpyAsync(h_out, d_out.p, (size_t)count * 32 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    d2h_bytes += (int64_t)count * 32 * (int64_t)sizeof(double);
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
     drain_timers();
@@ -643,7 +668,8 @@ struct lq_engine {
   void build_clusters(int32_t* labels_out, int64_t* nc_out, lq_collector* coll_out) {
     if (opt.nranks > 1) fail(LQ_E_UNSUPPORTED, "lq_build_clusters is a single-engine call");
     ensure_out(1);
-    label_clusters(d_out.p, 0xffffffffu);
+    stage_params(1, false);
+    label_clusters(d_out.p, d_params.p);
     labels.alloc(2 * (size_t)std::max<long long>(ncap, 1), nullptr);
     lq::k_export_labels<<<(unsigned)P, 256, 0, stream>>>(d, cur, labels.p);
     launches += 1;
@@ -810,7 +836,15 @@ int lq_get_info(lq_handle h, lq_info* out) {
   return LQ_OK;
 }
 
+int lq_enable_timers(lq_handle h, int on) {
+  if (!h) { g_err = "null handle"; return LQ_E_INVALID; }
+  h->timers_on = on != 0;
+  return LQ_OK;
+}
+
 int64_t lq_kernel_launches(lq_handle h) { return h ? h->launches : 0; }
+int64_t lq_h2d_bytes(lq_handle h) { return h ? h->h2d_bytes : 0; }
+int64_t lq_d2h_bytes(lq_handle h) { return h ? h->d2h_bytes : 0; }
 
 int lq_set_comm(lq_handle h, const lq_comm* comm) {
   if (!h || !comm) { g_err = "bad argument"; return LQ_E_INVALID; }

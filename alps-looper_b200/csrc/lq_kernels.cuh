@@ -51,8 +51,10 @@ __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
 //  * the new bucket sizes are scanned across the CTA and the page is rewritten compacted.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-k_diag_update(Dev d, int src, double beta, uint32_t key0, uint32_t key1, uint32_t mcs) {
+k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   __shared__ int s_scan[34];
+  const double beta = sp->beta;
+  const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
   const int dst = src ^ 1;
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl), wg = d.w0 + wl;
@@ -507,8 +509,9 @@ __global__ void k_estimate_sites(Dev d) {
 // ------------------------------------------------------------------------------------------
 #define LQ_NSUM 14
 __global__ void __launch_bounds__(256)
-k_collect(Dev d, double* partial, uint32_t key0, uint32_t key1, uint32_t mcs) {
+k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
   __shared__ double s_red[8][LQ_NSUM];
+  const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
   const uint32_t nc = d.d_nc[0], ncs = d.d_nc[1];
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   double v[LQ_NSUM];

@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- loop-update throughput (operators/s and MCS/s) of the B200 engine.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line.  A "step" is one Monte Carlo step (diagonal update -> union-find labelling -> estimators ->
+cluster flip) of the S=1/2 Heisenberg antiferromagnet on the square lattice named in
+BASELINE.json.  `value` = operators processed per second, whole job, state resident in HBM,
+device-timed with CUDA events on the engine's stream.  `e2e` = the same metric through the
+reference-facing call (lq_sweep == loop_worker::run): one call per step, per-step inputs copied
+from pinned host memory, the step's collector read back to the host, host clock.
+
+`--impl reference` times the reference's own CPU algorithm (the oracle port of standalone/loop.C,
+validated bit-for-bit against the reference binary; the reference binary itself only knows the
+chain lattice) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALGO_BYTES_PER_OP = 104.0
+# algorithmic bytes per operator of the individual phases
+PHASE_BYTES = {5: ("k_diag_update", 24.0), 7: ("k_link", 28.0), 11: ("k_compress+k_relabel", 8.0),
+               12: ("k_estimate", 32.0), 15: ("k_flip", 12.0)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def workload(name):
+    """(L, beta, therm sweeps) of the named synthetic workload."""
+    table = {
+        "square1024_beta1024": (1024, 1024.0, 24),
+        "square1024_beta128": (1024, 128.0, 40),
+        "square256_beta64": (256, 64.0, 200),
+        "square64_beta8": (64, 8.0, 100),
+    }
+    return table[name]
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample, one independent replica per core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    L, beta, therm, steps, seed = args
+    import numpy as np  # noqa: F401
+    import oracle_util as orc
+    n = L * L
+    import numpy as np
+    idx = np.arange(n)
+    x, y = idx % L, idx // L
+    src = np.concatenate([idx, idx]).astype(np.int32)
+    dst = np.concatenate([(x + 1) % L + L * y, x + L * ((y + 1) % L)]).astype(np.int32)
+    lat = dict(num_sites=n, src=src, dst=dst, gauge=np.where((x + y) % 2 == 0, 1.0, -1.0))
+    sim = orc.OracleSim(lat, beta, seed)
+    for _ in range(therm):
+        sim.sweep()
+    times, nops = [], []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        c = sim.sweep()
+        times.append(time.perf_counter() - t0)
+        nops.append(c["nop"])
+    return times, nops
+
+
+def cpu_arm(L, beta, therm, steps, cores):
+    import oracle_util as orc
+    orc.build()
+    jobs = [(L, beta, therm, steps, 29833 + 7919 * i) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    # aggregate throughput of the replicas over the timed steps
+    per_core = [sum(n) / sum(t) for t, n in res]
+    ms_step = 1e3 * sum(sum(t) for t, _ in res) / (len(res) * steps)
+    nop = sum(sum(n) for _, n in res) / (len(res) * steps)
+    return dict(ops_per_s=sum(per_core), ms_per_step=ms_step, nop=nop, wall=wall)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    L, beta, therm = 128, 32.0, 60
+    r = cpu_arm(L, beta, therm, args.steps + args.warmup, cores)
+    sample = (f"oracle port of standalone/loop.C, {cores} independent replicas of square {L}x{L} "
+              f"beta={beta:g} (same model/lattice family as the GPU workload, bounded size), "
+              f"{therm} thermalisation + {args.warmup + args.steps} timed MCS each")
+    line = {
+        "impl": "reference", "metric": "loop_update_operators_per_sec", "value": r["ops_per_s"],
+        "unit": "operators/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": f"square{L}_beta{beta:g}",
+                   "operators_per_mcs": r["nop"]},
+        "cpu_baseline": {"value": r["ops_per_s"], "unit": "operators/s", "cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": r["ops_per_s"], "unit": "operators/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import looper_b200 as lq
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    L, beta, therm = workload(args.workload)
+    if args.therm >= 0:
+        therm = args.therm
+    lat = lq.hypercubic_lattice((L, L))
+    tile = args.tile_sites or (256 if L >= 512 else 64)
+    eng = make_engine(lq, lat, beta, tile, local, rank, world, args)
+    info = eng.info()
+    stream = torch.cuda.ExternalStream(eng.stream(), device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # thermalise (not timed) + warm-up steps
+    eng.sweep_many(therm, collect=False)
+    eng.sweep_many(max(args.warmup, 3), collect=False)
+
+    # ---- device-timed region: K steps, state resident in HBM -----------------------------------
+    launches0 = eng.kernel_launches()
+    sampler = ClockSampler(local)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        out = eng.sweep_many(args.steps)
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = eng.kernel_launches() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    nops = torch.tensor([float(out["nop"].sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if eng_is_slab(args):
+            pass  # every rank reports the global operator count of the shared configuration
+        else:
+            dist.all_reduce(nops, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    total_ops = float(nops.item())
+    value = total_ops / (ms * 1e-3)
+
+    # ---- end-to-end through the reference-facing call (lq_sweep == loop_worker::run) -----------
+    h0, d0 = eng.copied_bytes()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ops = 0.0
+    for _ in range(args.steps):
+        c = eng.sweep()          # pinned H2D of the step inputs, kernels, D2H of the collector, sync
+        e2e_ops += c["nop"]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h1, d1 = eng.copied_bytes()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    ne = torch.tensor([e2e_ops], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        if not eng_is_slab(args):
+            dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+    e2e_value = float(ne.item()) / float(te.item())
+
+    # ---- per-kernel durations (CUDA events around each phase, separate short run) --------------
+    roof = None
+    if rank == 0:
+        peak, which = measured_peaks()
+        eng_t = eng
+        if eng_t is not None:
+            eng_t.enable_timers(True)
+            before = {x["id"]: (x["seconds"], x["count"]) for x in eng_t.timers()}
+            o2 = eng_t.sweep_many(max(3, min(args.steps, 10)))
+            after = {x["id"]: (x["seconds"], x["count"]) for x in eng_t.timers()}
+            nop_t = float(o2["nop"].mean())
+            phases = {}
+            for pid, (sec, cnt) in after.items():
+                s0, c0 = before.get(pid, (0.0, 0))
+                if cnt > c0:
+                    phases[pid] = (sec - s0) / (cnt - c0)
+            tot = sum(phases.values())
+            dom = max((p for p in phases if p in PHASE_BYTES), key=lambda p: phases[p])
+            kname, bpo = PHASE_BYTES[dom]
+            ach = nop_t * bpo / phases[dom] / 1e9
+            roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": which,
+                    "kernel_ms": 1e3 * phases[dom], "kernel_share_of_step": phases[dom] / tot,
+                    "algorithmic_bytes_per_op": bpo,
+                    "phase_ms": {str(k): 1e3 * v for k, v in sorted(phases.items())},
+                    "step_frac": value / world * ALGO_BYTES_PER_OP / (peak * 1e9),
+                    "step_bytes_per_op": ALGO_BYTES_PER_OP}
+            eng_t.enable_timers(False)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_arm(128, 32.0, 40, 6, 1)
+        cpu = {"value": r["ops_per_s"], "unit": "operators/s", "cores": 1, "kind": "port",
+               "sample": "oracle port of standalone/loop.C (single-threaded like the reference), square "
+                         "128x128 beta=32, 40 thermalisation + 6 timed MCS, %.0f operators/MCS" % r["nop"]}
+
+    if rank == 0:
+        nop_mean = float(out["nop"].mean())
+        line = {
+            "metric": "loop_update_operators_per_sec", "value": value, "unit": "operators/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+            "mcs_per_sec": args.steps / (ms * 1e-3),
+            "config": {"workload": args.workload, "lattice": f"square {L}x{L} periodic",
+                       "model": "S=1/2 Heisenberg AF J=1", "beta": beta,
+                       "operators_per_mcs": nop_mean, "clusters_per_mcs": float(out["nc"].mean()),
+                       "thermalisation_mcs": therm, "tile_sites": tile, "windows": info["num_windows"],
+                       "tiles": info["num_tiles"], "device_bytes": info["device_bytes"],
+                       "l2_policy": "working set (%.1f GB) larger than L2" % (info["device_bytes"] / 1e9)
+                       if info["device_bytes"] > 2.5e8 else "working set comparable to L2",
+                       "multi_gpu": multi_gpu_mode(args, world)},
+            "e2e": {"value": e2e_value, "unit": "operators/s",
+                    "h2d_bytes_per_step": (h1 - h0) / args.steps,
+                    "d2h_bytes_per_step": (d1 - d0) / args.steps,
+                    "ms_per_step": 1e3 * float(te.item()) / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def eng_is_slab(args):
+    return False
+
+
+def multi_gpu_mode(args, world):
+    return "single GPU" if world == 1 else "independent replicas (one Markov chain per GPU)"
+
+
+def make_engine(lq, lat, beta, tile, local, rank, world, args, timers=False):
+    return lq.Engine(lat, beta, seed=29833 + 1000003 * rank, device=local, tile_sites=tile,
+                     timers=timers)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("LQ_BENCH_WORKLOAD", "square1024_beta1024"))
+    ap.add_argument("--tile-sites", type=int, default=0)
+    ap.add_argument("--therm", type=int, default=-1, help="override thermalisation sweeps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

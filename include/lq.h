@@ -130,9 +130,15 @@ int lq_sweep_many(lq_handle h, int32_t count, lq_collector* out);
 int lq_build_clusters(lq_handle h, int32_t* labels_out, int64_t* nc_out, lq_collector* coll_out);
 
 int lq_timers(lq_handle h, lq_timer* out, int32_t* count);   /* timer.summarize (timer.hpp:184) */
+/* ALPS_ENABLE_TIMER at run time (CMakeLists.txt:34-48): CUDA events around every phase */
+int lq_enable_timers(lq_handle h, int on);
 int lq_get_info(lq_handle h, lq_info* out);
 /* number of kernel launches issued by this handle so far */
 int64_t lq_kernel_launches(lq_handle h);
+/* bytes copied host->device (per-step inputs, from pinned memory) and device->host (collectors)
+ * by lq_sweep / lq_sweep_many so far */
+int64_t lq_h2d_bytes(lq_handle h);
+int64_t lq_d2h_bytes(lq_handle h);
 
 /* Multi-GPU (imaginary-time slabs, one engine per GPU; replaces
  * parallel_cluster_unifier::unify, looper/parallel.h:1609-1809): the engine calls
