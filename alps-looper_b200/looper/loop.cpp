@@ -1,0 +1,42 @@
+// loop.cpp -- minimal driver around looper::loop_worker (stand-in for loop.C:25-34 +
+// alps::parapack::start): reads "KEY = value" parameters from a file or stdin, or the standalone
+// kernel's flags -l/-t/-n (standalone/options.h:40-63), runs the worker on the GPU and prints the
+// observables.  Usage: loop [-l L] [-t T] [-n sweeps] [--lattice "square lattice"] [params-file]
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include "loop_worker.h"
+
+int main(int argc, char** argv) {
+  looper::Parameters p;
+  p["LATTICE"] = "chain lattice";
+  p.set("L", 8);
+  p.set("T", 0.2);
+  p.set("SWEEPS", 1u << 16);
+  try {
+    for (int i = 1; i < argc; ++i) {
+      if (!std::strcmp(argv[i], "-l") && i + 1 < argc) p["L"] = argv[++i];
+      else if (!std::strcmp(argv[i], "-t") && i + 1 < argc) p["T"] = argv[++i];
+      else if (!std::strcmp(argv[i], "-n") && i + 1 < argc) p["SWEEPS"] = argv[++i];
+      else if (!std::strcmp(argv[i], "--lattice") && i + 1 < argc) p["LATTICE"] = argv[++i];
+      else if (!std::strcmp(argv[i], "-")) p.parse(std::cin);
+      else { std::ifstream f(argv[i]); if (!f) throw std::invalid_argument(std::string("cannot open ") + argv[i]); p.parse(f); }
+    }
+    looper::loop_worker w(p);
+    looper::observable_set obs;
+    w.init_observables(p, obs);
+    while (w.progress() < 1) w.run(obs);
+    const double N = w.lat().volume(), beta = 1 / obs["Temperature"].mean();
+    // the five lines of standalone/loop.C:186-195, from the looper-named observables
+    std::cout << "Number of Clusters        = " << obs["Number of Clusters"].mean() << " +- " << obs["Number of Clusters"].error() << "\n"
+              << "Energy Density            = " << obs["Energy Density"].mean() << " +- " << obs["Energy Density"].error() << "\n"
+              << "Uniform Susceptibility    = " << beta * obs["Magnetization^2"].mean() / N << " +- " << beta * obs["Magnetization^2"].error() / N << "\n"
+              << "Staggered Magnetization^2 = " << obs["Staggered Magnetization^2"].mean() << " +- " << obs["Staggered Magnetization^2"].error() << "\n"
+              << "Staggered Susceptibility  = " << obs["Staggered Susceptibility"].mean() << " +- " << obs["Staggered Susceptibility"].error() << "\n";
+    if (p.defined("VERBOSE")) obs.print(std::cout);
+  } catch (const std::exception& e) {
+    std::cerr << "error: " << e.what() << "\n";
+    return 1;
+  }
+  return 0;
+}

@@ -1,0 +1,127 @@
+// loop_worker.h -- the reference's worker interface ("loop; path integral",
+// path_integral.C:57-125,202-351,831-862) with its dispatch() body replaced by calls into the C ABI
+// of include/lq.h.  Same member names, argument meaning and error behaviour (exceptions for bad
+// parameters), minus the ALPS base classes: Parameters / observable_set are the stand-ins of
+// parameters.h / measurement.h.
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/lq.h"
+#include "lattice.h"
+#include "measurement.h"
+#include "model.h"
+#include "montecarlo.h"
+#include "parameters.h"
+
+namespace looper {
+
+class loop_worker {
+public:
+  typedef double weight_parameter_type;
+
+  explicit loop_worker(const Parameters& p)
+      : lattice(p), model(p, lattice), temp(p), mcs(p) {
+    if (temp.annealing_steps() > mcs.thermalization())
+      throw std::invalid_argument("longer annealing steps than thermalization");  // path_integral.C:213
+    enable_improved_estimator = !p.defined("DISABLE_IMPROVED_ESTIMATOR");
+    if (!enable_improved_estimator)
+      throw std::invalid_argument("the accelerated path implements the improved estimators only");
+    const virtual_graph& g = lattice.vg();
+    lq_lattice L;
+    L.num_sites = num_sites(g);
+    L.num_bonds = num_bonds(g);
+    L.src = g.src.data();
+    L.dst = g.dst.data();
+    L.gauge = lattice.is_bipartite() ? g.gauge.data() : nullptr;
+    for (int k = 0; k < 3; ++k) L.dims[k] = g.dims[k];
+    lq_model M;
+    M.bond_weights = model.bond_weights().data();
+    for (int k = 0; k < 4; ++k) M.uniform_weights[k] = 0;
+    M.energy_offset = model.energy_offset();
+    lq_options o = lq_options();
+    o.seed = p.value_or_default<unsigned long long>("WORKER_SEED", p.value_or_default<unsigned long long>("SEED", 29833ull));
+    o.device = p.value_or_default<int>("DEVICE", 0);
+    o.tile_sites = p.value_or_default<int>("TILE_SITES", 0);
+    o.reserve = p.value_or_default<double>("RESERVE_OPERATORS_FACTOR", 0.0);  // cf. RESERVE_OPERATORS (:241)
+    o.cluster_reserve = p.value_or_default<double>("RESERVE_ESTIMATES_FACTOR", 0.0);
+    o.flags = p.defined("ENABLE_TIMER") ? 1 : 0;
+    beta_ = 1.0 / temp(0);
+    check(lq_create(&h_, &L, &M, beta_, &o));
+  }
+  ~loop_worker() { lq_destroy(h_); }
+  loop_worker(const loop_worker&) = delete;
+  loop_worker& operator=(const loop_worker&) = delete;
+
+  void init_observables(const Parameters&, observable_set& obs) {  // path_integral.C:307-321
+    obs["Temperature"]; obs["Inverse Temperature"]; obs["Volume"]; obs["Number of Sites"];
+    obs["Number of Clusters"];
+    energy::init_observables(obs);
+  }
+  bool is_thermalized() const { return mcs.is_thermalized(); }
+  double progress() const { return mcs.progress(); }
+
+  // one Monte Carlo step (path_integral.C:323-351): the update runs on the GPU, the observables
+  // of the step are appended on the host once thermalised
+  void run(observable_set& obs) {
+    if (!mcs.can_work()) return;
+    const double b = 1.0 / temp(mcs());
+    if (b != beta_) { check(lq_set_beta(h_, b)); beta_ = b; }
+    lq_collector coll;
+    check(lq_sweep(h_, &coll));
+    ++mcs;
+    if (!mcs.is_thermalized()) return;
+    const double vol = lattice.volume();
+    obs["Temperature"] << 1 / beta_;            // path_integral.C:832-836
+    obs["Inverse Temperature"] << beta_;
+    obs["Volume"] << vol;
+    obs["Number of Sites"] << double(num_sites(lattice.rg()));
+    obs["Number of Clusters"] << coll.nc;
+    energy::commit(obs, coll, beta_, vol);
+    susceptibility::commit(obs, coll, beta_, vol, lattice.is_bipartite());
+    last_ = coll;
+  }
+
+  // exchange Monte Carlo hooks (path_integral.C:98-109)
+  void set_beta(double beta) { temp.set_beta(beta); }
+  weight_parameter_type weight_parameter() const {
+    long long n = 0;
+    check(lq_get_state(h_, nullptr, nullptr, (int64_t*)&n));
+    return double(n);
+  }
+  static double log_weight(double gw, double beta) { return std::log(beta) * gw; }
+
+  // checkpoint payload (path_integral.C:111-124): mcs, spins, operators {type_, loc_, time_}
+  void save(unsigned& mcs_out, std::vector<int32_t>& spins, std::vector<lq_op>& ops) const {
+    int64_t n = 0;
+    check(lq_get_state(h_, nullptr, nullptr, &n));
+    spins.resize(num_sites(lattice.vg()));
+    ops.resize(size_t(n));
+    check(lq_get_state(h_, spins.data(), ops.data(), &n));
+    mcs_out = mcs();
+  }
+  void load(unsigned mcs_in, const std::vector<int32_t>& spins, const std::vector<lq_op>& ops) {
+    check(lq_set_state(h_, spins.data(), ops.data(), int64_t(ops.size())));
+    mcs.set(mcs_in);
+  }
+
+  const lq_collector& last_collector() const { return last_; }
+  lq_handle handle() const { return h_; }
+  const lattice_helper& lat() const { return lattice; }
+
+private:
+  static void check(int rc) {
+    if (rc != LQ_OK) throw std::runtime_error(std::string("lq: ") + lq_last_error());
+  }
+  lattice_helper lattice;
+  spinmodel_helper model;
+  temperature temp;
+  mc_steps mcs;
+  bool enable_improved_estimator = true;
+  double beta_ = 1;
+  lq_handle h_ = nullptr;
+  lq_collector last_ = lq_collector();
+};
+
+}  // namespace looper

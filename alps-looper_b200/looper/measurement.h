@@ -1,0 +1,131 @@
+// measurement.h -- host side of the measurement framework for the accelerated path:
+// observable_set (stand-in for alps::ObservableSet with a binning error analysis) and the
+// commit() arithmetic of the estimators the GPU fills in
+//   energy          looper/energy.h:74-83
+//   susceptibility  looper/susceptibility.h:199-254 (improved collector, path-integral and SSE forms)
+// The per-cluster sums themselves (susceptibility.h:117-155,182-198) are computed on the device
+// (csrc/lq_kernels.cuh k_estimate / k_collect); lq_collector carries the 14 collector sums.
+#pragma once
+#include <cmath>
+#include <map>
+#include <ostream>
+#include <string>
+#include <vector>
+#include "../../include/lq.h"
+
+namespace looper {
+
+inline double power2(double x) { return x * x; }
+inline double power4(double x) { return power2(power2(x)); }
+inline double dip(double x, double y) { return y > 0 ? x / y : 0.0; }  // divide_if_positive.h:42
+
+// scalar observable with logarithmic binning (mean, error from the largest level with >= 32 bins)
+class observable {
+public:
+  void operator<<(double x) {
+    ++n_; sum_ += x;
+    size_t l = 0;
+    double v = x;
+    for (;;) {
+      if (lv_.size() <= l) lv_.push_back(level());
+      level& L = lv_[l];
+      L.s += v; L.s2 += v * v; ++L.n;
+      if (!L.have) { L.pend = v; L.have = true; break; }
+      v = 0.5 * (L.pend + v); L.have = false; ++l;
+    }
+  }
+  unsigned long count() const { return n_; }
+  double mean() const { return n_ ? sum_ / n_ : 0.0; }
+  double naive_error() const { return lv_.empty() ? 0.0 : err(lv_[0]); }
+  double error() const {
+    double e = 0;
+    for (const level& L : lv_) if (L.n >= 32) e = std::max(e, err(L));
+    return e > 0 ? e : naive_error();
+  }
+  double tau() const {  // integrated autocorrelation time estimate
+    const double e0 = naive_error(), e = error();
+    return e0 > 0 ? 0.5 * (power2(e / e0) - 1) : 0.0;
+  }
+private:
+  struct level { double s = 0, s2 = 0, pend = 0; unsigned long n = 0; bool have = false; };
+  static double err(const level& L) {
+    if (L.n < 2) return 0.0;
+    const double m = L.s / L.n, var = L.s2 / L.n - m * m;
+    return var > 0 ? std::sqrt(var / (L.n - 1)) : 0.0;
+  }
+  unsigned long n_ = 0;
+  double sum_ = 0;
+  std::vector<level> lv_;
+};
+
+class observable_set {
+public:
+  observable& operator[](const std::string& name) {
+    auto it = obs_.find(name);
+    if (it == obs_.end()) { order_.push_back(name); return obs_[name]; }
+    return it->second;
+  }
+  bool has(const std::string& name) const { return obs_.count(name) != 0; }
+  const observable& at(const std::string& name) const { return obs_.at(name); }
+  const std::vector<std::string>& names() const { return order_; }
+  void print(std::ostream& os) const {
+    for (const std::string& n : order_) {
+      const observable& o = obs_.at(n);
+      os << n << ": " << o.mean() << " +/- " << o.error() << "; tau = " << o.tau() << "\n";
+    }
+  }
+private:
+  std::map<std::string, observable> obs_;
+  std::vector<std::string> order_;
+};
+
+struct energy {
+  static void init_observables(observable_set& m) { m["Energy"]; m["Energy Density"]; m["Energy^2"]; }
+  static void commit(observable_set& m, const lq_collector& c, double beta, double vol, double sign = 1) {
+    m["Energy"] << sign * c.ene;
+    m["Energy Density"] << sign * c.ene / vol;
+    m["Energy^2"] << sign * (power2(c.ene) - c.nop / power2(beta));
+  }
+};
+
+struct susceptibility {
+  static void commit(observable_set& m, const lq_collector& c, double beta, double vol, bool bipartite,
+                     bool sse = false, double sign = 1) {
+    const double nop = c.nop;
+    m["Magnetization"] << 0.0;
+    m["Magnetization Density"] << 0.0;
+    m["|Magnetization|"] << sign * std::abs(c.umag0);
+    m["|Magnetization Density|"] << sign * std::abs(c.umag0) / vol;
+    m["Magnetization^2"] << sign * c.umag2;
+    m["Magnetization Density^2"] << sign * c.umag2 / power2(vol);
+    m["Magnetization^4"] << sign * (3 * power2(c.umag2) - 2 * c.umag4);
+    m["Magnetization Density^4"] << sign * (3 * power2(c.umag2) - 2 * c.umag4) / power4(vol);
+    m["Susceptibility"] << (sse ? sign * beta * (dip(c.umag, nop) + c.umag2) / (nop + 1) / vol
+                                : sign * beta * c.umag / vol);
+    m["Generalized Magnetization^2"] << sign * c.usize2;
+    m["Generalized Magnetization Density^2"] << sign * c.usize2 / power2(vol);
+    m["Generalized Magnetization^4"] << sign * (3 * power2(c.usize2) - 2 * c.usize4);
+    m["Generalized Magnetization Density^4"] << sign * (3 * power2(c.usize2) - 2 * c.usize4) / power4(vol);
+    m["Generalized Susceptibility"] << (sse ? sign * beta * (dip(c.usize, nop) + c.usize2) / (nop + 1) / vol
+                                            : sign * beta * c.usize / vol);
+    if (!bipartite) return;
+    m["Staggered Magnetization"] << 0.0;
+    m["Staggered Magnetization Density"] << 0.0;
+    m["|Staggered Magnetization|"] << sign * std::abs(c.smag0);
+    m["|Staggered Magnetization Density|"] << sign * std::abs(c.smag0) / vol;
+    m["Staggered Magnetization^2"] << sign * c.smag2;
+    m["Staggered Magnetization Density^2"] << sign * c.smag2 / power2(vol);
+    m["Staggered Magnetization^4"] << sign * (3 * power2(c.smag2) - 2 * c.smag4);
+    m["Staggered Magnetization Density^4"] << sign * (3 * power2(c.smag2) - 2 * c.smag4) / power4(vol);
+    m["Staggered Susceptibility"] << (sse ? sign * beta * (dip(c.smag, nop) + c.smag2) / (nop + 1) / vol
+                                          : sign * beta * c.smag / vol);
+    m["Generalized Staggered Magnetization^2"] << sign * c.ssize2;
+    m["Generalized Staggered Magnetization Density^2"] << sign * c.ssize2 / power2(vol);
+    m["Generalized Staggered Magnetization^4"] << sign * (3 * power2(c.ssize2) - 2 * c.ssize4);
+    m["Generalized Staggered Magnetization Density^4"] << sign * (3 * power2(c.ssize2) - 2 * c.ssize4) / power4(vol);
+    m["Generalized Staggered Susceptibility"] << (sse ? sign * beta * (dip(c.ssize, nop) + c.ssize2) / (nop + 1) / vol
+                                                      : sign * beta * c.ssize / vol);
+  }
+};
+
+}  // namespace looper

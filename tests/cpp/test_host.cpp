@@ -1,0 +1,98 @@
+// CPU unit test of the host-side looper:: mirror (no GPU needed, no liblq.so calls).
+#include <cassert>
+#include <cmath>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include "../../alps-looper_b200/looper/lattice.h"
+#include "../../alps-looper_b200/looper/measurement.h"
+#include "../../alps-looper_b200/looper/model.h"
+#include "../../alps-looper_b200/looper/montecarlo.h"
+#include "../../alps-looper_b200/looper/parameters.h"
+#include "../../alps-looper_b200/looper/union_find.h"
+
+#define CHECK(x) do { if (!(x)) { std::cerr << "FAILED " #x " at line " << __LINE__ << "\n"; return 1; } } while (0)
+
+int main() {
+  using namespace looper;
+  // --- union_find: the sequence of test/union_find.C:40-58; partition printed as min-index labels
+  {
+    const int n = 100;
+    std::mt19937 eng(29833u);
+    auto rng = [&]() { return eng() / 4294967296.0; };
+    std::vector<union_find::node> nodes(n);
+    std::vector<union_find::node_noweight> nw(n);
+    for (int i = 0; i < n; ++i) {
+      int i0 = int(n * rng()), i1 = int(n * rng());
+      union_find::unify(nodes, i0, i1);
+      union_find::unify(nw, i0, i1);
+    }
+    int nc = union_find::set_id(nodes, 0, n, 0);
+    union_find::copy_id(nodes, 0, n);
+    CHECK(nc == union_find::count_root(nodes, 0, n));
+    std::cout << "uf";
+    for (int i = 0; i < n; ++i) {
+      CHECK(union_find::root_index(nodes, i) == union_find::root_index(nw, i));
+      CHECK(union_find::root_index(nodes, i) <= i);  // min-index roots
+      std::cout << ' ' << union_find::root_index(nodes, i);
+    }
+    std::cout << "\n";
+    int wsum = 0;
+    for (int i = 0; i < n; ++i) if (nodes[i].is_root()) wsum += nodes[i].weight();
+    CHECK(wsum == n);
+  }
+  // --- weights: test/weight.op rows
+  {
+    xxz_bond_weight_helper w(bond_parameter_xxz(0, 1, 1));
+    CHECK(w.v[0] == 0.5 && w.v[1] == 0 && w.v[2] == 0 && w.v[3] == 0 && w.offset == 0.25 && w.sign == -1);
+    xxz_bond_weight_helper w2(bond_parameter_xxz(0, 1, 0.5));
+    CHECK(w2.v[0] == 0.375 && w2.v[1] == 0.125 && w2.offset == 0.25);
+    xxz_bond_weight_helper w3(bond_parameter_xxz(0, 1, 2));
+    CHECK(w3.v[0] == 0.5 && w3.v[2] == 0.5 && w3.offset == 0.5);
+    xxz_bond_weight_helper w4(bond_parameter_xxz(0, 1, 1), 0.1);
+    CHECK(std::abs(w4.v[0] - 0.45) < 1e-15 && std::abs(w4.v[1] - 0.05) < 1e-15 && std::abs(w4.v[2] - 0.1) < 1e-15 && std::abs(w4.offset - 0.3) < 1e-15);
+  }
+  // --- parameters + lattice + model
+  {
+    Parameters p;
+    std::istringstream in("LATTICE = \"square lattice\";\nL = 4; W = 6  // comment\nJ = 1;\nT = 0.5\nSWEEPS = 1024;\nT_START_0 = 2; T_DURATION_0 = 64;\n");
+    p.parse(in);
+    CHECK(p.value_or_default<int>("L", 0) == 4 && p.value_or_default<int>("W", 0) == 6);
+    lattice_helper lat(p);
+    CHECK(num_sites(lat.vg()) == 24 && num_bonds(lat.vg()) == 48 && lat.is_bipartite());
+    for (int b = 0; b < num_bonds(lat.vg()); ++b)
+      CHECK(gauge(source(b, lat.vg()), lat.vg()) * gauge(target(b, lat.vg()), lat.vg()) == -1);
+    spinmodel_helper m(p, lat);
+    CHECK(std::abs(m.graph_weight() - 24.0) < 1e-12);       // 48 bonds * 1/2
+    CHECK(std::abs(m.energy_offset() - 12.0) < 1e-12);      // B/4 (standalone/loop.C:175)
+    mc_steps mcs(p);
+    CHECK(mcs.thermalization() == 128 && mcs.sweeps() == 1024);
+    temperature t(p);
+    CHECK(t.annealing_steps() == 64 && t(0) == 2.0 && std::abs(t(32) - 1.25) < 1e-12 && t(64) == 0.5 && t(1000) == 0.5);
+    Parameters q; q["LATTICE"] = "chain lattice"; q.set("L", 8);
+    lattice_helper ch(q);
+    CHECK(target(7, ch.vg()) == 0 && source(3, ch.vg()) == 3);  // standalone/common.h:92-93
+  }
+  // --- observable binning: AR(1) series, error must exceed the naive one
+  {
+    std::mt19937 eng(1);
+    std::normal_distribution<> g;
+    observable o;
+    double x = 0;
+    for (int i = 0; i < (1 << 16); ++i) { x = 0.9 * x + g(eng); o << x; }
+    CHECK(o.count() == (1u << 16));
+    CHECK(o.error() > 2.5 * o.naive_error());
+    CHECK(std::abs(o.mean()) < 6 * o.error());
+    observable_set s;
+    lq_collector c = lq_collector();
+    c.nop = 100; c.ene = -5; c.umag2 = 2; c.umag4 = 3; c.usize = 7; c.smag = 7; c.smag2 = 4;
+    energy::commit(s, c, 10.0, 16.0);
+    susceptibility::commit(s, c, 10.0, 16.0, true);
+    CHECK(s["Energy Density"].mean() == -5.0 / 16);
+    CHECK(s["Energy^2"].mean() == 25 - 100 / 100.0);
+    CHECK(s["Magnetization^4"].mean() == 3 * 4 - 2 * 3);
+    CHECK(s["Staggered Susceptibility"].mean() == 10.0 * 7 / 16);
+  }
+  std::cout << "host ok\n";
+  return 0;
+}

@@ -1,0 +1,61 @@
+"""Host-side C++ mirror of the reference API (alps-looper_b200/looper/): CPU unit test binary,
+its union-find partition against the oracle's restatement of looper/union_find.h, and (GPU) the
+loop driver against exact diagonalisation."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import oracle_util as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build_host_test(tmp_path):
+    exe = os.path.join(str(tmp_path), "test_host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/cpp/test_host.cpp")])
+    return exe
+
+
+def test_host_mirror_unit(tmp_path):
+    exe = _build_host_test(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "host ok" in out.stdout
+    # min-index roots of the host union_find == partition of the reference union_find on the
+    # same 100 unions (test/union_find.op, via the oracle replay text)
+    roots = [int(x) for x in out.stdout.splitlines()[0].split()[1:]]
+    n = orc.lib().orc_union_find_replay(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    orc.lib().orc_union_find_replay(buf, n + 1)
+    ref_root = list(range(100))
+    for m in re.finditer(r"node (\d+)'s parent is \d+ and its root is (\d+)", buf.value.decode().split("[results]")[1]):
+        ref_root[int(m.group(1))] = int(m.group(2))
+    groups = {}
+    for i, r in enumerate(ref_root[:100]):
+        groups.setdefault(r, []).append(i)
+    canon = list(range(100))
+    for members in groups.values():
+        for i in members:
+            canon[i] = min(members)
+    assert roots == canon
+
+
+@pytest.mark.gpu
+def test_loop_driver_vs_exact_diagonalisation():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "alps-looper_b200/looper")])
+    exe = os.path.join(ROOT, "alps-looper_b200/looper/loop")
+    out = subprocess.run([exe, "-l", "8", "-t", "0.2", "-n", "16384"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    vals = {}
+    for ln in out.stdout.splitlines():
+        m = re.match(r"(.+?)\s*=\s*(\S+) \+- (\S+)", ln)
+        if m:
+            vals[m.group(1).strip()] = (float(m.group(2)), float(m.group(3)))
+    ed = {"Energy Density": -0.441438, "Uniform Susceptibility": 0.0804441,
+          "Staggered Magnetization^2": 6.59939, "Staggered Susceptibility": 2.40159}
+    for k, ex in ed.items():
+        mean, err = vals[k]
+        assert abs(mean - ex) < 4 * err + 1e-9, (k, mean, err, ex)
