@@ -1,0 +1,127 @@
+"""Communicator adapters for the multi-GPU (imaginary-time slab) engine.
+
+The C ABI (include/lq.h, lq_comm) asks the host for two collectives on DEVICE buffers:
+an all-gather of the boundary cluster ids and an integer sum all-reduce of the open-cluster
+partial sums.  `attach_torch_distributed` provides them with torch.distributed (NCCL over
+NVLink/NVSwitch) on the engine's own CUDA stream; `LoopbackGroup` provides them for several
+engines living in ONE process on ONE GPU (one Python thread per rank) so that the slab logic
+can be tested without a multi-GPU box.
+"""
+import threading
+
+import torch
+
+
+class _DevBuf:
+    """exposes a raw device pointer through __cuda_array_interface__ (zero copy)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, nbytes, device):
+    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+
+
+def attach_torch_distributed(engine, device, group=None):
+    import torch.distributed as dist
+    dev = torch.device("cuda", device)
+    stream = torch.cuda.ExternalStream(engine.stream(), device=dev)
+
+    def all_gather(ctx, send, recv, nbytes, strm):
+        try:
+            with torch.cuda.stream(stream):
+                s = device_tensor(send, nbytes, dev)
+                r = device_tensor(recv, nbytes * dist.get_world_size(group), dev)
+                dist.all_gather_into_tensor(r, s, group=group)
+            return 0
+        except Exception as e:  # noqa: BLE001  (must not propagate through the C ABI)
+            print("lq comm all_gather failed:", e, flush=True)
+            return 1
+
+    def all_reduce_i64(ctx, buf, count, strm):
+        try:
+            with torch.cuda.stream(stream):
+                t = device_tensor(buf, count * 8, dev).view(torch.int64)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return 0
+        except Exception as e:  # noqa: BLE001
+            print("lq comm all_reduce failed:", e, flush=True)
+            return 1
+
+    engine.set_comm(all_gather, all_reduce_i64)
+
+
+class LoopbackGroup:
+    """P engines in one process / one GPU, one thread each; collectives = device copies."""
+
+    def __init__(self, nranks, device=0):
+        self.n = nranks
+        self.dev = torch.device("cuda", device)
+        self.barrier = threading.Barrier(nranks)
+        self.slots = [None] * nranks
+        self.lock = threading.Lock()
+
+    def attach(self, engine, rank):
+        stream = torch.cuda.ExternalStream(engine.stream(), device=self.dev)
+
+        def all_gather(ctx, send, recv, nbytes, strm):
+            try:
+                stream.synchronize()
+                self.slots[rank] = device_tensor(send, nbytes, self.dev)
+                self.barrier.wait()
+                with torch.cuda.stream(stream):
+                    r = device_tensor(recv, nbytes * self.n, self.dev)
+                    for k in range(self.n):
+                        r[k * nbytes:(k + 1) * nbytes].copy_(self.slots[k])
+                stream.synchronize()
+                self.barrier.wait()
+                return 0
+            except Exception as e:  # noqa: BLE001
+                print("loopback all_gather failed:", e, flush=True)
+                return 1
+
+        def all_reduce_i64(ctx, buf, count, strm):
+            try:
+                stream.synchronize()
+                self.slots[rank] = device_tensor(buf, count * 8, self.dev).view(torch.int64)
+                self.barrier.wait()
+                with torch.cuda.stream(stream):
+                    total = torch.zeros(count, dtype=torch.int64, device=self.dev)
+                    for k in range(self.n):
+                        total += self.slots[k]
+                stream.synchronize()
+                self.barrier.wait()          # everybody has read all inputs
+                with torch.cuda.stream(stream):
+                    self.slots[rank].copy_(total)
+                stream.synchronize()
+                self.barrier.wait()
+                return 0
+            except Exception as e:  # noqa: BLE001
+                print("loopback all_reduce failed:", e, flush=True)
+                return 1
+
+        engine.set_comm(all_gather, all_reduce_i64)
+
+    def run(self, fn):
+        """fn(rank) in one thread per rank; returns the list of results (re-raises errors)."""
+        out, err = [None] * self.n, [None] * self.n
+
+        def body(r):
+            try:
+                torch.cuda.set_device(self.dev)
+                out[r] = fn(r)
+            except BaseException as e:  # noqa: BLE001
+                err[r] = e
+                self.barrier.abort()
+
+        th = [threading.Thread(target=body, args=(r,)) for r in range(self.n)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out

@@ -200,6 +200,13 @@ struct lq_engine {
   size_t nblk_collect = 0;
   lq_comm comm{};
   bool has_comm = false;
+  // multi-rank (imaginary-time slabs)
+  lq::MrDev mr{};
+  DBuf<uint32_t> mr_topmin, mr_sendb, mr_recvb, mr_gparent, mr_gbitmap, mr_gwcount, mr_gwbase, mr_dg;
+  DBuf<uint8_t> mr_gused;
+  DBuf<long long> mr_gest;
+  DBuf<double> mr_rankvec, mr_allvec, mr_gsum;
+  uint32_t* h_mr = nullptr;  // pinned: ngc read-back
   // timers
   struct TimerAcc { double sec = 0; int count = 0; } tacc[17];
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tpending;
@@ -207,6 +214,7 @@ struct lq_engine {
   ~lq_engine() {
     if (h_out) cudaFreeHost(h_out);
     if (h_params) cudaFreeHost(h_params);
+    if (h_mr) cudaFreeHost(h_mr);
     for (auto& t : tpending) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     if (stream) cudaStreamDestroy(stream);
   }
@@ -349,6 +357,26 @@ struct lq_engine {
     flipb.alloc((size_t)nccap, tb);
     nblk_collect = ((size_t)nccap + 255) / 256;
     partial.alloc(nblk_collect * LQ_NSUM, tb);
+    if (opt.nranks > 1) {
+      const size_t g2 = (size_t)opt.nranks * 2 * N, gw = (g2 + 31) / 32 + 1;
+      mr_topmin.alloc((size_t)nccap, tb);
+      mr_sendb.alloc(2 * (size_t)N, tb);
+      mr_recvb.alloc(g2, tb);
+      mr_gparent.alloc(g2, tb);
+      mr_gused.alloc(g2, tb);
+      mr_gbitmap.alloc(gw, tb); mr_gwcount.alloc(gw, tb); mr_gwbase.alloc(gw + 1, tb);
+      mr_gest.alloc(g2 * 8, tb);
+      mr_dg.alloc(4, tb);
+      mr_rankvec.alloc(32, tb); mr_allvec.alloc(32 * (size_t)opt.nranks, tb); mr_gsum.alloc(16, tb);
+      CK(cudaMemset(mr_topmin.p, 0xff, mr_topmin.n * sizeof(uint32_t)));
+      CK(cudaMemset(mr_gest.p, 0, mr_gest.n * sizeof(long long)));
+      CK(cudaMemset(mr_dg.p, 0, 4 * sizeof(uint32_t)));
+      if (!h_mr) CK(cudaMallocHost((void**)&h_mr, 4 * sizeof(uint32_t)));
+      mr.topmin = mr_topmin.p; mr.sendb = mr_sendb.p; mr.recvb = mr_recvb.p; mr.gparent = mr_gparent.p;
+      mr.gused = mr_gused.p; mr.gbitmap = mr_gbitmap.p; mr.gwcount = mr_gwcount.p; mr.gwbase = mr_gwbase.p;
+      mr.gest = mr_gest.p; mr.d_g = mr_dg.p; mr.rankvec = mr_rankvec.p; mr.allvec = mr_allvec.p;
+      mr.gsum = mr_gsum.p;
+    }
     CK(cudaMemset(est.p, 0, est.n * sizeof(long long)));
     CK(cudaMemset(est0.p, 0, est0.n * sizeof(int)));
     CK(cudaMemset(bitmap.p, 0, bitmap.n * sizeof(uint32_t)));
@@ -451,12 +479,58 @@ struct lq_engine {
       lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
       launches += 2;
     }
+    if (opt.nranks > 1) merge_open_clusters();
     {
       Section s(this, 13);
       lq::k_collect<<<(unsigned)nblk_collect, 256, 0, stream>>>(d, partial.p, sp);
       lq::k_collect_final<<<1, 256, 0, stream>>>(d, partial.p, nblk_collect, out_slot);
       launches += 2;
     }
+    if (opt.nranks > 1) finish_open_clusters(out_slot, sp);
+  }
+
+  // ---- multi-rank exchange (looper/parallel.h:1609-1809 restated for one all-gather + one
+  // all-reduce over NVLink; timer ids 21.. of parallel.h:1562-1583 are folded into id 13) -------
+  void comm_check(int rc, const char* what) {
+    if (rc != 0) fail(LQ_E_COMM, std::string(what) + " failed in the communicator callback");
+  }
+
+  void merge_open_clusters() {
+    Section s(this, 13);
+    const int N = part.N;
+    const size_t g2 = (size_t)opt.nranks * 2 * N;
+    lq::k_mr_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
+    lq::k_mr_ids<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
+    launches += 2;
+    comm_check(comm.all_gather(comm.ctx, mr.sendb, mr.recvb, (int64_t)(2 * (size_t)N * sizeof(uint32_t)), stream),
+               "all_gather(boundary ids)");
+    CK(cudaMemsetAsync(mr.d_g, 0, 4 * sizeof(uint32_t), stream));
+    lq::k_mr_ginit<<<grid_for(g2, 256), 256, 0, stream>>>(d, mr);
+    lq::k_mr_gunion<<<grid_for(g2 / 2, 256), 256, 0, stream>>>(d, mr);
+    lq::k_mr_gcompress<<<grid_for(((g2 + 31) / 32) * 32, 256), 256, 0, stream>>>(d, mr);
+    launches += 3;
+    scan_u32(mr.gwcount, mr.gwbase, (g2 + 31) / 32, mr.gwbase + (g2 + 31) / 32, (int*)mr.d_g);
+    lq::k_mr_gather<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
+    launches += 1;
+  }
+
+  void finish_open_clusters(double* out_slot, const lq::StepParams* sp) {
+    Section s(this, 13);
+    const int N = part.N;
+    lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
+    lq::k_mr_reset_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
+    launches += 2;
+    // the all-reduce length is the number of global open clusters: one 16-byte read-back
+    CK(cudaMemcpyAsync(h_mr, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const int64_t ngc = h_mr[0];
+    if (ngc > 0) comm_check(comm.all_reduce_i64(comm.ctx, mr.gest, ngc * 8, stream), "all_reduce(open-cluster sums)");
+    lq::k_mr_gcollect<<<1, 256, 0, stream>>>(d, mr);
+    lq::k_mr_rankvec<<<1, 32, 0, stream>>>(d, mr, out_slot);
+    launches += 2;
+    comm_check(comm.all_gather(comm.ctx, mr.rankvec, mr.allvec, 32 * sizeof(double), stream), "all_gather(collectors)");
+    lq::k_mr_final<<<1, 32, 0, stream>>>(d, mr, out_slot);
+    launches += 1;
   }
 
   void ensure_out(size_t slots) {
@@ -510,7 +584,7 @@ struct lq_engine {
     c->usize = o[5]; c->umag = o[6];
     c->smag0 = o[7]; c->ssize2 = o[8]; c->smag2 = o[9]; c->ssize4 = o[10]; c->smag4 = o[11];
     c->ssize = o[12]; c->smag = o[13];
-    c->nc = o[14]; c->nop = o[15]; c->noc = 0;
+    c->nc = o[14]; c->nop = o[15]; c->noc = o[17];
     c->ene = energy_offset - c->nop / beta;  // path_integral.C:851
   }
 
@@ -666,7 +740,8 @@ struct lq_engine {
   }
 
   void build_clusters(int32_t* labels_out, int64_t* nc_out, lq_collector* coll_out) {
-    if (opt.nranks > 1) fail(LQ_E_UNSUPPORTED, "lq_build_clusters is a single-engine call");
+    if (opt.nranks > 1 && labels_out) fail(LQ_E_UNSUPPORTED, "labels are only exported by a serial engine");
+    if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
     ensure_out(1);
     stage_params(1, false);
     label_clusters(d_out.p, d_params.p);

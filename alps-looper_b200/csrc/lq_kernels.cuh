@@ -587,6 +587,7 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
     out[14] = (double)nc;
     out[15] = (double)(*d.d_ntotal);
     out[16] = (double)(*d.d_err);
+    out[17] = 0.0;
   }
 }
 
@@ -633,6 +634,215 @@ __global__ void k_export_labels(Dev d, int buf, uint32_t* out /* [2*ncap-ish], b
     out[2 * (size_t)idx] = d.parent[upper_node(d, idx, 0)];
     out[2 * (size_t)idx + 1] = d.parent[upper_node(d, idx, 1)];
   }
+}
+
+// ==========================================================================================
+// Multi-GPU: imaginary-time slabs (path_integral_mpi.C:231-232).  Rank r owns the windows
+// [w0, w0+Wl) of ALL sites; its bottom boundary nodes are the site nodes s (ids [0,N)), its top
+// boundary nodes are curW[Wl][s] (path_integral_mpi.C:478-479,662).  After the local labelling
+// every rank publishes, per site, the "open id" of the cluster touching its bottom and its top
+// boundary (the 2N links of a chunk, looper/parallel.h:139-229); the P x 2N ids are all-gathered
+// and EVERY rank unifies top(r) with bottom(r+1) redundantly (parallel.h:524-531,1739) -- on
+// NVSwitch one all-gather replaces the staged ring shifts of parallel.h:1675-1789.  Partial
+// estimates of open clusters are summed with one integer all-reduce indexed by global cluster id;
+// flip bits of open clusters are Philox draws keyed by that id, identical on all ranks.
+// ==========================================================================================
+struct MrDev {
+  uint32_t* topmin;   // [nccap] min boundary site of a local cluster (NONE if it touches none)
+  uint32_t* sendb;    // [2N]  botoid[s], topoid[s]
+  uint32_t* recvb;    // [P*2N]
+  uint32_t* gparent;  // [P*2N]
+  uint8_t* gused;     // [P*2N]
+  uint32_t* gbitmap;  // [(P*2N)/32 + 1]
+  uint32_t* gwcount;
+  uint32_t* gwbase;
+  long long* gest;    // [gcap][8]
+  uint32_t* d_g;      // [0] ngc (global open clusters), [1] noc_local
+  double* rankvec;    // [32] this rank's closed-cluster sums
+  double* allvec;     // [P*32]
+  double* gsum;       // [16] sums over global clusters
+};
+
+__global__ void k_mr_topmin(Dev d, MrDev m) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  const uint32_t cb = d.parent[s];
+  const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  // bottom-touching clusters (cid < ncs) are represented by their smallest BOTTOM site,
+  // clusters that only touch the top boundary by their smallest top site
+  if ((long long)cb < d.nccap) atomicMin(m.topmin + cb, (uint32_t)s);
+  if (ct >= d.d_nc[1] && (long long)ct < d.nccap) atomicMin(m.topmin + ct, (uint32_t)s);
+}
+
+// open id of a local cluster: its cid if it touches the bottom boundary (cid < ncs), else
+// N + (smallest top site)
+__device__ __forceinline__ uint32_t open_id(const Dev& d, const MrDev& m, uint32_t cid) {
+  if (cid < d.d_nc[1]) return cid;
+  return (uint32_t)d.N + (((long long)cid < d.nccap) ? m.topmin[cid] : 0u);
+}
+
+__global__ void k_mr_ids(Dev d, MrDev m) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  m.sendb[s] = d.parent[s];
+  m.sendb[d.N + s] = open_id(d, m, d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
+}
+
+__global__ void k_mr_ginit(Dev d, MrDev m) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)d.nranks * 2 * d.N) return;
+  m.gparent[i] = (uint32_t)i;
+  m.gused[i] = 0;
+}
+
+__global__ void k_mr_gunion(Dev d, MrDev m) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)d.nranks * d.N) return;
+  const int r = (int)(i / d.N), s = (int)(i % d.N), rn = (r + 1) % d.nranks;
+  const size_t N2 = 2 * (size_t)d.N;
+  const uint32_t a = (uint32_t)(r * N2 + m.recvb[r * N2 + d.N + s]);   // top of slab r
+  const uint32_t b = (uint32_t)(rn * N2 + m.recvb[rn * N2 + s]);       // bottom of slab r+1
+  m.gused[a] = 1;
+  m.gused[b] = 1;
+  uf_union(m.gparent, a, b);
+}
+
+__global__ void k_mr_gcompress(Dev d, MrDev m) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nn = (size_t)d.nranks * 2 * d.N;
+  if ((x >> 5) >= ((nn + 31) >> 5)) return;
+  bool isroot = false;
+  if (x < nn) {
+    node_t r = (node_t)x, pr = uf_load(m.gparent + r);
+    while (pr != r) { r = pr; pr = uf_load(m.gparent + r); }
+    m.gparent[x] = r;
+    isroot = (r == (node_t)x) && m.gused[x];
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, isroot);
+  if ((threadIdx.x & 31) == 0) { m.gbitmap[x >> 5] = word; m.gwcount[x >> 5] = (uint32_t)__popc(word); }
+}
+
+__device__ __forceinline__ uint32_t global_cid(const Dev& d, const MrDev& m, uint32_t oid) {
+  const uint32_t r = m.gparent[(size_t)d.rank * 2 * d.N + oid];
+  return m.gwbase[r >> 5] + (uint32_t)__popc(m.gbitmap[r >> 5] & ((1u << (r & 31)) - 1u));
+}
+
+// representative threads move the partial sums of their open cluster into the global table
+// (collect_estimates, parallel.h:415-427) and clear the local entry
+__global__ void k_mr_gather(Dev d, MrDev m) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  const uint32_t ncs = d.d_nc[1];
+  uint32_t cl[2];
+  cl[0] = d.parent[s];
+  cl[1] = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t c = cl[k];
+    if (k == 1 && c == cl[0]) break;
+    if ((long long)c >= d.nccap || m.topmin[c] != (uint32_t)s) continue;  // not the representative
+    if (k == 1 && c < ncs) continue;  // bottom-touching clusters are handled through their bottom rep
+    const uint32_t gid = global_cid(d, m, open_id(d, m, c));
+    unsigned long long* ge = (unsigned long long*)m.gest + (size_t)gid * 8;
+    for (int f = 0; f < 4; ++f) {
+      const long long v = d.est[f * d.nccap + c];
+      if (v) atomicAdd(ge + f, (unsigned long long)v);
+      d.est[f * d.nccap + c] = 0;
+    }
+    if (c < ncs)
+      for (int f = 0; f < 4; ++f) {
+        const int v = d.est0[f * (size_t)d.N + c];
+        if (v) atomicAdd(ge + 4 + f, (unsigned long long)(long long)v);
+        d.est0[f * (size_t)d.N + c] = 0;
+      }
+    atomicAdd(m.d_g + 1, 1u);
+  }
+}
+
+// flip bits of open clusters: one Philox draw per GLOBAL cluster id (same on every rank)
+__global__ void k_mr_openflips(Dev d, MrDev m, const StepParams* __restrict__ sp) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  const uint32_t ncs = d.d_nc[1];
+  uint32_t cl[2];
+  cl[0] = d.parent[s];
+  cl[1] = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t c = cl[k];
+    if (k == 1 && c == cl[0]) break;
+    if ((long long)c >= d.nccap || m.topmin[c] != (uint32_t)s) continue;
+    if (k == 1 && c < ncs) continue;
+    const uint32_t gid = global_cid(d, m, open_id(d, m, c));
+    philox_t x = philox4x32_10(gid, 0xffffffffu, sp->mcs, LQ_STREAM_FLIP, sp->key0, sp->key1);
+    d.flipb[c] = (uint8_t)(x.x & 1u);
+  }
+}
+
+__global__ void k_mr_reset_topmin(Dev d, MrDev m) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.N) return;
+  const uint32_t cb = d.parent[s];
+  const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  if ((long long)cb < d.nccap) m.topmin[cb] = 0xffffffffu;
+  if ((long long)ct < d.nccap) m.topmin[ct] = 0xffffffffu;
+}
+
+// sums over the all-reduced global clusters (one CTA, deterministic order); clears the table
+__global__ void __launch_bounds__(256)
+k_mr_gcollect(Dev d, MrDev m) {
+  __shared__ double s_red[8][LQ_NSUM];
+  const uint32_t ngc = m.d_g[0];
+  double v[LQ_NSUM];
+#pragma unroll
+  for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;
+  const double sc = 0.5 / LQ_FX;
+  for (size_t c = threadIdx.x; c < ngc; c += blockDim.x) {
+    long long* ge = m.gest + c * 8;
+    const double usize = sc * (double)ge[0], umag = sc * (double)ge[1];
+    const double ssize = sc * (double)ge[2], smag = sc * (double)ge[3];
+    const double usize0 = 0.5 * (double)ge[4], umag0 = 0.5 * (double)ge[5];
+    const double ssize0 = 0.5 * (double)ge[6], smag0 = 0.5 * (double)ge[7];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) ge[f] = 0;
+    const double a = usize0 * usize0, b = umag0 * umag0, e = ssize0 * ssize0, g = smag0 * smag0;
+    v[0] += umag0; v[1] += a; v[2] += b; v[3] += a * a; v[4] += b * b; v[5] += usize * usize; v[6] += umag * umag;
+    v[7] += smag0; v[8] += e; v[9] += g; v[10] += e * e; v[11] += g * g; v[12] += ssize * ssize; v[13] += smag * smag;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < LQ_NSUM; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[wid][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < LQ_NSUM) {
+    double x = 0;
+    for (int w = 0; w < 8; ++w) x += s_red[w][threadIdx.x];
+    m.gsum[threadIdx.x] = x;
+  }
+}
+
+// rankvec = local closed sums (from k_collect_final's slot) with nc_closed; then after the
+// all-gather: out = sum over ranks (fixed order) + global-cluster sums
+__global__ void k_mr_rankvec(Dev d, MrDev m, const double* slot) {
+  const int i = threadIdx.x;
+  if (i < LQ_NSUM) m.rankvec[i] = slot[i];
+  if (i == 14) m.rankvec[14] = slot[14] - (double)m.d_g[1];  // closed clusters of this rank
+  if (i == 15) m.rankvec[15] = slot[15];                     // operators of this slab
+  if (i == 16) m.rankvec[16] = slot[16];                     // error flags
+  if (i > 16 && i < 32) m.rankvec[i] = 0;
+}
+
+__global__ void k_mr_final(Dev d, MrDev m, double* slot) {
+  const int i = threadIdx.x;
+  if (i >= 32) return;
+  double x = 0;
+  for (int r = 0; r < d.nranks; ++r) x += m.allvec[r * 32 + i];
+  if (i < LQ_NSUM) x += m.gsum[i];
+  if (i == 14) x += (double)m.d_g[0];
+  if (i == 17) x = (double)m.d_g[0];  // number of clusters that were open (diagnostic)
+  slot[i] = x;
 }
 
 }  // namespace lq

@@ -1,0 +1,102 @@
+"""Multi-rank (imaginary-time slab) engine on ONE GPU through the in-process loopback
+communicator: P engines, P threads.  The collectives are the ones the real multi-GPU run makes
+(torch.distributed/NCCL adapter in alps-looper_b200/comm.py); only the transport differs."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import oracle_util as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mods():
+    import looper_b200 as lq
+    spec = importlib.util.spec_from_file_location("lq_comm", os.path.join(ROOT, "alps-looper_b200", "comm.py"))
+    comm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(comm)
+    return lq, comm
+
+
+SUMS = ["umag0", "usize2", "umag2", "usize4", "umag4", "usize", "umag",
+        "smag0", "ssize2", "smag2", "ssize4", "smag4", "ssize", "smag"]
+
+
+@pytest.mark.parametrize("P", [2, 3, 4])
+@pytest.mark.parametrize("case", ["chain16", "square8"])
+def test_slab_merge_equals_serial_partition(P, case):
+    """same configuration loaded into P slab engines: the merged cluster count and all collector
+    sums equal the oracle's (reference union-find on the whole configuration)."""
+    lq, comm = _mods()
+    lat, beta = (lq.chain_lattice(16), 10.0) if case == "chain16" else (lq.hypercubic_lattice((8, 8)), 6.0)
+    sim = orc.OracleSim(lat, beta)
+    for _ in range(200):
+        sim.sweep()
+    spins, ops = sim.get_state()
+    ref_labels, ref_nc, ref = orc.build_clusters(lat, spins, ops)
+    grp = comm.LoopbackGroup(P)
+
+    def body(r):
+        eng = lq.Engine(lat, beta, rank=r, nranks=P, seed=99)
+        grp.attach(eng, r)
+        eng.set_state(spins, ops)
+        nloc = eng.num_ops()
+        import ctypes as C
+        nc = C.c_int64(0)
+        c = lq.LqCollector()
+        lq._check(lq.lib.lq_build_clusters(eng._h, None, C.byref(nc), C.byref(c)))
+        d = c.as_dict()
+        eng.close()
+        return nloc, nc.value, d
+
+    res = grp.run(body)
+    assert sum(r[0] for r in res) == len(ops)
+    for nloc, nc, d in res:
+        assert nc == ref_nc
+        assert d["nop"] == len(ops)
+        for f in SUMS:
+            assert d[f] == pytest.approx(ref[f], rel=1e-8, abs=1e-7), f
+
+
+def test_slab_sweeps_are_legal_and_physical():
+    """P=2 slabs sweeping a chain: the union of the slabs stays a legal configuration, every rank
+    reports the same collector, and the observables agree with exact diagonalisation."""
+    lq, comm = _mods()
+    L, T = 8, 0.2
+    beta = 1 / T
+    lat = lq.chain_lattice(L)
+    P = 2
+    grp = comm.LoopbackGroup(P)
+    nsweeps = 6000
+
+    def body(r):
+        eng = lq.Engine(lat, beta, rank=r, nranks=P, seed=4242)
+        grp.attach(eng, r)
+        eng.sweep_many(500, collect=False)
+        out = eng.sweep_many(nsweeps)
+        spins, ops = eng.get_state()
+        eng.close()
+        return out, spins, ops
+
+    res = grp.run(body)
+    for f in res[0][0].dtype.names:
+        assert np.array_equal(res[0][0][f], res[1][0][f]), f
+    ops = np.concatenate([res[0][2], res[1][2]])
+    assert np.all(np.diff(ops["time"]) >= 0)
+    orc.build_clusters(lat, res[0][1], ops)      # rank 0 holds the spins at tau = 0
+    out = res[0][0]
+    assert out["nop"][-1] == len(ops)
+    ene = (0.25 * L - out["nop"] / beta) / L
+    ssus = beta * out["usize"] / L
+    smag = out["usize2"]
+
+    def berr(x, nb=30):
+        m = len(x) // nb
+        b = x[: m * nb].reshape(nb, m).mean(axis=1)
+        return b.std(ddof=1) / np.sqrt(nb)
+
+    for name, series, ex in [("energy", ene, -0.441438), ("smag", smag, 6.59939), ("ssus", ssus, 2.40159)]:
+        assert abs(series.mean() - ex) < 4 * berr(series) + 1e-12, (name, series.mean(), ex, berr(series))
