@@ -63,6 +63,17 @@ struct Dev {
   const float4* bond_p;     // [B] {P(g=0|anti), P(accept|anti), P(g=1|par), P(accept|par)}
   const float* bond_q;      // [B] P(g=0 | offdiagonal)  (graph_impl.h:311-313)
   const signed char* gauge;  // [N] +1/-1/0
+  // ---- static per-tile halo lists and per-class stencils (see Partition in lq_engine.cu) ----
+  const int* halo_off;    // [T+1]
+  const int* halo_bond;   // global bond ids of the halo buckets of a tile
+  const int* tile_class;  // [T]
+  const int* cls_off;     // [nclasses+1] start of the class in st_off
+  const int* st_off;      // per class 2*nb+1 offsets
+  const int* cls_st;      // [nclasses] start of the class in st
+  const int* st;          // (local bucket << 1 | side)
+  int hmax;               // max halo buckets per tile
+  int scap;               // operators that fit the shared-memory stage (own page + halo)
+  int ccap;               // candidates per page that fit the stage (K1)
   // ---- pages (double buffered) ----
   double* time[2];
   uint32_t* info[2];

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -61,6 +62,16 @@ struct Partition {
   int N = 0, B = 0, T = 0, nbmax = 0;
   std::vector<int> site_e2i, site_i2e, bond_e2i, bond_i2e;
   std::vector<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj;
+  // per-tile halo (bonds owned by other tiles that touch an end site of an owned bond) and the
+  // per-bond stencils in LOCAL bucket ids (own bonds 0..nb-1, halo nb..nb+H-1); stencils are
+  // shared by all tiles of the same shape ("class")
+  int hmax = 0, nclasses = 0;
+  std::vector<int> halo_off, halo_bond;   // [T+1], [sum H]
+  std::vector<int> tile_class;            // [T]
+  std::vector<int> cls_off;               // [nclasses+1] start of a class in st_off (units: entries)
+  std::vector<int> st_off;                // per class: 2*nb+1 offsets into st (relative to cls_st)
+  std::vector<int> cls_st;                // [nclasses] start of a class in st
+  std::vector<int> st;                    // entries (local bucket << 1 | side)
 };
 
 void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
@@ -145,6 +156,50 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
     P.adj[fill[P.bond_s0[i]]++] = (i << 1) | 0;
     P.adj[fill[P.bond_s1[i]]++] = (i << 1) | 1;
   }
+  // halos and stencils
+  P.halo_off.assign(T + 1, 0);
+  P.tile_class.assign(T, 0);
+  P.cls_off.assign(1, 0);
+  std::map<std::vector<int>, int> classes;
+  std::vector<int> local(B, -1);
+  for (int t = 0; t < T; ++t) {
+    const int b0 = P.bond_base[t], nb = P.bond_base[t + 1] - b0;
+    std::vector<int> halo;
+    std::vector<int> sig;  // serialised stencil = class signature
+    sig.push_back(nb);
+    std::vector<int> offs(1, 0), ent;
+    for (int lb = 0; lb < nb; ++lb) local[b0 + lb] = lb;
+    for (int lb = 0; lb < nb; ++lb)
+      for (int side = 0; side < 2; ++side) {
+        const int sgl = side ? P.bond_s1[b0 + lb] : P.bond_s0[b0 + lb];
+        for (int a = P.adj_off[sgl]; a < P.adj_off[sgl + 1]; ++a) {
+          const int b2 = P.adj[a] >> 1, side2 = P.adj[a] & 1;
+          if (local[b2] < 0) { local[b2] = nb + (int)halo.size(); halo.push_back(b2); }
+          ent.push_back((local[b2] << 1) | side2);
+        }
+        offs.push_back((int)ent.size());
+      }
+    for (int lb = 0; lb < nb; ++lb) local[b0 + lb] = -1;
+    for (int h : halo) local[h] = -1;
+    sig.insert(sig.end(), offs.begin(), offs.end());
+    sig.insert(sig.end(), ent.begin(), ent.end());
+    auto it = classes.find(sig);
+    if (it == classes.end()) {
+      const int c = (int)classes.size();
+      classes[sig] = c;
+      P.tile_class[t] = c;
+      P.cls_st.push_back((int)P.st.size());
+      P.st_off.insert(P.st_off.end(), offs.begin(), offs.end());
+      P.cls_off.push_back((int)P.st_off.size());
+      P.st.insert(P.st.end(), ent.begin(), ent.end());
+    } else {
+      P.tile_class[t] = it->second;
+    }
+    P.halo_off[t + 1] = P.halo_off[t] + (int)halo.size();
+    P.halo_bond.insert(P.halo_bond.end(), halo.begin(), halo.end());
+    P.hmax = std::max(P.hmax, (int)halo.size());
+  }
+  P.nclasses = (int)classes.size();
 }
 
 inline int window_of(double t, int W) {
@@ -182,6 +237,9 @@ struct lq_engine {
   lq::Dev d{};
   cudaStream_t stream = nullptr;
   DBuf<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
+  DBuf<int> halo_off, halo_bond, tile_class, cls_off, st_off, cls_st, st;
+  int scap = 0, ccap = 0;
+  size_t stage_smem = 0;
   DBuf<double> bond_rate, time_[2], partial, d_out;
   DBuf<float4> bond_p;
   DBuf<float> bond_q;
@@ -263,7 +321,9 @@ struct lq_engine {
     make_partition(L, opt.tile_sites, part);
     if (part.nbmax + 1 > 1024)
       fail(LQ_E_INVALID, "tile owns more than 1023 bonds: lower lq_options.tile_sites");
-    tpb = ((part.nbmax + 1 + 31) / 32) * 32;
+    if (part.hmax > 1024)
+      fail(LQ_E_INVALID, "tile halo has more than 1024 buckets: lower lq_options.tile_sites");
+    tpb = ((std::max(part.nbmax + 1, part.hmax) + 31) / 32) * 32;
 
     // static tables
     const int N = part.N, B = part.B;
@@ -294,6 +354,13 @@ struct lq_engine {
     bond_p.upload(bp, &device_bytes);
     bond_q.upload(bq, &device_bytes);
     gauge.upload(gi, &device_bytes);
+    halo_off.upload(part.halo_off, &device_bytes);
+    halo_bond.upload(part.halo_bond, &device_bytes);
+    tile_class.upload(part.tile_class, &device_bytes);
+    cls_off.upload(part.cls_off, &device_bytes);
+    st_off.upload(part.st_off, &device_bytes);
+    cls_st.upload(part.cls_st, &device_bytes);
+    st.upload(part.st, &device_bytes);
     d_ntotal.alloc(1, &device_bytes);
     d_err.alloc(1, &device_bytes);
     d_nc.alloc(2, &device_bytes);
@@ -327,6 +394,25 @@ struct lq_engine {
     long long c = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
     if (c > 65535) fail(LQ_E_INVALID, "page capacity exceeds 65535 operators: lower tile_sites or window_ops");
     cap = (int)c;
+    {
+      // shared-memory stage: own page + halo buckets (halo/own bucket ratio, 1.5x head room)
+      const double ratio = (double)part.hmax / std::max(1, part.nbmax);
+      const double hm = m * ratio;
+      scap = cap + (int)std::ceil(hm + 6.0 * std::sqrt(hm) + 16.0);
+      const double cm = mu;  // mean candidates per page
+      ccap = (int)std::ceil(cm + 8.0 * std::sqrt(cm) + 32.0);
+      if (ccap > 65535) fail(LQ_E_INVALID, "too many candidates per page: lower tile_sites or window_ops");
+      stage_smem = lq::stage_bytes(scap, part.nbmax, part.hmax, ccap);
+      if (stage_smem > 200 * 1024)
+        fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
+      const int sm = (int)stage_smem;
+      CK(cudaFuncSetAttribute(lq::k_diag_update<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_diag_update<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_diag_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_link<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_link<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_link<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    }
     P = (size_t)T * Wl;
     ncap = (long long)P * cap;
     const long long nodes_cap = (long long)N + (long long)npo * ncap;
@@ -391,6 +477,8 @@ struct lq_engine {
     d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_tile = bond_tile.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
     d.bond_q = bond_q.p; d.gauge = gauge.p;
+    d.halo_off = halo_off.p; d.halo_bond = halo_bond.p; d.tile_class = tile_class.p; d.cls_off = cls_off.p;
+    d.st_off = st_off.p; d.cls_st = cls_st.p; d.st = st.p; d.hmax = part.hmax; d.scap = scap; d.ccap = ccap;
     for (int k = 0; k < 2; ++k) {
       d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
     }
@@ -459,7 +547,9 @@ struct lq_engine {
     }
     {
       Section s(this, 7);
-      lq::k_link<<<(unsigned)P, tpb, 0, stream>>>(d, cur);
+      if (tpb <= 256) lq::k_link<256><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
+      else if (tpb <= 640) lq::k_link<640><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
+      else lq::k_link<1024><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
       launches += 1;
     }
     {
@@ -565,7 +655,9 @@ struct lq_engine {
   void enqueue_step(double* out_slot, const lq::StepParams* sp) {
     {
       Section s(this, 5);
-      lq::k_diag_update<<<(unsigned)P, tpb, 0, stream>>>(d, cur, sp);
+      if (tpb <= 256) lq::k_diag_update<256><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
+      else if (tpb <= 640) lq::k_diag_update<640><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
+      else lq::k_diag_update<1024><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
       launches += 1;
       cur ^= 1;
     }

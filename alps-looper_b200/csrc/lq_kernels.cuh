@@ -42,122 +42,240 @@ __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: diagonal update.  One CTA per page, one thread per (bond, window) bucket.
-//  * old diagonal operators are dropped, off-diagonal ones kept (graph re-chosen, graph_impl.h:324)
-//  * candidates: Poisson process of rate beta * sum_g v_g on the bond, realised as exponential gaps
-//    (= Knuth's product method of poisson_distribution.h:60-75 with the arrival times kept)
-//  * acceptance needs only the RELATIVE orientation of the two spins: operators on this bond flip
-//    both, so only off-diagonal operators of the OTHER bonds at the two sites matter.
-//  * the new bucket sizes are scanned across the CTA and the page is rewritten compacted.
+// Shared-memory stage of one page and its halo (the "time-slice tile"): the operators of the
+// tile's own buckets are copied as one contiguous stream, the buckets of foreign bonds that touch
+// an end site of an owned bond are gathered behind them.  All neighbour look-ups of K1 and K2
+// then run on shared memory through the static per-class stencils (local bucket ids).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+struct Stage {
+  double* time;    // [scap]
+  double* ctime;   // [ccap]   candidate times (K1)
+  uint32_t* info;  // [scap]
+  int* off;        // [nloc+1] first staged slot of each local bucket
+  int* idx0;       // [nloc]   dense operator index of the first operator of the bucket
+  int* gbond;      // [nloc]   global bond id (tie-break order)
+  int* cbase;      // [nbmax+1] first candidate of each own bucket (K1)
+  int* noff;       // [nbmax+1] new bucket offsets (K1)
+  uint16_t* clb;   // [ccap]   owning local bucket of a candidate (K1)
+  uint8_t* cacc;   // [ccap]   accepted bit | graph << 1 (K1)
+  uint8_t* rel;    // [nbmax]  relative spin orientation at the window start (K1)
+  int nb, nh;
+};
+
+__host__ __device__ inline size_t stage_bytes(int scap, int nbmax, int hmax, int ccap) {
+  const size_t nloc = (size_t)nbmax + hmax;
+  return ((size_t)scap + ccap) * 8 + (size_t)scap * 4 + (3 * nloc + 1) * 4 + 2 * ((size_t)nbmax + 1) * 4 +
+         (size_t)ccap * 3 + (size_t)nbmax + 64;
+}
+
+__device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl, unsigned char* smem,
+                                           Stage& S, int* s_scan) {
+  const int nloc_max = d.nbmax + d.hmax;
+  S.time = (double*)smem;
+  S.ctime = S.time + d.scap;
+  S.info = (uint32_t*)(S.ctime + d.ccap);
+  S.off = (int*)(S.info + d.scap);
+  S.idx0 = S.off + nloc_max + 1;
+  S.gbond = S.idx0 + nloc_max;
+  S.cbase = S.gbond + nloc_max;
+  S.noff = S.cbase + d.nbmax + 1;
+  S.clb = (uint16_t*)(S.noff + d.nbmax + 1);
+  S.cacc = (uint8_t*)(S.clb + d.ccap);
+  S.rel = S.cacc + d.ccap;
+  const size_t p = (size_t)t * d.Wl + wl;
+  const int b0 = d.bond_base[t];
+  S.nb = d.bond_base[t + 1] - b0;
+  const int h0 = d.halo_off[t];
+  S.nh = d.halo_off[t + 1] - h0;
+  const int n_own = d.pcount[buf][p];
+  const int base_idx = d.nbase[p];
+  const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1);
+  const int tid = threadIdx.x;
+  if (tid < S.nb) {
+    const int o = bo[tid];
+    S.off[tid] = o;
+    S.idx0[tid] = base_idx + o;
+    S.gbond[tid] = b0 + tid;
+  }
+  const double* gt = d.time[buf] + p * (size_t)d.cap;
+  const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
+  for (int j = tid; j < n_own; j += blockDim.x) { S.time[j] = gt[j]; S.info[j] = gi[j]; }
+  // halo buckets
+  BucketRef r; r.base = 0; r.n = 0; r.idx0 = 0;
+  int b2 = 0;
+  if (tid < S.nh) { b2 = d.halo_bond[h0 + tid]; r = bucket_of(d, buf, b2, wl); }
+  int total;
+  const int hoff = block_exscan(r.n, &total, s_scan);
+  const bool ok = (n_own + total <= d.scap);
+  if (tid < S.nh) {
+    S.off[S.nb + tid] = n_own + hoff;
+    S.idx0[S.nb + tid] = r.idx0;
+    S.gbond[S.nb + tid] = b2;
+    if (ok)
+      for (int j = 0; j < r.n; ++j) {
+        S.time[n_own + hoff + j] = d.time[buf][r.base + j];
+        S.info[n_own + hoff + j] = d.info[buf][r.base + j];
+      }
+  }
+  if (tid == 0) S.off[S.nb + S.nh] = n_own + total;
+  __syncthreads();
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: diagonal update.  One CTA per page (staged with its halo).  FLAT work mapping -- every
+// phase gives each thread one bucket, one candidate or one old operator, so warps stay full:
+//  1. per bucket: number of candidates K ~ Poisson(beta * sum_g v_g * window) by inverse CDF
+//     (replaces poisson_distribution.h:60-75 / the exponential gaps of path_integral.C:413-423);
+//     CTA-wide prefix sum (warp shuffles) -> candidate slots
+//  2. per candidate: uniform time in the window, Philox4x32-10 keyed by (bond, window, step, i);
+//     acceptance needs only the RELATIVE orientation of the two spins (operators on this bond
+//     flip both), i.e. the parity of off-diagonal operators of the OTHER bonds at the two sites
+//     before the candidate; graph chosen with the model's weights (graph_impl.h:679)
+//  3. per bucket: new size = kept off-diagonal + accepted; prefix sum -> new bucket offsets
+//  4. per accepted candidate / per kept operator: rank inside the new bucket -> scatter into the
+//     compacted new page (old diagonal operators are dropped, path_integral.C:519-521)
+// ------------------------------------------------------------------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
 k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
+  extern __shared__ __align__(16) unsigned char s_stage[];
   __shared__ int s_scan[34];
   const double beta = sp->beta;
   const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
   const int dst = src ^ 1;
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl), wg = d.w0 + wl;
-  const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
-  const int lb = threadIdx.x;
-  const bool active = lb < nb;
-
-  double ctime[LQ_MAXC];
-  uint8_t cgraph[LQ_MAXC];
-  int nacc = 0, nkeep = 0;
-  size_t obase = 0;
-  int on = 0;
-  int b = 0;
-  if (active) {
-    b = b0 + lb;
-    const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
-    int rel = d.spinW[(size_t)wl * d.N + s0] ^ d.spinW[(size_t)wl * d.N + s1];
-    // off-diagonal legs of the other bonds at the two sites
-    double nt[LQ_MAXN];
-    int nn = 0;
-    for (int side = 0; side < 2; ++side) {
-      const int s = side ? s1 : s0;
-      for (int a = d.adj_off[s]; a < d.adj_off[s + 1]; ++a) {
-        const int b2 = d.adj[a] >> 1;
-        if (b2 == b) continue;
-        BucketRef r = bucket_of(d, src, b2, wl);
-        for (int j = 0; j < r.n; ++j) {
-          if (d.info[src][r.base + j] & LQ_INFO_OFFDIAG) {
-            if (nn < LQ_MAXN) nt[nn++] = d.time[src][r.base + j];
-            else atomicOr(d.d_err, LQ_ERR_NEIGH_FULL);
-          }
-        }
-      }
-    }
-    // own old bucket
-    BucketRef r = bucket_of(d, src, b, wl);
-    obase = r.base;
-    on = r.n;
-    for (int j = 0; j < on; ++j) nkeep += (d.info[src][obase + j] & LQ_INFO_OFFDIAG);
-    // candidates
-    const double rate = beta * d.bond_rate[b];
-    if (rate > 0) {
-      const float4 pr = d.bond_p[b];
-      const double tlo = window_lo(wg, d.W), thi = window_hi(wg, d.W);
-      const double inv = 1.0 / rate;
-      double tc = tlo;
-      for (uint32_t i = 0;; ++i) {
-        philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + i, key0, key1);
-        tc += -log(u53(x.x, x.y)) * inv;
-        if (!(tc < thi)) break;
-        int c = 0;
-        for (int k = 0; k < nn; ++k) c += (nt[k] < tc);
-        const int anti = rel ^ (c & 1);
-        const float u = u24(x.z);
-        int g = -1;
-        if (anti) { if (u < pr.x) g = 0; else if (u < pr.y) g = 2; }
-        else      { if (u < pr.z) g = 1; else if (u < pr.w) g = 3; }
-        if (g >= 0) {
-          if (nacc < LQ_MAXC) { ctime[nacc] = tc; cgraph[nacc] = (uint8_t)g; ++nacc; }
-          else atomicOr(d.d_err, LQ_ERR_CAND_FULL);
-        }
-      }
-    }
-  }
-  int total;
-  const int cnt = active ? (nkeep + nacc) : 0;
-  const int off = block_exscan(cnt, &total, s_scan);
+  Stage S;
+  const bool staged = stage_page(d, src, t, wl, s_stage, S, s_scan);
+  const int nb = S.nb;
+  const int tid = threadIdx.x;
   uint16_t* bo = d.boff[dst] + p * (size_t)(d.nbmax + 1);
-  if (total > d.cap) {
-    if (threadIdx.x == 0) { atomicOr(d.d_err, LQ_ERR_PAGE_FULL); d.pcount[dst][p] = 0; }
-    if (lb <= nb) bo[lb] = 0;
+  if (!staged) {
+    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_PAGE_FULL); d.pcount[dst][p] = 0; }
+    if (tid <= nb) bo[tid] = 0;
     return;
   }
-  if (active) bo[lb] = (uint16_t)off;
-  if (lb == nb) { bo[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
-  if (active) {
-    // merge kept off-diagonal operators with the accepted candidates, both time-ordered
-    const size_t wbase = p * (size_t)d.cap + off;
+  const int b0 = d.bond_base[t];
+  const int n_own = S.off[nb];
+  const double tlo = window_lo(wg, d.W), thi = window_hi(wg, d.W), width = thi - tlo;
+  const int cls = d.tile_class[t];
+  const int* so = d.st_off + d.cls_off[cls];
+  const int* se = d.st + d.cls_st[cls];
+
+  // ---- phase 1: candidates per bucket ------------------------------------------------------
+  int K = 0, nkeep = 0;
+  if (tid < nb) {
+    const int b = b0 + tid;
+    const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
+    S.rel[tid] = d.spinW[(size_t)wl * d.N + s0] ^ d.spinW[(size_t)wl * d.N + s1];
+    for (int j = S.off[tid]; j < S.off[tid + 1]; ++j) nkeep += (int)(S.info[j] & LQ_INFO_OFFDIAG);
+    const double mu = beta * d.bond_rate[b] * width;
+    if (mu > 0) {
+      const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND, key0, key1);
+      const double u = u53(x.x, x.y);
+      double pk = exp(-mu), cdf = pk;
+      while (u > cdf && K < 32) { ++K; pk *= mu / K; cdf += pk; }
+      if (K >= 32 && u > cdf) atomicOr(d.d_err, LQ_ERR_CAND_FULL);
+    }
+  }
+  int C;
+  const int cb = block_exscan(K, &C, s_scan);
+  if (C > d.ccap) {
+    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_CAND_FULL); d.pcount[dst][p] = 0; }
+    if (tid <= nb) bo[tid] = 0;
+    return;
+  }
+  if (tid < nb) {
+    S.cbase[tid] = cb;
+    for (int i = 0; i < K; ++i) S.clb[cb + i] = (uint16_t)tid;
+  }
+  if (tid == nb) S.cbase[nb] = C;
+  __syncthreads();
+
+  // ---- phase 2: time, acceptance and graph of every candidate ---------------------------------
+  for (int c = tid; c < C; c += blockDim.x) {
+    const int lb = S.clb[c];
+    const int i = c - S.cbase[lb];
+    const int b = b0 + lb;
+    const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + 1u + (uint32_t)i, key0, key1);
+    double tc = tlo + (u53(x.x, x.y) - 1.0 / 9007199254740992.0) * width;
+    if (!(tc < thi)) tc = tlo;
+    int par = S.rel[lb];
+    const int e1 = so[2 * lb + 2];
+    for (int e = so[2 * lb]; e < e1; ++e) {
+      const int lid = se[e] >> 1;
+      if (lid == lb) continue;
+      const int q1 = S.off[lid + 1];
+      for (int j = S.off[lid]; j < q1; ++j)
+        par ^= (int)(S.info[j] & LQ_INFO_OFFDIAG) & (int)(S.time[j] < tc);
+    }
+    const float4 pr = d.bond_p[b];
+    const float u = u24(x.z);
+    int g = -1;
+    if (par) { if (u < pr.x) g = 0; else if (u < pr.y) g = 2; }
+    else     { if (u < pr.z) g = 1; else if (u < pr.w) g = 3; }
+    S.ctime[c] = tc;
+    S.cacc[c] = (g >= 0) ? (uint8_t)(1 | (g << 1)) : (uint8_t)0;
+  }
+  __syncthreads();
+
+  // ---- phase 3: new bucket sizes -> offsets -------------------------------------------------
+  int cnt = 0;
+  if (tid < nb) {
+    int nacc = 0;
+    for (int i = 0; i < K; ++i) nacc += S.cacc[cb + i] & 1;
+    cnt = nkeep + nacc;
+  }
+  int total;
+  const int off = block_exscan(cnt, &total, s_scan);
+  if (total > d.cap) {
+    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_PAGE_FULL); d.pcount[dst][p] = 0; }
+    if (tid <= nb) bo[tid] = 0;
+    return;
+  }
+  if (tid < nb) { bo[tid] = (uint16_t)off; S.noff[tid] = off; }
+  if (tid == nb) { bo[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
+  __syncthreads();
+
+  // ---- phase 4: scatter into the compacted new page ------------------------------------------
+  double* wt = d.time[dst] + p * (size_t)d.cap;
+  uint32_t* wi = d.info[dst] + p * (size_t)d.cap;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const uint32_t acc = S.cacc[c];
+    if (!(acc & 1)) continue;
+    const int lb = S.clb[c];
+    const double tc = S.ctime[c];
+    int rank = 0;
+    for (int j = S.off[lb]; j < S.off[lb + 1]; ++j)      // kept operators come first on ties
+      rank += (int)(S.info[j] & LQ_INFO_OFFDIAG) & (int)(S.time[j] <= tc);
+    const int c0 = S.cbase[lb], c1 = S.cbase[lb + 1];
+    for (int k = c0; k < c1; ++k)
+      rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] < tc || (S.ctime[k] == tc && k < c));
+    const int pos = S.noff[lb] + rank;
+    wt[pos] = tc;
+    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((acc >> 1) << LQ_INFO_GSHIFT);
+  }
+  for (int j = tid; j < n_own; j += blockDim.x) {
+    const uint32_t inf = S.info[j];
+    if (!(inf & LQ_INFO_OFFDIAG)) continue;
+    const int lb = (int)(inf >> LQ_INFO_LBSHIFT);
+    const double tt = S.time[j];
+    const int o0 = S.off[lb];
+    int rank = 0;
+    for (int k = o0; k < j; ++k) rank += (int)(S.info[k] & LQ_INFO_OFFDIAG);
+    const int c0 = S.cbase[lb], c1 = S.cbase[lb + 1];
+    for (int k = c0; k < c1; ++k) rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] < tt);
+    uint32_t g = 0;
+    const int b = b0 + lb;
     const float q0 = d.bond_q[b];
-    int k = 0, ci = 0;
-    for (int j = 0; j < on; ++j) {
-      const uint32_t inf = d.info[src][obase + j];
-      if (!(inf & LQ_INFO_OFFDIAG)) continue;
-      const double tt = d.time[src][obase + j];
-      while (ci < nacc && ctime[ci] < tt) {
-        d.time[dst][wbase + k] = ctime[ci];
-        d.info[dst][wbase + k] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)cgraph[ci] << LQ_INFO_GSHIFT);
-        ++k; ++ci;
-      }
-      uint32_t g = 0;
-      if (q0 < 1.0f) {  // graph_impl.h:324-327 choose_offdiagonal
-        philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)j, key0, key1);
-        g = (u24(x.x) < q0) ? 0u : 1u;
-      }
-      d.time[dst][wbase + k] = tt;
-      d.info[dst][wbase + k] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG;
-      ++k;
+    if (q0 < 1.0f) {  // graph_impl.h:324-327 choose_offdiagonal
+      const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)(j - o0), key0, key1);
+      g = (u24(x.x) < q0) ? 0u : 1u;
     }
-    while (ci < nacc) {
-      d.time[dst][wbase + k] = ctime[ci];
-      d.info[dst][wbase + k] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)cgraph[ci] << LQ_INFO_GSHIFT);
-      ++k; ++ci;
-    }
+    const int pos = S.noff[lb] + rank;
+    wt[pos] = tt;
+    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG;
   }
 }
 
@@ -261,25 +379,27 @@ __global__ void k_carry(Dev d, int buf) {
   d.curW[(size_t)d.Wl * d.N + s] = cur;
 }
 
-// node of the leg arriving from below at (site s, time tt of bond b) and the spin on it
-__device__ __forceinline__ node_t scan_below(const Dev& d, int buf, int s, int wl, double tt, int b,
-                                             int jself, int* spin_out) {
-  node_t best = d.curW[(size_t)wl * d.N + s];
-  int spin = d.spinW[(size_t)wl * d.N + s];
+// node of the leg arriving from below at one end site of operator j (staged slot) of local
+// bucket lb, and the spin on that leg; [e0,e1) is the stencil of that end site
+__device__ __forceinline__ node_t scan_below(const Dev& d, const Stage& S, const int* se, int e0, int e1,
+                                             int lb, int b, int j, double tt, node_t carry, int spin0,
+                                             int* spin_out) {
+  node_t best = carry;
+  int spin = spin0;
   double bt = -1.0;
   int bb = -1;
-  for (int a = d.adj_off[s]; a < d.adj_off[s + 1]; ++a) {
-    const int e = d.adj[a];
-    const int b2 = e >> 1;
-    BucketRef r = bucket_of(d, buf, b2, wl);
-    const int lim = (b2 == b) ? jself : r.n;
-    for (int j = 0; j < lim; ++j) {
-      const double t2 = d.time[buf][r.base + j];
-      if (b2 != b && !(t2 < tt || (t2 == tt && b2 < b))) break;
-      spin ^= (int)(d.info[buf][r.base + j] & LQ_INFO_OFFDIAG);
+  for (int e = e0; e < e1; ++e) {
+    const int lid = se[e] >> 1, side2 = se[e] & 1;
+    const int q0 = S.off[lid];
+    const int q1 = (lid == lb) ? j : S.off[lid + 1];
+    const int b2 = S.gbond[lid];
+    for (int j2 = q0; j2 < q1; ++j2) {
+      const double t2 = S.time[j2];
+      if (lid != lb && !(t2 < tt || (t2 == tt && b2 < b))) break;
+      spin ^= (int)(S.info[j2] & LQ_INFO_OFFDIAG);
       if (t2 > bt || (t2 == bt && b2 > bb)) {
         bt = t2; bb = b2;
-        best = upper_node(d, r.idx0 + j, e & 1);
+        best = upper_node(d, S.idx0[lid] + (j2 - q0), side2);
       }
     }
   }
@@ -288,31 +408,44 @@ __device__ __forceinline__ node_t scan_below(const Dev& d, int buf, int s, int w
 }
 
 // ------------------------------------------------------------------------------------------
-// K2c: link.  One CTA per page, one thread per bucket: for every operator find the two nodes
-// arriving from below, record them, and apply the graph's unions (graph_impl.h:277-295):
+// K2c: link.  One CTA per page (staged in shared memory with its halo), one thread per OPERATOR
+// (flat over the page): find the two nodes arriving from below, record them, and apply the graph's
+// unions (graph_impl.h:277-295) with the lock-free union-find:
 //   g = 0      unify(below0, below1); the upper legs are the operator's own new node
 //   g = 1      cross: upper0 ~ below1, upper1 ~ below0            (needs npo == 2)
 //   g = 2, 3   freeze: all four legs in one cluster
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
 k_link(Dev d, int buf) {
+  extern __shared__ __align__(16) unsigned char s_stage[];
+  __shared__ int s_scan[34];
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl);
-  const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
-  const int lb = threadIdx.x;
-  if (lb >= nb) return;
-  const int b = b0 + lb;
-  const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
-  BucketRef r = bucket_of(d, buf, b, wl);
-  for (int j = 0; j < r.n; ++j) {
-    const double tt = d.time[buf][r.base + j];
-    uint32_t inf = d.info[buf][r.base + j];
+  Stage S;
+  const bool staged = stage_page(d, buf, t, wl, s_stage, S, s_scan);
+  if (!staged) { if (threadIdx.x == 0) atomicOr(d.d_err, LQ_ERR_PAGE_FULL); return; }
+  const int b0 = d.bond_base[t];
+  const int n_own = S.off[S.nb];
+  const int cls = d.tile_class[t];
+  const int* so = d.st_off + d.cls_off[cls];
+  const int* se = d.st + d.cls_st[cls];
+  uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
+  for (int j = threadIdx.x; j < n_own; j += blockDim.x) {
+    uint32_t inf = S.info[j];
+    const int lb = (int)(inf >> LQ_INFO_LBSHIFT);
+    const int b = b0 + lb;
+    const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
+    const int e0 = so[2 * lb], e1 = so[2 * lb + 1], e2 = so[2 * lb + 2];
+    const double tt = S.time[j];
     int c0, c1;
-    const node_t p0 = scan_below(d, buf, s0, wl, tt, b, j, &c0);
-    const node_t p1 = scan_below(d, buf, s1, wl, tt, b, j, &c1);
+    const node_t p0 = scan_below(d, S, se, e0, e1, lb, b, j, tt, d.curW[(size_t)wl * d.N + s0],
+                                 d.spinW[(size_t)wl * d.N + s0], &c0);
+    const node_t p1 = scan_below(d, S, se, e1, e2, lb, b, j, tt, d.curW[(size_t)wl * d.N + s1],
+                                 d.spinW[(size_t)wl * d.N + s1], &c1);
     inf = (inf & ~(LQ_INFO_C0 | LQ_INFO_C1)) | (c0 ? LQ_INFO_C0 : 0u) | (c1 ? LQ_INFO_C1 : 0u);
-    d.info[buf][r.base + j] = inf;
-    const int idx = r.idx0 + j;
+    gi[j] = inf;  // own operators are staged at their page slot
+    const int idx = S.idx0[lb] + (j - S.off[lb]);
     d.low0[idx] = p0;
     const int g = (inf >> LQ_INFO_GSHIFT) & 3;
     const node_t u0 = upper_node(d, idx, 0);
