@@ -441,7 +441,7 @@ struct lq_engine {
     est.alloc(4 * (size_t)nccap, tb);
     est0.alloc(4 * (size_t)N, tb);
     flipb.alloc((size_t)nccap, tb);
-    nblk_collect = ((size_t)nccap + 255) / 256;
+    nblk_collect = std::min<size_t>(((size_t)nccap + 255) / 256, (size_t)sm_count * 8);
     partial.alloc(nblk_collect * LQ_NSUM, tb);
     if (opt.nranks > 1) {
       const size_t g2 = (size_t)opt.nranks * 2 * N, gw = (g2 + 31) / 32 + 1;

@@ -384,12 +384,12 @@ __global__ void k_carry(Dev d, int buf) {
 __device__ __forceinline__ node_t scan_below(const Dev& d, const Stage& S, const int* se, int e0, int e1,
                                              int lb, int b, int j, double tt, node_t carry, int spin0,
                                              int* spin_out) {
-  node_t best = carry;
   int spin = spin0;
   double bt = -1.0;
-  int bb = -1;
+  int bb = -1, bidx = -1, bside = 0;
   for (int e = e0; e < e1; ++e) {
-    const int lid = se[e] >> 1, side2 = se[e] & 1;
+    const int ent = se[e];
+    const int lid = ent >> 1;
     const int q0 = S.off[lid];
     const int q1 = (lid == lb) ? j : S.off[lid + 1];
     const int b2 = S.gbond[lid];
@@ -399,12 +399,13 @@ __device__ __forceinline__ node_t scan_below(const Dev& d, const Stage& S, const
       spin ^= (int)(S.info[j2] & LQ_INFO_OFFDIAG);
       if (t2 > bt || (t2 == bt && b2 > bb)) {
         bt = t2; bb = b2;
-        best = upper_node(d, S.idx0[lid] + (j2 - q0), side2);
+        bidx = S.idx0[lid] + (j2 - q0);
+        bside = ent & 1;
       }
     }
   }
   *spin_out = spin;
-  return best;
+  return (bidx < 0) ? carry : upper_node(d, bidx, bside);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -527,8 +528,16 @@ __global__ void k_relabel(Dev d) {
 #define LQ_HASH 1024
 struct EstHash {
   uint32_t key[LQ_HASH];
-  unsigned long long val[4][LQ_HASH];
+  uint32_t lo[4][LQ_HASH];  // 64-bit sums as (lo, hi) pairs: native 32-bit shared atomics with an
+  uint32_t hi[4][LQ_HASH];  // explicit carry instead of the CAS loop a 64-bit shared atomicAdd compiles to
 };
+
+__device__ __forceinline__ void smem_add64(uint32_t* lo, uint32_t* hi, long long v) {
+  const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)((unsigned long long)v >> 32);
+  const uint32_t old = atomicAdd(lo, vlo);
+  const uint32_t add = vhi + ((uint32_t)(old + vlo) < old ? 1u : 0u);
+  if (add) atomicAdd(hi, add);
+}
 
 __device__ __forceinline__ void est_global_add(const Dev& d, uint32_t cid, long long a, long long b,
                                                long long c, long long e) {
@@ -546,10 +555,10 @@ __device__ __forceinline__ void est_hash_add(const Dev& d, EstHash* h, uint32_t 
   for (int probe = 0; probe < 8; ++probe) {
     const uint32_t k = atomicCAS(&h->key[slot], 0xffffffffu, cid);
     if (k == 0xffffffffu || k == cid) {
-      if (a) atomicAdd(&h->val[0][slot], (unsigned long long)a);
-      if (b) atomicAdd(&h->val[1][slot], (unsigned long long)b);
-      if (c) atomicAdd(&h->val[2][slot], (unsigned long long)c);
-      if (e) atomicAdd(&h->val[3][slot], (unsigned long long)e);
+      if (a) smem_add64(&h->lo[0][slot], &h->hi[0][slot], a);
+      if (b) smem_add64(&h->lo[1][slot], &h->hi[1][slot], b);
+      if (c) smem_add64(&h->lo[2][slot], &h->hi[2][slot], c);
+      if (e) smem_add64(&h->lo[3][slot], &h->hi[3][slot], e);
       return;
     }
     slot = (slot + 1) & (LQ_HASH - 1);
@@ -563,7 +572,8 @@ k_estimate(Dev d, int buf) {
   EstHash* h = (EstHash*)s_raw;
   for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
     h->key[i] = 0xffffffffu;
-    h->val[0][i] = h->val[1][i] = h->val[2][i] = h->val[3][i] = 0ull;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { h->lo[f][i] = 0u; h->hi[f][i] = 0u; }
   }
   __syncthreads();
   const size_t p = blockIdx.x;
@@ -602,9 +612,12 @@ k_estimate(Dev d, int buf) {
   __syncthreads();
   for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
     const uint32_t k = h->key[i];
-    if (k != 0xffffffffu)
-      est_global_add(d, k, (long long)h->val[0][i], (long long)h->val[1][i],
-                     (long long)h->val[2][i], (long long)h->val[3][i]);
+    if (k != 0xffffffffu) {
+      long long v[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) v[f] = (long long)(((unsigned long long)h->hi[f][i] << 32) | h->lo[f][i]);
+      est_global_add(d, k, v[0], v[1], v[2], v[3]);
+    }
   }
 }
 
@@ -646,11 +659,13 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
   __shared__ double s_red[8][LQ_NSUM];
   const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
   const uint32_t nc = d.d_nc[0], ncs = d.d_nc[1];
-  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   double v[LQ_NSUM];
 #pragma unroll
   for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;
-  if (c < nc && (long long)c < d.nccap) {
+  // persistent grid: every thread strides over the clusters and keeps its 14 running sums in
+  // registers, so the warp-shuffle reduction runs once per thread instead of once per cluster
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc && (long long)c < d.nccap;
+       c += (size_t)gridDim.x * blockDim.x) {
     const double sc = 0.5 / LQ_FX;
     const double usize = sc * (double)d.est[0 * d.nccap + c];
     const double umag = sc * (double)d.est[1 * d.nccap + c];
@@ -666,10 +681,11 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
       d.est0[2 * (size_t)d.N + c] = 0; d.est0[3 * (size_t)d.N + c] = 0;
     }
     // order = lq_collector: umag0 usize2 umag2 usize4 umag4 usize umag | smag0 ssize2 smag2 ssize4 smag4 ssize smag
-    v[0] = umag0; v[1] = usize0 * usize0; v[2] = umag0 * umag0;
-    v[3] = v[1] * v[1]; v[4] = v[2] * v[2]; v[5] = usize * usize; v[6] = umag * umag;
-    v[7] = smag0; v[8] = ssize0 * ssize0; v[9] = smag0 * smag0;
-    v[10] = v[8] * v[8]; v[11] = v[9] * v[9]; v[12] = ssize * ssize; v[13] = smag * smag;
+    const double a2 = usize0 * usize0, b2 = umag0 * umag0, e2 = ssize0 * ssize0, g2 = smag0 * smag0;
+    v[0] += umag0; v[1] += a2; v[2] += b2; v[3] += a2 * a2; v[4] += b2 * b2;
+    v[5] += usize * usize; v[6] += umag * umag;
+    v[7] += smag0; v[8] += e2; v[9] += g2; v[10] += e2 * e2; v[11] += g2 * g2;
+    v[12] += ssize * ssize; v[13] += smag * smag;
     philox_t x = philox4x32_10((uint32_t)c, (uint32_t)d.rank, mcs, LQ_STREAM_FLIP, key0, key1);
     d.flipb[c] = (uint8_t)(x.x & 1u);
   }
@@ -694,8 +710,7 @@ __global__ void __launch_bounds__(256)
 k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
   __shared__ double s_red[8][LQ_NSUM];
   const uint32_t nc = d.d_nc[0];
-  size_t nblk = ((size_t)nc + 255) / 256;
-  if (nblk > nblk_cap) nblk = nblk_cap;
+  const size_t nblk = nblk_cap;
   double v[LQ_NSUM];
 #pragma unroll
   for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;
