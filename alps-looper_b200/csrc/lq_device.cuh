@@ -64,14 +64,22 @@ struct Dev {
   const float* bond_q;      // [B] P(g=0 | offdiagonal)  (graph_impl.h:311-313)
   const signed char* gauge;  // [N] +1/-1/0
   // ---- static per-tile halo lists and per-class stencils (see Partition in lq_engine.cu) ----
+  const int* site_base;   // [T+1] first site of a tile (sites are tile-contiguous)
   const int* halo_off;    // [T+1]
   const int* halo_bond;   // global bond ids of the halo buckets of a tile
+  const int* hsite_off;   // [T+1]
+  const int* hsite;       // global ids of the halo K-sites of a tile
   const int* tile_class;  // [T]
-  const int* cls_off;     // [nclasses+1] start of the class in st_off
-  const int* st_off;      // per class 2*nb+1 offsets
-  const int* cls_st;      // [nclasses] start of the class in st
-  const int* st;          // (local bucket << 1 | side)
+  const int* cls_bs;      // [nclasses] start of the class in bs
+  const int* cls_sso;     // [nclasses] start of the class in sst_off
+  const int* cls_sst;     // [nclasses] start of the class in sst
+  const int* cls_nks;     // [nclasses] K-sites of the class
+  const int* bs;          // per class [2*nb] K-site of the two ends of an owned bond
+  const int* sst_off;     // per class [nks+1]
+  const int* sst;         // (local bucket << 1 | side) incident to a K-site
   int hmax;               // max halo buckets per tile
+  int nksmax, zmax;       // max K-sites per tile, max coordination number
+  int fcap;               // off-diagonal leg slots in the stage (K1 site lists)
   int scap;               // operators that fit the shared-memory stage (own page + halo)
   int ccap;               // candidates per page that fit the stage (K1)
   // ---- pages (double buffered) ----

@@ -65,13 +65,15 @@ struct Partition {
   // per-tile halo (bonds owned by other tiles that touch an end site of an owned bond) and the
   // per-bond stencils in LOCAL bucket ids (own bonds 0..nb-1, halo nb..nb+H-1); stencils are
   // shared by all tiles of the same shape ("class")
-  int hmax = 0, nclasses = 0;
-  std::vector<int> halo_off, halo_bond;   // [T+1], [sum H]
+  int hmax = 0, nclasses = 0, nksmax = 0, nsmax = 0, zmax = 0;
+  std::vector<int> site_base;             // [T+1] first (internal) site of a tile
+  std::vector<int> halo_off, halo_bond;   // [T+1], global bond ids of the halo buckets
+  std::vector<int> hsite_off, hsite;      // [T+1], global site ids of the halo K-sites
   std::vector<int> tile_class;            // [T]
-  std::vector<int> cls_off;               // [nclasses+1] start of a class in st_off (units: entries)
-  std::vector<int> st_off;                // per class: 2*nb+1 offsets into st (relative to cls_st)
-  std::vector<int> cls_st;                // [nclasses] start of a class in st
-  std::vector<int> st;                    // entries (local bucket << 1 | side)
+  std::vector<int> cls_bs, cls_sso, cls_sst, cls_nks;  // [nclasses] starts in bs / sst_off / sst; K-sites
+  std::vector<int> bs;                    // per class [2*nb] K-site of the two ends of a bond
+  std::vector<int> sst_off;               // per class [nks+1] offsets into sst
+  std::vector<int> sst;                   // (local bucket << 1 | side)
 };
 
 void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
@@ -156,31 +158,50 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
     P.adj[fill[P.bond_s0[i]]++] = (i << 1) | 0;
     P.adj[fill[P.bond_s1[i]]++] = (i << 1) | 1;
   }
-  // halos and stencils
+  // ---- halos and stencils -------------------------------------------------------------------
+  // "K-sites" of a tile = its own sites followed by the far end sites of its owned bonds that lie
+  // in other tiles; bucket halo = foreign bonds touching any K-site.  Per tile CLASS (tiles of
+  // identical shape share one copy): the two K-sites of every owned bond and, per K-site, the
+  // list of incident local buckets (own bonds 0..nb-1, halo buckets nb..) with the side at which
+  // the site sits on that bond.
+  P.site_base.assign(T + 1, 0);
+  for (int i = 0; i < N; ++i) P.site_base[tile_of[P.site_i2e[i]] + 1]++;
+  for (int t = 0; t < T; ++t) P.site_base[t + 1] += P.site_base[t];
   P.halo_off.assign(T + 1, 0);
+  P.hsite_off.assign(T + 1, 0);
   P.tile_class.assign(T, 0);
-  P.cls_off.assign(1, 0);
   std::map<std::vector<int>, int> classes;
-  std::vector<int> local(B, -1);
+  std::vector<int> local(B, -1), lsite(N, -1);
   for (int t = 0; t < T; ++t) {
     const int b0 = P.bond_base[t], nb = P.bond_base[t + 1] - b0;
-    std::vector<int> halo;
-    std::vector<int> sig;  // serialised stencil = class signature
-    sig.push_back(nb);
-    std::vector<int> offs(1, 0), ent;
+    const int s0 = P.site_base[t], ns = P.site_base[t + 1] - s0;
+    std::vector<int> halo, hsites, bs, offs(1, 0), ent;
+    for (int ls = 0; ls < ns; ++ls) lsite[s0 + ls] = ls;
     for (int lb = 0; lb < nb; ++lb) local[b0 + lb] = lb;
     for (int lb = 0; lb < nb; ++lb)
       for (int side = 0; side < 2; ++side) {
-        const int sgl = side ? P.bond_s1[b0 + lb] : P.bond_s0[b0 + lb];
-        for (int a = P.adj_off[sgl]; a < P.adj_off[sgl + 1]; ++a) {
-          const int b2 = P.adj[a] >> 1, side2 = P.adj[a] & 1;
-          if (local[b2] < 0) { local[b2] = nb + (int)halo.size(); halo.push_back(b2); }
-          ent.push_back((local[b2] << 1) | side2);
-        }
-        offs.push_back((int)ent.size());
+        const int sg = side ? P.bond_s1[b0 + lb] : P.bond_s0[b0 + lb];
+        if (lsite[sg] < 0) { lsite[sg] = ns + (int)hsites.size(); hsites.push_back(sg); }
+        bs.push_back(lsite[sg]);
       }
+    const int nks = ns + (int)hsites.size();
+    for (int ks = 0; ks < nks; ++ks) {
+      const int sg = ks < ns ? s0 + ks : hsites[ks - ns];
+      for (int a = P.adj_off[sg]; a < P.adj_off[sg + 1]; ++a) {
+        const int b2 = P.adj[a] >> 1, side2 = P.adj[a] & 1;
+        if (local[b2] < 0) { local[b2] = nb + (int)halo.size(); halo.push_back(b2); }
+        ent.push_back((local[b2] << 1) | side2);
+      }
+      offs.push_back((int)ent.size());
+      P.zmax = std::max(P.zmax, P.adj_off[sg + 1] - P.adj_off[sg]);
+    }
     for (int lb = 0; lb < nb; ++lb) local[b0 + lb] = -1;
     for (int h : halo) local[h] = -1;
+    for (int ls = 0; ls < ns; ++ls) lsite[s0 + ls] = -1;
+    for (int h : hsites) lsite[h] = -1;
+    std::vector<int> sig;
+    sig.push_back(nb); sig.push_back(ns); sig.push_back(nks);
+    sig.insert(sig.end(), bs.begin(), bs.end());
     sig.insert(sig.end(), offs.begin(), offs.end());
     sig.insert(sig.end(), ent.begin(), ent.end());
     auto it = classes.find(sig);
@@ -188,16 +209,23 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
       const int c = (int)classes.size();
       classes[sig] = c;
       P.tile_class[t] = c;
-      P.cls_st.push_back((int)P.st.size());
-      P.st_off.insert(P.st_off.end(), offs.begin(), offs.end());
-      P.cls_off.push_back((int)P.st_off.size());
-      P.st.insert(P.st.end(), ent.begin(), ent.end());
+      P.cls_bs.push_back((int)P.bs.size());
+      P.cls_sso.push_back((int)P.sst_off.size());
+      P.cls_sst.push_back((int)P.sst.size());
+      P.cls_nks.push_back(nks);
+      P.bs.insert(P.bs.end(), bs.begin(), bs.end());
+      P.sst_off.insert(P.sst_off.end(), offs.begin(), offs.end());
+      P.sst.insert(P.sst.end(), ent.begin(), ent.end());
     } else {
       P.tile_class[t] = it->second;
     }
     P.halo_off[t + 1] = P.halo_off[t] + (int)halo.size();
     P.halo_bond.insert(P.halo_bond.end(), halo.begin(), halo.end());
+    P.hsite_off[t + 1] = P.hsite_off[t] + (int)hsites.size();
+    P.hsite.insert(P.hsite.end(), hsites.begin(), hsites.end());
     P.hmax = std::max(P.hmax, (int)halo.size());
+    P.nksmax = std::max(P.nksmax, nks);
+    P.nsmax = std::max(P.nsmax, ns);
   }
   P.nclasses = (int)classes.size();
 }
@@ -237,8 +265,8 @@ struct lq_engine {
   lq::Dev d{};
   cudaStream_t stream = nullptr;
   DBuf<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
-  DBuf<int> halo_off, halo_bond, tile_class, cls_off, st_off, cls_st, st;
-  int scap = 0, ccap = 0;
+  DBuf<int> site_base, halo_off, halo_bond, hsite_off, hsite, tile_class, cls_bs, cls_sso, cls_sst, cls_nks, bs, sst_off, sst;
+  int scap = 0, ccap = 0, fcap = 0;
   size_t stage_smem = 0;
   DBuf<double> bond_rate, time_[2], partial, d_out;
   DBuf<float4> bond_p;
@@ -323,7 +351,8 @@ struct lq_engine {
       fail(LQ_E_INVALID, "tile owns more than 1023 bonds: lower lq_options.tile_sites");
     if (part.hmax > 1024)
       fail(LQ_E_INVALID, "tile halo has more than 1024 buckets: lower lq_options.tile_sites");
-    tpb = ((std::max(part.nbmax + 1, part.hmax) + 31) / 32) * 32;
+    if (part.nksmax > 1024) fail(LQ_E_INVALID, "tile touches more than 1024 sites: lower lq_options.tile_sites");
+    tpb = ((std::max(std::max(part.nbmax + 1, part.hmax), part.nksmax) + 31) / 32) * 32;
 
     // static tables
     const int N = part.N, B = part.B;
@@ -354,13 +383,19 @@ struct lq_engine {
     bond_p.upload(bp, &device_bytes);
     bond_q.upload(bq, &device_bytes);
     gauge.upload(gi, &device_bytes);
+    site_base.upload(part.site_base, &device_bytes);
     halo_off.upload(part.halo_off, &device_bytes);
     halo_bond.upload(part.halo_bond, &device_bytes);
+    hsite_off.upload(part.hsite_off, &device_bytes);
+    hsite.upload(part.hsite, &device_bytes);
     tile_class.upload(part.tile_class, &device_bytes);
-    cls_off.upload(part.cls_off, &device_bytes);
-    st_off.upload(part.st_off, &device_bytes);
-    cls_st.upload(part.cls_st, &device_bytes);
-    st.upload(part.st, &device_bytes);
+    cls_bs.upload(part.cls_bs, &device_bytes);
+    cls_sso.upload(part.cls_sso, &device_bytes);
+    cls_sst.upload(part.cls_sst, &device_bytes);
+    cls_nks.upload(part.cls_nks, &device_bytes);
+    bs.upload(part.bs, &device_bytes);
+    sst_off.upload(part.sst_off, &device_bytes);
+    sst.upload(part.sst, &device_bytes);
     d_ntotal.alloc(1, &device_bytes);
     d_err.alloc(1, &device_bytes);
     d_nc.alloc(2, &device_bytes);
@@ -402,21 +437,22 @@ struct lq_engine {
       const double cm = mu;  // mean candidates per page
       ccap = (int)std::ceil(cm + 8.0 * std::sqrt(cm) + 32.0);
       if (ccap > 65535) fail(LQ_E_INVALID, "too many candidates per page: lower tile_sites or window_ops");
-      stage_smem = lq::stage_bytes(scap, part.nbmax, part.hmax, ccap);
+      fcap = 2 * scap;  // off-diagonal legs of the staged operators (two per operator at most)
+      stage_smem = lq::stage_bytes(scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb);
       if (stage_smem > 200 * 1024)
         fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
       const int sm = (int)stage_smem;
       CK(cudaFuncSetAttribute(lq::k_diag_update<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_diag_update<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_diag_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_link<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_link<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_link<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_walk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_walk<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_walk<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     }
     P = (size_t)T * Wl;
     ncap = (long long)P * cap;
     const long long nodes_cap = (long long)N + (long long)npo * ncap;
-    if (nodes_cap >= 0xfffffff0ll) fail(LQ_E_INVALID, "more than 2^32 graph nodes: split the run over more GPUs");
+    if (nodes_cap >= 0x7ffffff0ll) fail(LQ_E_INVALID, "more than 2^31 graph nodes on one GPU: lower lq_options.reserve or split the run over more GPUs");
     nccap = std::min<long long>(nodes_cap, (long long)N + (long long)std::ceil(opt.cluster_reserve * (double)(npo * ncap)));
     nwords_cap = (size_t)((nodes_cap + 31) / 32);
 
@@ -432,7 +468,7 @@ struct lq_engine {
     curW.alloc((size_t)(Wl + 1) * N, tb);
     parent.alloc((size_t)nodes_cap, tb);
     low0.alloc((size_t)ncap, tb);
-    if (npo == 2) low1.alloc((size_t)ncap, tb); else low1.release();
+    low1.alloc((size_t)ncap, tb);
     bitmap.alloc(nwords_cap + 1, tb);
     wcount.alloc(nwords_cap + 1, tb);
     wbase.alloc(nwords_cap + 1, tb);
@@ -477,8 +513,11 @@ struct lq_engine {
     d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_tile = bond_tile.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
     d.bond_q = bond_q.p; d.gauge = gauge.p;
-    d.halo_off = halo_off.p; d.halo_bond = halo_bond.p; d.tile_class = tile_class.p; d.cls_off = cls_off.p;
-    d.st_off = st_off.p; d.cls_st = cls_st.p; d.st = st.p; d.hmax = part.hmax; d.scap = scap; d.ccap = ccap;
+    d.site_base = site_base.p; d.halo_off = halo_off.p; d.halo_bond = halo_bond.p;
+    d.hsite_off = hsite_off.p; d.hsite = hsite.p; d.tile_class = tile_class.p;
+    d.cls_bs = cls_bs.p; d.cls_sso = cls_sso.p; d.cls_sst = cls_sst.p; d.cls_nks = cls_nks.p;
+    d.bs = bs.p; d.sst_off = sst_off.p; d.sst = sst.p;
+    d.hmax = part.hmax; d.nksmax = part.nksmax; d.zmax = part.zmax; d.scap = scap; d.ccap = ccap; d.fcap = fcap;
     for (int k = 0; k < 2; ++k) {
       d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
     }
@@ -547,10 +586,11 @@ struct lq_engine {
     }
     {
       Section s(this, 7);
-      if (tpb <= 256) lq::k_link<256><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
-      else if (tpb <= 640) lq::k_link<640><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
-      else lq::k_link<1024><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
-      launches += 1;
+      if (tpb <= 256) lq::k_walk<256><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
+      else if (tpb <= 640) lq::k_walk<640><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
+      else lq::k_walk<1024><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
+      lq::k_union<<<(unsigned)P, 256, 0, stream>>>(d, cur);
+      launches += 2;
     }
     {
       Section s(this, 9);

@@ -50,22 +50,27 @@ __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
 struct Stage {
   double* time;    // [scap]
   double* ctime;   // [ccap]   candidate times (K1)
+  double* ftime;   // [fcap]   off-diagonal leg times grouped by K-site (K1)
   uint32_t* info;  // [scap]
   int* off;        // [nloc+1] first staged slot of each local bucket
   int* idx0;       // [nloc]   dense operator index of the first operator of the bucket
   int* gbond;      // [nloc]   global bond id (tie-break order)
   int* cbase;      // [nbmax+1] first candidate of each own bucket (K1)
   int* noff;       // [nbmax+1] new bucket offsets (K1)
+  int* foff;       // [nksmax+1] first ftime slot of each K-site (K1)
   uint16_t* clb;   // [ccap]   owning local bucket of a candidate (K1)
+  uint16_t* head;  // [zmax*blockDim] merge heads of the site walk (K2)
   uint8_t* cacc;   // [ccap]   accepted bit | graph << 1 (K1)
-  uint8_t* rel;    // [nbmax]  relative spin orientation at the window start (K1)
+  uint8_t* kspin;  // [nksmax] spin of every K-site at the window start (K1)
   int nb, nh;
 };
 
-__host__ __device__ inline size_t stage_bytes(int scap, int nbmax, int hmax, int ccap) {
+__host__ __device__ inline size_t stage_bytes(int scap, int nbmax, int hmax, int ccap, int fcap, int nksmax,
+                                              int zmax, int tpb) {
   const size_t nloc = (size_t)nbmax + hmax;
-  return ((size_t)scap + ccap) * 8 + (size_t)scap * 4 + (3 * nloc + 1) * 4 + 2 * ((size_t)nbmax + 1) * 4 +
-         (size_t)ccap * 3 + (size_t)nbmax + 64;
+  return ((size_t)scap + ccap + fcap) * 8 + (size_t)scap * 4 + (3 * nloc + 1) * 4 +
+         2 * ((size_t)nbmax + 1) * 4 + ((size_t)nksmax + 1) * 4 + ((size_t)ccap + (size_t)zmax * tpb) * 2 +
+         (size_t)ccap + (size_t)nksmax + 64;
 }
 
 __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl, unsigned char* smem,
@@ -73,15 +78,18 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   const int nloc_max = d.nbmax + d.hmax;
   S.time = (double*)smem;
   S.ctime = S.time + d.scap;
-  S.info = (uint32_t*)(S.ctime + d.ccap);
+  S.ftime = S.ctime + d.ccap;
+  S.info = (uint32_t*)(S.ftime + d.fcap);
   S.off = (int*)(S.info + d.scap);
   S.idx0 = S.off + nloc_max + 1;
   S.gbond = S.idx0 + nloc_max;
   S.cbase = S.gbond + nloc_max;
   S.noff = S.cbase + d.nbmax + 1;
-  S.clb = (uint16_t*)(S.noff + d.nbmax + 1);
-  S.cacc = (uint8_t*)(S.clb + d.ccap);
-  S.rel = S.cacc + d.ccap;
+  S.foff = S.noff + d.nbmax + 1;
+  S.clb = (uint16_t*)(S.foff + d.nksmax + 1);
+  S.head = S.clb + d.ccap;
+  S.cacc = (uint8_t*)(S.head + (size_t)d.zmax * blockDim.x);
+  S.kspin = S.cacc + d.ccap;
   const size_t p = (size_t)t * d.Wl + wl;
   const int b0 = d.bond_base[t];
   S.nb = d.bond_base[t + 1] - b0;
@@ -124,14 +132,16 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
 
 // ------------------------------------------------------------------------------------------
 // K1: diagonal update.  One CTA per page (staged with its halo).  FLAT work mapping -- every
-// phase gives each thread one bucket, one candidate or one old operator, so warps stay full:
+// phase gives each thread one site, one bucket, one candidate or one old operator:
+//  0. per K-site (own sites + far ends of owned bonds): spin at the window start and the list of
+//     off-diagonal leg times on that site in this window (from the buckets incident to it)
 //  1. per bucket: number of candidates K ~ Poisson(beta * sum_g v_g * window) by inverse CDF
 //     (replaces poisson_distribution.h:60-75 / the exponential gaps of path_integral.C:413-423);
 //     CTA-wide prefix sum (warp shuffles) -> candidate slots
 //  2. per candidate: uniform time in the window, Philox4x32-10 keyed by (bond, window, step, i);
-//     acceptance needs only the RELATIVE orientation of the two spins (operators on this bond
-//     flip both), i.e. the parity of off-diagonal operators of the OTHER bonds at the two sites
-//     before the candidate; graph chosen with the model's weights (graph_impl.h:679)
+//     is_compatible (graph_impl.h:257) needs the two spins at that time = spin at the window start
+//     xor parity of the off-diagonal legs before it on each site; graph chosen with the model's
+//     weights (graph_impl.h:679)
 //  3. per bucket: new size = kept off-diagonal + accepted; prefix sum -> new bucket offsets
 //  4. per accepted candidate / per kept operator: rank inside the new bucket -> scatter into the
 //     compacted new page (old diagonal operators are dropped, path_integral.C:519-521)
@@ -160,15 +170,43 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   const int n_own = S.off[nb];
   const double tlo = window_lo(wg, d.W), thi = window_hi(wg, d.W), width = thi - tlo;
   const int cls = d.tile_class[t];
-  const int* so = d.st_off + d.cls_off[cls];
-  const int* se = d.st + d.cls_st[cls];
+  const int nks = d.cls_nks[cls];
+  const int ns = d.site_base[t + 1] - d.site_base[t];
+  const int* sso = d.sst_off + d.cls_sso[cls];
+  const int* sse = d.sst + d.cls_sst[cls];
+  const int* bsx = d.bs + d.cls_bs[cls];
+
+  // ---- phase 0: per K-site spin and off-diagonal leg list ---------------------------------------
+  int nf = 0;
+  if (tid < nks) {
+    const int sg = tid < ns ? d.site_base[t] + tid : d.hsite[d.hsite_off[t] + tid - ns];
+    S.kspin[tid] = d.spinW[(size_t)wl * d.N + sg];
+    for (int e = sso[tid]; e < sso[tid + 1]; ++e) {
+      const int lid = sse[e] >> 1;
+      for (int j = S.off[lid]; j < S.off[lid + 1]; ++j) nf += (int)(S.info[j] & LQ_INFO_OFFDIAG);
+    }
+  }
+  int F;
+  int fo = block_exscan(nf, &F, s_scan);
+  if (F > d.fcap) {
+    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_NEIGH_FULL); d.pcount[dst][p] = 0; }
+    if (tid <= nb) bo[tid] = 0;
+    return;
+  }
+  if (tid < nks) {
+    S.foff[tid] = fo;
+    for (int e = sso[tid]; e < sso[tid + 1]; ++e) {
+      const int lid = sse[e] >> 1;
+      for (int j = S.off[lid]; j < S.off[lid + 1]; ++j)
+        if (S.info[j] & LQ_INFO_OFFDIAG) S.ftime[fo++] = S.time[j];
+    }
+  }
+  if (tid == 0) S.foff[nks] = F;
 
   // ---- phase 1: candidates per bucket ------------------------------------------------------
   int K = 0, nkeep = 0;
   if (tid < nb) {
     const int b = b0 + tid;
-    const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
-    S.rel[tid] = d.spinW[(size_t)wl * d.N + s0] ^ d.spinW[(size_t)wl * d.N + s1];
     for (int j = S.off[tid]; j < S.off[tid + 1]; ++j) nkeep += (int)(S.info[j] & LQ_INFO_OFFDIAG);
     const double mu = beta * d.bond_rate[b] * width;
     if (mu > 0) {
@@ -201,15 +239,10 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
     const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + 1u + (uint32_t)i, key0, key1);
     double tc = tlo + (u53(x.x, x.y) - 1.0 / 9007199254740992.0) * width;
     if (!(tc < thi)) tc = tlo;
-    int par = S.rel[lb];
-    const int e1 = so[2 * lb + 2];
-    for (int e = so[2 * lb]; e < e1; ++e) {
-      const int lid = se[e] >> 1;
-      if (lid == lb) continue;
-      const int q1 = S.off[lid + 1];
-      for (int j = S.off[lid]; j < q1; ++j)
-        par ^= (int)(S.info[j] & LQ_INFO_OFFDIAG) & (int)(S.time[j] < tc);
-    }
+    const int k0 = bsx[2 * lb], k1 = bsx[2 * lb + 1];
+    int par = S.kspin[k0] ^ S.kspin[k1];   // operators on this bond sit in both lists and cancel
+    for (int f = S.foff[k0]; f < S.foff[k0 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
+    for (int f = S.foff[k1]; f < S.foff[k1 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
     const float4 pr = d.bond_p[b];
     const float u = u24(x.z);
     int g = -1;
@@ -379,46 +412,17 @@ __global__ void k_carry(Dev d, int buf) {
   d.curW[(size_t)d.Wl * d.N + s] = cur;
 }
 
-// node of the leg arriving from below at one end site of operator j (staged slot) of local
-// bucket lb, and the spin on that leg; [e0,e1) is the stencil of that end site
-__device__ __forceinline__ node_t scan_below(const Dev& d, const Stage& S, const int* se, int e0, int e1,
-                                             int lb, int b, int j, double tt, node_t carry, int spin0,
-                                             int* spin_out) {
-  int spin = spin0;
-  double bt = -1.0;
-  int bb = -1, bidx = -1, bside = 0;
-  for (int e = e0; e < e1; ++e) {
-    const int ent = se[e];
-    const int lid = ent >> 1;
-    const int q0 = S.off[lid];
-    const int q1 = (lid == lb) ? j : S.off[lid + 1];
-    const int b2 = S.gbond[lid];
-    for (int j2 = q0; j2 < q1; ++j2) {
-      const double t2 = S.time[j2];
-      if (lid != lb && !(t2 < tt || (t2 == tt && b2 < b))) break;
-      spin ^= (int)(S.info[j2] & LQ_INFO_OFFDIAG);
-      if (t2 > bt || (t2 == bt && b2 > bb)) {
-        bt = t2; bb = b2;
-        bidx = S.idx0[lid] + (j2 - q0);
-        bside = ent & 1;
-      }
-    }
-  }
-  *spin_out = spin;
-  return (bidx < 0) ? carry : upper_node(d, bidx, bside);
-}
-
 // ------------------------------------------------------------------------------------------
-// K2c: link.  One CTA per page (staged in shared memory with its halo), one thread per OPERATOR
-// (flat over the page): find the two nodes arriving from below, record them, and apply the graph's
-// unions (graph_impl.h:277-295) with the lock-free union-find:
-//   g = 0      unify(below0, below1); the upper legs are the operator's own new node
-//   g = 1      cross: upper0 ~ below1, upper1 ~ below0            (needs npo == 2)
-//   g = 2, 3   freeze: all four legs in one cluster
+// K2c: world-line walk.  One CTA per page (staged with its halo), one thread per SITE of the
+// tile: a z-way merge of the time-sorted buckets incident to the site replays the reference's
+// sequential sweep for this site and window (path_integral.C:539-566 with current[s] and
+// spins_c[s] in registers): every leg gets the node arriving from below and the spin on it.
+// Each leg of the page is visited exactly once -- O(legs x z) instead of one neighbourhood scan
+// per operator.  low0/low1[idx] = node below on the source/target side | spin << 31.
 // ------------------------------------------------------------------------------------------
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT)
-k_link(Dev d, int buf) {
+k_walk(Dev d, int buf) {
   extern __shared__ __align__(16) unsigned char s_stage[];
   __shared__ int s_scan[34];
   const size_t p = blockIdx.x;
@@ -426,32 +430,66 @@ k_link(Dev d, int buf) {
   Stage S;
   const bool staged = stage_page(d, buf, t, wl, s_stage, S, s_scan);
   if (!staged) { if (threadIdx.x == 0) atomicOr(d.d_err, LQ_ERR_PAGE_FULL); return; }
-  const int b0 = d.bond_base[t];
-  const int n_own = S.off[S.nb];
+  const int tid = threadIdx.x;
+  const int sb = d.site_base[t];
+  if (tid >= d.site_base[t + 1] - sb) return;
+  const int s = sb + tid;
   const int cls = d.tile_class[t];
-  const int* so = d.st_off + d.cls_off[cls];
-  const int* se = d.st + d.cls_st[cls];
+  const int* sso = d.sst_off + d.cls_sso[cls];
+  const int* sse = d.sst + d.cls_sst[cls] + sso[tid];
+  const int z = sso[tid + 1] - sso[tid];
+  uint16_t* head = S.head + tid;
+  const int hs = blockDim.x;
+  for (int k = 0; k < z; ++k) head[k * hs] = (uint16_t)S.off[sse[k] >> 1];
+  node_t cur = d.curW[(size_t)wl * d.N + s];
+  uint32_t spin = d.spinW[(size_t)wl * d.N + s];
+  for (;;) {
+    int best = -1, bh = 0, bent = 0, bb = 0;
+    double bt = 0;
+    for (int k = 0; k < z; ++k) {
+      const int ent = sse[k];
+      const int lid = ent >> 1;
+      const int h = head[k * hs];
+      if (h < S.off[lid + 1]) {
+        const double t2 = S.time[h];
+        const int b2 = S.gbond[lid];
+        if (best < 0 || t2 < bt || (t2 == bt && b2 < bb)) { best = k; bt = t2; bb = b2; bh = h; bent = ent; }
+      }
+    }
+    if (best < 0) break;
+    head[best * hs] = (uint16_t)(bh + 1);
+    const int lid = bent >> 1, side = bent & 1;
+    const int idx = S.idx0[lid] + (bh - S.off[lid]);
+    (side ? d.low1 : d.low0)[idx] = cur | (spin << 31);
+    spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
+    cur = upper_node(d, idx, side);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2d: unions.  Flat over the operators of a page: apply the graph's unions (graph_impl.h:277-295)
+// to the two nodes found by the walk, with the lock-free union-find, and record the spins below
+// the operator in its info word:
+//   g = 0      unify(below0, below1); the upper legs are the operator's own new node
+//   g = 1      cross: upper0 ~ below1, upper1 ~ below0            (needs npo == 2)
+//   g = 2, 3   freeze: all four legs in one cluster
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_union(Dev d, int buf) {
+  const size_t p = blockIdx.x;
+  const int n = d.pcount[buf][p];
+  const int idx0 = d.nbase[p];
   uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
-  for (int j = threadIdx.x; j < n_own; j += blockDim.x) {
-    uint32_t inf = S.info[j];
-    const int lb = (int)(inf >> LQ_INFO_LBSHIFT);
-    const int b = b0 + lb;
-    const int s0 = d.bond_s0[b], s1 = d.bond_s1[b];
-    const int e0 = so[2 * lb], e1 = so[2 * lb + 1], e2 = so[2 * lb + 2];
-    const double tt = S.time[j];
-    int c0, c1;
-    const node_t p0 = scan_below(d, S, se, e0, e1, lb, b, j, tt, d.curW[(size_t)wl * d.N + s0],
-                                 d.spinW[(size_t)wl * d.N + s0], &c0);
-    const node_t p1 = scan_below(d, S, se, e1, e2, lb, b, j, tt, d.curW[(size_t)wl * d.N + s1],
-                                 d.spinW[(size_t)wl * d.N + s1], &c1);
-    inf = (inf & ~(LQ_INFO_C0 | LQ_INFO_C1)) | (c0 ? LQ_INFO_C0 : 0u) | (c1 ? LQ_INFO_C1 : 0u);
-    gi[j] = inf;  // own operators are staged at their page slot
-    const int idx = S.idx0[lb] + (j - S.off[lb]);
-    d.low0[idx] = p0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int idx = idx0 + j;
+    const uint32_t l0 = d.low0[idx], l1 = d.low1[idx];
+    const node_t p0 = l0 & 0x7fffffffu, p1 = l1 & 0x7fffffffu;
+    uint32_t inf = gi[j];
+    inf = (inf & ~(LQ_INFO_C0 | LQ_INFO_C1)) | ((l0 >> 31) ? LQ_INFO_C0 : 0u) | ((l1 >> 31) ? LQ_INFO_C1 : 0u);
+    gi[j] = inf;
     const int g = (inf >> LQ_INFO_GSHIFT) & 3;
     const node_t u0 = upper_node(d, idx, 0);
     if (d.npo == 2) {
-      d.low1[idx] = p1;
       const node_t u1 = upper_node(d, idx, 1);
       if (g == 0) { uf_union(d.parent, p0, p1); uf_union(d.parent, u0, u1); }
       else if (g == 1) { uf_union(d.parent, u0, p1); uf_union(d.parent, u1, p0); }
@@ -487,9 +525,11 @@ __global__ void k_compress(Dev d, size_t nwords_cap) {
   }
   bool isroot = false;
   if (x < nn) {
+    // all unions are done: plain (L1-allocating) loads are safe here and neighbouring nodes
+    // mostly chase to the same few roots
     node_t r = (node_t)x;
-    node_t pr = uf_load(d.parent + r);
-    while (pr != r) { r = pr; pr = uf_load(d.parent + r); }
+    node_t pr = d.parent[r];
+    while (pr != r) { r = pr; pr = d.parent[r]; }
     d.parent[x] = r;
     isroot = (r == (node_t)x);
   }
@@ -594,14 +634,14 @@ k_estimate(Dev d, int buf) {
     const int m0 = 1 - 2 * c0, m1 = 1 - 2 * c1;              // 2(1/2-c) below
     const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
     const int idx = idx0 + j;
-    const uint32_t cl0 = d.parent[d.low0[idx]];
+    const uint32_t cl0 = d.parent[d.low0[idx] & 0x7fffffffu];
     const uint32_t cu0 = d.parent[upper_node(d, idx, 0)];
     if (d.npo == 1) {
       // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
       est_hash_add(d, h, cl0, 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
       est_hash_add(d, h, cu0, -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
     } else {
-      const uint32_t cl1 = d.parent[d.low1[idx]];
+      const uint32_t cl1 = d.parent[d.low1[idx] & 0x7fffffffu];
       const uint32_t cu1 = d.parent[upper_node(d, idx, 1)];
       est_hash_add(d, h, cl0, q, q * m0, q * g0, q * g0 * m0);
       est_hash_add(d, h, cl1, q, q * m1, q * g1, q * g1 * m1);
@@ -756,7 +796,7 @@ k_flip(Dev d, int buf) {
   const int idx0 = d.nbase[p];
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int idx = idx0 + j;
-    const uint32_t cl = d.parent[d.low0[idx]];
+    const uint32_t cl = d.parent[d.low0[idx] & 0x7fffffffu];
     const uint32_t cu = d.parent[upper_node(d, idx, 0)];
     const uint32_t f = (flip_of(d, cl) ^ flip_of(d, cu)) & 1u;
     if (f) d.info[buf][p * (size_t)d.cap + j] ^= LQ_INFO_OFFDIAG;
