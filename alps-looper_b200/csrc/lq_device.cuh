@@ -156,10 +156,11 @@ __host__ __device__ __forceinline__ float u24(uint32_t a) { return (float)(a >> 
 // the SMALLER one with one atomicCAS, so the final root of a cluster is its minimum node index --
 // the reference's LOOPER_USE_DETERMINISTIC_UNIFY rule (union_find.h:229-233, 260-264) -- and the
 // partition is independent of the order in which threads win.
-// Reads go through L2 (ld.cg): stale L1 lines would still be valid ancestors, but L2 keeps the
-// retry loops short.
+// Reads may hit stale L1 lines: a stale parent is still a valid ancestor (links only ever move
+// towards smaller indices) and every hook is validated by the atomicCAS at L2, so staleness costs
+// at most extra hops, while hot roots of big clusters are served from L1.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ node_t uf_load(const node_t* p) { return __ldcg(p); }
+__device__ __forceinline__ node_t uf_load(const node_t* p) { return *(const volatile node_t*)p; }
 
 __device__ __forceinline__ node_t uf_find(node_t* parent, node_t x) {
   node_t p = uf_load(parent + x);

@@ -267,7 +267,8 @@ struct lq_engine {
   DBuf<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
   DBuf<int> site_base, halo_off, halo_bond, hsite_off, hsite, tile_class, cls_bs, cls_sso, cls_sst, cls_nks, bs, sst_off, sst;
   int scap = 0, ccap = 0, fcap = 0;
-  size_t stage_smem = 0;
+  size_t stage_smem = 0, walk_smem = 0;
+  int tpb_walk = 32;
   DBuf<double> bond_rate, time_[2], partial, d_out;
   DBuf<float4> bond_p;
   DBuf<float> bond_q;
@@ -437,8 +438,10 @@ struct lq_engine {
       const double cm = mu;  // mean candidates per page
       ccap = (int)std::ceil(cm + 8.0 * std::sqrt(cm) + 32.0);
       if (ccap > 65535) fail(LQ_E_INVALID, "too many candidates per page: lower tile_sites or window_ops");
-      fcap = 2 * scap;  // off-diagonal legs of the staged operators (two per operator at most)
-      stage_smem = lq::stage_bytes(scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb);
+      fcap = scap + scap / 2;  // off-diagonal legs of the staged operators (checked at run time)
+      tpb_walk = ((std::max(part.nsmax, part.hmax) + 31) / 32) * 32;
+      stage_smem = lq::stage_bytes(true, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb);
+      walk_smem = lq::stage_bytes(false, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb_walk);
       if (stage_smem > 200 * 1024)
         fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
       const int sm = (int)stage_smem;
@@ -586,9 +589,9 @@ struct lq_engine {
     }
     {
       Section s(this, 7);
-      if (tpb <= 256) lq::k_walk<256><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
-      else if (tpb <= 640) lq::k_walk<640><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
-      else lq::k_walk<1024><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur);
+      if (tpb_walk <= 256) lq::k_walk<256><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
+      else if (tpb_walk <= 640) lq::k_walk<640><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
+      else lq::k_walk<1024><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
       lq::k_union<<<(unsigned)P, 256, 0, stream>>>(d, cur);
       launches += 2;
     }

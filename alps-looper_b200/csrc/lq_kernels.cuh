@@ -65,31 +65,41 @@ struct Stage {
   int nb, nh;
 };
 
-__host__ __device__ inline size_t stage_bytes(int scap, int nbmax, int hmax, int ccap, int fcap, int nksmax,
-                                              int zmax, int tpb) {
+// FULL = the K1 layout (candidate and site-list arrays); otherwise the lean layout of the walk
+__host__ __device__ inline size_t stage_bytes(bool full, int scap, int nbmax, int hmax, int ccap, int fcap,
+                                              int nksmax, int zmax, int tpb) {
   const size_t nloc = (size_t)nbmax + hmax;
+  if (!full) return (size_t)scap * 12 + (3 * nloc + 1) * 4 + (size_t)zmax * tpb * 2 + 64;
   return ((size_t)scap + ccap + fcap) * 8 + (size_t)scap * 4 + (3 * nloc + 1) * 4 +
-         2 * ((size_t)nbmax + 1) * 4 + ((size_t)nksmax + 1) * 4 + ((size_t)ccap + (size_t)zmax * tpb) * 2 +
+         2 * ((size_t)nbmax + 1) * 4 + ((size_t)nksmax + 1) * 4 + (size_t)ccap * 2 +
          (size_t)ccap + (size_t)nksmax + 64;
 }
 
+template <bool FULL>
 __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl, unsigned char* smem,
                                            Stage& S, int* s_scan) {
   const int nloc_max = d.nbmax + d.hmax;
   S.time = (double*)smem;
-  S.ctime = S.time + d.scap;
-  S.ftime = S.ctime + d.ccap;
-  S.info = (uint32_t*)(S.ftime + d.fcap);
+  if (FULL) {
+    S.ctime = S.time + d.scap;
+    S.ftime = S.ctime + d.ccap;
+    S.info = (uint32_t*)(S.ftime + d.fcap);
+  } else {
+    S.info = (uint32_t*)(S.time + d.scap);
+  }
   S.off = (int*)(S.info + d.scap);
   S.idx0 = S.off + nloc_max + 1;
   S.gbond = S.idx0 + nloc_max;
-  S.cbase = S.gbond + nloc_max;
-  S.noff = S.cbase + d.nbmax + 1;
-  S.foff = S.noff + d.nbmax + 1;
-  S.clb = (uint16_t*)(S.foff + d.nksmax + 1);
-  S.head = S.clb + d.ccap;
-  S.cacc = (uint8_t*)(S.head + (size_t)d.zmax * blockDim.x);
-  S.kspin = S.cacc + d.ccap;
+  if (FULL) {
+    S.cbase = S.gbond + nloc_max;
+    S.noff = S.cbase + d.nbmax + 1;
+    S.foff = S.noff + d.nbmax + 1;
+    S.clb = (uint16_t*)(S.foff + d.nksmax + 1);
+    S.cacc = (uint8_t*)(S.clb + d.ccap);
+    S.kspin = S.cacc + d.ccap;
+  } else {
+    S.head = (uint16_t*)(S.gbond + nloc_max);
+  }
   const size_t p = (size_t)t * d.Wl + wl;
   const int b0 = d.bond_base[t];
   S.nb = d.bond_base[t + 1] - b0;
@@ -99,11 +109,11 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   const int base_idx = d.nbase[p];
   const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1);
   const int tid = threadIdx.x;
-  if (tid < S.nb) {
-    const int o = bo[tid];
-    S.off[tid] = o;
-    S.idx0[tid] = base_idx + o;
-    S.gbond[tid] = b0 + tid;
+  for (int i = tid; i < S.nb; i += blockDim.x) {
+    const int o = bo[i];
+    S.off[i] = o;
+    S.idx0[i] = base_idx + o;
+    S.gbond[i] = b0 + i;
   }
   const double* gt = d.time[buf] + p * (size_t)d.cap;
   const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
@@ -147,7 +157,7 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
 //     compacted new page (old diagonal operators are dropped, path_integral.C:519-521)
 // ------------------------------------------------------------------------------------------
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 5 : (MAXT <= 640 ? 2 : 1)))
 k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   extern __shared__ __align__(16) unsigned char s_stage[];
   __shared__ int s_scan[34];
@@ -157,7 +167,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl), wg = d.w0 + wl;
   Stage S;
-  const bool staged = stage_page(d, src, t, wl, s_stage, S, s_scan);
+  const bool staged = stage_page<true>(d, src, t, wl, s_stage, S, s_scan);
   const int nb = S.nb;
   const int tid = threadIdx.x;
   uint16_t* bo = d.boff[dst] + p * (size_t)(d.nbmax + 1);
@@ -428,7 +438,7 @@ k_walk(Dev d, int buf) {
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl);
   Stage S;
-  const bool staged = stage_page(d, buf, t, wl, s_stage, S, s_scan);
+  const bool staged = stage_page<false>(d, buf, t, wl, s_stage, S, s_scan);
   if (!staged) { if (threadIdx.x == 0) atomicOr(d.d_err, LQ_ERR_PAGE_FULL); return; }
   const int tid = threadIdx.x;
   const int sb = d.site_base[t];
