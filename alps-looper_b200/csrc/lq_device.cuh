@@ -108,6 +108,7 @@ struct Dev {
   int* d_ntotal;     // total operators after the update (nbase[P])
   uint32_t* d_nc;    // [0] number of clusters, [1] clusters rooted at a site node
   int* d_err;
+  int dbg;           // LQ_DBG environment variable (experiments only)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -214,6 +215,15 @@ __device__ __forceinline__ int block_exscan(int v, int* total, int* smem /* >= 3
   *total = smem[32];
   __syncthreads();
   return res;
+}
+
+// 64-bit integer <-> double without the (very slow on sm_100) I2F.F64.S64 / F2I.S64.F64 paths
+__device__ __forceinline__ double i64_to_f64(long long v) {
+  return __int2double_rn((int)(v >> 32)) * 4294967296.0 + __uint2double_rn((unsigned)v);
+}
+// imaginary time in [0,1) -> 40-bit fixed point (truncated): mantissa bits of 1 + t
+__device__ __forceinline__ long long time_to_fx(double t) {
+  return (__double_as_longlong(t + 1.0) & 0x000fffffffffffffll) >> 12;
 }
 
 // time window bounds; identical arithmetic on host (bucketing in lq_set_state) and device

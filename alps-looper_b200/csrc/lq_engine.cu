@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -528,6 +529,7 @@ struct lq_engine {
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
     d.est = est.p; d.est0 = est0.p; d.flipb = flipb.p; d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
+    d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
   }
 
   void clear_state() {

@@ -636,7 +636,7 @@ k_estimate(Dev d, int buf) {
     const int g = (inf >> LQ_INFO_GSHIFT) & 3;
     if (g & 2) continue;  // frozen graphs are skipped (path_integral.C:692)
     const double tt = d.time[buf][p * (size_t)d.cap + j];
-    const long long q = (long long)llrint(tt * LQ_FX);
+    const long long q = time_to_fx(tt);
     const int b = b0 + (int)(inf >> LQ_INFO_LBSHIFT);
     const int g0 = d.gauge[d.bond_s0[b]], g1 = d.gauge[d.bond_s1[b]];
     const int c0 = (inf & LQ_INFO_C0) ? 1 : 0, c1 = (inf & LQ_INFO_C1) ? 1 : 0;
@@ -682,8 +682,8 @@ __global__ void k_estimate_sites(Dev d) {
   const int m = 1 - 2 * c;
   const uint32_t cb = d.parent[s];
   const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
-  const long long qlo = (long long)llrint(window_lo(d.w0, d.W) * LQ_FX);
-  const long long qhi = (long long)llrint(window_hi(d.w0 + d.Wl - 1, d.W) * LQ_FX);
+  const long long qlo = time_to_fx(window_lo(d.w0, d.W));
+  const long long qhi = (d.w0 + d.Wl >= d.W) ? (1ll << 40) : time_to_fx(window_hi(d.w0 + d.Wl - 1, d.W));
   if (d.rank == 0) {
     atomicAdd(d.est0 + 0 * (size_t)d.N + cb, 1);
     atomicAdd(d.est0 + 1 * (size_t)d.N + cb, m);
@@ -717,12 +717,17 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc && (long long)c < d.nccap;
        c += (size_t)gridDim.x * blockDim.x) {
     const double sc = 0.5 / LQ_FX;
-    const double usize = sc * (double)d.est[0 * d.nccap + c];
-    const double umag = sc * (double)d.est[1 * d.nccap + c];
-    const double ssize = sc * (double)d.est[2 * d.nccap + c];
-    const double smag = sc * (double)d.est[3 * d.nccap + c];
+    double usize = 0, umag = 0, ssize = 0, smag = 0;
+    if (!(d.dbg & 1)) {
+    usize = sc * i64_to_f64(d.est[0 * d.nccap + c]);
+    umag = sc * i64_to_f64(d.est[1 * d.nccap + c]);
+    ssize = sc * i64_to_f64(d.est[2 * d.nccap + c]);
+    smag = sc * i64_to_f64(d.est[3 * d.nccap + c]);
+    }
+    if (!(d.dbg & 2)) {
     d.est[0 * d.nccap + c] = 0; d.est[1 * d.nccap + c] = 0;
     d.est[2 * d.nccap + c] = 0; d.est[3 * d.nccap + c] = 0;
+    }
     double usize0 = 0, umag0 = 0, ssize0 = 0, smag0 = 0;
     if (c < ncs) {
       usize0 = 0.5 * d.est0[0 * (size_t)d.N + c]; umag0 = 0.5 * d.est0[1 * (size_t)d.N + c];
@@ -736,8 +741,10 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
     v[5] += usize * usize; v[6] += umag * umag;
     v[7] += smag0; v[8] += e2; v[9] += g2; v[10] += e2 * e2; v[11] += g2 * g2;
     v[12] += ssize * ssize; v[13] += smag * smag;
+    if (!(d.dbg & 4)) {
     philox_t x = philox4x32_10((uint32_t)c, (uint32_t)d.rank, mcs, LQ_STREAM_FLIP, key0, key1);
     d.flipb[c] = (uint8_t)(x.x & 1u);
+    }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -995,10 +1002,10 @@ k_mr_gcollect(Dev d, MrDev m) {
   const double sc = 0.5 / LQ_FX;
   for (size_t c = threadIdx.x; c < ngc; c += blockDim.x) {
     long long* ge = m.gest + c * 8;
-    const double usize = sc * (double)ge[0], umag = sc * (double)ge[1];
-    const double ssize = sc * (double)ge[2], smag = sc * (double)ge[3];
-    const double usize0 = 0.5 * (double)ge[4], umag0 = 0.5 * (double)ge[5];
-    const double ssize0 = 0.5 * (double)ge[6], smag0 = 0.5 * (double)ge[7];
+    const double usize = sc * i64_to_f64(ge[0]), umag = sc * i64_to_f64(ge[1]);
+    const double ssize = sc * i64_to_f64(ge[2]), smag = sc * i64_to_f64(ge[3]);
+    const double usize0 = 0.5 * i64_to_f64(ge[4]), umag0 = 0.5 * i64_to_f64(ge[5]);
+    const double ssize0 = 0.5 * i64_to_f64(ge[6]), smag0 = 0.5 * i64_to_f64(ge[7]);
 #pragma unroll
     for (int f = 0; f < 8; ++f) ge[f] = 0;
     const double a = usize0 * usize0, b = umag0 * umag0, e = ssize0 * ssize0, g = smag0 * smag0;
