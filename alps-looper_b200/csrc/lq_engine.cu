@@ -449,6 +449,8 @@ struct lq_engine {
       CK(cudaFuncSetAttribute(lq::k_diag_update<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_diag_update<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_diag_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((size_t)npo * cap * sizeof(uint32_t))));
       CK(cudaFuncSetAttribute(lq::k_walk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_walk<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_walk<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -585,7 +587,7 @@ struct lq_engine {
     {
       Section s(this, 6);
       scan_u32((const uint32_t*)pcount[cur].p, (uint32_t*)nbase.p, P, (uint32_t*)(nbase.p + P), d_ntotal.p);
-      lq::k_init_nodes<<<grid_for(nodes_cap, 256), 256, 0, stream>>>(d);
+      lq::k_init_nodes<<<grid_for(N, 256), 256, 0, stream>>>(d);
       lq::k_carry<<<grid_for(N, 128), 128, 0, stream>>>(d, cur);
       launches += 2;
     }
@@ -594,8 +596,9 @@ struct lq_engine {
       if (tpb_walk <= 256) lq::k_walk<256><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
       else if (tpb_walk <= 640) lq::k_walk<640><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
       else lq::k_walk<1024><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
-      lq::k_union<<<(unsigned)P, 256, 0, stream>>>(d, cur);
-      launches += 2;
+      lq::k_union_local<<<(unsigned)P, 256, (size_t)npo * cap * sizeof(uint32_t), stream>>>(d, cur);
+      lq::k_union_global<<<(unsigned)P, 256, 0, stream>>>(d, cur);
+      launches += 3;
     }
     {
       Section s(this, 9);

@@ -386,10 +386,9 @@ k_scan_final(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t
 // ------------------------------------------------------------------------------------------
 // K2a: parent[x] = x for every node of this step (sites + operator legs)
 // ------------------------------------------------------------------------------------------
-__global__ void k_init_nodes(Dev d) {
+__global__ void k_init_nodes(Dev d) {  // site nodes; operator nodes are written by k_union_local
   const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
-  if (x < nn) d.parent[x] = (node_t)x;
+  if (x < (size_t)d.N) d.parent[x] = (node_t)x;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -477,18 +476,58 @@ k_walk(Dev d, int buf) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K2d: unions.  Flat over the operators of a page: apply the graph's unions (graph_impl.h:277-295)
-// to the two nodes found by the walk, with the lock-free union-find, and record the spins below
-// the operator in its info word:
+// K2d: unions, in two levels (the chunk idea of looper/parallel.h applied inside one GPU: resolve
+// what is local to a time-slice tile in shared memory, send only its boundary to HBM).
+//  k_union_local   one CTA per page.  Edges whose two ends are operator nodes of THIS page are
+//                  unified in a shared-memory union-find (same min-index hooking); every node of
+//                  the page is then written to parent[] already pointing at its page-local root,
+//                  so no separate initialisation pass and shorter global chains.
+//  k_union_global  flat over the operators: the remaining edges (an end outside the page: carry
+//                  nodes, other windows, other tiles) go to the lock-free union-find in HBM.
+// Graph rules (graph_impl.h:277-295):
 //   g = 0      unify(below0, below1); the upper legs are the operator's own new node
 //   g = 1      cross: upper0 ~ below1, upper1 ~ below0            (needs npo == 2)
 //   g = 2, 3   freeze: all four legs in one cluster
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sm_find(uint32_t* par, uint32_t x) {
+  uint32_t p = ((volatile uint32_t*)par)[x];
+  while (p != x) {
+    const uint32_t gp = ((volatile uint32_t*)par)[p];
+    if (gp != p) par[x] = gp;
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+__device__ __forceinline__ void sm_union(uint32_t* par, uint32_t a, uint32_t b) {
+  uint32_t ra = sm_find(par, a), rb = sm_find(par, b);
+  while (ra != rb) {
+    if (ra < rb) { const uint32_t t = ra; ra = rb; rb = t; }
+    const uint32_t old = atomicCAS(par + ra, ra, rb);
+    if (old == ra) return;
+    ra = sm_find(par, old);
+    rb = sm_find(par, rb);
+  }
+}
+
+// edge (a, b) of the page whose node range is [lo, hi): local union if both ends are inside
+__device__ __forceinline__ void edge_local(uint32_t* par, node_t lo, node_t hi, node_t a, node_t b) {
+  if (a >= lo && a < hi && b >= lo && b < hi) sm_union(par, a - lo, b - lo);
+}
+__device__ __forceinline__ void edge_global(node_t* parent, node_t lo, node_t hi, node_t a, node_t b) {
+  if (!(a >= lo && a < hi && b >= lo && b < hi)) uf_union(parent, a, b);
+}
+
 __global__ void __launch_bounds__(256)
-k_union(Dev d, int buf) {
+k_union_local(Dev d, int buf) {
+  extern __shared__ uint32_t s_par[];
   const size_t p = blockIdx.x;
   const int n = d.pcount[buf][p];
   const int idx0 = d.nbase[p];
+  const int nn = d.npo * n;                       // nodes of this page
+  const node_t lo = upper_node(d, idx0, 0), hi = lo + (node_t)nn;
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) s_par[i] = (uint32_t)i;
+  __syncthreads();
   uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int idx = idx0 + j;
@@ -501,12 +540,42 @@ k_union(Dev d, int buf) {
     const node_t u0 = upper_node(d, idx, 0);
     if (d.npo == 2) {
       const node_t u1 = upper_node(d, idx, 1);
-      if (g == 0) { uf_union(d.parent, p0, p1); uf_union(d.parent, u0, u1); }
-      else if (g == 1) { uf_union(d.parent, u0, p1); uf_union(d.parent, u1, p0); }
-      else { uf_union(d.parent, p0, p1); uf_union(d.parent, u0, p0); uf_union(d.parent, u1, p0); }
+      if (g == 0) { edge_local(s_par, lo, hi, p0, p1); edge_local(s_par, lo, hi, u0, u1); }
+      else if (g == 1) { edge_local(s_par, lo, hi, u0, p1); edge_local(s_par, lo, hi, u1, p0); }
+      else { edge_local(s_par, lo, hi, p0, p1); edge_local(s_par, lo, hi, u0, p0); edge_local(s_par, lo, hi, u1, p0); }
     } else {
-      uf_union(d.parent, p0, p1);
-      if (g & 2) uf_union(d.parent, u0, p0);
+      edge_local(s_par, lo, hi, p0, p1);
+      if (g & 2) edge_local(s_par, lo, hi, u0, p0);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+    uint32_t r = (uint32_t)i, pr = s_par[r];
+    while (pr != r) { r = pr; pr = s_par[r]; }
+    d.parent[lo + i] = lo + r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_union_global(Dev d, int buf) {
+  const size_t p = blockIdx.x;
+  const int n = d.pcount[buf][p];
+  const int idx0 = d.nbase[p];
+  const node_t lo = upper_node(d, idx0, 0), hi = lo + (node_t)(d.npo * n);
+  const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int idx = idx0 + j;
+    const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
+    const int g = (gi[j] >> LQ_INFO_GSHIFT) & 3;
+    const node_t u0 = upper_node(d, idx, 0);
+    if (d.npo == 2) {
+      const node_t u1 = upper_node(d, idx, 1);
+      if (g == 0) { edge_global(d.parent, lo, hi, p0, p1); edge_global(d.parent, lo, hi, u0, u1); }
+      else if (g == 1) { edge_global(d.parent, lo, hi, u0, p1); edge_global(d.parent, lo, hi, u1, p0); }
+      else { edge_global(d.parent, lo, hi, p0, p1); edge_global(d.parent, lo, hi, u0, p0); edge_global(d.parent, lo, hi, u1, p0); }
+    } else {
+      edge_global(d.parent, lo, hi, p0, p1);
+      if (g & 2) edge_global(d.parent, lo, hi, u0, p0);
     }
   }
 }
