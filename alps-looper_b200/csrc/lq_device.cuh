@@ -74,7 +74,7 @@ struct Dev {
   const int* cls_sso;     // [nclasses] start of the class in sst_off
   const int* cls_sst;     // [nclasses] start of the class in sst
   const int* cls_nks;     // [nclasses] K-sites of the class
-  const int* bs;          // per class [2*nb] K-site of the two ends of an owned bond
+  const int* bs;          // per class [2*(nb+H)] K-site of the two ends of a local bucket (-1: none)
   const int* sst_off;     // per class [nks+1]
   const int* sst;         // (local bucket << 1 | side) incident to a K-site
   int hmax;               // max halo buckets per tile

@@ -72,7 +72,7 @@ struct Partition {
   std::vector<int> hsite_off, hsite;      // [T+1], global site ids of the halo K-sites
   std::vector<int> tile_class;            // [T]
   std::vector<int> cls_bs, cls_sso, cls_sst, cls_nks;  // [nclasses] starts in bs / sst_off / sst; K-sites
-  std::vector<int> bs;                    // per class [2*nb] K-site of the two ends of a bond
+  std::vector<int> bs;                    // per class [2*(nb+H)] K-site of the two ends of a local bucket (-1: none)
   std::vector<int> sst_off;               // per class [nks+1] offsets into sst
   std::vector<int> sst;                   // (local bucket << 1 | side)
 };
@@ -195,6 +195,10 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
       }
       offs.push_back((int)ent.size());
       P.zmax = std::max(P.zmax, P.adj_off[sg + 1] - P.adj_off[sg]);
+    }
+    for (int h : halo) {  // K-sites at the two ends of the halo buckets (-1: not a K-site)
+      bs.push_back(lsite[P.bond_s0[h]]);
+      bs.push_back(lsite[P.bond_s1[h]]);
     }
     for (int lb = 0; lb < nb; ++lb) local[b0 + lb] = -1;
     for (int h : halo) local[h] = -1;

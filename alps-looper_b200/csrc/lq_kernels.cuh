@@ -62,6 +62,10 @@ struct Stage {
   uint16_t* head;  // [zmax*blockDim] merge heads of the site walk (K2)
   uint8_t* cacc;   // [ccap]   accepted bit | graph << 1 (K1)
   uint8_t* kspin;  // [nksmax] spin of every K-site at the window start (K1)
+  int* fpos;       // [nksmax] fill cursors of the site lists (K1)
+  int* nkb;        // [nbmax]  kept (off-diagonal) operators per own bucket (K1)
+  uint16_t* klist; // [cap]    staged slots of the kept own operators, compacted (K1)
+  uint16_t* alist; // [ccap]   accepted candidates, compacted (K1)
   int nb, nh;
 };
 
@@ -71,7 +75,7 @@ __host__ __device__ inline size_t stage_bytes(bool full, int scap, int nbmax, in
   const size_t nloc = (size_t)nbmax + hmax;
   if (!full) return (size_t)scap * 12 + (3 * nloc + 1) * 4 + (size_t)zmax * tpb * 2 + 64;
   return ((size_t)scap + ccap + fcap) * 8 + (size_t)scap * 4 + (3 * nloc + 1) * 4 +
-         2 * ((size_t)nbmax + 1) * 4 + ((size_t)nksmax + 1) * 4 + (size_t)ccap * 2 +
+         3 * ((size_t)nbmax + 1) * 4 + 2 * ((size_t)nksmax + 1) * 4 + ((size_t)ccap * 2 + scap) * 2 +
          (size_t)ccap + (size_t)nksmax + 64;
 }
 
@@ -94,8 +98,12 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
     S.cbase = S.gbond + nloc_max;
     S.noff = S.cbase + d.nbmax + 1;
     S.foff = S.noff + d.nbmax + 1;
-    S.clb = (uint16_t*)(S.foff + d.nksmax + 1);
-    S.cacc = (uint8_t*)(S.clb + d.ccap);
+    S.fpos = S.foff + d.nksmax + 1;
+    S.nkb = S.fpos + d.nksmax + 1;
+    S.clb = (uint16_t*)(S.nkb + d.nbmax + 1);
+    S.alist = S.clb + d.ccap;
+    S.klist = S.alist + d.ccap;
+    S.cacc = (uint8_t*)(S.klist + d.scap);
     S.kspin = S.cacc + d.ccap;
   } else {
     S.head = (uint16_t*)(S.gbond + nloc_max);
@@ -132,7 +140,9 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
     if (ok)
       for (int j = 0; j < r.n; ++j) {
         S.time[n_own + hoff + j] = d.time[buf][r.base + j];
-        S.info[n_own + hoff + j] = d.info[buf][r.base + j];
+        // the staged copy carries the LOCAL bucket id of this tile in the bond bits
+        S.info[n_own + hoff + j] = (d.info[buf][r.base + j] & ((1u << LQ_INFO_LBSHIFT) - 1u)) |
+                                   ((uint32_t)(S.nb + tid) << LQ_INFO_LBSHIFT);
       }
   }
   if (tid == 0) S.off[S.nb + S.nh] = n_own + total;
@@ -186,38 +196,62 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   const int* sse = d.sst + d.cls_sst[cls];
   const int* bsx = d.bs + d.cls_bs[cls];
 
-  // ---- phase 0: per K-site spin and off-diagonal leg list ---------------------------------------
-  int nf = 0;
+  // ---- phase 0: per K-site spin; off-diagonal legs grouped by K-site (flat over staged ops) -----
+  __shared__ int s_cnt[2];
   if (tid < nks) {
     const int sg = tid < ns ? d.site_base[t] + tid : d.hsite[d.hsite_off[t] + tid - ns];
     S.kspin[tid] = d.spinW[(size_t)wl * d.N + sg];
-    for (int e = sso[tid]; e < sso[tid + 1]; ++e) {
-      const int lid = sse[e] >> 1;
-      for (int j = S.off[lid]; j < S.off[lid + 1]; ++j) nf += (int)(S.info[j] & LQ_INFO_OFFDIAG);
-    }
+    S.fpos[tid] = 0;
   }
+  if (tid < nb) S.nkb[tid] = 0;
+  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+  __syncthreads();
+  const int n_all = S.off[nb + S.nh];
+  const unsigned lane = tid & 31u;
+  for (int j0 = 0; j0 < n_all; j0 += blockDim.x) {
+    const int j = j0 + tid;
+    const uint32_t inf = (j < n_all) ? S.info[j] : 0u;
+    const bool offd = (inf & LQ_INFO_OFFDIAG) != 0;
+    if (offd) {
+      const int lid = (int)(inf >> LQ_INFO_LBSHIFT);
+      const int k0 = bsx[2 * lid], k1 = bsx[2 * lid + 1];
+      if (k0 >= 0) atomicAdd(&S.fpos[k0], 1);
+      if (k1 >= 0) atomicAdd(&S.fpos[k1], 1);
+      if (j < n_own) atomicAdd(&S.nkb[lid], 1);
+    }
+    const bool keep = offd && j < n_own;     // compact the kept own operators
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&s_cnt[0], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) S.klist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+  }
+  __syncthreads();
   int F;
-  int fo = block_exscan(nf, &F, s_scan);
+  const int nf = (tid < nks) ? S.fpos[tid] : 0;
+  const int fo = block_exscan(nf, &F, s_scan);
   if (F > d.fcap) {
     if (tid == 0) { atomicOr(d.d_err, LQ_ERR_NEIGH_FULL); d.pcount[dst][p] = 0; }
     if (tid <= nb) bo[tid] = 0;
     return;
   }
-  if (tid < nks) {
-    S.foff[tid] = fo;
-    for (int e = sso[tid]; e < sso[tid + 1]; ++e) {
-      const int lid = sse[e] >> 1;
-      for (int j = S.off[lid]; j < S.off[lid + 1]; ++j)
-        if (S.info[j] & LQ_INFO_OFFDIAG) S.ftime[fo++] = S.time[j];
-    }
-  }
+  if (tid < nks) { S.foff[tid] = fo; S.fpos[tid] = fo; }
   if (tid == 0) S.foff[nks] = F;
+  __syncthreads();
+  for (int j = tid; j < n_all; j += blockDim.x) {
+    const uint32_t inf = S.info[j];
+    if (!(inf & LQ_INFO_OFFDIAG)) continue;
+    const int lid = (int)(inf >> LQ_INFO_LBSHIFT);
+    const int k0 = bsx[2 * lid], k1 = bsx[2 * lid + 1];
+    const double tt = S.time[j];
+    if (k0 >= 0) S.ftime[atomicAdd(&S.fpos[k0], 1)] = tt;
+    if (k1 >= 0) S.ftime[atomicAdd(&S.fpos[k1], 1)] = tt;
+  }
 
   // ---- phase 1: candidates per bucket ------------------------------------------------------
-  int K = 0, nkeep = 0;
+  int K = 0;
   if (tid < nb) {
     const int b = b0 + tid;
-    for (int j = S.off[tid]; j < S.off[tid + 1]; ++j) nkeep += (int)(S.info[j] & LQ_INFO_OFFDIAG);
     const double mu = beta * d.bond_rate[b] * width;
     if (mu > 0) {
       const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND, key0, key1);
@@ -242,24 +276,34 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   __syncthreads();
 
   // ---- phase 2: time, acceptance and graph of every candidate ---------------------------------
-  for (int c = tid; c < C; c += blockDim.x) {
-    const int lb = S.clb[c];
-    const int i = c - S.cbase[lb];
-    const int b = b0 + lb;
-    const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + 1u + (uint32_t)i, key0, key1);
-    double tc = tlo + (u53(x.x, x.y) - 1.0 / 9007199254740992.0) * width;
-    if (!(tc < thi)) tc = tlo;
-    const int k0 = bsx[2 * lb], k1 = bsx[2 * lb + 1];
-    int par = S.kspin[k0] ^ S.kspin[k1];   // operators on this bond sit in both lists and cancel
-    for (int f = S.foff[k0]; f < S.foff[k0 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
-    for (int f = S.foff[k1]; f < S.foff[k1 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
-    const float4 pr = d.bond_p[b];
-    const float u = u24(x.z);
-    int g = -1;
-    if (par) { if (u < pr.x) g = 0; else if (u < pr.y) g = 2; }
-    else     { if (u < pr.z) g = 1; else if (u < pr.w) g = 3; }
-    S.ctime[c] = tc;
-    S.cacc[c] = (g >= 0) ? (uint8_t)(1 | (g << 1)) : (uint8_t)0;
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = c0 + tid;
+    bool accepted = false;
+    if (c < C) {
+      const int lb = S.clb[c];
+      const int i = c - S.cbase[lb];
+      const int b = b0 + lb;
+      const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + 1u + (uint32_t)i, key0, key1);
+      double tc = tlo + (u53(x.x, x.y) - 1.0 / 9007199254740992.0) * width;
+      if (!(tc < thi)) tc = tlo;
+      const int k0 = bsx[2 * lb], k1 = bsx[2 * lb + 1];
+      int par = S.kspin[k0] ^ S.kspin[k1];   // operators on this bond sit in both lists and cancel
+      for (int f = S.foff[k0]; f < S.foff[k0 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
+      for (int f = S.foff[k1]; f < S.foff[k1 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
+      const float4 pr = d.bond_p[b];
+      const float u = u24(x.z);
+      int g = -1;
+      if (par) { if (u < pr.x) g = 0; else if (u < pr.y) g = 2; }
+      else     { if (u < pr.z) g = 1; else if (u < pr.w) g = 3; }
+      S.ctime[c] = tc;
+      S.cacc[c] = (g >= 0) ? (uint8_t)(1 | (g << 1)) : (uint8_t)0;
+      accepted = g >= 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, accepted);   // compact the accepted candidates
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&s_cnt[1], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (accepted) S.alist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)c;
   }
   __syncthreads();
 
@@ -268,7 +312,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   if (tid < nb) {
     int nacc = 0;
     for (int i = 0; i < K; ++i) nacc += S.cacc[cb + i] & 1;
-    cnt = nkeep + nacc;
+    cnt = S.nkb[tid] + nacc;
   }
   int total;
   const int off = block_exscan(cnt, &total, s_scan);
@@ -284,9 +328,10 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   // ---- phase 4: scatter into the compacted new page ------------------------------------------
   double* wt = d.time[dst] + p * (size_t)d.cap;
   uint32_t* wi = d.info[dst] + p * (size_t)d.cap;
-  for (int c = tid; c < C; c += blockDim.x) {
+  const int n_acc = s_cnt[1], n_keep = s_cnt[0];
+  for (int ia = tid; ia < n_acc; ia += blockDim.x) {
+    const int c = S.alist[ia];
     const uint32_t acc = S.cacc[c];
-    if (!(acc & 1)) continue;
     const int lb = S.clb[c];
     const double tc = S.ctime[c];
     int rank = 0;
@@ -299,9 +344,9 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
     wt[pos] = tc;
     wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((acc >> 1) << LQ_INFO_GSHIFT);
   }
-  for (int j = tid; j < n_own; j += blockDim.x) {
+  for (int ik = tid; ik < n_keep; ik += blockDim.x) {
+    const int j = S.klist[ik];
     const uint32_t inf = S.info[j];
-    if (!(inf & LQ_INFO_OFFDIAG)) continue;
     const int lb = (int)(inf >> LQ_INFO_LBSHIFT);
     const double tt = S.time[j];
     const int o0 = S.off[lb];
