@@ -274,6 +274,18 @@ struct lq_engine {
   int scap = 0, ccap = 0, fcap = 0;
   size_t stage_smem = 0, walk_smem = 0;
   int tpb_walk = 32;
+  typedef void (*walk_fn_t)(lq::Dev, int);
+  walk_fn_t walk_fn = nullptr;
+  // world-line walk specialised on block size and coordination number
+  walk_fn_t pick_walk() const {
+    const int z = part.zmax;
+#define LQ_PICK(MT) (z <= 2 ? lq::k_walk<MT, 2> : z <= 4 ? lq::k_walk<MT, 4> : z <= 6 ? lq::k_walk<MT, 6> : \
+                     z <= 8 ? lq::k_walk<MT, 8> : lq::k_walk<MT, 0>)
+    if (tpb_walk <= 256) return LQ_PICK(256);
+    if (tpb_walk <= 640) return LQ_PICK(640);
+    return LQ_PICK(1024);
+#undef LQ_PICK
+  }
   DBuf<double> bond_rate, time_[2], partial, d_out;
   DBuf<float4> bond_p;
   DBuf<float> bond_q;
@@ -455,9 +467,8 @@ struct lq_engine {
       CK(cudaFuncSetAttribute(lq::k_diag_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)((size_t)npo * cap * sizeof(uint32_t))));
-      CK(cudaFuncSetAttribute(lq::k_walk<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_walk<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_walk<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      walk_fn = pick_walk();
+      CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     }
     P = (size_t)T * Wl;
     ncap = (long long)P * cap;
@@ -597,9 +608,7 @@ struct lq_engine {
     }
     {
       Section s(this, 7);
-      if (tpb_walk <= 256) lq::k_walk<256><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
-      else if (tpb_walk <= 640) lq::k_walk<640><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
-      else lq::k_walk<1024><<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
+      walk_fn<<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
       lq::k_union_local<<<(unsigned)P, 256, (size_t)npo * cap * sizeof(uint32_t), stream>>>(d, cur);
       lq::k_union_global<<<(unsigned)P, 256, 0, stream>>>(d, cur);
       launches += 3;

@@ -474,7 +474,11 @@ __global__ void k_carry(Dev d, int buf) {
 // Each leg of the page is visited exactly once -- O(legs x z) instead of one neighbourhood scan
 // per operator.  low0/low1[idx] = node below on the source/target side | spin << 31.
 // ------------------------------------------------------------------------------------------
-template <int MAXT>
+// Z = compile-time bound on the coordination number: the merge heads (position, end, time, bond
+// of the next unread operator of every incident bucket) live in registers; every step compares Z
+// register values and reloads only the head that advanced.  Z == 0: generic version with the head
+// positions in shared memory.
+template <int MAXT, int Z>
 __global__ void __launch_bounds__(MAXT)
 k_walk(Dev d, int buf) {
   extern __shared__ __align__(16) unsigned char s_stage[];
@@ -492,31 +496,67 @@ k_walk(Dev d, int buf) {
   const int* sso = d.sst_off + d.cls_sso[cls];
   const int* sse = d.sst + d.cls_sst[cls] + sso[tid];
   const int z = sso[tid + 1] - sso[tid];
-  uint16_t* head = S.head + tid;
-  const int hs = blockDim.x;
-  for (int k = 0; k < z; ++k) head[k * hs] = (uint16_t)S.off[sse[k] >> 1];
   node_t cur = d.curW[(size_t)wl * d.N + s];
   uint32_t spin = d.spinW[(size_t)wl * d.N + s];
-  for (;;) {
-    int best = -1, bh = 0, bent = 0, bb = 0;
-    double bt = 0;
-    for (int k = 0; k < z; ++k) {
-      const int ent = sse[k];
-      const int lid = ent >> 1;
-      const int h = head[k * hs];
-      if (h < S.off[lid + 1]) {
-        const double t2 = S.time[h];
-        const int b2 = S.gbond[lid];
-        if (best < 0 || t2 < bt || (t2 == bt && b2 < bb)) { best = k; bt = t2; bb = b2; bh = h; bent = ent; }
+  if (Z > 0) {
+    int hd[Z > 0 ? Z : 1], en[Z > 0 ? Z : 1], gb[Z > 0 ? Z : 1], ix[Z > 0 ? Z : 1], sd[Z > 0 ? Z : 1];
+    double tk[Z > 0 ? Z : 1];
+#pragma unroll
+    for (int k = 0; k < Z; ++k) {
+      hd[k] = 0; en[k] = 0; gb[k] = 0; ix[k] = 0; sd[k] = 0; tk[k] = 2.0;
+      if (k < z) {
+        const int ent = sse[k], lid = ent >> 1;
+        hd[k] = S.off[lid]; en[k] = S.off[lid + 1]; gb[k] = S.gbond[lid];
+        ix[k] = S.idx0[lid] - hd[k];   // dense index = ix + slot
+        sd[k] = ent & 1;
+        if (hd[k] < en[k]) tk[k] = S.time[hd[k]];
       }
     }
-    if (best < 0) break;
-    head[best * hs] = (uint16_t)(bh + 1);
-    const int lid = bent >> 1, side = bent & 1;
-    const int idx = S.idx0[lid] + (bh - S.off[lid]);
-    (side ? d.low1 : d.low0)[idx] = cur | (spin << 31);
-    spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
-    cur = upper_node(d, idx, side);
+    for (;;) {
+      int best = -1, bb = 0;
+      double bt = 2.0;
+#pragma unroll
+      for (int k = 0; k < Z; ++k)
+        if (tk[k] < bt || (tk[k] == bt && tk[k] < 2.0 && gb[k] < bb)) { best = k; bt = tk[k]; bb = gb[k]; }
+      if (best < 0) break;
+      int bh = 0, bix = 0, bsd = 0;
+#pragma unroll
+      for (int k = 0; k < Z; ++k)
+        if (k == best) {
+          bh = hd[k]; bix = ix[k]; bsd = sd[k];
+          hd[k] = bh + 1;
+          tk[k] = (bh + 1 < en[k]) ? S.time[bh + 1] : 2.0;
+        }
+      const int idx = bix + bh;
+      (bsd ? d.low1 : d.low0)[idx] = cur | (spin << 31);
+      spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
+      cur = upper_node(d, idx, bsd);
+    }
+  } else {
+    uint16_t* head = S.head + tid;
+    const int hs = blockDim.x;
+    for (int k = 0; k < z; ++k) head[k * hs] = (uint16_t)S.off[sse[k] >> 1];
+    for (;;) {
+      int best = -1, bh = 0, bent = 0, bb = 0;
+      double bt = 0;
+      for (int k = 0; k < z; ++k) {
+        const int ent = sse[k];
+        const int lid = ent >> 1;
+        const int h = head[k * hs];
+        if (h < S.off[lid + 1]) {
+          const double t2 = S.time[h];
+          const int b2 = S.gbond[lid];
+          if (best < 0 || t2 < bt || (t2 == bt && b2 < bb)) { best = k; bt = t2; bb = b2; bh = h; bent = ent; }
+        }
+      }
+      if (best < 0) break;
+      head[best * hs] = (uint16_t)(bh + 1);
+      const int lid = bent >> 1, side = bent & 1;
+      const int idx = S.idx0[lid] + (bh - S.off[lid]);
+      (side ? d.low1 : d.low0)[idx] = cur | (spin << 31);
+      spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
+      cur = upper_node(d, idx, side);
+    }
   }
 }
 
