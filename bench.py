@@ -27,8 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ALGO_BYTES_PER_OP = 104.0
 # algorithmic bytes per operator of the individual phases
-PHASE_BYTES = {5: ("k_diag_update", 24.0), 7: ("k_link", 28.0), 11: ("k_compress+k_relabel", 8.0),
-               12: ("k_estimate", 32.0), 15: ("k_flip", 12.0)}
+PHASE_BYTES = {5: ("k_diag_update", 24.0), 7: ("k_walk+k_union_local+k_union_global", 28.0),
+               11: ("k_compress+k_relabel", 8.0), 12: ("k_estimate", 32.0), 15: ("k_flip", 12.0)}
 
 
 def measured_peaks():
