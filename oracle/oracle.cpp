@@ -394,8 +394,14 @@ int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t
     tprev = ops[k].time;
     const int s0 = src[b], s1 = dst[b];
     const int g = ops[k].type >> 2;
-    // graph_impl.h:257 is_compatible(g, c0, c1) = (g & 1) ^ c0 ^ c1, evaluated BELOW the operator
-    if (!((g & 1) ^ sc[s0] ^ sc[s1])) return -1;
+    if (ops[k].type & 1) {
+      // off-diagonal (S+S- / S-S+): antiparallel spins below; its graph comes from
+      // choose_offdiagonal (graph_impl.h:324-327), i.e. 0 or 1, with no compatibility test
+      if (sc[s0] == sc[s1] || (g & 2)) return -1;
+    } else {
+      // diagonal: graph_impl.h:257 is_compatible(g, c0, c1) = (g & 1) ^ c0 ^ c1 (path_integral.C:503)
+      if (!((g & 1) ^ sc[s0] ^ sc[s1])) return -1;
+    }
     if (ops[k].type & 1) {
       sc[s0] ^= 1;
       sc[s1] ^= 1;
