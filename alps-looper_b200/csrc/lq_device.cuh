@@ -101,7 +101,7 @@ struct Dev {
   // ---- clusters ----
   long long* est;  // [4][nccap] usize, umag, ssize, smag in half units of LQ_FX
   int* est0;       // [4][N]     usize0, umag0, ssize0, smag0 in half units
-  uint8_t* flipb;  // [nccap]
+  uint32_t* flipw; // [nccap/32 + 1] flip decision per cluster id, packed
   long long ncap;   // operator arena (= P*cap)
   long long nccap;  // cluster arena
   // ---- scalars on device ----

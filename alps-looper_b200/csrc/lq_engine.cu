@@ -292,7 +292,8 @@ struct lq_engine {
   DBuf<signed char> gauge;
   DBuf<uint32_t> info[2], parent, low0, low1, bitmap, wcount, wbase, scan_tmp, d_nc, curW, labels;
   DBuf<uint16_t> boff[2];
-  DBuf<uint8_t> spinW, flipb;
+  DBuf<uint8_t> spinW;
+  DBuf<uint32_t> flipw;
   DBuf<long long> est;
   DBuf<int> est0;
   double* h_out = nullptr;  // pinned
@@ -497,7 +498,7 @@ struct lq_engine {
     scan_tmp.alloc((scan_n + LQ_SCAN_CHUNK - 1) / LQ_SCAN_CHUNK + 1, tb);
     est.alloc(4 * (size_t)nccap, tb);
     est0.alloc(4 * (size_t)N, tb);
-    flipb.alloc((size_t)nccap, tb);
+    flipw.alloc((size_t)nccap / 32 + 2, tb);
     nblk_collect = std::min<size_t>(((size_t)nccap + 255) / 256, (size_t)sm_count * 8);
     partial.alloc(nblk_collect * LQ_NSUM, tb);
     if (opt.nranks > 1) {
@@ -544,7 +545,7 @@ struct lq_engine {
     }
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
-    d.est = est.p; d.est0 = est0.p; d.flipb = flipb.p; d.ncap = ncap; d.nccap = nccap;
+    d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
     d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
   }
@@ -596,7 +597,7 @@ struct lq_engine {
   static unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
   // K2 + K3 on the live buffer (+ K4/K5 sums); used by the step and by lq_build_clusters
-  void label_clusters(double* out_slot, const lq::StepParams* sp) {
+  void label_clusters(double* out_slot, const lq::StepParams* sp, bool flip) {
     const int N = part.N;
     const size_t nodes_cap = (size_t)N + (size_t)npo * (size_t)ncap;
     {
@@ -624,13 +625,25 @@ struct lq_engine {
       lq::k_relabel<<<grid_for(nodes_cap, 256), 256, 0, stream>>>(d);
       launches += 2;
     }
+    if (opt.nranks > 1) merge_open_clusters();
+    {
+      Section s(this, 14);  // flip decision per cluster (path_integral.C:796-799)
+      lq::k_flipbits<<<(unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
+      launches += 1;
+      if (opt.nranks > 1) { lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp); launches += 1; }
+    }
     {
       Section s(this, 12);
-      lq::k_estimate<<<(unsigned)P, 256, sizeof(lq::EstHash), stream>>>(d, cur);
+      if (flip) lq::k_estimate<true><<<(unsigned)P, 256, sizeof(lq::EstHash), stream>>>(d, cur);
+      else lq::k_estimate<false><<<(unsigned)P, 256, sizeof(lq::EstHash), stream>>>(d, cur);
       lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
       launches += 2;
+      if (opt.nranks > 1) {
+        lq::k_mr_gather<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
+        lq::k_mr_reset_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
+        launches += 2;
+      }
     }
-    if (opt.nranks > 1) merge_open_clusters();
     {
       Section s(this, 13);
       lq::k_collect<<<(unsigned)nblk_collect, 256, 0, stream>>>(d, partial.p, sp);
@@ -661,16 +674,10 @@ struct lq_engine {
     lq::k_mr_gcompress<<<grid_for(((g2 + 31) / 32) * 32, 256), 256, 0, stream>>>(d, mr);
     launches += 3;
     scan_u32(mr.gwcount, mr.gwbase, (g2 + 31) / 32, mr.gwbase + (g2 + 31) / 32, (int*)mr.d_g);
-    lq::k_mr_gather<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
-    launches += 1;
   }
 
   void finish_open_clusters(double* out_slot, const lq::StepParams* sp) {
     Section s(this, 13);
-    const int N = part.N;
-    lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
-    lq::k_mr_reset_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
-    launches += 2;
     // the all-reduce length is the number of global open clusters: one 16-byte read-back
     CK(cudaMemcpyAsync(h_mr, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -722,12 +729,11 @@ struct lq_engine {
       launches += 1;
       cur ^= 1;
     }
-    label_clusters(out_slot, sp);
+    label_clusters(out_slot, sp, true);   // includes the flip of the operators (fused into K4)
     {
       Section s(this, 15);
-      lq::k_flip<<<(unsigned)P, 256, 0, stream>>>(d, cur);
       lq::k_flip_spins<<<grid_for((size_t)(Wl + 1) * part.N, 256), 256, 0, stream>>>(d);
-      launches += 2;
+      launches += 1;
     }
     ++mcs;
   }
@@ -897,7 +903,7 @@ struct lq_engine {
     if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
     ensure_out(1);
     stage_params(1, false);
-    label_clusters(d_out.p, d_params.p);
+    label_clusters(d_out.p, d_params.p, false);
     labels.alloc(2 * (size_t)std::max<long long>(ncap, 1), nullptr);
     lq::k_export_labels<<<(unsigned)P, 256, 0, stream>>>(d, cur, labels.p);
     launches += 1;

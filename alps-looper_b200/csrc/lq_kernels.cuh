@@ -37,6 +37,12 @@ __device__ __forceinline__ BucketRef bucket_of(const Dev& d, int buf, int b, int
   return r;
 }
 
+// flip decision of a cluster (path_integral.C:796-799): one bit per cluster id, packed; written by
+// k_flipbits right after the ids are known (and overridden for open clusters on slab engines)
+__device__ __forceinline__ uint32_t flip_of(const Dev& d, uint32_t cid) {
+  return ((long long)cid < d.nccap) ? ((d.flipw[cid >> 5] >> (cid & 31u)) & 1u) : 0u;
+}
+
 __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
   return (node_t)d.N + (d.npo == 2 ? (node_t)(2 * (size_t)idx + side) : (node_t)idx);
 }
@@ -770,6 +776,28 @@ __device__ __forceinline__ void est_hash_add(const Dev& d, EstHash* h, uint32_t 
   est_global_add(d, cid, a, b, c, e);  // table crowded: go straight to HBM
 }
 
+// Bernoulli(1/2) per cluster (path_integral.C:796-799): Philox4x32-10 keyed by (cluster id, rank,
+// step); 32 clusters per thread, one packed word each.  Persistent grid.
+__global__ void __launch_bounds__(256)
+k_flipbits(Dev d, const StepParams* __restrict__ sp) {
+  const uint32_t nc = d.d_nc[0];
+  const size_t nw = ((size_t)nc + 31) >> 5;
+  const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw && (long long)(w << 5) < d.nccap;
+       w += (size_t)gridDim.x * blockDim.x) {
+    uint32_t word = 0;
+    for (int i = 0; i < 32; i += 4) {   // one Philox call yields four bits' worth of words
+      const philox_t x = philox4x32_10((uint32_t)(w * 8 + (i >> 2)), (uint32_t)d.rank, mcs, LQ_STREAM_FLIP, key0, key1);
+      word |= (x.x & 1u) << i | (x.y & 1u) << (i + 1) | (x.z & 1u) << (i + 2) | (x.w & 1u) << (i + 3);
+    }
+    d.flipw[w] = word;
+  }
+}
+
+// FLIP: also apply the cluster flip to the operator (K6, path_integral.C:815-819): its type changes
+// iff the cluster arriving from below on the source side and the one leaving upwards are flipped
+// differently -- the two cluster ids are already in registers here.
+template <bool FLIP>
 __global__ void __launch_bounds__(256)
 k_estimate(Dev d, int buf) {
   extern __shared__ unsigned char s_raw[];
@@ -788,7 +816,7 @@ k_estimate(Dev d, int buf) {
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const uint32_t inf = d.info[buf][p * (size_t)d.cap + j];
     const int g = (inf >> LQ_INFO_GSHIFT) & 3;
-    if (g & 2) continue;  // frozen graphs are skipped (path_integral.C:692)
+    if (g & 2) continue;  // frozen graphs: skipped by the estimators (path_integral.C:692), never flip
     const double tt = d.time[buf][p * (size_t)d.cap + j];
     const long long q = time_to_fx(tt);
     const int b = b0 + (int)(inf >> LQ_INFO_LBSHIFT);
@@ -800,6 +828,8 @@ k_estimate(Dev d, int buf) {
     const int idx = idx0 + j;
     const uint32_t cl0 = d.parent[d.low0[idx] & 0x7fffffffu];
     const uint32_t cu0 = d.parent[upper_node(d, idx, 0)];
+    if (FLIP && ((flip_of(d, cl0) ^ flip_of(d, cu0)) & 1u))
+      d.info[buf][p * (size_t)d.cap + j] = inf ^ LQ_INFO_OFFDIAG;
     if (d.npo == 1) {
       // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
       est_hash_add(d, h, cl0, 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
@@ -828,9 +858,32 @@ k_estimate(Dev d, int buf) {
 // start_bottom / stop_top of every world line (path_integral.C:666-669,729-733;
 // susceptibility.h:139-155); for a slab [tau0,tau1) they are start(tau0) / stop(tau1)
 // (path_integral_mpi.C), and only rank 0 owns the tau = 0 magnetisations.
-__global__ void k_estimate_sites(Dev d) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= d.N) return;
+// At low temperature most world lines belong to a few long loops, so the lanes of a warp are first
+// grouped by cluster id (match.any) and reduced with the integer warp reduction; one atomic per
+// group and field reaches L2 instead of one per site.
+__device__ __forceinline__ void site_group_add(const Dev& d, bool valid, uint32_t cid, int a, int b, int c, int e,
+                                               long long q, bool to_est0) {
+  const uint32_t key = valid ? cid : 0xffffffffu;
+  const unsigned grp = __match_any_sync(0xffffffffu, key);
+  const int sa = __reduce_add_sync(grp, a), sb = __reduce_add_sync(grp, b);
+  const int sc = __reduce_add_sync(grp, c), se = __reduce_add_sync(grp, e);
+  const unsigned lane = threadIdx.x & 31u;
+  if (!valid || lane != (unsigned)(__ffs(grp) - 1)) return;
+  if (to_est0) {
+    if (sa) atomicAdd(d.est0 + 0 * (size_t)d.N + cid, sa);
+    if (sb) atomicAdd(d.est0 + 1 * (size_t)d.N + cid, sb);
+    if (sc) atomicAdd(d.est0 + 2 * (size_t)d.N + cid, sc);
+    if (se) atomicAdd(d.est0 + 3 * (size_t)d.N + cid, se);
+  } else {
+    est_global_add(d, cid, q * sa, q * sb, q * sc, q * se);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_estimate_sites(Dev d) {
+  const int s0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = s0 < d.N;
+  const int s = valid ? s0 : 0;
   const int g = d.gauge[s];
   const int c = d.spinW[s];
   const int m = 1 - 2 * c;
@@ -838,18 +891,13 @@ __global__ void k_estimate_sites(Dev d) {
   const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
   const long long qlo = time_to_fx(window_lo(d.w0, d.W));
   const long long qhi = (d.w0 + d.Wl >= d.W) ? (1ll << 40) : time_to_fx(window_hi(d.w0 + d.Wl - 1, d.W));
-  if (d.rank == 0) {
-    atomicAdd(d.est0 + 0 * (size_t)d.N + cb, 1);
-    atomicAdd(d.est0 + 1 * (size_t)d.N + cb, m);
-    atomicAdd(d.est0 + 2 * (size_t)d.N + cb, g);
-    atomicAdd(d.est0 + 3 * (size_t)d.N + cb, g * m);
-  }
-  if (qlo) est_global_add(d, cb, -qlo, -qlo * m, -qlo * g, -qlo * g * m);
+  if (d.rank == 0) site_group_add(d, valid, cb, 1, m, g, g * m, 0, true);
+  if (qlo) site_group_add(d, valid, cb, 1, m, g, g * m, -qlo, false);
   // periodic in imaginary time: the spin at the top of the slab stack equals the one at tau = 0;
   // inside a slab it is the spin at the start of the next slab = spinW[Wl]
   const int ctop = d.spinW[(size_t)d.Wl * d.N + s];
   const int mt = 1 - 2 * ctop;
-  est_global_add(d, ct, qhi, qhi * mt, qhi * g, qhi * g * mt);
+  site_group_add(d, valid, ct, 1, mt, g, g * mt, qhi, false);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -895,10 +943,6 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
     v[5] += usize * usize; v[6] += umag * umag;
     v[7] += smag0; v[8] += e2; v[9] += g2; v[10] += e2 * e2; v[11] += g2 * g2;
     v[12] += ssize * ssize; v[13] += smag * smag;
-    if (!(d.dbg & 4)) {
-    philox_t x = philox4x32_10((uint32_t)c, (uint32_t)d.rank, mcs, LQ_STREAM_FLIP, key0, key1);
-    d.flipb[c] = (uint8_t)(x.x & 1u);
-    }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -956,10 +1000,6 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
 // flipped differently (loop_0 / loop_1 of graph_impl.h:277-295 in leg form).  The spin carried
 // into every window flips with the cluster of the segment crossing the window start.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t flip_of(const Dev& d, uint32_t cid) {
-  return ((long long)cid < d.nccap) ? (uint32_t)d.flipb[cid] : 0u;
-}
-
 __global__ void __launch_bounds__(256)
 k_flip(Dev d, int buf) {
   const size_t p = blockIdx.x;
@@ -1132,7 +1172,8 @@ __global__ void k_mr_openflips(Dev d, MrDev m, const StepParams* __restrict__ sp
     if (k == 1 && c < ncs) continue;
     const uint32_t gid = global_cid(d, m, open_id(d, m, c));
     philox_t x = philox4x32_10(gid, 0xffffffffu, sp->mcs, LQ_STREAM_FLIP, sp->key0, sp->key1);
-    d.flipb[c] = (uint8_t)(x.x & 1u);
+    if (x.x & 1u) atomicOr(d.flipw + (c >> 5), 1u << (c & 31u));
+    else atomicAnd(d.flipw + (c >> 5), ~(1u << (c & 31u)));
   }
 }
 

@@ -55,5 +55,5 @@ def src(fl):
             L = src_cache[pth]
             return L[ln - 1].strip()[:100] if ln - 1 < len(L) else ""
     return ""
-for fl, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:32]:
+for fl, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("TOPN","32"))]:
     print(f"{100*v[0]/tot:5.1f}% inst  {100*v[2]/tots:5.1f}% stall  lanes={v[1]/max(v[0],1):4.1f}  {fl}: {src(fl)}")
