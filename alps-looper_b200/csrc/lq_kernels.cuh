@@ -919,23 +919,18 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc && (long long)c < d.nccap;
        c += (size_t)gridDim.x * blockDim.x) {
     const double sc = 0.5 / LQ_FX;
-    double usize = 0, umag = 0, ssize = 0, smag = 0;
-    if (!(d.dbg & 1)) {
-    usize = sc * i64_to_f64(d.est[0 * d.nccap + c]);
-    umag = sc * i64_to_f64(d.est[1 * d.nccap + c]);
-    ssize = sc * i64_to_f64(d.est[2 * d.nccap + c]);
-    smag = sc * i64_to_f64(d.est[3 * d.nccap + c]);
-    }
-    if (!(d.dbg & 2)) {
-    d.est[0 * d.nccap + c] = 0; d.est[1 * d.nccap + c] = 0;
-    d.est[2 * d.nccap + c] = 0; d.est[3 * d.nccap + c] = 0;
-    }
+    // read-and-clear with one L2 atomic per field: the sums were built by RED atomics, and on this
+    // part plain loads of lines last touched by atomics are an order of magnitude slower than
+    // atomics on them (measured: 0.11 ms -> 0.03 ms for 1.5e6 clusters, profiles/)
+    unsigned long long* e = (unsigned long long*)d.est;
+    const double usize = sc * i64_to_f64((long long)atomicExch(e + 0 * d.nccap + c, 0ull));
+    const double umag = sc * i64_to_f64((long long)atomicExch(e + 1 * d.nccap + c, 0ull));
+    const double ssize = sc * i64_to_f64((long long)atomicExch(e + 2 * d.nccap + c, 0ull));
+    const double smag = sc * i64_to_f64((long long)atomicExch(e + 3 * d.nccap + c, 0ull));
     double usize0 = 0, umag0 = 0, ssize0 = 0, smag0 = 0;
     if (c < ncs) {
-      usize0 = 0.5 * d.est0[0 * (size_t)d.N + c]; umag0 = 0.5 * d.est0[1 * (size_t)d.N + c];
-      ssize0 = 0.5 * d.est0[2 * (size_t)d.N + c]; smag0 = 0.5 * d.est0[3 * (size_t)d.N + c];
-      d.est0[0 * (size_t)d.N + c] = 0; d.est0[1 * (size_t)d.N + c] = 0;
-      d.est0[2 * (size_t)d.N + c] = 0; d.est0[3 * (size_t)d.N + c] = 0;
+      usize0 = 0.5 * atomicExch(d.est0 + 0 * (size_t)d.N + c, 0); umag0 = 0.5 * atomicExch(d.est0 + 1 * (size_t)d.N + c, 0);
+      ssize0 = 0.5 * atomicExch(d.est0 + 2 * (size_t)d.N + c, 0); smag0 = 0.5 * atomicExch(d.est0 + 3 * (size_t)d.N + c, 0);
     }
     // order = lq_collector: umag0 usize2 umag2 usize4 umag4 usize umag | smag0 ssize2 smag2 ssize4 smag4 ssize smag
     const double a2 = usize0 * usize0, b2 = umag0 * umag0, e2 = ssize0 * ssize0, g2 = smag0 * smag0;
@@ -1143,15 +1138,13 @@ __global__ void k_mr_gather(Dev d, MrDev m) {
     const uint32_t gid = global_cid(d, m, open_id(d, m, c));
     unsigned long long* ge = (unsigned long long*)m.gest + (size_t)gid * 8;
     for (int f = 0; f < 4; ++f) {
-      const long long v = d.est[f * d.nccap + c];
+      const long long v = (long long)atomicExch((unsigned long long*)d.est + f * d.nccap + c, 0ull);
       if (v) atomicAdd(ge + f, (unsigned long long)v);
-      d.est[f * d.nccap + c] = 0;
     }
     if (c < ncs)
       for (int f = 0; f < 4; ++f) {
-        const int v = d.est0[f * (size_t)d.N + c];
+        const int v = atomicExch(d.est0 + f * (size_t)d.N + c, 0);
         if (v) atomicAdd(ge + 4 + f, (unsigned long long)(long long)v);
-        d.est0[f * (size_t)d.N + c] = 0;
       }
     atomicAdd(m.d_g + 1, 1u);
   }
