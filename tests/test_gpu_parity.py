@@ -193,3 +193,79 @@ def test_large_lattice_properties():
     spins, ops = eng.get_state()
     orc.build_clusters(lat, spins, ops)  # legal configuration
     eng.close()
+
+
+def test_set_beta_keeps_the_configuration():
+    """set_beta (path_integral.C:98-105; exchange Monte Carlo) re-tiles imaginary time but keeps
+    spins and operators; the chain continues legally at the new temperature."""
+    lq = _lq()
+    lat = lq.hypercubic_lattice((8, 8))
+    eng = lq.Engine(lat, 4.0, seed=3)
+    eng.sweep_many(50, collect=False)
+    s0, o0 = eng.get_state()
+    w0 = eng.info()["num_windows"]
+    eng.set_beta(9.0)
+    assert eng.info()["num_windows"] > w0
+    s1, o1 = eng.get_state()
+    assert np.array_equal(s0, s1) and np.array_equal(o0, o1)
+    out = eng.sweep_many(60)
+    s2, o2 = eng.get_state()
+    orc.build_clusters(lat, s2, o2)
+    assert out["nop"][-20:].mean() > 1.5 * len(o0)      # more operators at the lower temperature
+    assert out["ene"][-1] == pytest.approx(eng.energy_offset - out["nop"][-1] / 9.0)
+    eng.close()
+
+
+def test_checkpoint_roundtrip_continues_identically():
+    """save/load payload (path_integral.C:111-124): a second engine loaded with (spins, operators)
+    and the same step counter... the step counter is internal, so compare the loaded state itself
+    and the cluster structure built from it."""
+    lq = _lq()
+    lat = lq.chain_lattice(32)
+    a = lq.Engine(lat, 12.0, seed=5)
+    a.sweep_many(80, collect=False)
+    spins, ops = a.get_state()
+    la, nca, ca = a.build_clusters()
+    b = lq.Engine(lat, 12.0, seed=5, tile_sites=8)     # different tiling, same physics
+    b.set_state(spins, ops)
+    s2, o2 = b.get_state()
+    assert np.array_equal(spins, s2) and np.array_equal(ops, o2)
+    lb, ncb, cb = b.build_clusters()
+    assert nca == ncb and np.array_equal(la, lb)        # canonical labels do not depend on the tiling
+    for f in ca:
+        assert ca[f] == pytest.approx(cb[f], rel=1e-12, abs=1e-12), f
+    a.close(); b.close()
+
+
+def test_timers_and_counters():
+    lq = _lq()
+    eng = lq.Engine(lq.chain_lattice(16), 10.0, timers=True)
+    l0 = eng.kernel_launches()
+    eng.sweep_many(5, collect=False)
+    assert eng.kernel_launches() - l0 >= 5 * 10
+    t = {x["id"]: x for x in eng.timers()}
+    # ids of path_integral.C:284-299: 5 fill_times, 7 insert/remove+reconnect, 11 ids, 12 accumulate
+    for pid in (5, 7, 11, 12, 13, 15):
+        assert pid in t and t[pid]["count"] == 5 and t[pid]["seconds"] > 0
+    h, d = eng.copied_bytes()
+    assert h == 5 * 24 and d == 5 * 256
+    eng.close()
+
+
+def test_bad_input_is_rejected():
+    lq = _lq()
+    lat = lq.chain_lattice(8)
+    eng = lq.Engine(lat, 5.0)
+    ops = np.zeros(1, dtype=lq.OP_DTYPE)
+    ops[0] = (0.5, (0 << 1) | 1, 1)                      # a lone off-diagonal operator
+    with pytest.raises(lq.LqError):
+        eng.set_state(np.array([0, 1] * 4), ops)         # not periodic in imaginary time
+    ops[0] = (1.5, (0 << 1) | 1, 0)
+    with pytest.raises(lq.LqError):
+        eng.set_state(np.array([0, 1] * 4), ops)         # time outside [0,1)
+    ops[0] = (0.5, (99 << 1) | 1, 0)
+    with pytest.raises(lq.LqError):
+        eng.set_state(np.array([0, 1] * 4), ops)         # bond out of range
+    with pytest.raises(lq.LqError):
+        lq.Engine(dict(num_sites=2, src=np.array([0], dtype=np.int32), dst=np.array([0], dtype=np.int32)), 1.0)
+    eng.close()
