@@ -258,9 +258,16 @@ def run_gpu(args):
             tot = sum(phases.values())
             dom = max((p for p in phases if p in PHASE_BYTES), key=lambda p: phases[p])
             kname, bpo = PHASE_BYTES[dom]
+            traffic = None
+            try:  # dram__bytes_read+write per launch of that kernel from the committed ncu capture
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                if tj.get("workload") == args.workload and world == 1:
+                    traffic = sum(tj["kernels"][k]["dram_bytes_per_launch"] for k in kname.split("+"))
+            except Exception:
+                traffic = None
             ach = (nop_t / world) * bpo / phases[dom] / 1e9   # this rank's slab
             roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": which,
+                    "frac": ach / peak, "traffic": traffic, "peak_source": which,
                     "kernel_ms": 1e3 * phases[dom], "kernel_share_of_step": phases[dom] / tot,
                     "algorithmic_bytes_per_op": bpo,
                     "phase_ms": {str(k): 1e3 * v for k, v in sorted(phases.items())},
@@ -270,10 +277,10 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_arm(128, 32.0, 40, 6, 1)
+        r = cpu_arm(128, 32.0, 40, 60, 1)
         cpu = {"value": r["ops_per_s"], "unit": "operators/s", "cores": 1, "kind": "port",
                "sample": "oracle port of standalone/loop.C (single-threaded like the reference), square "
-                         "128x128 beta=32, 40 thermalisation + 6 timed MCS, %.0f operators/MCS" % r["nop"]}
+                         "128x128 beta=32, 40 thermalisation + 60 timed MCS, %.0f operators/MCS" % r["nop"]}
 
     if rank == 0:
         nop_mean = float(out["nop"].mean())
