@@ -56,6 +56,9 @@ struct Dev {
   const int* bond_s0;    // [B] source site
   const int* bond_s1;    // [B] target site
   const int* bond_tile;  // [B] owning tile
+  const int* bond_tl;    // [B] owning tile << 10 | local bond index
+  const double* bond_emu;  // [B] exp(-beta * rate / W): P(no candidate in a window)
+  const int* whalo_cnt;  // [T] leading halo buckets that touch an own site (walk halo)
   const int* bond_base;  // [T+1] first bond of tile
   const int* adj_off;    // [N+1]
   const int* adj;        // [2B] (bond << 1 | side)

@@ -66,9 +66,10 @@ struct Partition {
   // per-tile halo (bonds owned by other tiles that touch an end site of an owned bond) and the
   // per-bond stencils in LOCAL bucket ids (own bonds 0..nb-1, halo nb..nb+H-1); stencils are
   // shared by all tiles of the same shape ("class")
-  int hmax = 0, nclasses = 0, nksmax = 0, nsmax = 0, zmax = 0;
+  int hmax = 0, whmax = 0, nclasses = 0, nksmax = 0, nsmax = 0, zmax = 0;
   std::vector<int> site_base;             // [T+1] first (internal) site of a tile
   std::vector<int> halo_off, halo_bond;   // [T+1], global bond ids of the halo buckets
+  std::vector<int> whalo_cnt;             // [T] leading halo buckets that touch an OWN site (walk halo)
   std::vector<int> hsite_off, hsite;      // [T+1], global site ids of the halo K-sites
   std::vector<int> tile_class;            // [T]
   std::vector<int> cls_bs, cls_sso, cls_sst, cls_nks;  // [nclasses] starts in bs / sst_off / sst; K-sites
@@ -186,7 +187,9 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
         bs.push_back(lsite[sg]);
       }
     const int nks = ns + (int)hsites.size();
+    int nwalk = 0;
     for (int ks = 0; ks < nks; ++ks) {
+      if (ks == ns) nwalk = (int)halo.size();
       const int sg = ks < ns ? s0 + ks : hsites[ks - ns];
       for (int a = P.adj_off[sg]; a < P.adj_off[sg + 1]; ++a) {
         const int b2 = P.adj[a] >> 1, side2 = P.adj[a] & 1;
@@ -224,6 +227,9 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
     } else {
       P.tile_class[t] = it->second;
     }
+    if (nks == ns) nwalk = (int)halo.size();
+    P.whalo_cnt.push_back(nwalk);
+    P.whmax = std::max(P.whmax, nwalk);
     P.halo_off[t + 1] = P.halo_off[t] + (int)halo.size();
     P.halo_bond.insert(P.halo_bond.end(), halo.begin(), halo.end());
     P.hsite_off[t + 1] = P.hsite_off[t] + (int)hsites.size();
@@ -270,6 +276,8 @@ struct lq_engine {
   lq::Dev d{};
   cudaStream_t stream = nullptr;
   DBuf<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
+  DBuf<int> whalo_cnt, bond_tl;
+  DBuf<double> bond_emu;
   DBuf<int> site_base, halo_off, halo_bond, hsite_off, hsite, tile_class, cls_bs, cls_sso, cls_sst, cls_nks, bs, sst_off, sst;
   int scap = 0, ccap = 0, fcap = 0;
   size_t stage_smem = 0, walk_smem = 0;
@@ -370,6 +378,7 @@ struct lq_engine {
       fail(LQ_E_INVALID, "tile owns more than 1023 bonds: lower lq_options.tile_sites");
     if (part.hmax > 1024)
       fail(LQ_E_INVALID, "tile halo has more than 1024 buckets: lower lq_options.tile_sites");
+    if (part.T >= (1 << 21)) fail(LQ_E_INVALID, "more than 2^21 tiles: raise lq_options.tile_sites");
     if (part.nksmax > 1024) fail(LQ_E_INVALID, "tile touches more than 1024 sites: lower lq_options.tile_sites");
     tpb = ((std::max(std::max(part.nbmax + 1, part.hmax), part.nksmax) + 31) / 32) * 32;
 
@@ -402,6 +411,12 @@ struct lq_engine {
     bond_p.upload(bp, &device_bytes);
     bond_q.upload(bq, &device_bytes);
     gauge.upload(gi, &device_bytes);
+    whalo_cnt.upload(part.whalo_cnt, &device_bytes);
+    {
+      std::vector<int> tl(B);
+      for (int i = 0; i < B; ++i) tl[i] = (part.bond_tile[i] << 10) | (i - part.bond_base[part.bond_tile[i]]);
+      bond_tl.upload(tl, &device_bytes);
+    }
     site_base.upload(part.site_base, &device_bytes);
     halo_off.upload(part.halo_off, &device_bytes);
     halo_bond.upload(part.halo_bond, &device_bytes);
@@ -444,6 +459,14 @@ struct lq_engine {
     w0 = opt.rank * Wl;
     double mu = 0;
     for (int t = 0; t < T; ++t) mu = std::max(mu, tile_rate[t] * beta / W);
+    {
+      std::vector<double> emu(B);
+      for (int i = 0; i < B; ++i) {
+        const double* v = &weights[4 * (size_t)part.bond_i2e[i]];
+        emu[i] = std::exp(-beta * (v[0] + v[1] + v[2] + v[3]) / W);
+      }
+      bond_emu.upload(emu, nullptr);
+    }
     const double m = opt.reserve * mu;
     long long c = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
     if (c > 65535) fail(LQ_E_INVALID, "page capacity exceeds 65535 operators: lower tile_sites or window_ops");
@@ -457,7 +480,7 @@ struct lq_engine {
       ccap = (int)std::ceil(cm + 8.0 * std::sqrt(cm) + 32.0);
       if (ccap > 65535) fail(LQ_E_INVALID, "too many candidates per page: lower tile_sites or window_ops");
       fcap = scap + scap / 2;  // off-diagonal legs of the staged operators (checked at run time)
-      tpb_walk = ((std::max(part.nsmax, part.hmax) + 31) / 32) * 32;
+      tpb_walk = ((std::max(part.nsmax, part.whmax) + 31) / 32) * 32;
       stage_smem = lq::stage_bytes(true, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb);
       walk_smem = lq::stage_bytes(false, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb_walk);
       if (stage_smem > 200 * 1024)
@@ -535,6 +558,7 @@ struct lq_engine {
     d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_tile = bond_tile.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
     d.bond_q = bond_q.p; d.gauge = gauge.p;
+    d.whalo_cnt = whalo_cnt.p; d.bond_tl = bond_tl.p; d.bond_emu = bond_emu.p;
     d.site_base = site_base.p; d.halo_off = halo_off.p; d.halo_bond = halo_bond.p;
     d.hsite_off = hsite_off.p; d.hsite = hsite.p; d.tile_class = tile_class.p;
     d.cls_bs = cls_bs.p; d.cls_sso = cls_sso.p; d.cls_sst = cls_sst.p; d.cls_nks = cls_nks.p;

@@ -18,6 +18,12 @@ namespace lq {
 #define LQ_MAXC 32  /* accepted candidates kept per (bond, window) bucket */
 #define LQ_MAXN 64  /* off-diagonal neighbour legs per bond and window    */
 
+// 1/K for the Poisson inverse-CDF recursion p_K = p_{K-1} * mu / K
+__constant__ double c_rcp[33] = {
+    0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
+    1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
+    1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32};
+
 struct BucketRef {
   size_t base;  // first slot of the bucket in the page arrays
   int n;        // operators in the bucket
@@ -25,8 +31,8 @@ struct BucketRef {
 };
 
 __device__ __forceinline__ BucketRef bucket_of(const Dev& d, int buf, int b, int wl) {
-  const int t = d.bond_tile[b];
-  const int lb = b - d.bond_base[t];
+  const int tl = d.bond_tl[b];
+  const int t = tl >> 10, lb = tl & 1023;
   const size_t p = (size_t)t * d.Wl + wl;
   const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1) + lb;
   const int o0 = bo[0], o1 = bo[1];
@@ -118,7 +124,7 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   const int b0 = d.bond_base[t];
   S.nb = d.bond_base[t + 1] - b0;
   const int h0 = d.halo_off[t];
-  S.nh = d.halo_off[t + 1] - h0;
+  S.nh = FULL ? d.halo_off[t + 1] - h0 : d.whalo_cnt[t];  // the walk only needs buckets at own sites
   const int n_own = d.pcount[buf][p];
   const int base_idx = d.nbase[p];
   const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1);
@@ -262,8 +268,8 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
     if (mu > 0) {
       const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND, key0, key1);
       const double u = u53(x.x, x.y);
-      double pk = exp(-mu), cdf = pk;
-      while (u > cdf && K < 32) { ++K; pk *= mu / K; cdf += pk; }
+      double pk = d.bond_emu[b], cdf = pk;
+      while (u > cdf && K < 32) { ++K; pk *= mu * c_rcp[K]; cdf += pk; }
       if (K >= 32 && u > cdf) atomicOr(d.d_err, LQ_ERR_CAND_FULL);
     }
   }
