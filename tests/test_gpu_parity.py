@@ -269,3 +269,26 @@ def test_bad_input_is_rejected():
     with pytest.raises(lq.LqError):
         lq.Engine(dict(num_sites=2, src=np.array([0], dtype=np.int32), dst=np.array([0], dtype=np.int32)), 1.0)
     eng.close()
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 at full size (square 256x256, beta=64, ~4.9e6 operators): the state after
+    GPU steps is a legal world-line configuration for the reference's sequential walk, the GPU
+    partition of that state is bit-identical to the reference union-find's, and the energy is in
+    the physical window of the 2-D Heisenberg antiferromagnet (E/N -> -0.669 as T -> 0)."""
+    lq = _lq()
+    lat = lq.hypercubic_lattice((256, 256))
+    N = 256 * 256
+    eng = lq.Engine(lat, 64.0, seed=12, tile_sites=256)
+    out = eng.sweep_many(120)
+    spins, ops = eng.get_state()
+    assert len(ops) == out["nop"][-1]
+    ref_labels, ref_nc, ref = orc.build_clusters(lat, spins, ops)     # raises if illegal
+    labels, nc, coll = eng.build_clusters()
+    assert nc == ref_nc
+    assert np.array_equal(labels, ref_labels)
+    for f in ("usize2", "umag2", "smag2", "usize", "smag"):
+        assert coll[f] == pytest.approx(ref[f], rel=1e-8), f
+    e = out["ene"][-20:].mean() / N
+    assert -0.70 < e < -0.60
+    eng.close()
