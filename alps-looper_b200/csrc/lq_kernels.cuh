@@ -531,14 +531,22 @@ k_walk(Dev d, int buf) {
       for (int k = 0; k < Z; ++k)
         if (tk[k] < bt || (tk[k] == bt && tk[k] < 2.0 && gb[k] < bb)) { best = k; bt = tk[k]; bb = gb[k]; }
       if (best < 0) break;
-      int bh = 0, bix = 0, bsd = 0;
+      // branch-free head update: select the winner's registers, ONE shared-memory load for the
+      // whole warp, then predicated write-back (a load inside `if (k == best)` would serialise
+      // the warp Z times)
+      int bh = 0, bix = 0, bsd = 0, ben = 0;
 #pragma unroll
-      for (int k = 0; k < Z; ++k)
-        if (k == best) {
-          bh = hd[k]; bix = ix[k]; bsd = sd[k];
-          hd[k] = bh + 1;
-          tk[k] = (bh + 1 < en[k]) ? S.time[bh + 1] : 2.0;
-        }
+      for (int k = 0; k < Z; ++k) {
+        const bool m = (k == best);
+        bh = m ? hd[k] : bh; bix = m ? ix[k] : bix; bsd = m ? sd[k] : bsd; ben = m ? en[k] : ben;
+      }
+      const double tn = (bh + 1 < ben) ? S.time[bh + 1] : 2.0;
+#pragma unroll
+      for (int k = 0; k < Z; ++k) {
+        const bool m = (k == best);
+        hd[k] = m ? bh + 1 : hd[k];
+        tk[k] = m ? tn : tk[k];
+      }
       const int idx = bix + bh;
       (bsd ? d.low1 : d.low0)[idx] = cur | (spin << 31);
       spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
