@@ -20,8 +20,19 @@ class _DevBuf:
                                          "data": (int(ptr), False), "version": 2}
 
 
+_tensor_cache = {}
+
+
 def device_tensor(ptr, nbytes, device):
-    return torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+    """zero-copy uint8 tensor over a raw device pointer (cached: the engine reuses its buffers)"""
+    key = (int(ptr), int(nbytes), str(device))
+    t = _tensor_cache.get(key)
+    if t is None:
+        if len(_tensor_cache) > 64:
+            _tensor_cache.clear()
+        t = torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+        _tensor_cache[key] = t
+    return t
 
 
 def attach_torch_distributed(engine, device, group=None):

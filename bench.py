@@ -191,13 +191,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # thermalise (not timed) + warm-up steps
+    # thermalise (not timed) + warm-up steps; the clock sampler runs from here on (nvidia-smi needs
+    # ~1 s to start), every sample is taken under load
+    sampler = ClockSampler(local)
     eng.sweep_many(therm, collect=False)
     eng.sweep_many(max(args.warmup, 3), collect=False)
 
     # ---- device-timed region: K steps, state resident in HBM -----------------------------------
     launches0 = eng.kernel_launches()
-    sampler = ClockSampler(local)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -294,6 +295,7 @@ def run_gpu(args):
             "config": {"workload": args.workload, "lattice": f"square {L}x{L} periodic",
                        "model": "S=1/2 Heisenberg AF J=1", "beta": beta,
                        "operators_per_mcs": nop_mean, "clusters_per_mcs": float(out["nc"].mean()),
+                       "open_clusters_per_mcs": float(out["noc"].mean()),
                        "thermalisation_mcs": therm, "tile_sites": tile, "windows": info["num_windows"],
                        "tiles": info["num_tiles"], "device_bytes": info["device_bytes"],
                        "l2_policy": "working set (%.1f GB) larger than L2" % (info["device_bytes"] / 1e9)
