@@ -19,12 +19,10 @@ static const node_t NODE_NONE = 0xffffffffu;
 // info word of an operator (mirrors looper/operator.h type_ in the low bits)
 //   bit 0      offdiagonal            (local_operator_type::offdiagonal, operator.h:44)
 //   bits 2..3  graph type g           (type_ >> 2, operator.h:76; graph_impl.h:93-103)
-//   bit 4, 5   spin below the operator on source / target site (filled by k_link)
+//   (the spins below the operator travel in bit 31 of low0 / low1, written by the walk)
 //   bits 8..   local bond index inside the owning tile
 #define LQ_INFO_OFFDIAG 1u
 #define LQ_INFO_GSHIFT 2
-#define LQ_INFO_C0 16u
-#define LQ_INFO_C1 32u
 #define LQ_INFO_LBSHIFT 8
 
 // error bits raised by kernels (sticky, read back by the host after a sweep)

@@ -478,21 +478,23 @@ struct lq_engine {
       scap = cap + (int)std::ceil(hm + 6.0 * std::sqrt(hm) + 16.0);
       const double cm = mu;  // mean candidates per page
       ccap = (int)std::ceil(cm + 8.0 * std::sqrt(cm) + 32.0);
-      if (ccap > 65535) fail(LQ_E_INVALID, "too many candidates per page: lower tile_sites or window_ops");
+      if (ccap > 32767 || scap > 65535)
+        fail(LQ_E_INVALID, "too many candidates / staged operators per page: lower tile_sites or window_ops");
       fcap = scap + scap / 2;  // off-diagonal legs of the staged operators (checked at run time)
       tpb_walk = ((std::max(part.nsmax, part.whmax) + 31) / 32) * 32;
-      stage_smem = lq::stage_bytes(true, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb);
+      stage_smem = lq::k1_smem_bytes(scap, ccap, cap, part.nbmax, part.hmax, part.nksmax);
       walk_smem = lq::stage_bytes(false, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb_walk);
       if (stage_smem > 200 * 1024)
         fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
       const int sm = (int)stage_smem;
-      CK(cudaFuncSetAttribute(lq::k_diag_update<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_diag_update<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_diag_update<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_diag_update<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_diag_update<576>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_diag_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)((size_t)npo * cap * sizeof(uint32_t))));
       walk_fn = pick_walk();
-      CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
     }
     P = (size_t)T * Wl;
     ncap = (long long)P * cap;
@@ -644,9 +646,9 @@ struct lq_engine {
     }
     {
       Section s(this, 11);
-      lq::k_compress<<<grid_for(nwords_cap * 32, 256), 256, 0, stream>>>(d, nwords_cap);
+      lq::k_compress<<<grid_for(nwords_cap * 32, 256 * LQ_NPT), 256, 0, stream>>>(d, nwords_cap);
       scan_u32(wcount.p, wbase.p, nwords_cap, wbase.p + nwords_cap, (int*)d_nc.p);
-      lq::k_relabel<<<grid_for(nodes_cap, 256), 256, 0, stream>>>(d);
+      lq::k_relabel<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d);
       launches += 2;
     }
     if (opt.nranks > 1) merge_open_clusters();
@@ -658,8 +660,9 @@ struct lq_engine {
     }
     {
       Section s(this, 12);
-      if (flip) lq::k_estimate<true><<<(unsigned)P, 256, sizeof(lq::EstHash), stream>>>(d, cur);
-      else lq::k_estimate<false><<<(unsigned)P, 256, sizeof(lq::EstHash), stream>>>(d, cur);
+      const size_t est_smem = sizeof(lq::EstHash) + 2 * (size_t)part.nbmax + 16;
+      if (flip) lq::k_estimate<true><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+      else lq::k_estimate<false><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
       lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
       launches += 2;
       if (opt.nranks > 1) {
@@ -747,8 +750,9 @@ struct lq_engine {
   void enqueue_step(double* out_slot, const lq::StepParams* sp) {
     {
       Section s(this, 5);
-      if (tpb <= 256) lq::k_diag_update<256><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
-      else if (tpb <= 640) lq::k_diag_update<640><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
+      if (tpb <= 192) lq::k_diag_update<192><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
+      else if (tpb <= 320) lq::k_diag_update<320><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
+      else if (tpb <= 576) lq::k_diag_update<576><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
       else lq::k_diag_update<1024><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
       launches += 1;
       cur ^= 1;

@@ -12,17 +12,12 @@
 // with a device-side bound so that a whole step needs no host synchronisation.
 #pragma once
 #include "lq_device.cuh"
+#include "lq_k1.cuh"
 
 namespace lq {
 
 #define LQ_MAXC 32  /* accepted candidates kept per (bond, window) bucket */
 #define LQ_MAXN 64  /* off-diagonal neighbour legs per bond and window    */
-
-// 1/K for the Poisson inverse-CDF recursion p_K = p_{K-1} * mu / K
-__constant__ double c_rcp[33] = {
-    0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
-    1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
-    1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32};
 
 struct BucketRef {
   size_t base;  // first slot of the bucket in the page arrays
@@ -160,223 +155,6 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   if (tid == 0) S.off[S.nb + S.nh] = n_own + total;
   __syncthreads();
   return ok;
-}
-
-// ------------------------------------------------------------------------------------------
-// K1: diagonal update.  One CTA per page (staged with its halo).  FLAT work mapping -- every
-// phase gives each thread one site, one bucket, one candidate or one old operator:
-//  0. per K-site (own sites + far ends of owned bonds): spin at the window start and the list of
-//     off-diagonal leg times on that site in this window (from the buckets incident to it)
-//  1. per bucket: number of candidates K ~ Poisson(beta * sum_g v_g * window) by inverse CDF
-//     (replaces poisson_distribution.h:60-75 / the exponential gaps of path_integral.C:413-423);
-//     CTA-wide prefix sum (warp shuffles) -> candidate slots
-//  2. per candidate: uniform time in the window, Philox4x32-10 keyed by (bond, window, step, i);
-//     is_compatible (graph_impl.h:257) needs the two spins at that time = spin at the window start
-//     xor parity of the off-diagonal legs before it on each site; graph chosen with the model's
-//     weights (graph_impl.h:679)
-//  3. per bucket: new size = kept off-diagonal + accepted; prefix sum -> new bucket offsets
-//  4. per accepted candidate / per kept operator: rank inside the new bucket -> scatter into the
-//     compacted new page (old diagonal operators are dropped, path_integral.C:519-521)
-// ------------------------------------------------------------------------------------------
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 5 : (MAXT <= 640 ? 2 : 1)))
-k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
-  extern __shared__ __align__(16) unsigned char s_stage[];
-  __shared__ int s_scan[34];
-  const double beta = sp->beta;
-  const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
-  const int dst = src ^ 1;
-  const size_t p = blockIdx.x;
-  const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl), wg = d.w0 + wl;
-  Stage S;
-  const bool staged = stage_page<true>(d, src, t, wl, s_stage, S, s_scan);
-  const int nb = S.nb;
-  const int tid = threadIdx.x;
-  uint16_t* bo = d.boff[dst] + p * (size_t)(d.nbmax + 1);
-  if (!staged) {
-    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_PAGE_FULL); d.pcount[dst][p] = 0; }
-    if (tid <= nb) bo[tid] = 0;
-    return;
-  }
-  const int b0 = d.bond_base[t];
-  const int n_own = S.off[nb];
-  const double tlo = window_lo(wg, d.W), thi = window_hi(wg, d.W), width = thi - tlo;
-  const int cls = d.tile_class[t];
-  const int nks = d.cls_nks[cls];
-  const int ns = d.site_base[t + 1] - d.site_base[t];
-  const int* sso = d.sst_off + d.cls_sso[cls];
-  const int* sse = d.sst + d.cls_sst[cls];
-  const int* bsx = d.bs + d.cls_bs[cls];
-
-  // ---- phase 0: per K-site spin; off-diagonal legs grouped by K-site (flat over staged ops) -----
-  __shared__ int s_cnt[2];
-  if (tid < nks) {
-    const int sg = tid < ns ? d.site_base[t] + tid : d.hsite[d.hsite_off[t] + tid - ns];
-    S.kspin[tid] = d.spinW[(size_t)wl * d.N + sg];
-    S.fpos[tid] = 0;
-  }
-  if (tid < nb) S.nkb[tid] = 0;
-  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-  __syncthreads();
-  const int n_all = S.off[nb + S.nh];
-  const unsigned lane = tid & 31u;
-  for (int j0 = 0; j0 < n_all; j0 += blockDim.x) {
-    const int j = j0 + tid;
-    const uint32_t inf = (j < n_all) ? S.info[j] : 0u;
-    const bool offd = (inf & LQ_INFO_OFFDIAG) != 0;
-    if (offd) {
-      const int lid = (int)(inf >> LQ_INFO_LBSHIFT);
-      const int k0 = bsx[2 * lid], k1 = bsx[2 * lid + 1];
-      if (k0 >= 0) atomicAdd(&S.fpos[k0], 1);
-      if (k1 >= 0) atomicAdd(&S.fpos[k1], 1);
-      if (j < n_own) atomicAdd(&S.nkb[lid], 1);
-    }
-    const bool keep = offd && j < n_own;     // compact the kept own operators
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    int base = 0;
-    if (lane == 0 && m) base = atomicAdd(&s_cnt[0], __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep) S.klist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
-  }
-  __syncthreads();
-  int F;
-  const int nf = (tid < nks) ? S.fpos[tid] : 0;
-  const int fo = block_exscan(nf, &F, s_scan);
-  if (F > d.fcap) {
-    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_NEIGH_FULL); d.pcount[dst][p] = 0; }
-    if (tid <= nb) bo[tid] = 0;
-    return;
-  }
-  if (tid < nks) { S.foff[tid] = fo; S.fpos[tid] = fo; }
-  if (tid == 0) S.foff[nks] = F;
-  __syncthreads();
-  for (int j = tid; j < n_all; j += blockDim.x) {
-    const uint32_t inf = S.info[j];
-    if (!(inf & LQ_INFO_OFFDIAG)) continue;
-    const int lid = (int)(inf >> LQ_INFO_LBSHIFT);
-    const int k0 = bsx[2 * lid], k1 = bsx[2 * lid + 1];
-    const double tt = S.time[j];
-    if (k0 >= 0) S.ftime[atomicAdd(&S.fpos[k0], 1)] = tt;
-    if (k1 >= 0) S.ftime[atomicAdd(&S.fpos[k1], 1)] = tt;
-  }
-
-  // ---- phase 1: candidates per bucket ------------------------------------------------------
-  int K = 0;
-  if (tid < nb) {
-    const int b = b0 + tid;
-    const double mu = beta * d.bond_rate[b] * width;
-    if (mu > 0) {
-      const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND, key0, key1);
-      const double u = u53(x.x, x.y);
-      double pk = d.bond_emu[b], cdf = pk;
-      while (u > cdf && K < 32) { ++K; pk *= mu * c_rcp[K]; cdf += pk; }
-      if (K >= 32 && u > cdf) atomicOr(d.d_err, LQ_ERR_CAND_FULL);
-    }
-  }
-  int C;
-  const int cb = block_exscan(K, &C, s_scan);
-  if (C > d.ccap) {
-    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_CAND_FULL); d.pcount[dst][p] = 0; }
-    if (tid <= nb) bo[tid] = 0;
-    return;
-  }
-  if (tid < nb) {
-    S.cbase[tid] = cb;
-    for (int i = 0; i < K; ++i) S.clb[cb + i] = (uint16_t)tid;
-  }
-  if (tid == nb) S.cbase[nb] = C;
-  __syncthreads();
-
-  // ---- phase 2: time, acceptance and graph of every candidate ---------------------------------
-  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
-    const int c = c0 + tid;
-    bool accepted = false;
-    if (c < C) {
-      const int lb = S.clb[c];
-      const int i = c - S.cbase[lb];
-      const int b = b0 + lb;
-      const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + 1u + (uint32_t)i, key0, key1);
-      double tc = tlo + (u53(x.x, x.y) - 1.0 / 9007199254740992.0) * width;
-      if (!(tc < thi)) tc = tlo;
-      const int k0 = bsx[2 * lb], k1 = bsx[2 * lb + 1];
-      int par = S.kspin[k0] ^ S.kspin[k1];   // operators on this bond sit in both lists and cancel
-      for (int f = S.foff[k0]; f < S.foff[k0 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
-      for (int f = S.foff[k1]; f < S.foff[k1 + 1]; ++f) par ^= (int)(S.ftime[f] < tc);
-      const float4 pr = d.bond_p[b];
-      const float u = u24(x.z);
-      int g = -1;
-      if (par) { if (u < pr.x) g = 0; else if (u < pr.y) g = 2; }
-      else     { if (u < pr.z) g = 1; else if (u < pr.w) g = 3; }
-      S.ctime[c] = tc;
-      S.cacc[c] = (g >= 0) ? (uint8_t)(1 | (g << 1)) : (uint8_t)0;
-      accepted = g >= 0;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, accepted);   // compact the accepted candidates
-    int base = 0;
-    if (lane == 0 && m) base = atomicAdd(&s_cnt[1], __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (accepted) S.alist[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)c;
-  }
-  __syncthreads();
-
-  // ---- phase 3: new bucket sizes -> offsets -------------------------------------------------
-  int cnt = 0;
-  if (tid < nb) {
-    int nacc = 0;
-    for (int i = 0; i < K; ++i) nacc += S.cacc[cb + i] & 1;
-    cnt = S.nkb[tid] + nacc;
-  }
-  int total;
-  const int off = block_exscan(cnt, &total, s_scan);
-  if (total > d.cap) {
-    if (tid == 0) { atomicOr(d.d_err, LQ_ERR_PAGE_FULL); d.pcount[dst][p] = 0; }
-    if (tid <= nb) bo[tid] = 0;
-    return;
-  }
-  if (tid < nb) { bo[tid] = (uint16_t)off; S.noff[tid] = off; }
-  if (tid == nb) { bo[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
-  __syncthreads();
-
-  // ---- phase 4: scatter into the compacted new page ------------------------------------------
-  double* wt = d.time[dst] + p * (size_t)d.cap;
-  uint32_t* wi = d.info[dst] + p * (size_t)d.cap;
-  const int n_acc = s_cnt[1], n_keep = s_cnt[0];
-  for (int ia = tid; ia < n_acc; ia += blockDim.x) {
-    const int c = S.alist[ia];
-    const uint32_t acc = S.cacc[c];
-    const int lb = S.clb[c];
-    const double tc = S.ctime[c];
-    int rank = 0;
-    for (int j = S.off[lb]; j < S.off[lb + 1]; ++j)      // kept operators come first on ties
-      rank += (int)(S.info[j] & LQ_INFO_OFFDIAG) & (int)(S.time[j] <= tc);
-    const int c0 = S.cbase[lb], c1 = S.cbase[lb + 1];
-    for (int k = c0; k < c1; ++k)
-      rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] < tc || (S.ctime[k] == tc && k < c));
-    const int pos = S.noff[lb] + rank;
-    wt[pos] = tc;
-    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((acc >> 1) << LQ_INFO_GSHIFT);
-  }
-  for (int ik = tid; ik < n_keep; ik += blockDim.x) {
-    const int j = S.klist[ik];
-    const uint32_t inf = S.info[j];
-    const int lb = (int)(inf >> LQ_INFO_LBSHIFT);
-    const double tt = S.time[j];
-    const int o0 = S.off[lb];
-    int rank = 0;
-    for (int k = o0; k < j; ++k) rank += (int)(S.info[k] & LQ_INFO_OFFDIAG);
-    const int c0 = S.cbase[lb], c1 = S.cbase[lb + 1];
-    for (int k = c0; k < c1; ++k) rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] < tt);
-    uint32_t g = 0;
-    const int b = b0 + lb;
-    const float q0 = d.bond_q[b];
-    if (q0 < 1.0f) {  // graph_impl.h:324-327 choose_offdiagonal
-      const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)(j - o0), key0, key1);
-      g = (u24(x.x) < q0) ? 0u : 1u;
-    }
-    const int pos = S.noff[lb] + rank;
-    wt[pos] = tt;
-    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG;
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -633,15 +411,12 @@ k_union_local(Dev d, int buf) {
   const node_t lo = upper_node(d, idx0, 0), hi = lo + (node_t)nn;
   for (int i = threadIdx.x; i < nn; i += blockDim.x) s_par[i] = (uint32_t)i;
   __syncthreads();
-  uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
+  const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int idx = idx0 + j;
     const uint32_t l0 = d.low0[idx], l1 = d.low1[idx];
     const node_t p0 = l0 & 0x7fffffffu, p1 = l1 & 0x7fffffffu;
-    uint32_t inf = gi[j];
-    inf = (inf & ~(LQ_INFO_C0 | LQ_INFO_C1)) | ((l0 >> 31) ? LQ_INFO_C0 : 0u) | ((l1 >> 31) ? LQ_INFO_C1 : 0u);
-    gi[j] = inf;
-    const int g = (inf >> LQ_INFO_GSHIFT) & 3;
+    const int g = (gi[j] >> LQ_INFO_GSHIFT) & 3;
     const node_t u0 = upper_node(d, idx, 0);
     if (d.npo == 2) {
       const node_t u1 = upper_node(d, idx, 1);
@@ -698,29 +473,43 @@ __global__ void k_close(Dev d) {
 // flags of 32 consecutive nodes are one ballot word, ranks come from a scan over the words, and
 // copy_id (:338-343) becomes one gather per node.  parent[] ends up holding the cluster id.
 // ------------------------------------------------------------------------------------------
-__global__ void k_compress(Dev d, size_t nwords_cap) {
-  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#define LQ_NPT 4  /* nodes per thread: independent pointer chases in flight */
+__global__ void __launch_bounds__(256)
+k_compress(Dev d, size_t nwords_cap) {
   const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
   const size_t nwords = (nn + 31) >> 5;
-  if ((x >> 5) >= nwords_cap) return;
-  if ((x >> 5) >= nwords) {  // whole warp beyond the live nodes: keep the scan input clean
-    if ((threadIdx.x & 31) == 0) { d.bitmap[x >> 5] = 0u; d.wcount[x >> 5] = 0u; }
-    return;
+  const size_t base = (size_t)blockIdx.x * (256 * LQ_NPT) + threadIdx.x;
+  // all unions are done: plain (L1-allocating) loads are safe here and neighbouring nodes mostly
+  // chase to the same few roots
+  node_t r[LQ_NPT], pr[LQ_NPT];
+#pragma unroll
+  for (int k = 0; k < LQ_NPT; ++k) {
+    const size_t x = base + (size_t)k * 256;
+    r[k] = (node_t)x;
+    pr[k] = (x < nn) ? d.parent[x] : (node_t)x;
   }
-  bool isroot = false;
-  if (x < nn) {
-    // all unions are done: plain (L1-allocating) loads are safe here and neighbouring nodes
-    // mostly chase to the same few roots
-    node_t r = (node_t)x;
-    node_t pr = d.parent[r];
-    while (pr != r) { r = pr; pr = d.parent[r]; }
-    d.parent[x] = r;
-    isroot = (r == (node_t)x);
+  bool any = true;
+  while (any) {
+    any = false;
+#pragma unroll
+    for (int k = 0; k < LQ_NPT; ++k)
+      if (pr[k] != r[k]) { r[k] = pr[k]; pr[k] = d.parent[r[k]]; any = true; }
   }
-  const uint32_t word = __ballot_sync(0xffffffffu, isroot);
-  if ((threadIdx.x & 31) == 0) {
-    d.bitmap[x >> 5] = word;
-    d.wcount[x >> 5] = (uint32_t)__popc(word);
+#pragma unroll
+  for (int k = 0; k < LQ_NPT; ++k) {
+    const size_t x = base + (size_t)k * 256;
+    const size_t w = x >> 5;
+    if (w >= nwords_cap) continue;   // warp-uniform
+    bool isroot = false;
+    if (x < nn) {
+      if (r[k] != (node_t)x) d.parent[x] = r[k];
+      isroot = (r[k] == (node_t)x);
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, isroot);
+    if ((threadIdx.x & 31) == 0) {   // words beyond the live nodes are cleared: the scan input stays clean
+      d.bitmap[w] = (w < nwords) ? word : 0u;
+      d.wcount[w] = (w < nwords) ? (uint32_t)__popc(word) : 0u;
+    }
   }
 }
 
@@ -728,16 +517,29 @@ __device__ __forceinline__ uint32_t cid_of_root(const Dev& d, node_t r) {
   return d.wbase[r >> 5] + (uint32_t)__popc(d.bitmap[r >> 5] & ((1u << (r & 31)) - 1u));
 }
 
-__global__ void k_relabel(Dev d) {
-  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+k_relabel(Dev d) {
   const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
-  if (x == 0) {
+  const size_t base = (size_t)blockIdx.x * (256 * LQ_NPT) + threadIdx.x;
+  if (base == 0) {
     // clusters rooted at a site node come first (site ids are the smallest node ids)
     d.d_nc[1] = cid_of_root(d, (node_t)d.N);
     if ((long long)d.d_nc[0] > d.nccap) atomicOr(d.d_err, LQ_ERR_CLUSTER_FULL);
   }
-  if (x >= nn) return;
-  d.parent[x] = cid_of_root(d, d.parent[x]);
+  node_t r[LQ_NPT];
+  uint32_t wb[LQ_NPT], bm[LQ_NPT];
+#pragma unroll
+  for (int k = 0; k < LQ_NPT; ++k) {
+    const size_t x = base + (size_t)k * 256;
+    r[k] = (x < nn) ? d.parent[x] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < LQ_NPT; ++k) { wb[k] = d.wbase[r[k] >> 5]; bm[k] = d.bitmap[r[k] >> 5]; }
+#pragma unroll
+  for (int k = 0; k < LQ_NPT; ++k) {
+    const size_t x = base + (size_t)k * 256;
+    if (x < nn) d.parent[x] = wb[k] + (uint32_t)__popc(bm[k] & ((1u << (r[k] & 31)) - 1u));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -811,50 +613,79 @@ k_flipbits(Dev d, const StepParams* __restrict__ sp) {
 // FLIP: also apply the cluster flip to the operator (K6, path_integral.C:815-819): its type changes
 // iff the cluster arriving from below on the source side and the one leaving upwards are flipped
 // differently -- the two cluster ids are already in registers here.
+#define LQ_EST_U 1  /* operators per thread and iteration: independent gathers in flight */
 template <bool FLIP>
 __global__ void __launch_bounds__(256)
 k_estimate(Dev d, int buf) {
   extern __shared__ unsigned char s_raw[];
   EstHash* h = (EstHash*)s_raw;
+  signed char* s_gg = (signed char*)(h + 1);   // [2*nbmax] gauge of the two ends of every own bond
   for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
     h->key[i] = 0xffffffffu;
 #pragma unroll
     for (int f = 0; f < 4; ++f) { h->lo[f][i] = 0u; h->hi[f][i] = 0u; }
   }
-  __syncthreads();
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl);
-  const int b0 = d.bond_base[t];
+  const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    s_gg[2 * i] = d.gauge[d.bond_s0[b0 + i]];
+    s_gg[2 * i + 1] = d.gauge[d.bond_s1[b0 + i]];
+  }
+  __syncthreads();
   const int n = d.pcount[buf][p];
   const int idx0 = d.nbase[p];
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const uint32_t inf = d.info[buf][p * (size_t)d.cap + j];
-    const int g = (inf >> LQ_INFO_GSHIFT) & 3;
-    if (g & 2) continue;  // frozen graphs: skipped by the estimators (path_integral.C:692), never flip
-    const double tt = d.time[buf][p * (size_t)d.cap + j];
-    const long long q = time_to_fx(tt);
-    const int b = b0 + (int)(inf >> LQ_INFO_LBSHIFT);
-    const int g0 = d.gauge[d.bond_s0[b]], g1 = d.gauge[d.bond_s1[b]];
-    const int c0 = (inf & LQ_INFO_C0) ? 1 : 0, c1 = (inf & LQ_INFO_C1) ? 1 : 0;
-    const int off = (int)(inf & LQ_INFO_OFFDIAG);
-    const int m0 = 1 - 2 * c0, m1 = 1 - 2 * c1;              // 2(1/2-c) below
-    const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
-    const int idx = idx0 + j;
-    const uint32_t cl0 = d.parent[d.low0[idx] & 0x7fffffffu];
-    const uint32_t cu0 = d.parent[upper_node(d, idx, 0)];
-    if (FLIP && ((flip_of(d, cl0) ^ flip_of(d, cu0)) & 1u))
-      d.info[buf][p * (size_t)d.cap + j] = inf ^ LQ_INFO_OFFDIAG;
-    if (d.npo == 1) {
-      // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
-      est_hash_add(d, h, cl0, 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
-      est_hash_add(d, h, cu0, -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
-    } else {
-      const uint32_t cl1 = d.parent[d.low1[idx] & 0x7fffffffu];
-      const uint32_t cu1 = d.parent[upper_node(d, idx, 1)];
-      est_hash_add(d, h, cl0, q, q * m0, q * g0, q * g0 * m0);
-      est_hash_add(d, h, cl1, q, q * m1, q * g1, q * g1 * m1);
-      est_hash_add(d, h, cu0, -q, -q * n0, -q * g0, -q * g0 * n0);
-      est_hash_add(d, h, cu1, -q, -q * n1, -q * g1, -q * g1 * n1);
+  uint32_t* ginfo = d.info[buf] + p * (size_t)d.cap;
+  const double* gtime = d.time[buf] + p * (size_t)d.cap;
+  for (int j0 = threadIdx.x; j0 < n; j0 += blockDim.x * LQ_EST_U) {
+    uint32_t inf[LQ_EST_U], l0[LQ_EST_U], l1[LQ_EST_U], cl0[LQ_EST_U], cu0[LQ_EST_U], cl1[LQ_EST_U], cu1[LQ_EST_U];
+    double tt[LQ_EST_U];
+    bool act[LQ_EST_U];
+    // all loads of the LQ_EST_U operators are issued before the first use
+#pragma unroll
+    for (int u = 0; u < LQ_EST_U; ++u) {
+      const int j = j0 + u * (int)blockDim.x;
+      act[u] = j < n;
+      const int jj = act[u] ? j : j0;
+      inf[u] = ginfo[jj];
+      tt[u] = gtime[jj];
+      l0[u] = d.low0[idx0 + jj];
+      l1[u] = d.low1[idx0 + jj];
+    }
+#pragma unroll
+    for (int u = 0; u < LQ_EST_U; ++u) {
+      const int idx = idx0 + (act[u] ? j0 + u * (int)blockDim.x : j0);
+      cl0[u] = d.parent[l0[u] & 0x7fffffffu];
+      cu0[u] = d.parent[upper_node(d, idx, 0)];
+      if (d.npo == 2) {
+        cl1[u] = d.parent[l1[u] & 0x7fffffffu];
+        cu1[u] = d.parent[upper_node(d, idx, 1)];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LQ_EST_U; ++u) {
+      if (!act[u]) continue;
+      const int g = (inf[u] >> LQ_INFO_GSHIFT) & 3;
+      if (g & 2) continue;  // frozen graphs: skipped by the estimators (path_integral.C:692), never flip
+      const int j = j0 + u * (int)blockDim.x;
+      const long long q = time_to_fx(tt[u]);
+      const int lb = (int)(inf[u] >> LQ_INFO_LBSHIFT);
+      const int g0 = s_gg[2 * lb], g1 = s_gg[2 * lb + 1];
+      const int c0 = (int)(l0[u] >> 31), c1 = (int)(l1[u] >> 31);   // spins below (written by the walk)
+      const int off = (int)(inf[u] & LQ_INFO_OFFDIAG);
+      const int m0 = 1 - 2 * c0, m1 = 1 - 2 * c1;              // 2(1/2-c) below
+      const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
+      if (FLIP && ((flip_of(d, cl0[u]) ^ flip_of(d, cu0[u])) & 1u)) ginfo[j] = inf[u] ^ LQ_INFO_OFFDIAG;
+      if (d.npo == 1) {
+        // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
+        est_hash_add(d, h, cl0[u], 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
+        est_hash_add(d, h, cu0[u], -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
+      } else {
+        est_hash_add(d, h, cl0[u], q, q * m0, q * g0, q * g0 * m0);
+        est_hash_add(d, h, cl1[u], q, q * m1, q * g1, q * g1 * m1);
+        est_hash_add(d, h, cu0[u], -q, -q * n0, -q * g0, -q * g0 * n0);
+        est_hash_add(d, h, cu1[u], -q, -q * n1, -q * g1, -q * g1 * n1);
+      }
     }
   }
   __syncthreads();
