@@ -31,7 +31,8 @@ class LqLattice(C.Structure):
 
 class LqModel(C.Structure):
     _fields_ = [("bond_weights", C.POINTER(C.c_double)), ("uniform_weights", C.c_double * 4),
-                ("energy_offset", C.c_double)]
+                ("energy_offset", C.c_double), ("site_weights", C.POINTER(C.c_double)),
+                ("uniform_site_weight", C.c_double)]
 
 
 class LqOptions(C.Structure):
@@ -49,7 +50,7 @@ OP_DTYPE = np.dtype([("time", "<f8"), ("loc", "<i4"), ("type", "<i4")])
 
 COLLECTOR_FIELDS = ["nop", "nc", "noc", "ene",
                     "umag0", "usize2", "umag2", "usize4", "umag4", "usize", "umag",
-                    "smag0", "ssize2", "smag2", "ssize4", "smag4", "ssize", "smag"]
+                    "smag0", "ssize2", "smag2", "ssize4", "smag4", "ssize", "smag", "tlen"]
 
 
 class LqCollector(C.Structure):
@@ -192,7 +193,7 @@ class Engine:
 
     def __init__(self, lattice, beta, weights=(0.5, 0.0, 0.0, 0.0), energy_offset=None, seed=29833,
                  device=0, tile_sites=0, window_ops=0.0, reserve=0.0, cluster_reserve=0.0,
-                 rank=0, nranks=1, timers=False, bond_weights=None):
+                 rank=0, nranks=1, timers=False, bond_weights=None, site_weight=0.0, site_weights=None):
         self.lattice = lattice
         self.N = int(lattice["num_sites"])
         self._src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
@@ -219,9 +220,21 @@ class Engine:
         else:
             mod.bond_weights = None
             wsum = float(sum(weights)) * self.B
+        # site graph weights v0 = |Hx|/2 (weight_impl.h:62-88); their offsets (= v0 each) join the
+        # energy offset like the bond offsets do
+        self._sw = None
+        if site_weights is not None:
+            self._sw = np.ascontiguousarray(site_weights, dtype=np.float64).reshape(-1)
+            assert self._sw.size == self.N
+            mod.site_weights = self._sw.ctypes.data_as(C.POINTER(C.c_double))
+            swsum = float(self._sw.sum())
+        else:
+            mod.site_weights = None
+            swsum = float(site_weight) * self.N
+        mod.uniform_site_weight = float(site_weight)
         mod.uniform_weights = (C.c_double * 4)(*weights)
         # energy_offset = sum of bond offsets = sum of weights / 2 (weight_impl.h:187)
-        mod.energy_offset = wsum / 2 if energy_offset is None else energy_offset
+        mod.energy_offset = wsum / 2 + swsum if energy_offset is None else energy_offset
         self.energy_offset = mod.energy_offset
         opt = LqOptions(seed=seed, device=device, tile_sites=tile_sites, window_ops=window_ops,
                         reserve=reserve, cluster_reserve=cluster_reserve, rank=rank,
@@ -340,4 +353,7 @@ def observables(coll, beta, num_sites, sse=False):
     o["Staggered Susceptibility"] = beta * coll["smag"] / vol
     o["Generalized Staggered Magnetization^2"] = coll["ssize2"]
     o["Generalized Staggered Susceptibility"] = beta * coll["ssize"] / vol
+    # transmag.h:106-109
+    o["Transverse Magnetization"] = 0.5 * coll["tlen"]
+    o["Transverse Magnetization Density"] = 0.5 * coll["tlen"] / vol
     return o

@@ -19,10 +19,12 @@ static const node_t NODE_NONE = 0xffffffffu;
 // info word of an operator (mirrors looper/operator.h type_ in the low bits)
 //   bit 0      offdiagonal            (local_operator_type::offdiagonal, operator.h:44)
 //   bits 2..3  graph type g           (type_ >> 2, operator.h:76; graph_impl.h:93-103)
+//   bit 4      site operator (the "bond" is a pseudo-bond with one end, see lq_engine.cu)
 //   (the spins below the operator travel in bit 31 of low0 / low1, written by the walk)
 //   bits 8..   local bond index inside the owning tile
 #define LQ_INFO_OFFDIAG 1u
 #define LQ_INFO_GSHIFT 2
+#define LQ_INFO_SITE 16u   /* site operator (location_impl.h:37 is_site): cuts the world line */
 #define LQ_INFO_LBSHIFT 8
 
 // error bits raised by kernels (sticky, read back by the host after a sweep)
@@ -50,6 +52,8 @@ struct Dev {
   int w0, Wl;       // this rank owns windows [w0, w0+Wl)
   int cap;          // page capacity (operators)
   int npo;          // nodes per operator (1: graphs {0,2,3}; 2: cross graph present)
+  int ug;           // windows per union group (k_union_local / k_union_global)
+  int has_site;     // the model has site graphs: bonds with bond_s1 < 0 are site pseudo-bonds
   int rank, nranks;
   const int* bond_s0;    // [B] source site
   const int* bond_s1;    // [B] target site
@@ -103,6 +107,7 @@ struct Dev {
   long long* est;  // [4][nccap] usize, umag, ssize, smag in half units of LQ_FX
   int* est0;       // [4][N]     usize0, umag0, ssize0, smag0 in half units
   uint32_t* flipw; // [nccap/32 + 1] flip decision per cluster id, packed
+  uint32_t* openw; // [nccap/32 + 1] cluster is cut by a site operator (has_site only), packed
   long long ncap;   // operator arena (= P*cap)
   long long nccap;  // cluster arena
   // ---- scalars on device ----

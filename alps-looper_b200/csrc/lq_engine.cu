@@ -78,8 +78,10 @@ struct Partition {
   std::vector<int> sst;                   // (local bucket << 1 | side)
 };
 
-void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
-  const int N = L.num_sites, B = L.num_bonds;
+// src/dst: end sites of the B internal "bonds"; dst < 0 marks the pseudo-bond that carries the site
+// operators of src (graph_impl.h:67-87): it has one end only.
+void make_partition(const lq_lattice& L, int B, const int* Lsrc, const int* Ldst, int tile_sites, Partition& P) {
+  const int N = L.num_sites;
   P.N = N;
   P.B = B;
   std::vector<int> tile_of(N);
@@ -131,7 +133,7 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
   P.bond_i2e.resize(B);
   std::iota(P.bond_i2e.begin(), P.bond_i2e.end(), 0);
   std::stable_sort(P.bond_i2e.begin(), P.bond_i2e.end(),
-                   [&](int a, int b) { return tile_of[L.src[a]] < tile_of[L.src[b]]; });
+                   [&](int a, int b) { return tile_of[Lsrc[a]] < tile_of[Lsrc[b]]; });
   P.bond_e2i.resize(B);
   P.bond_s0.resize(B);
   P.bond_s1.resize(B);
@@ -140,9 +142,9 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
   for (int i = 0; i < B; ++i) {
     const int e = P.bond_i2e[i];
     P.bond_e2i[e] = i;
-    P.bond_s0[i] = P.site_e2i[L.src[e]];
-    P.bond_s1[i] = P.site_e2i[L.dst[e]];
-    P.bond_tile[i] = tile_of[L.src[e]];
+    P.bond_s0[i] = P.site_e2i[Lsrc[e]];
+    P.bond_s1[i] = Ldst[e] >= 0 ? P.site_e2i[Ldst[e]] : -1;
+    P.bond_tile[i] = tile_of[Lsrc[e]];
     P.bond_base[P.bond_tile[i] + 1]++;
   }
   P.nbmax = 0;
@@ -152,13 +154,13 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
   }
   // adjacency
   P.adj_off.assign(N + 1, 0);
-  for (int i = 0; i < B; ++i) { P.adj_off[P.bond_s0[i] + 1]++; P.adj_off[P.bond_s1[i] + 1]++; }
+  for (int i = 0; i < B; ++i) { P.adj_off[P.bond_s0[i] + 1]++; if (P.bond_s1[i] >= 0) P.adj_off[P.bond_s1[i] + 1]++; }
   for (int s = 0; s < N; ++s) P.adj_off[s + 1] += P.adj_off[s];
-  P.adj.resize(2 * (size_t)B);
+  P.adj.resize((size_t)P.adj_off[N]);
   std::vector<int> fill(P.adj_off.begin(), P.adj_off.end() - 1);
   for (int i = 0; i < B; ++i) {
     P.adj[fill[P.bond_s0[i]]++] = (i << 1) | 0;
-    P.adj[fill[P.bond_s1[i]]++] = (i << 1) | 1;
+    if (P.bond_s1[i] >= 0) P.adj[fill[P.bond_s1[i]]++] = (i << 1) | 1;
   }
   // ---- halos and stencils -------------------------------------------------------------------
   // "K-sites" of a tile = its own sites followed by the far end sites of its owned bonds that lie
@@ -183,6 +185,7 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
     for (int lb = 0; lb < nb; ++lb)
       for (int side = 0; side < 2; ++side) {
         const int sg = side ? P.bond_s1[b0 + lb] : P.bond_s0[b0 + lb];
+        if (sg < 0) { bs.push_back(-1); continue; }
         if (lsite[sg] < 0) { lsite[sg] = ns + (int)hsites.size(); hsites.push_back(sg); }
         bs.push_back(lsite[sg]);
       }
@@ -201,7 +204,7 @@ void make_partition(const lq_lattice& L, int tile_sites, Partition& P) {
     }
     for (int h : halo) {  // K-sites at the two ends of the halo buckets (-1: not a K-site)
       bs.push_back(lsite[P.bond_s0[h]]);
-      bs.push_back(lsite[P.bond_s1[h]]);
+      bs.push_back(P.bond_s1[h] >= 0 ? lsite[P.bond_s1[h]] : -1);
     }
     for (int lb = 0; lb < nb; ++lb) local[b0 + lb] = -1;
     for (int h : halo) local[h] = -1;
@@ -263,7 +266,9 @@ struct lq_engine {
   std::vector<signed char> gauge_e;
   double energy_offset = 0, beta = 1;
   lq_options opt{};
-  int W = 1, Wl = 1, w0 = 0, cap = 0, tpb = 32, npo = 1;
+  int W = 1, Wl = 1, w0 = 0, cap = 0, tpb = 32, npo = 1, ug = 1;
+  int Breal = 0;          // bonds of the caller's lattice; internal bonds Breal.. are site pseudo-bonds
+  bool has_site = false;
   size_t P = 0;
   long long ncap = 0, nccap = 0;
   size_t nwords_cap = 0, device_bytes = 0;
@@ -301,7 +306,7 @@ struct lq_engine {
   DBuf<uint32_t> info[2], parent, low0, low1, bitmap, wcount, wbase, scan_tmp, d_nc, curW, labels;
   DBuf<uint16_t> boff[2];
   DBuf<uint8_t> spinW;
-  DBuf<uint32_t> flipw;
+  DBuf<uint32_t> flipw, openw;
   DBuf<long long> est;
   DBuf<int> est0;
   double* h_out = nullptr;  // pinned
@@ -358,6 +363,26 @@ struct lq_engine {
         if (!(v >= 0)) fail(LQ_E_INVALID, "negative graph weight");
         weights[4 * (size_t)b + g] = v;
       }
+    // site graphs (weight_impl.h:62-88: v0 = |Hx|/2): every site gets a one-ended pseudo-bond
+    // B + s behind the real bonds; its candidates are always accepted (graph_impl.h:69)
+    Breal = L.num_bonds;
+    has_site = false;
+    std::vector<int> xsrc(L.src, L.src + L.num_bonds), xdst(L.dst, L.dst + L.num_bonds);
+    {
+      std::vector<double> sw(L.num_sites, M.uniform_site_weight);
+      if (M.site_weights) sw.assign(M.site_weights, M.site_weights + L.num_sites);
+      for (double v : sw) {
+        if (!(v >= 0)) fail(LQ_E_INVALID, "negative site graph weight");
+        if (v > 0) has_site = true;
+      }
+      if (has_site)
+        for (int s = 0; s < L.num_sites; ++s) {
+          xsrc.push_back(s);
+          xdst.push_back(-1);
+          weights.push_back(sw[s]);
+          weights.push_back(0); weights.push_back(0); weights.push_back(0);
+        }
+    }
     gauge_e.assign(L.num_sites, 0);
     if (L.gauge)
       for (int s = 0; s < L.num_sites; ++s) gauge_e[s] = (signed char)(L.gauge[s] > 0 ? 1 : (L.gauge[s] < 0 ? -1 : 0));
@@ -373,7 +398,7 @@ struct lq_engine {
     sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 
-    make_partition(L, opt.tile_sites, part);
+    make_partition(L, (int)xsrc.size(), xsrc.data(), xdst.data(), opt.tile_sites, part);
     if (part.nbmax + 1 > 1024)
       fail(LQ_E_INVALID, "tile owns more than 1023 bonds: lower lq_options.tile_sites");
     if (part.hmax > 1024)
@@ -491,8 +516,15 @@ struct lq_engine {
       CK(cudaFuncSetAttribute(lq::k_diag_update<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_diag_update<576>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       CK(cudaFuncSetAttribute(lq::k_diag_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      // union groups: consecutive windows of a tile unified in one shared-memory union-find
+      // (measured at 512x512 beta=128: groups of 6 windows make the two union kernels 15 % slower
+      // than single pages -- deeper shared-memory trees, fewer CTAs; LQ_UG overrides for experiments)
+      ug = 1;
+      if (getenv("LQ_UG")) ug = std::max(1, atoi(getenv("LQ_UG")));
+      ug = (int)std::min<size_t>((size_t)ug, std::max<size_t>(1, (96 * 1024) / ((size_t)npo * cap * sizeof(uint32_t))));
+      ug = std::min(ug, Wl);
       CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)((size_t)npo * cap * sizeof(uint32_t))));
+                              (int)((size_t)ug * npo * cap * sizeof(uint32_t))));
       walk_fn = pick_walk();
       CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
     }
@@ -524,6 +556,8 @@ struct lq_engine {
     est.alloc(4 * (size_t)nccap, tb);
     est0.alloc(4 * (size_t)N, tb);
     flipw.alloc((size_t)nccap / 32 + 2, tb);
+    openw.alloc(has_site ? (size_t)nccap / 32 + 2 : 1, tb);
+    CK(cudaMemset(openw.p, 0, openw.n * sizeof(uint32_t)));
     nblk_collect = std::min<size_t>(((size_t)nccap + 255) / 256, (size_t)sm_count * 8);
     partial.alloc(nblk_collect * LQ_NSUM, tb);
     if (opt.nranks > 1) {
@@ -534,7 +568,7 @@ struct lq_engine {
       mr_gparent.alloc(g2, tb);
       mr_gused.alloc(g2, tb);
       mr_gbitmap.alloc(gw, tb); mr_gwcount.alloc(gw, tb); mr_gwbase.alloc(gw + 1, tb);
-      mr_gest.alloc(g2 * 8, tb);
+      mr_gest.alloc(g2 * LQ_GEST, tb);
       mr_dg.alloc(4, tb);
       mr_rankvec.alloc(32, tb); mr_allvec.alloc(32 * (size_t)opt.nranks, tb); mr_gsum.alloc(16, tb);
       CK(cudaMemset(mr_topmin.p, 0xff, mr_topmin.n * sizeof(uint32_t)));
@@ -555,7 +589,7 @@ struct lq_engine {
 
   void fill_dev() {
     d.N = part.N; d.B = part.B; d.T = part.T; d.nbmax = part.nbmax;
-    d.W = W; d.w0 = w0; d.Wl = Wl; d.cap = cap; d.npo = npo;
+    d.W = W; d.w0 = w0; d.Wl = Wl; d.cap = cap; d.npo = npo; d.ug = ug; d.has_site = has_site ? 1 : 0;
     d.rank = opt.rank; d.nranks = opt.nranks;
     d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_tile = bond_tile.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
@@ -571,7 +605,7 @@ struct lq_engine {
     }
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
-    d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.ncap = ncap; d.nccap = nccap;
+    d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p; d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
     d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
   }
@@ -636,8 +670,9 @@ struct lq_engine {
     {
       Section s(this, 7);
       walk_fn<<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
-      lq::k_union_local<<<(unsigned)P, 256, (size_t)npo * cap * sizeof(uint32_t), stream>>>(d, cur);
-      lq::k_union_global<<<(unsigned)P, 256, 0, stream>>>(d, cur);
+      const unsigned ngroups = (unsigned)((size_t)part.T * ((Wl + ug - 1) / ug));
+      lq::k_union_local<<<ngroups, 256, (size_t)ug * npo * cap * sizeof(uint32_t), stream>>>(d, cur);
+      lq::k_union_global<<<ngroups, 256, 0, stream>>>(d, cur);
       launches += 3;
     }
     {
@@ -709,7 +744,7 @@ struct lq_engine {
     CK(cudaMemcpyAsync(h_mr, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     const int64_t ngc = h_mr[0];
-    if (ngc > 0) comm_check(comm.all_reduce_i64(comm.ctx, mr.gest, ngc * 8, stream), "all_reduce(open-cluster sums)");
+    if (ngc > 0) comm_check(comm.all_reduce_i64(comm.ctx, mr.gest, ngc * LQ_GEST, stream), "all_reduce(open-cluster sums)");
     lq::k_mr_gcollect<<<1, 256, 0, stream>>>(d, mr);
     lq::k_mr_rankvec<<<1, 32, 0, stream>>>(d, mr, out_slot);
     launches += 2;
@@ -771,7 +806,7 @@ struct lq_engine {
     c->usize = o[5]; c->umag = o[6];
     c->smag0 = o[7]; c->ssize2 = o[8]; c->smag2 = o[9]; c->ssize4 = o[10]; c->smag4 = o[11];
     c->ssize = o[12]; c->smag = o[13];
-    c->nc = o[14]; c->nop = o[15]; c->noc = o[17];
+    c->nc = o[14]; c->nop = o[15]; c->noc = o[17]; c->tlen = o[18];
     c->ene = energy_offset - c->nop / beta;  // path_integral.C:851
   }
 
@@ -818,26 +853,30 @@ struct lq_engine {
     std::vector<uint8_t> par((size_t)(W + 1) * N, 0);
     double tprev = -1;
     for (int64_t k = 0; k < n; ++k) {
-      if (!(ops[k].loc & 1)) fail(LQ_E_UNSUPPORTED, "site operators are not supported yet");
-      const int be = ops[k].loc >> 1;
-      if (be < 0 || be >= B) fail(LQ_E_INVALID, "operator bond out of range");
+      const bool is_site = !(ops[k].loc & 1);   // location_impl.h:37: loc = pos << 1 | is_bond
+      if (is_site && !has_site) fail(LQ_E_INVALID, "site operator on a model without site graph weights");
+      const int pos = ops[k].loc >> 1;
+      if (pos < 0 || pos >= (is_site ? N : Breal)) fail(LQ_E_INVALID, "operator position out of range");
+      const int be = is_site ? Breal + pos : pos;
       const double t = ops[k].time;
       if (!(t >= 0 && t < 1)) fail(LQ_E_INVALID, "operator time outside [0,1)");
       if (t < tprev) fail(LQ_E_INVALID, "operators must be sorted by time");
       tprev = t;
       const int g = (ops[k].type >> 2) & 3;
       if (g == 1 && npo != 2) fail(LQ_E_INVALID, "cross graph on a model without v[1] weight");
+      if (is_site && g != 0) fail(LQ_E_INVALID, "site operators carry graph 0 (graph_impl.h:68)");
       const int bi = part.bond_e2i[be];
       const int w = window_of(t, W);
       if (ops[k].type & 1) {
         par[(size_t)(w + 1) * N + part.bond_s0[bi]] ^= 1;
-        par[(size_t)(w + 1) * N + part.bond_s1[bi]] ^= 1;
+        if (!is_site) par[(size_t)(w + 1) * N + part.bond_s1[bi]] ^= 1;
       }
       if (w < w0 || w >= w0 + Wl) continue;
       const int tl = part.bond_tile[bi];
       const int lb = bi - part.bond_base[tl];
       const size_t p = (size_t)tl * Wl + (w - w0);
-      const uint32_t inf = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)g << LQ_INFO_GSHIFT) | (uint32_t)(ops[k].type & 1);
+      const uint32_t inf = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)g << LQ_INFO_GSHIFT) |
+                           (uint32_t)(ops[k].type & 1) | (is_site ? LQ_INFO_SITE : 0u);
       buckets[p * part.nbmax + lb].push_back({t, inf});
     }
     std::vector<uint8_t> sw((size_t)(Wl + 1) * N);
@@ -916,7 +955,8 @@ struct lq_engine {
     if (ops)
       for (size_t k = 0; k < v.size(); ++k) {
         ops[k].time = v[k].time;
-        ops[k].loc = (part.bond_i2e[v[k].bi] << 1) | 1;
+        const int be = part.bond_i2e[v[k].bi];
+        ops[k].loc = be < Breal ? ((be << 1) | 1) : ((be - Breal) << 1);
         ops[k].type = (int32_t)(v[k].info & 0xf) & ~2;  // offdiag bit + graph bits
       }
     if (spins) {

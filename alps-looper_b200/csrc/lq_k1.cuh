@@ -277,7 +277,8 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
       rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] < tc || (S.ctime[k] == tc && k < c));
     const int pos = S.noff[lb] + rank;
     wt[pos] = tc;
-    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((acc >> 1) << LQ_INFO_GSHIFT);
+    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((acc >> 1) << LQ_INFO_GSHIFT) |
+              ((d.has_site && bsx[2 * lb + 1] < 0) ? LQ_INFO_SITE : 0u);
   }
   for (int ik = tid; ik < n_keep; ik += blockDim.x) {
     const int j = S.klist[ik];
@@ -298,7 +299,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
     }
     const int pos = S.noff[lb] + rank;
     wt[pos] = tt;
-    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG;
+    wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG | (inf & LQ_INFO_SITE);
   }
 }
 

@@ -361,7 +361,7 @@ k_walk(Dev d, int buf) {
 // ------------------------------------------------------------------------------------------
 // K2d: unions, in two levels (the chunk idea of looper/parallel.h applied inside one GPU: resolve
 // what is local to a time-slice tile in shared memory, send only its boundary to HBM).
-//  k_union_local   one CTA per page.  Edges whose two ends are operator nodes of THIS page are
+//  k_union_local   one CTA per group of pages.  Edges whose two ends are operator nodes of THIS group are
 //                  unified in a shared-memory union-find (same min-index hooking); every node of
 //                  the page is then written to parent[] already pointing at its page-local root,
 //                  so no separate initialisation pass and shorter global chains.
@@ -393,39 +393,52 @@ __device__ __forceinline__ void sm_union(uint32_t* par, uint32_t a, uint32_t b) 
   }
 }
 
-// edge (a, b) of the page whose node range is [lo, hi): local union if both ends are inside
-__device__ __forceinline__ void edge_local(uint32_t* par, node_t lo, node_t hi, node_t a, node_t b) {
-  if (a >= lo && a < hi && b >= lo && b < hi) sm_union(par, a - lo, b - lo);
-}
-__device__ __forceinline__ void edge_global(node_t* parent, node_t lo, node_t hi, node_t a, node_t b) {
-  if (!(a >= lo && a < hi && b >= lo && b < hi)) uf_union(parent, a, b);
+// edges of one operator (graph rules above); site graphs (graph_impl.h:79-86) cut the world line:
+// a new node and no union
+template <class F>
+__device__ __forceinline__ void op_edges(const Dev& d, uint32_t inf, int idx, node_t p0, node_t p1, F edge) {
+  const node_t u0 = upper_node(d, idx, 0);
+  if (inf & LQ_INFO_SITE) {   // (with two nodes per operator the spare one joins the new segment)
+    if (d.npo == 2) edge(u0, upper_node(d, idx, 1));
+    return;
+  }
+  const int g = (inf >> LQ_INFO_GSHIFT) & 3;
+  if (d.npo == 2) {
+    const node_t u1 = upper_node(d, idx, 1);
+    if (g == 0) { edge(p0, p1); edge(u0, u1); }
+    else if (g == 1) { edge(u0, p1); edge(u1, p0); }
+    else { edge(p0, p1); edge(u0, p0); edge(u1, p0); }
+  } else {
+    edge(p0, p1);
+    if (g & 2) edge(u0, p0);
+  }
 }
 
+// Both kernels run one CTA per GROUP of d.ug consecutive windows of one tile: the pages of a group
+// are consecutive, so their operator nodes form one contiguous range [lo, hi).  Grouping windows
+// makes the links that cross a window boundary (one per site and window) local as well.
 __global__ void __launch_bounds__(256)
 k_union_local(Dev d, int buf) {
   extern __shared__ uint32_t s_par[];
-  const size_t p = blockIdx.x;
-  const int n = d.pcount[buf][p];
-  const int idx0 = d.nbase[p];
-  const int nn = d.npo * n;                       // nodes of this page
-  const node_t lo = upper_node(d, idx0, 0), hi = lo + (node_t)nn;
+  const int ngw = (d.Wl + d.ug - 1) / d.ug;
+  const int t = blockIdx.x / ngw, w_first = (blockIdx.x % ngw) * d.ug;
+  const int w_last = min(w_first + d.ug, d.Wl);
+  const size_t p_first = (size_t)t * d.Wl + w_first, p_end = (size_t)t * d.Wl + w_last;
+  const int idx_lo = d.nbase[p_first], idx_hi = d.nbase[p_end];
+  const int nn = d.npo * (idx_hi - idx_lo);
+  const node_t lo = upper_node(d, idx_lo, 0), hi = lo + (node_t)nn;
   for (int i = threadIdx.x; i < nn; i += blockDim.x) s_par[i] = (uint32_t)i;
   __syncthreads();
-  const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const int idx = idx0 + j;
-    const uint32_t l0 = d.low0[idx], l1 = d.low1[idx];
-    const node_t p0 = l0 & 0x7fffffffu, p1 = l1 & 0x7fffffffu;
-    const int g = (gi[j] >> LQ_INFO_GSHIFT) & 3;
-    const node_t u0 = upper_node(d, idx, 0);
-    if (d.npo == 2) {
-      const node_t u1 = upper_node(d, idx, 1);
-      if (g == 0) { edge_local(s_par, lo, hi, p0, p1); edge_local(s_par, lo, hi, u0, u1); }
-      else if (g == 1) { edge_local(s_par, lo, hi, u0, p1); edge_local(s_par, lo, hi, u1, p0); }
-      else { edge_local(s_par, lo, hi, p0, p1); edge_local(s_par, lo, hi, u0, p0); edge_local(s_par, lo, hi, u1, p0); }
-    } else {
-      edge_local(s_par, lo, hi, p0, p1);
-      if (g & 2) edge_local(s_par, lo, hi, u0, p0);
+  for (size_t p = p_first; p < p_end; ++p) {
+    const int n = d.pcount[buf][p];
+    const int idx0 = d.nbase[p];
+    const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int idx = idx0 + j;
+      const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
+      op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
+        if (a >= lo && a < hi && b >= lo && b < hi) sm_union(s_par, a - lo, b - lo);
+      });
     }
   }
   __syncthreads();
@@ -438,24 +451,21 @@ k_union_local(Dev d, int buf) {
 
 __global__ void __launch_bounds__(256)
 k_union_global(Dev d, int buf) {
-  const size_t p = blockIdx.x;
-  const int n = d.pcount[buf][p];
-  const int idx0 = d.nbase[p];
-  const node_t lo = upper_node(d, idx0, 0), hi = lo + (node_t)(d.npo * n);
-  const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const int idx = idx0 + j;
-    const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
-    const int g = (gi[j] >> LQ_INFO_GSHIFT) & 3;
-    const node_t u0 = upper_node(d, idx, 0);
-    if (d.npo == 2) {
-      const node_t u1 = upper_node(d, idx, 1);
-      if (g == 0) { edge_global(d.parent, lo, hi, p0, p1); edge_global(d.parent, lo, hi, u0, u1); }
-      else if (g == 1) { edge_global(d.parent, lo, hi, u0, p1); edge_global(d.parent, lo, hi, u1, p0); }
-      else { edge_global(d.parent, lo, hi, p0, p1); edge_global(d.parent, lo, hi, u0, p0); edge_global(d.parent, lo, hi, u1, p0); }
-    } else {
-      edge_global(d.parent, lo, hi, p0, p1);
-      if (g & 2) edge_global(d.parent, lo, hi, u0, p0);
+  const int ngw = (d.Wl + d.ug - 1) / d.ug;
+  const int t = blockIdx.x / ngw, w_first = (blockIdx.x % ngw) * d.ug;
+  const int w_last = min(w_first + d.ug, d.Wl);
+  const size_t p_first = (size_t)t * d.Wl + w_first, p_end = (size_t)t * d.Wl + w_last;
+  const node_t lo = upper_node(d, d.nbase[p_first], 0), hi = upper_node(d, d.nbase[p_end], 0);
+  for (size_t p = p_first; p < p_end; ++p) {
+    const int n = d.pcount[buf][p];
+    const int idx0 = d.nbase[p];
+    const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const int idx = idx0 + j;
+      const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
+      op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
+        if (!(a >= lo && a < hi && b >= lo && b < hi)) uf_union(d.parent, a, b);
+      });
     }
   }
 }
@@ -607,6 +617,7 @@ k_flipbits(Dev d, const StepParams* __restrict__ sp) {
       word |= (x.x & 1u) << i | (x.y & 1u) << (i + 1) | (x.z & 1u) << (i + 2) | (x.w & 1u) << (i + 3);
     }
     d.flipw[w] = word;
+    if (d.has_site) d.openw[w] = 0u;   // "cut by a site operator" flags of this step (transmag.h:72-81)
   }
 }
 
@@ -630,7 +641,8 @@ k_estimate(Dev d, int buf) {
   const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     s_gg[2 * i] = d.gauge[d.bond_s0[b0 + i]];
-    s_gg[2 * i + 1] = d.gauge[d.bond_s1[b0 + i]];
+    const int s1 = d.bond_s1[b0 + i];
+    s_gg[2 * i + 1] = s1 >= 0 ? d.gauge[s1] : (signed char)0;
   }
   __syncthreads();
   const int n = d.pcount[buf][p];
@@ -657,7 +669,7 @@ k_estimate(Dev d, int buf) {
       const int idx = idx0 + (act[u] ? j0 + u * (int)blockDim.x : j0);
       cl0[u] = d.parent[l0[u] & 0x7fffffffu];
       cu0[u] = d.parent[upper_node(d, idx, 0)];
-      if (d.npo == 2) {
+      if (d.npo == 2 && !(inf[u] & LQ_INFO_SITE)) {   // (low1 of a site operator is never written)
         cl1[u] = d.parent[l1[u] & 0x7fffffffu];
         cu1[u] = d.parent[upper_node(d, idx, 1)];
       }
@@ -676,6 +688,15 @@ k_estimate(Dev d, int buf) {
       const int m0 = 1 - 2 * c0, m1 = 1 - 2 * c1;              // 2(1/2-c) below
       const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
       if (FLIP && ((flip_of(d, cl0[u]) ^ flip_of(d, cu0[u])) & 1u)) ginfo[j] = inf[u] ^ LQ_INFO_OFFDIAG;
+      if (inf[u] & LQ_INFO_SITE) {
+        // site operator: end_s below / begin_s above on its one site (path_integral.C:718-726);
+        // both clusters are cut open for the transverse magnetisation (transmag.h:72-81)
+        est_hash_add(d, h, cl0[u], q, q * m0, q * g0, q * g0 * m0);
+        est_hash_add(d, h, cu0[u], -q, -q * n0, -q * g0, -q * g0 * n0);
+        if ((long long)cl0[u] < d.nccap) atomicOr(d.openw + (cl0[u] >> 5), 1u << (cl0[u] & 31u));
+        if ((long long)cu0[u] < d.nccap) atomicOr(d.openw + (cu0[u] >> 5), 1u << (cu0[u] & 31u));
+        continue;
+      }
       if (d.npo == 1) {
         // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
         est_hash_add(d, h, cl0[u], 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
@@ -750,7 +771,9 @@ k_estimate_sites(Dev d) {
 // decision per cluster (path_integral.C:796-799).  Deterministic two-stage reduction
 // (warp shuffles -> per-CTA partials -> one CTA).  The cluster arena is zeroed on the way.
 // ------------------------------------------------------------------------------------------
-#define LQ_NSUM 14
+#define LQ_NSUM 15   /* 14 susceptibility sums (susceptibility.h:158-160) + transmag length (transmag.h:98) */
+#define LQ_NSUS 14
+#define LQ_GEST 10   /* int64 fields per global open cluster: 4 sums, 4 tau=0 sums, site-leg count, spare */
 __global__ void __launch_bounds__(256)
 k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
   __shared__ double s_red[8][LQ_NSUM];
@@ -783,6 +806,8 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
     v[5] += usize * usize; v[6] += umag * umag;
     v[7] += smag0; v[8] += e2; v[9] += g2; v[10] += e2 * e2; v[11] += g2 * g2;
     v[12] += ssize * ssize; v[13] += smag * smag;
+    // transmag.h:98-101: only clusters cut by a site operator count, with their total length = 2 usize
+    if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[14] += 2.0 * usize;
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -824,7 +849,7 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
   if (threadIdx.x < LQ_NSUM) {
     double x = 0;
     for (int w = 0; w < 8; ++w) x += s_red[w][threadIdx.x];
-    out[threadIdx.x] = x;
+    out[threadIdx.x < LQ_NSUS ? threadIdx.x : 18] = x;   // slot 18: transmag length
   }
   if (threadIdx.x == 0) {
     out[14] = (double)nc;
@@ -981,7 +1006,7 @@ __global__ void k_mr_gather(Dev d, MrDev m) {
     if ((long long)c >= d.nccap || m.topmin[c] != (uint32_t)s) continue;  // not the representative
     if (k == 1 && c < ncs) continue;  // bottom-touching clusters are handled through their bottom rep
     const uint32_t gid = global_cid(d, m, open_id(d, m, c));
-    unsigned long long* ge = (unsigned long long*)m.gest + (size_t)gid * 8;
+    unsigned long long* ge = (unsigned long long*)m.gest + (size_t)gid * LQ_GEST;
     for (int f = 0; f < 4; ++f) {
       const long long v = (long long)atomicExch((unsigned long long*)d.est + f * d.nccap + c, 0ull);
       if (v) atomicAdd(ge + f, (unsigned long long)v);
@@ -991,6 +1016,7 @@ __global__ void k_mr_gather(Dev d, MrDev m) {
         const int v = atomicExch(d.est0 + f * (size_t)d.N + c, 0);
         if (v) atomicAdd(ge + 4 + f, (unsigned long long)(long long)v);
       }
+    if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) atomicAdd(ge + 8, 1ull);
     atomicAdd(m.d_g + 1, 1u);
   }
 }
@@ -1034,13 +1060,15 @@ k_mr_gcollect(Dev d, MrDev m) {
   for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;
   const double sc = 0.5 / LQ_FX;
   for (size_t c = threadIdx.x; c < ngc; c += blockDim.x) {
-    long long* ge = m.gest + c * 8;
+    long long* ge = m.gest + c * LQ_GEST;
     const double usize = sc * i64_to_f64(ge[0]), umag = sc * i64_to_f64(ge[1]);
     const double ssize = sc * i64_to_f64(ge[2]), smag = sc * i64_to_f64(ge[3]);
     const double usize0 = 0.5 * i64_to_f64(ge[4]), umag0 = 0.5 * i64_to_f64(ge[5]);
     const double ssize0 = 0.5 * i64_to_f64(ge[6]), smag0 = 0.5 * i64_to_f64(ge[7]);
 #pragma unroll
-    for (int f = 0; f < 8; ++f) ge[f] = 0;
+    if (ge[8] > 0) v[14] += 2.0 * usize;
+#pragma unroll
+    for (int f = 0; f < LQ_GEST; ++f) ge[f] = 0;
     const double a = usize0 * usize0, b = umag0 * umag0, e = ssize0 * ssize0, g = smag0 * smag0;
     v[0] += umag0; v[1] += a; v[2] += b; v[3] += a * a; v[4] += b * b; v[5] += usize * usize; v[6] += umag * umag;
     v[7] += smag0; v[8] += e; v[9] += g; v[10] += e * e; v[11] += g * g; v[12] += ssize * ssize; v[13] += smag * smag;
@@ -1065,11 +1093,12 @@ k_mr_gcollect(Dev d, MrDev m) {
 // all-gather: out = sum over ranks (fixed order) + global-cluster sums
 __global__ void k_mr_rankvec(Dev d, MrDev m, const double* slot) {
   const int i = threadIdx.x;
-  if (i < LQ_NSUM) m.rankvec[i] = slot[i];
+  if (i < LQ_NSUS) m.rankvec[i] = slot[i];
+  if (i == 18) m.rankvec[18] = slot[18];                     // transmag length of the closed clusters
   if (i == 14) m.rankvec[14] = slot[14] - (double)m.d_g[1];  // closed clusters of this rank
   if (i == 15) m.rankvec[15] = slot[15];                     // operators of this slab
   if (i == 16) m.rankvec[16] = slot[16];                     // error flags
-  if (i > 16 && i < 32) m.rankvec[i] = 0;
+  if (i > 16 && i < 32 && i != 18) m.rankvec[i] = 0;
 }
 
 __global__ void k_mr_final(Dev d, MrDev m, double* slot) {
@@ -1077,7 +1106,8 @@ __global__ void k_mr_final(Dev d, MrDev m, double* slot) {
   if (i >= 32) return;
   double x = 0;
   for (int r = 0; r < d.nranks; ++r) x += m.allvec[r * 32 + i];
-  if (i < LQ_NSUM) x += m.gsum[i];
+  if (i < LQ_NSUS) x += m.gsum[i];
+  if (i == 18) x += m.gsum[14];
   if (i == 14) x += (double)m.d_g[0];
   if (i == 17) x = (double)m.d_g[0];  // number of clusters that were open (diagnostic)
   slot[i] = x;

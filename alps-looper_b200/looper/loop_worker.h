@@ -40,6 +40,8 @@ public:
     M.bond_weights = model.bond_weights().data();
     for (int k = 0; k < 4; ++k) M.uniform_weights[k] = 0;
     M.energy_offset = model.energy_offset();
+    M.site_weights = nullptr;
+    M.uniform_site_weight = model.site_weight();
     lq_options o = lq_options();
     o.seed = p.value_or_default<unsigned long long>("WORKER_SEED", p.value_or_default<unsigned long long>("SEED", 29833ull));
     o.device = p.value_or_default<int>("DEVICE", 0);
@@ -80,6 +82,7 @@ public:
     obs["Number of Clusters"] << coll.nc;
     energy::commit(obs, coll, beta_, vol);
     susceptibility::commit(obs, coll, beta_, vol, lattice.is_bipartite());
+    if (model.site_weight() > 0) transverse_magnetization::commit(obs, coll, vol);
     last_ = coll;
   }
 

@@ -128,4 +128,12 @@ struct susceptibility {
   }
 };
 
+// transmag.h:95-110: length of the clusters cut by a site operator
+struct transverse_magnetization {
+  static void commit(observable_set& m, const lq_collector& c, double vol, double sign = 1) {
+    m["Transverse Magnetization"] << 0.5 * sign * c.tlen;
+    m["Transverse Magnetization Density"] << 0.5 * sign * c.tlen / vol;
+  }
+};
+
 }  // namespace looper

@@ -1,5 +1,5 @@
-// model.h -- host-side spinmodel_helper / weight_helper for S=1/2 XXZ bonds
-// (reference: looper/model.h:38-127, looper/weight_impl.h:90-188,349-423).  The loop equations
+// model.h -- host-side spinmodel_helper / weight_helper for S=1/2 XXZ bonds and transverse-field
+// sites (reference: looper/model.h:38-127, looper/weight_impl.h:62-88,90-188,349-423).  The loop equations
 //   -offset + v1 + v3 = -Jz/4,  -offset + v0 + v2 = +Jz/4,  v0 + v1 = |Jxy|/2
 // are solved as in weight_impl.h (standard solution, or the "ergodic" one for FORCE_SCATTER = a).
 #pragma once
@@ -48,6 +48,17 @@ struct xxz_bond_weight_helper {
   bool has_weight() const { return weight() > 1e-10; }
 };
 
+// weight_impl.h:62-88: site graph weight v0 = |Hx|/2, offset = v0
+struct site_weight_helper {
+  int sign = 1;
+  double offset = 0;
+  double v[1] = {0};
+  site_weight_helper() {}
+  explicit site_weight_helper(double hx) { sign = hx >= 0 ? 1 : -1; v[0] = std::abs(hx) / 2; offset = v[0]; }
+  double weight() const { return v[0]; }
+  bool has_weight() const { return weight() > 1e-10; }
+};
+
 class spinmodel_helper {
 public:
   spinmodel_helper() {}
@@ -56,12 +67,17 @@ public:
     const double J = p.value_or_default<double>("J", 1.0);
     const double jxy = p.value_or_default<double>("Jxy", J), jz = p.value_or_default<double>("Jz", J);
     if (p.value_or_default<double>("S", 0.5) != 0.5) throw std::invalid_argument("only S = 1/2 is supported");
-    if (p.value_or_default<double>("h", 0.0) != 0.0 || p.value_or_default<double>("Gamma", 0.0) != 0.0)
-      throw std::invalid_argument("longitudinal/transverse fields are outside the accelerated path");
+    if (p.value_or_default<double>("h", 0.0) != 0.0)
+      throw std::invalid_argument("longitudinal fields are outside the accelerated path");
+    // transverse field Gamma (ALPS "spin" model: H -= Gamma Sx): site graphs
+    site_weight_helper sw(p.value_or_default<double>("Gamma", 0.0));
+    if (sw.sign < 0) throw std::invalid_argument("negative sign (Gamma < 0) is not supported");
     const double a = p.value_or_default<double>("FORCE_SCATTER", 0.0);
     const int nb = num_bonds(lat.vg());
     xxz_bond_weight_helper w(bond_parameter_xxz(0, jxy, jz), a);
     if (w.sign < 0 && !lat.is_bipartite()) throw std::invalid_argument("negative sign (frustration) is not supported");
+    if (w.sign < 0 && sw.has_weight())
+      throw std::invalid_argument("negative sign (antiferromagnetic Jxy with a transverse field) is not supported");
     weights_.assign(4 * size_t(nb), 0.0);
     gw_ = 0;
     offset_ = 0;
@@ -70,16 +86,23 @@ public:
       gw_ += w.weight();
       offset_ += w.offset;
     }
+    site_weight_ = sw.weight();
+    if (sw.has_weight()) {
+      const int ns = num_sites(lat.vg());
+      gw_ += ns * sw.weight();
+      offset_ += ns * sw.offset;
+    }
   }
   double graph_weight() const { return gw_; }       // model.h:114, graph_impl.h:694
   double energy_offset() const { return offset_; }  // model.h:84, weight_impl.h:396-404
   bool is_signed() const { return false; }
   bool has_field() const { return false; }
   const std::vector<double>& bond_weights() const { return weights_; }
+  double site_weight() const { return site_weight_; }   // uniform |Hx|/2 (0: no site graphs)
 
 private:
   std::vector<double> weights_;
-  double gw_ = 0, offset_ = 0;
+  double gw_ = 0, offset_ = 0, site_weight_ = 0;
 };
 
 }  // namespace looper

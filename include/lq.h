@@ -54,6 +54,10 @@ typedef struct lq_model {
   const double* bond_weights;     /* 4 * num_bonds, or NULL                                      */
   double        uniform_weights[4];
   double        energy_offset;
+  /* site graph weight v0 = |Hx|/2 of site_weight_helper (weight_impl.h:62-88; transverse field):
+   * per site, or NULL = uniform_site_weight for all sites.  0 = no site operators. */
+  const double* site_weights;     /* num_sites, or NULL                                          */
+  double        uniform_site_weight;
 } lq_model;
 
 typedef struct lq_options {
@@ -78,12 +82,14 @@ typedef struct lq_op {
 } lq_op;
 
 /* basic_measurement::collector nop_/nc_/noc_ (looper/measurement.h:366-372), energy ene_
- * (energy.h:56), susceptibility improved collector (susceptibility.h:158-160). */
+ * (energy.h:56), susceptibility improved collector (susceptibility.h:158-160), transmag. */
 typedef struct lq_collector {
   double nop, nc, noc;
   double ene;
   double umag0, usize2, umag2, usize4, umag4, usize, umag;
   double smag0, ssize2, smag2, ssize4, smag4, ssize, smag;
+  double tlen;   /* transverse_magnetization collector length (transmag.h:95-101): total length of
+                    the clusters cut by a site operator; "Transverse Magnetization" = tlen / 2   */
 } lq_collector;
 
 /* Section timers; ids mirror path_integral.C:284-299 (4 init .. 16 measurement). */

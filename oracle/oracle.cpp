@@ -374,24 +374,42 @@ void orc_get_last_graph(const orc_sim* S, int32_t* spins_before, orc_op* ops_bui
 }
 
 // path_integral.C:539-566 (walk) + graph_impl.h:277-295 (xxz reconnect; g=0 is the HAF case
-// :168-177) + path_integral.C:584-588 (close) + union_find.h:325-343 (set_id/copy_id) +
-// path_integral.C:666-734 (improved accumulators) + :774-777 (collect).
-int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
-                       const double* gauge, const int32_t* spins, const orc_op* ops, int64_t n,
-                       int32_t* labels_out, int64_t* nc_out, orc_collector* coll_out) {
+// :168-177) + graph_impl.h:79-86 (site reconnect) + path_integral.C:584-588 (close) +
+// union_find.h:325-343 (set_id/copy_id): the cluster graph of a GIVEN configuration.
+struct cluster_graph {
+  std::vector<int> l0, l1, u0, u1;  // fragment of the four legs of every operator
+  std::vector<int> current;         // fragment crossing tau = 1 on every site
+  std::vector<int> id;              // cluster id of every fragment
+  int nc = 0;
+};
+
+static int build_graph(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                       const int32_t* spins, const orc_op* ops, int64_t n, cluster_graph& G) {
   std::vector<lp_node> fragments(nsites);
   fragments.reserve(size_t(nsites) + size_t(n));
-  std::vector<int> current(nsites), sc(spins, spins + nsites);
+  std::vector<int>& current = G.current;
+  current.resize(nsites);
+  std::vector<int> sc(spins, spins + nsites);
   for (int s = 0; s < nsites; ++s) current[s] = s;
-  // per operator: fragment index of the four legs
-  std::vector<int> l0(n), l1(n), u0(n), u1(n);
+  std::vector<int>&l0 = G.l0, &l1 = G.l1, &u0 = G.u0, &u1 = G.u1;
+  l0.assign(n, 0); l1.assign(n, 0); u0.assign(n, 0); u1.assign(n, 0);
   double tprev = -1;
   for (int64_t k = 0; k < n; ++k) {
-    if (!(ops[k].loc & 1)) return -2;  // site operators are not handled by this routine
-    const int b = ops[k].loc >> 1;
-    if (b < 0 || b >= nbonds) return -3;
     if (ops[k].time < tprev) return -4;
     tprev = ops[k].time;
+    if (!(ops[k].loc & 1)) {
+      // site operator (path_integral.C:552-561): graph_impl.h:79-86 site_graph_type::reconnect --
+      // the world line is cut, the part above is a new fragment; no compatibility condition (:69)
+      const int s = ops[k].loc >> 1;
+      if (s < 0 || s >= nsites || (ops[k].type >> 2) != 0) return -3;
+      if (ops[k].type & 1) sc[s] ^= 1;
+      fragments.push_back(lp_node());
+      l0[k] = l1[k] = current[s];
+      u0[k] = u1[k] = current[s] = int(fragments.size()) - 1;
+      continue;
+    }
+    const int b = ops[k].loc >> 1;
+    if (b < 0 || b >= nbonds) return -3;
     const int s0 = src[b], s1 = dst[b];
     const int g = ops[k].type >> 2;
     if (ops[k].type & 1) {
@@ -430,11 +448,27 @@ int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t
 
   // union_find.h:325-343
   const int nf = int(fragments.size());
-  std::vector<int> id(nf, -1);
+  std::vector<int>& id = G.id;
+  id.assign(nf, -1);
   int nc = 0;
   for (int i = 0; i < nf; ++i)
     if (fragments[i].is_root()) id[i] = nc++;
   for (int i = 0; i < nf; ++i) id[i] = id[lp_root_index(fragments, i)];
+  G.nc = nc;
+  return 0;
+}
+
+// orc_build_clusters: the graph above + path_integral.C:666-734 (improved accumulators) +
+// :774-777 (collect).
+int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                       const double* gauge, const int32_t* spins, const orc_op* ops, int64_t n,
+                       int32_t* labels_out, int64_t* nc_out, orc_collector* coll_out) {
+  cluster_graph G;
+  const int rc = build_graph(nsites, nbonds, src, dst, spins, ops, n, G);
+  if (rc != 0) return rc;
+  const std::vector<int>&l0 = G.l0, &l1 = G.l1, &u0 = G.u0, &u1 = G.u1, &current = G.current, &id = G.id;
+  const int nc = G.nc;
+  std::vector<int> sc(spins, spins + nsites);
 
   // canonical min-index labels over leg nodes: site s -> s, upper legs of op k -> N+2k, N+2k+1
   if (labels_out) {
@@ -458,6 +492,7 @@ int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t
   if (coll_out) {
     std::vector<lp_estimate> lest(nc);
     std::vector<sa_estimate> est(nc);
+    std::vector<char> cut(nc, 0);  // transmag.h:64-81: closed == false once a site leg touches it
     std::vector<double> gg(nsites, 0.0);
     if (gauge) gg.assign(gauge, gauge + nsites);
     sc.assign(spins, spins + nsites);
@@ -468,10 +503,20 @@ int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t
       est[id[s]].length += 1;
     }
     for (int64_t k = 0; k < n; ++k) {
+      const double t = ops[k].time;
+      if (!(ops[k].loc & 1)) {  // path_integral.C:716-726
+        const int s = ops[k].loc >> 1;
+        lest[id[l0[k]]].end_s(gg[s], t, sc[s]);
+        est[id[l0[k]]].length += t;
+        if (ops[k].type & 1) sc[s] ^= 1;
+        lest[id[u0[k]]].begin_s(gg[s], t, sc[s]);
+        est[id[u0[k]]].length -= t;
+        cut[id[l0[k]]] = cut[id[u0[k]]] = 1;
+        continue;
+      }
       const int b = ops[k].loc >> 1;
       const int s0 = src[b], s1 = dst[b];
       const int g = ops[k].type >> 2;
-      const double t = ops[k].time;
       if ((g & 2) == 2) {  // frozen graphs are skipped by the accumulators (path_integral.C:692)
         if (ops[k].type & 1) { sc[s0] ^= 1; sc[s1] ^= 1; }
         continue;
@@ -497,8 +542,143 @@ int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t
       coll.sa_smag += e.size * e.size;
       coll.sa_ssus += e.length * e.length;
     }
+    // transmag.h:98-101: collector.length += closed ? 0 : estimate.length, where the estimate's
+    // length (begin/end/start_bottom/stop_top, :72-92) is the total length of the cluster's legs
+    // = 2 * usize of susceptibility.h:126-132 (every leg adds +-t there with weight 1/2)
+    for (int c = 0; c < nc; ++c)
+      if (cut[c]) coll.tlen += 2 * lest[c].usize;
     *coll_out = coll;
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic model: path_integral.C:403-864 restated (XXZ bond graphs 0..3 + site graphs), serial.
+// RNG: std::mt19937 + std::exponential_distribution for the gaps (path_integral.C:413-423 uses
+// boost's with the ALPS generator -- unpinned in the reference) and a cumulative-weight
+// table in place of alps::random_choice (graph_impl.h:679; same distribution).
+// ---------------------------------------------------------------------------------------------
+struct orc_model_sim {
+  int nsites, nbonds;
+  std::vector<int> src, dst;
+  std::vector<double> gauge, bw, sw;
+  std::vector<double> cum;          // cumulative graph weights
+  std::vector<int> cum_graph;       // (pos << 3 | g << 1 | is_bond)
+  double beta, total;
+  std::mt19937 eng;
+  std::uniform_real_distribution<> uni;
+  std::vector<int> spins;
+  std::vector<orc_op> ops;
+};
+
+orc_model_sim* orc_model_create(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                                const double* gauge, const double* bond_weights,
+                                const double* site_weights, double beta, uint32_t seed) {
+  orc_model_sim* S = new orc_model_sim();
+  S->nsites = nsites; S->nbonds = nbonds;
+  S->src.assign(src, src + nbonds); S->dst.assign(dst, dst + nbonds);
+  S->gauge.assign(nsites, 0.0);
+  if (gauge) S->gauge.assign(gauge, gauge + nsites);
+  S->bw.assign(bond_weights, bond_weights + 4 * size_t(nbonds));
+  S->sw.assign(nsites, 0.0);
+  if (site_weights) S->sw.assign(site_weights, site_weights + nsites);
+  S->beta = beta;
+  S->eng.seed(seed);
+  S->spins.assign(nsites, 0);  // path_integral.C:225
+  double acc = 0;
+  for (int s = 0; s < nsites; ++s)     // graph_impl.h:560-600: site graphs, then bond graphs
+    if (S->sw[s] > 0) { acc += S->sw[s]; S->cum.push_back(acc); S->cum_graph.push_back(s << 3); }
+  for (int b = 0; b < nbonds; ++b)
+    for (int g = 0; g < 4; ++g)
+      if (S->bw[4 * size_t(b) + g] > 0) {
+        acc += S->bw[4 * size_t(b) + g];
+        S->cum.push_back(acc);
+        S->cum_graph.push_back((b << 3) | (g << 1) | 1);
+      }
+  S->total = acc;
+  return S;
+}
+void orc_model_destroy(orc_model_sim* S) { delete S; }
+int64_t orc_model_num_ops(const orc_model_sim* S) { return int64_t(S->ops.size()); }
+void orc_model_get_state(const orc_model_sim* S, int32_t* spins, orc_op* ops) {
+  for (int s = 0; s < S->nsites; ++s) spins[s] = S->spins[s];
+  for (size_t i = 0; i < S->ops.size(); ++i) ops[i] = S->ops[i];
+}
+
+int orc_model_sweep(orc_model_sim* S, orc_collector* out) {
+  const int nsites = S->nsites;
+  std::vector<orc_op> ops_p;
+  std::swap(ops_p, S->ops);
+  std::vector<int> sc(S->spins);
+  // path_integral.C:403-425 fill times
+  std::vector<double> times;
+  if (S->total > 0) {
+    std::exponential_distribution<> expdist(S->beta * S->total);
+    double t = 0;
+    while (t < 1) { t += expdist(S->eng); times.push_back(t); }
+  } else {
+    times.push_back(2.0);
+  }
+  // path_integral.C:484-566 diagonal update (the reconnect part is done by build_graph below)
+  size_t tmi = 0, opi = 0;
+  while (opi < ops_p.size() || times[tmi] < 1) {
+    orc_op o;
+    if (opi == ops_p.size() || times[tmi] < ops_p[opi].time) {
+      const double r = S->uni(S->eng) * S->total;
+      size_t k = size_t(std::upper_bound(S->cum.begin(), S->cum.end(), r) - S->cum.begin());
+      if (k >= S->cum.size()) k = S->cum.size() - 1;
+      const int cg = S->cum_graph[k];
+      o.time = times[tmi++];
+      if (cg & 1) {
+        const int b = cg >> 3, g = (cg >> 1) & 3;
+        // graph_impl.h:257 is_compatible(g, c0, c1) = (g & 1) ^ c0 ^ c1
+        if (!((g & 1) ^ sc[S->src[b]] ^ sc[S->dst[b]])) continue;
+        o.loc = (b << 1) | 1;
+        o.type = g << 2;
+      } else {
+        o.loc = (cg >> 3) << 1;
+        o.type = 0;
+      }
+    } else {
+      o = ops_p[opi++];
+      if (!(o.type & 1)) continue;  // diagonal operators are removed (path_integral.C:519-521)
+      if (o.loc & 1) {
+        const int b = o.loc >> 1;
+        // graph_impl.h:311-327 choose_offdiagonal: g = 0 with probability v0 / (v0 + v1), else 1
+        const double v0 = S->bw[4 * size_t(b)], v1 = S->bw[4 * size_t(b) + 1];
+        const double pr = (v0 + v1 > 1e-10) ? v0 / (v0 + v1) : 1;
+        const int g = (S->uni(S->eng) < pr) ? 0 : 1;
+        o.type = (g << 2) | 1;
+        sc[S->src[b]] ^= 1;
+        sc[S->dst[b]] ^= 1;
+      } else {
+        sc[o.loc >> 1] ^= 1;
+      }
+    }
+    S->ops.push_back(o);
+  }
+  cluster_graph G;
+  const int rc = build_graph(nsites, S->nbonds, S->src.data(), S->dst.data(), S->spins.data(),
+                             S->ops.data(), int64_t(S->ops.size()), G);
+  if (rc != 0) return rc;
+  if (out) {
+    orc_build_clusters(nsites, S->nbonds, S->src.data(), S->dst.data(), S->gauge.data(),
+                       S->spins.data(), S->ops.data(), int64_t(S->ops.size()), nullptr, nullptr, out);
+    double off = 0;  // model.energy_offset(): bond offsets = weight/2 (weight_impl.h:187), site = v0 (:80)
+    for (double v : S->bw) off += v / 2;
+    for (double v : S->sw) off += v;
+    out->ene = off - out->nop / S->beta;   // path_integral.C:850-851
+  }
+  // path_integral.C:796-823 flip
+  std::vector<char> flip(G.nc);
+  for (int c = 0; c < G.nc; ++c) flip[c] = (S->uni(S->eng) < 0.5);
+  for (size_t k = 0; k < S->ops.size(); ++k) {
+    // operator.h loop_0 / loop_1 in leg form: the cluster below and the one above on the source side
+    // (frozen graphs never change type: both legs are one cluster)
+    if (flip[G.id[G.l0[k]]] ^ flip[G.id[G.u0[k]]]) S->ops[k].type ^= 1;
+  }
+  for (int s = 0; s < nsites; ++s)
+    if (flip[G.id[s]]) S->spins[s] ^= 1;
   return 0;
 }
 

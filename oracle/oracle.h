@@ -42,6 +42,8 @@ typedef struct orc_collector {
   double smag0, ssize2, smag2, ssize4, smag4, ssize, smag;
   /* standalone/common.h collector_t */
   double sa_usus, sa_smag, sa_ssus;
+  /* transverse_magnetization collector (looper/transmag.h:95-101) */
+  double tlen;
 } orc_collector;
 
 typedef struct orc_sim orc_sim;
@@ -67,8 +69,8 @@ void     orc_get_last_graph(const orc_sim*, int32_t* spins_before, orc_op* ops_b
 
 /* Cluster construction only (path_integral.C:539-588 / standalone/loop.C:117-128 restated for a
  * GIVEN configuration): spins at tau=0 and operators sorted by time (HAF graph 0 / XXZ graphs
- * 0..3 in type>>2).  Outputs canonical min-index labels for the N + n nodes (node N+k = k-th
- * operator in the given order; for graphs without a new fragment the label is that of the
+ * 0..3 in type>>2; site operators, loc bit 0 clear, with the site graph of graph_impl.h:67-87).
+ * Outputs canonical min-index labels for the N + n nodes (node N+k = k-th operator in the given order; for graphs without a new fragment the label is that of the
  * cluster passing above source site), the number of clusters, and the collector of
  * looper/susceptibility.h:97-198 and standalone/loop.C:141-157 for that configuration.
  * Returns 0, or -1 if the operator string is inconsistent with the spins. */
@@ -76,6 +78,18 @@ int      orc_build_clusters(int nsites, int nbonds, const int32_t* src, const in
                             const double* gauge, const int32_t* spins, const orc_op* ops,
                             int64_t n, int32_t* labels_out, int64_t* nc_out,
                             orc_collector* coll_out);
+
+/* Generic model, one Monte Carlo step of path_integral.C:403-864 (serial): per-bond XXZ graph
+ * weights v[4*b+g] (graph_impl.h:255-328) and per-site weights (graph_impl.h:67-87,
+ * weight_impl.h:62-88).  Returns 0, or the error of orc_build_clusters. */
+typedef struct orc_model_sim orc_model_sim;
+orc_model_sim* orc_model_create(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                                const double* gauge, const double* bond_weights,
+                                const double* site_weights, double beta, uint32_t seed);
+void     orc_model_destroy(orc_model_sim*);
+int      orc_model_sweep(orc_model_sim*, orc_collector* out);
+int64_t  orc_model_num_ops(const orc_model_sim*);
+void     orc_model_get_state(const orc_model_sim*, int32_t* spins, orc_op* ops);
 
 /* looper/union_find.h:57-82,145-172,242-284 replayed as test/union_find.C:40-74 does;
  * writes the exact text of test/union_find.op into buf (returns length needed). */

@@ -42,7 +42,55 @@ def ed_chain(L, jxy, jz, T):
                 smag2=smag2, ssus_density=ssus / L)
 
 
+def ed_tfi(L, jxy, jz, gamma, T):
+    """Transverse field: H = sum_b [Jz Sz Sz + Jxy/2 (S+S- + S-S+)] - Gamma sum_i Sx_i
+    (site term of weight_impl.h:62-88: offdiagonal element Hx/2).  Thermal averages of the energy,
+    of sum_i Sx_i (transmag.h:106-109), of the equal-time Mz^2 / staggered Mz^2 and the Kubo
+    susceptibilities of Mz and staggered Mz (susceptibility.h:199-254)."""
+    dim = 1 << L
+    H = np.zeros((dim, dim))
+    SX = np.zeros((dim, dim))
+    sz = lambda s, i: 0.5 - ((s >> i) & 1)
+    for s in range(dim):
+        for i in range(L):
+            j = (i + 1) % L
+            if L > 2 or i == 0:
+                H[s, s] += jz * sz(s, i) * sz(s, j)
+                if ((s >> i) & 1) != ((s >> j) & 1):
+                    H[s ^ (1 << i) ^ (1 << j), s] += 0.5 * jxy
+            SX[s ^ (1 << i), s] += 0.5
+    H -= gamma * SX
+    E, V = np.linalg.eigh(H)
+    beta = 1.0 / T
+    w = np.exp(-beta * (E - E.min()))
+    Z = w.sum()
+    states = np.arange(dim)
+    mu = sum(0.5 - ((states >> i) & 1) for i in range(L))
+    ms = sum((1 - 2 * (i % 2)) * (0.5 - ((states >> i) & 1)) for i in range(L))
+    P = V ** 2
+    dE = E[:, None] - E[None, :]
+    wn, wm = w[:, None], w[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        K = np.where(np.abs(dE) > 1e-12, (wm - wn) / dE, beta * wn)
+
+    def kubo(diag):
+        M = V.T @ (diag[:, None] * V)
+        return (M ** 2 * K).sum() / Z
+
+    return dict(L=L, jxy=jxy, jz=jz, gamma=gamma, T=T,
+                energy_density=(w * E).sum() / Z / L,
+                transmag_density=(w * np.einsum("sn,st,tn->n", V, SX, V)).sum() / Z / L,
+                umag2=(w * (P * (mu ** 2)[:, None]).sum(0)).sum() / Z,
+                smag2=(w * (P * (ms ** 2)[:, None]).sum(0)).sum() / Z,
+                usus_density=kubo(mu) / L, ssus_density=kubo(ms) / L)
+
+
 if __name__ == "__main__":
+    tfi = [ed_tfi(8, 0.0, 1.0, 0.7, 0.5), ed_tfi(8, 0.0, -1.0, 0.5, 0.4), ed_tfi(8, -1.0, 0.5, 0.6, 0.4),
+           ed_tfi(6, -1.0, -1.0, 1.0, 0.25)]   # Jxy <= 0 with a field: no sign problem
+    json.dump(tfi, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ed_tfi.json"), "w"), indent=1)
+    for o in tfi:
+        print(o)
     out = [ed_chain(8, 1.0, 1.0, 0.2), ed_chain(8, 1.0, 0.5, 0.25), ed_chain(8, 1.0, 2.0, 0.5),
            ed_chain(8, 1.0, 0.0, 0.2), ed_chain(10, 1.0, 0.5, 0.2)]
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ed_chain.json")

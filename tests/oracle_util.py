@@ -11,7 +11,7 @@ OP_DTYPE = np.dtype([("time", "<f8"), ("loc", "<i4"), ("type", "<i4")])
 COLL_FIELDS = ["nop", "nc", "noc", "ene",
                "umag0", "usize2", "umag2", "usize4", "umag4", "usize", "umag",
                "smag0", "ssize2", "smag2", "ssize4", "smag4", "ssize", "smag",
-               "sa_usus", "sa_smag", "sa_ssus"]
+               "sa_usus", "sa_smag", "sa_ssus", "tlen"]
 
 
 class OrcCollector(C.Structure):
@@ -49,6 +49,14 @@ def lib():
         L.orc_build_clusters.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.POINTER(C.c_int64), C.POINTER(OrcCollector)]
+        L.orc_model_create.restype = C.c_void_p
+        L.orc_model_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_double, C.c_uint32]
+        L.orc_model_destroy.argtypes = [C.c_void_p]
+        L.orc_model_sweep.argtypes = [C.c_void_p, C.POINTER(OrcCollector)]
+        L.orc_model_num_ops.argtypes = [C.c_void_p]
+        L.orc_model_num_ops.restype = C.c_int64
+        L.orc_model_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_union_find_replay.argtypes = [C.c_char_p, C.c_int]
         L.orc_xxz_weights.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -106,6 +114,51 @@ class OracleSim:
                                  up.ctypes.data, sid.ctypes.data, C.byref(nc), flip.ctypes.data)
         return dict(spins_before=sb, ops=ops, lower=lo, upper=up, site=sid, nc=nc.value,
                     flip=flip[:nc.value])
+
+
+def xxz_weights(jxy, jz, a=0.0):
+    """orc_xxz_weights (weight_impl.h:165-188): (v[4], offset, sign)."""
+    v = (C.c_double * 4)()
+    off, sg = C.c_double(0), C.c_int(0)
+    lib().orc_xxz_weights(jxy, jz, a, v, C.byref(off), C.byref(sg))
+    return list(v), off.value, sg.value
+
+
+class OracleModelSim:
+    """path_integral.C on an arbitrary bond table with XXZ bond graphs and site graphs."""
+
+    def __init__(self, lattice, beta, weights=(0.5, 0, 0, 0), site_weight=0.0, seed=29833):
+        self.N = int(lattice["num_sites"])
+        self.src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
+        self.dst = np.ascontiguousarray(lattice["dst"], dtype=np.int32)
+        self.B = len(self.src)
+        g = lattice.get("gauge")
+        self.gauge = np.ascontiguousarray(g if g is not None else np.zeros(self.N), dtype=np.float64)
+        self.bw = np.ascontiguousarray(np.tile(np.asarray(weights, dtype=np.float64), self.B))
+        self.sw = np.full(self.N, float(site_weight))
+        self.beta = beta
+        self.h = lib().orc_model_create(self.N, self.B, self.src.ctypes.data, self.dst.ctypes.data,
+                                        self.gauge.ctypes.data, self.bw.ctypes.data,
+                                        self.sw.ctypes.data, beta, seed)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_model_destroy(self.h)
+            self.h = None
+
+    def sweep(self):
+        c = OrcCollector()
+        rc = lib().orc_model_sweep(self.h, C.byref(c))
+        if rc != 0:
+            raise ValueError(f"orc_model_sweep failed with {rc}")
+        return c
+
+    def get_state(self):
+        n = lib().orc_model_num_ops(self.h)
+        spins = np.zeros(self.N, dtype=np.int32)
+        ops = np.zeros(n, dtype=OP_DTYPE)
+        lib().orc_model_get_state(self.h, spins.ctypes.data, ops.ctypes.data)
+        return spins, ops
 
 
 def build_clusters(lattice, spins, ops):

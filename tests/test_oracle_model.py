@@ -1,0 +1,103 @@
+"""The generic-model restatement in the oracle (path_integral.C:403-864 with XXZ bond graphs and
+site graphs, oracle/oracle.cpp orc_model_*) against exact diagonalisation: pins the site-graph
+reconnect (graph_impl.h:67-87), its estimator legs (path_integral.C:716-726) and the transverse
+magnetisation collector (transmag.h:62-117) that the GPU parity tests compare against."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_util as orc
+from looper_lattices import chain_lattice
+from oracle_util import xxz_weights
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _berr(x, nb=32):
+    m = len(x) // nb
+    b = np.asarray(x[: m * nb]).reshape(nb, m).mean(axis=1)
+    return b.std(ddof=1) / np.sqrt(nb)
+
+
+def test_single_site_transverse_field():
+    # one spin in a field: <Sx> = tanh(beta Gamma / 2) / 2, E = -Gamma <Sx>
+    lat = dict(num_sites=1, src=np.zeros(0, np.int32), dst=np.zeros(0, np.int32), gauge=np.ones(1))
+    beta, gamma = 1.3, 0.9
+    sim = orc.OracleModelSim(lat, beta, weights=(0, 0, 0, 0), site_weight=gamma / 2, seed=5)
+    tm, en = [], []
+    for i in range(60000):
+        c = sim.sweep()
+        if i >= 500:
+            tm.append(0.5 * c.tlen)
+            en.append(c.ene)
+    sx = 0.5 * np.tanh(beta * gamma / 2)
+    assert abs(np.mean(tm) - sx) < 4.5 * _berr(tm)
+    assert abs(np.mean(en) + gamma * sx) < 4.5 * _berr(en)
+
+
+def test_site_operator_clusters_by_hand():
+    # two sites, one bond, no bond operators; site 0 carries two cuts, site 1 none:
+    # clusters = {segment of site 0 through tau=0 (cut), inner segment of site 0 (cut), site 1 (closed)}
+    lat = dict(num_sites=2, src=np.array([0], np.int32), dst=np.array([1], np.int32), gauge=np.array([1.0, -1.0]))
+    ops = np.zeros(2, dtype=orc.OP_DTYPE)
+    ops["time"] = [0.25, 0.75]
+    ops["loc"] = [0, 0]          # site 0, is_bond bit clear
+    ops["type"] = [1, 1]         # both off-diagonal: spin 0 is flipped on [0.25, 0.75)
+    labels, nc, c = orc.build_clusters(lat, np.array([0, 0], np.int32), ops)
+    assert nc == 3
+    assert labels[0] == 0 and labels[1] == 1
+    assert labels[2 + 2] == labels[0]          # above the second cut = the segment through tau = 0
+    assert labels[2 + 0] not in (labels[0], labels[1])
+    assert c["tlen"] == pytest.approx(1.0)     # both segments of site 0, total length 1
+    # uniform magnetisation integral: site 1 contributes +1/2; site 0: (+1/2)(0.5) + (-1/2)(0.5) = 0
+    assert c["umag"] == pytest.approx(0.25 + (0.5 * 0.5) ** 2 + (-0.5 * 0.5) ** 2)
+    # an odd number of flips on a site is not periodic
+    with pytest.raises(ValueError):
+        orc.build_clusters(lat, np.array([0, 0], np.int32), ops[:1])
+
+
+@pytest.mark.parametrize("row", [0, 1, 2, 3])
+def test_oracle_model_vs_exact_diagonalisation_tfi(row):
+    ed = json.load(open(os.path.join(HERE, "golden", "ed_tfi.json")))[row]
+    L, beta = ed["L"], 1 / ed["T"]
+    v, off, sign = xxz_weights(ed["jxy"], ed["jz"])
+    assert sign == 1
+    lat = chain_lattice(L)
+    sim = orc.OracleModelSim(lat, beta, weights=tuple(v), site_weight=ed["gamma"] / 2, seed=11 + row)
+    keep = {k: [] for k in ("energy_density", "transmag_density", "umag2", "smag2", "usus_density", "ssus_density")}
+    for i in range(22000):
+        c = sim.sweep()
+        if i < 2000:
+            continue
+        keep["energy_density"].append(c.ene / L)
+        keep["transmag_density"].append(0.5 * c.tlen / L)
+        keep["umag2"].append(c.umag2)
+        keep["smag2"].append(c.smag2)
+        keep["usus_density"].append(beta * c.umag / L)
+        keep["ssus_density"].append(beta * c.smag / L)
+    for k, x in keep.items():
+        x = np.asarray(x)
+        if k == "transmag_density" and (v[2] > 0 or v[3] > 0):
+            # the reference's estimator (transmag.h:98: length of every cluster cut by a site
+            # operator) treats a cluster as ONE loop that can be cut anywhere; clusters bound by
+            # frozen graphs are not, and the reference only checks it without them
+            # (check/transmag-1: single site, check/transmag-3: Heisenberg chain).  Restated as is.
+            continue
+        assert abs(x.mean() - ed[k]) < 4.5 * _berr(x) + 1e-10, (k, x.mean(), ed[k], _berr(x))
+
+
+def test_oracle_model_vs_exact_diagonalisation_xxz():
+    ed = json.load(open(os.path.join(HERE, "golden", "ed_chain.json")))[1]   # Jxy = 1, Jz = 0.5: cross graphs
+    L, beta = ed["L"], 1 / ed["T"]
+    v, off, sign = xxz_weights(ed["jxy"], ed["jz"])
+    sim = orc.OracleModelSim(chain_lattice(L), beta, weights=tuple(v), seed=3)
+    e, s2 = [], []
+    for i in range(22000):
+        c = sim.sweep()
+        if i >= 2000:
+            e.append(c.ene / L)
+            s2.append(c.smag2)
+    assert abs(np.mean(e) - ed["energy_density"]) < 4.5 * _berr(e)
+    assert abs(np.mean(s2) - ed["smag2"]) < 4.5 * _berr(s2)
