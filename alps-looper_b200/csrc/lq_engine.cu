@@ -289,6 +289,18 @@ struct lq_engine {
   int tpb_walk = 32;
   typedef void (*walk_fn_t)(lq::Dev, int);
   walk_fn_t walk_fn = nullptr;
+  typedef void (*k1_fn_t)(lq::Dev, int, const lq::StepParams*);
+  k1_fn_t k1_fn = nullptr;
+  int k1_fc = 12;
+  // diagonal update specialised on block size and on the width of the per-site flip lists
+  k1_fn_t pick_k1() const {
+#define LQ_PICK1(MT) (k1_fc <= 8 ? lq::k_diag_update<MT, 8> : k1_fc <= 12 ? lq::k_diag_update<MT, 12> : lq::k_diag_update<MT, 16>)
+    if (tpb <= 192) return LQ_PICK1(192);
+    if (tpb <= 320) return LQ_PICK1(320);
+    if (tpb <= 576) return LQ_PICK1(576);
+    return LQ_PICK1(1024);
+#undef LQ_PICK1
+  }
   // world-line walk specialised on block size and coordination number
   walk_fn_t pick_walk() const {
     const int z = part.zmax;
@@ -348,7 +360,7 @@ struct lq_engine {
     }
     opt = o;
     if (opt.tile_sites <= 0) opt.tile_sites = 64;
-    if (!(opt.window_ops > 0)) opt.window_ops = 2.0;
+    if (!(opt.window_ops > 0)) opt.window_ops = 3.0;
     if (!(opt.reserve > 0)) opt.reserve = 1.7;
     if (!(opt.cluster_reserve > 0)) opt.cluster_reserve = 0.75;
     if (opt.nranks < 1) { opt.nranks = 1; opt.rank = 0; }
@@ -507,19 +519,31 @@ struct lq_engine {
         fail(LQ_E_INVALID, "too many candidates / staged operators per page: lower tile_sites or window_ops");
       fcap = scap + scap / 2;  // off-diagonal legs of the staged operators (checked at run time)
       tpb_walk = ((std::max(part.nsmax, part.whmax) + 31) / 32) * 32;
-      stage_smem = lq::k1_smem_bytes(scap, ccap, cap, part.nbmax, part.hmax, part.nksmax);
+      // width of the fast per-site flip lists of K1: mean legs per site and window ~ 0.6 z window_ops
+      {
+        const double m = 0.6 * part.zmax * opt.window_ops;
+        const double want = m + 2.5 * std::sqrt(m);
+        k1_fc = want <= 8 ? 8 : (want <= 12 ? 12 : 16);
+        // two resident CTAs per SM matter more than a wide list (measured: 74 vs 48 ps/operator);
+        // sites with more legs than the list holds take the slow path of K1
+        const size_t two_ctas = (size_t)(227 * 1024) / 2 - 1024;
+        while (k1_fc > 8 && tpb <= 576 &&
+               lq::k1_smem_bytes(k1_fc, scap, ccap, cap, part.nbmax, part.hmax, part.nksmax) > two_ctas)
+          k1_fc -= 4;
+        if (getenv("LQ_FC")) k1_fc = atoi(getenv("LQ_FC")) <= 8 ? 8 : (atoi(getenv("LQ_FC")) <= 12 ? 12 : 16);
+      }
+      stage_smem = lq::k1_smem_bytes(k1_fc, scap, ccap, cap, part.nbmax, part.hmax, part.nksmax);
       walk_smem = lq::stage_bytes(false, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb_walk);
       if (stage_smem > 200 * 1024)
         fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
       const int sm = (int)stage_smem;
-      CK(cudaFuncSetAttribute(lq::k_diag_update<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_diag_update<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_diag_update<576>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      CK(cudaFuncSetAttribute(lq::k_diag_update<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      k1_fn = pick_k1();
+      CK(cudaFuncSetAttribute(k1_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       // union groups: consecutive windows of a tile unified in one shared-memory union-find
-      // (measured at 512x512 beta=128: groups of 6 windows make the two union kernels 15 % slower
-      // than single pages -- deeper shared-memory trees, fewer CTAs; LQ_UG overrides for experiments)
-      ug = 1;
+      // (measured at 512x512 beta=128, ps per operator of walk + unions: 1 window 42.7, 2 windows
+      // 39.6, 3 windows 40.0, 6 windows 46.4 -- deeper shared-memory trees and fewer CTAs eat the
+      // gain; LQ_UG overrides for experiments)
+      ug = 2;
       if (getenv("LQ_UG")) ug = std::max(1, atoi(getenv("LQ_UG")));
       ug = (int)std::min<size_t>((size_t)ug, std::max<size_t>(1, (96 * 1024) / ((size_t)npo * cap * sizeof(uint32_t))));
       ug = std::min(ug, Wl);
@@ -785,10 +809,7 @@ struct lq_engine {
   void enqueue_step(double* out_slot, const lq::StepParams* sp) {
     {
       Section s(this, 5);
-      if (tpb <= 192) lq::k_diag_update<192><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
-      else if (tpb <= 320) lq::k_diag_update<320><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
-      else if (tpb <= 576) lq::k_diag_update<576><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
-      else lq::k_diag_update<1024><<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
+      k1_fn<<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
       launches += 1;
       cur ^= 1;
     }

@@ -15,7 +15,7 @@
 //      ballot-compacted
 //   4  per candidate: uniform time, Philox4x32-10 keyed by (bond, window, step, i); is_compatible
 //      (graph_impl.h:257) from the two spins at that time = start spins xor parity of the earlier
-//      off-diagonal legs -- LQ_FC branch-free compares per site; graph by the model's weights
+//      off-diagonal legs -- FC branch-free compares per site; graph by the model's weights
 //      (graph_impl.h:679).  Site-graph candidates (graph_impl.h:67-87) are always accepted.
 //   5  per bucket   new size = kept + accepted -> CTA prefix sum -> new bucket offsets
 //   6  per accepted candidate / kept operator: rank inside the new bucket -> scatter into the
@@ -25,7 +25,7 @@
 
 namespace lq {
 
-#define LQ_FC 12  /* off-diagonal legs per K-site and window held in the fast list */
+// template parameter FC (8, 12, 16): off-diagonal legs per K-site and window held in the fast list
 
 // 1/K for the Poisson inverse-CDF recursion p_K = p_{K-1} * mu / K
 __constant__ double c_rcp[33] = {
@@ -36,12 +36,12 @@ __constant__ double c_rcp[33] = {
 struct K1Smem {
   double* time;     // [scap]  staged operators (own page first, halo buckets behind)
   double* ctime;    // [ccap]  candidate times
-  double* flist;    // [LQ_FC][nksp] off-diagonal leg times per K-site, 2.0-padded
+  double* flist;    // [FC][nksp] off-diagonal leg times per K-site, 2.0-padded
   uint32_t* info;   // [scap]  (halo copies carry the LOCAL bucket id of this tile in the bond bits)
   int* off;         // [nloc+1] first staged slot of each local bucket
   int* cbase;       // [nbmax+1] first candidate of each own bucket
   int* noff;        // [nbmax+1] new bucket offsets
-  int* fcnt;        // [nksp]  off-diagonal legs on a K-site (may exceed LQ_FC -> slow path)
+  int* fcnt;        // [nksp]  off-diagonal legs on a K-site (may exceed FC -> slow path)
   int* nkb;         // [nbmax] kept operators per own bucket
   uint16_t* clb;    // [ccap]  owning local bucket of a candidate
   uint16_t* klist;  // [cap]   staged slots of the kept own operators, compacted
@@ -52,18 +52,18 @@ struct K1Smem {
 
 __host__ __device__ inline int k1_nksp(int nksmax) { return (nksmax + 31) & ~31; }
 
-__host__ __device__ inline size_t k1_smem_bytes(int scap, int ccap, int cap, int nbmax, int hmax, int nksmax) {
+__host__ __device__ inline size_t k1_smem_bytes(int fc, int scap, int ccap, int cap, int nbmax, int hmax, int nksmax) {
   const size_t nloc = (size_t)nbmax + hmax, nksp = k1_nksp(nksmax);
-  return ((size_t)scap + ccap + (size_t)LQ_FC * nksp) * 8 + (size_t)scap * 4 +
+  return ((size_t)scap + ccap + (size_t)fc * nksp) * 8 + (size_t)scap * 4 +
          (nloc + 1 + 3 * ((size_t)nbmax + 1) + nksp) * 4 + (2 * (size_t)ccap + cap) * 2 + (size_t)ccap + nksp + 64;
 }
 
-__device__ __forceinline__ void k1_carve(const Dev& d, unsigned char* smem, K1Smem& S) {
+__device__ __forceinline__ void k1_carve(const Dev& d, int fc, unsigned char* smem, K1Smem& S) {
   const size_t nloc = (size_t)d.nbmax + d.hmax, nksp = k1_nksp(d.nksmax);
   S.time = (double*)smem;
   S.ctime = S.time + d.scap;
   S.flist = S.ctime + d.ccap;
-  S.info = (uint32_t*)(S.flist + (size_t)LQ_FC * nksp);
+  S.info = (uint32_t*)(S.flist + (size_t)fc * nksp);
   S.off = (int*)(S.info + d.scap);
   S.cbase = S.off + nloc + 1;
   S.noff = S.cbase + d.nbmax + 1;
@@ -77,7 +77,7 @@ __device__ __forceinline__ void k1_carve(const Dev& d, unsigned char* smem, K1Sm
 }
 
 // parity of the off-diagonal legs before tc on K-site k, straight from the staged buckets
-// (only used when a site carries more than LQ_FC legs in one window)
+// (only used when a site carries more than FC legs in one window)
 __device__ __noinline__ int k1_parity_slow(const double* time, const uint32_t* info, const int* off,
                                            const int* sso, const int* sse, int k, double tc) {
   int par = 0;
@@ -89,14 +89,14 @@ __device__ __noinline__ int k1_parity_slow(const double* time, const uint32_t* i
   return par;
 }
 
-template <int MAXT>
+template <int MAXT, int FC>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 192 ? 6 : (MAXT <= 320 ? 4 : (MAXT <= 576 ? 2 : 1))))
 k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_scan[34];
   __shared__ int s_cnt[2];
   K1Smem S;
-  k1_carve(d, s_raw, S);
+  k1_carve(d, FC, s_raw, S);
   const double beta = sp->beta;
   const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
   const int dst = src ^ 1;
@@ -174,7 +174,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
       S.kspin[tid] = d.spinW[(size_t)wl * d.N + sg];
       S.fcnt[tid] = 0;
     }
-    for (int i = tid; i < LQ_FC * nksp; i += blockDim.x) S.flist[i] = 2.0;
+    for (int i = tid; i < FC * nksp; i += blockDim.x) S.flist[i] = 2.0;
     if (tid < nb)
       for (int i = 0; i < K; ++i) S.clb[cb + i] = (uint16_t)tid;
   }
@@ -189,8 +189,8 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
       const int lid = (int)(inf >> LQ_INFO_LBSHIFT);
       const int k0 = bsx[2 * lid], k1 = bsx[2 * lid + 1];
       const double tt = S.time[j];
-      if (k0 >= 0) { const int f = atomicAdd(&S.fcnt[k0], 1); if (f < LQ_FC) S.flist[f * nksp + k0] = tt; }
-      if (k1 >= 0) { const int f = atomicAdd(&S.fcnt[k1], 1); if (f < LQ_FC) S.flist[f * nksp + k1] = tt; }
+      if (k0 >= 0) { const int f = atomicAdd(&S.fcnt[k0], 1); if (f < FC) S.flist[f * nksp + k0] = tt; }
+      if (k1 >= 0) { const int f = atomicAdd(&S.fcnt[k1], 1); if (f < FC) S.flist[f * nksp + k1] = tt; }
       if (j < n_own) atomicAdd(&S.nkb[lid], 1);
     }
     const bool keep = offd && j < n_own;
@@ -218,9 +218,9 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
       if (k1 >= 0) {   // bond graph; k1 < 0: site graph, compatible with any spin (graph_impl.h:69)
         int par = S.kspin[k0] ^ S.kspin[k1];   // operators on this bond sit in both lists and cancel
 #pragma unroll
-        for (int f = 0; f < LQ_FC; ++f)
+        for (int f = 0; f < FC; ++f)
           par ^= (int)(S.flist[f * nksp + k0] < tc) ^ (int)(S.flist[f * nksp + k1] < tc);
-        if (S.fcnt[k0] > LQ_FC || S.fcnt[k1] > LQ_FC)
+        if (S.fcnt[k0] > FC || S.fcnt[k1] > FC)
           par = (S.kspin[k0] ^ S.kspin[k1]) ^ k1_parity_slow(S.time, S.info, S.off, sso, sse, k0, tc) ^
                 k1_parity_slow(S.time, S.info, S.off, sso, sse, k1, tc);
         const float4 pr = d.bond_p[b];

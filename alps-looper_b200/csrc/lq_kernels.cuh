@@ -456,16 +456,32 @@ k_union_global(Dev d, int buf) {
   const int w_last = min(w_first + d.ug, d.Wl);
   const size_t p_first = (size_t)t * d.Wl + w_first, p_end = (size_t)t * d.Wl + w_last;
   const node_t lo = upper_node(d, d.nbase[p_first], 0), hi = upper_node(d, d.nbase[p_end], 0);
+  const long long nodes_cap = (long long)d.N + (long long)d.npo * d.ncap;
   for (size_t p = p_first; p < p_end; ++p) {
     const int n = d.pcount[buf][p];
     const int idx0 = d.nbase[p];
     const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    // the find of every edge is a chain of dependent loads: the first hop of the NEXT operator's two
+    // lower nodes is requested (L2 prefetch) before the current one is chased
+    int j = threadIdx.x;
+    node_t p0 = 0, p1 = 0;
+    if (j < n) { p0 = d.low0[idx0 + j] & 0x7fffffffu; p1 = d.low1[idx0 + j] & 0x7fffffffu; }
+    for (; j < n; j += blockDim.x) {
       const int idx = idx0 + j;
-      const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
+      const int jn = j + blockDim.x;
+      node_t q0 = 0, q1 = 0;
+      if (jn < n) {
+        q0 = d.low0[idx0 + jn] & 0x7fffffffu; q1 = d.low1[idx0 + jn] & 0x7fffffffu;
+        if (!(q0 >= lo && q0 < hi && q1 >= lo && q1 < hi)) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + q0));
+          if ((long long)q1 < nodes_cap)   // (low1 of a site operator is never written)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + q1));
+        }
+      }
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
         if (!(a >= lo && a < hi && b >= lo && b < hi)) uf_union(d.parent, a, b);
       });
+      p0 = q0; p1 = q1;
     }
   }
 }

@@ -297,6 +297,7 @@ def run_gpu(args):
                        "operators_per_mcs": nop_mean, "clusters_per_mcs": float(out["nc"].mean()),
                        "open_clusters_per_mcs": float(out["noc"].mean()),
                        "thermalisation_mcs": therm, "tile_sites": tile, "windows": info["num_windows"],
+                       "page_capacity": info["page_capacity"], "reserve": args.reserve,
                        "tiles": info["num_tiles"], "device_bytes": info["device_bytes"],
                        "l2_policy": "working set (%.1f GB) larger than L2" % (info["device_bytes"] / 1e9)
                        if info["device_bytes"] > 2.5e8 else "working set comparable to L2",
@@ -339,6 +340,7 @@ def load_comm():
 
 def make_engine(lq, lat, beta, tile, local, rank, world, args, timers=False):
     eng = lq.Engine(lat, beta, seed=29833, device=local, tile_sites=tile, timers=timers,
+                    window_ops=args.window_ops, reserve=args.reserve,
                     rank=rank if world > 1 else 0, nranks=world)
     if world > 1:
         load_comm().attach_torch_distributed(eng, local)
@@ -353,6 +355,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("LQ_BENCH_WORKLOAD", "square1024_beta1024"))
     ap.add_argument("--tile-sites", type=int, default=0)
+    ap.add_argument("--window-ops", type=float, default=0.0, help="candidates per bond and window (0 = engine default)")
+    ap.add_argument("--reserve", type=float, default=1.4,
+                    help="page capacity / mean candidate count (engine default 1.7; the Heisenberg workloads "
+                         "hold 1.17 operators per candidate)")
     ap.add_argument("--therm", type=int, default=-1, help="override thermalisation sweeps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -64,7 +64,7 @@ typedef struct lq_options {
   uint64_t seed;             /* Philox key; the reference seeds mt19937 (loop.C:50)              */
   int32_t  device;           /* CUDA device ordinal                                              */
   int32_t  tile_sites;       /* spatial tile size in sites (0 = default 64)                      */
-  double   window_ops;       /* target mean candidate count per bond and time window (0 = 2.0)   */
+  double   window_ops;       /* target mean candidate count per bond and time window (0 = 3.0)   */
   double   reserve;          /* page capacity / mean candidate count (0 = default 1.7); the
                                 analogue of RESERVE_OPERATORS (path_integral.C:240-243)          */
   double   cluster_reserve;  /* cluster arena / operator arena (0 = default 0.75)                */
