@@ -115,6 +115,7 @@ struct Dev {
   uint32_t* d_nc;    // [0] number of clusters, [1] clusters rooted at a site node
   int* d_err;
   int dbg;           // LQ_DBG environment variable (experiments only)
+  unsigned long long* dbgc;  // [8] experiment counters (LQ_DBG & 1): edges, find hops, CAS retries, ...
 };
 
 // ------------------------------------------------------------------------------------------
@@ -178,6 +179,34 @@ __device__ __forceinline__ node_t uf_find(node_t* parent, node_t x) {
     p = gp;
   }
   return x;
+}
+
+// instrumented copy for LQ_DBG=1 (hop statistics of the global union-find)
+__device__ __forceinline__ node_t uf_find_count(node_t* parent, node_t x, unsigned& hops) {
+  node_t p = uf_load(parent + x);
+  while (p != x) {
+    node_t gp = uf_load(parent + p);
+    if (gp != p) parent[x] = gp;
+    x = p;
+    p = gp;
+    ++hops;
+  }
+  return x;
+}
+__device__ __forceinline__ void uf_union_count(node_t* parent, node_t a, node_t b, unsigned long long* c) {
+  unsigned hops = 0, retries = 0;
+  node_t ra = uf_find_count(parent, a, hops);
+  node_t rb = uf_find_count(parent, b, hops);
+  while (ra != rb) {
+    if (ra < rb) { node_t t = ra; ra = rb; rb = t; }
+    node_t old = atomicCAS(parent + ra, ra, rb);
+    if (old == ra) break;
+    ++retries;
+    ra = uf_find_count(parent, old, hops);
+    rb = uf_find_count(parent, rb, hops);
+  }
+  atomicAdd(c + 0, 1ull); atomicAdd(c + 1, (unsigned long long)hops); atomicAdd(c + 2, (unsigned long long)retries);
+  if (hops > 16) atomicAdd(c + 3, 1ull);
 }
 
 __device__ __forceinline__ void uf_union(node_t* parent, node_t a, node_t b) {

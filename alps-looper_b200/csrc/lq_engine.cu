@@ -319,6 +319,7 @@ struct lq_engine {
   DBuf<uint16_t> boff[2];
   DBuf<uint8_t> spinW;
   DBuf<uint32_t> flipw, openw;
+  DBuf<unsigned long long> dbgc;
   DBuf<long long> est;
   DBuf<int> est0;
   double* h_out = nullptr;  // pinned
@@ -632,6 +633,8 @@ struct lq_engine {
     d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p; d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
     d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
+    if (!dbgc.p) { dbgc.alloc(8, nullptr); CK(cudaMemset(dbgc.p, 0, 8 * sizeof(unsigned long long))); }
+    d.dbgc = dbgc.p;
   }
 
   void clear_state() {
@@ -1177,6 +1180,16 @@ int lq_set_comm(lq_handle h, const lq_comm* comm) {
 }
 
 void* lq_stream(lq_handle h) { return h ? (void*)h->stream : nullptr; }
+
+// experiment counters (LQ_DBG=1; not part of the public header): reads and clears 8 values
+int lq_debug_counters(lq_handle h, unsigned long long* out) {
+  if (!h || !out) return LQ_E_INVALID;
+  cudaSetDevice(h->opt.device);
+  cudaStreamSynchronize(h->stream);
+  cudaMemcpy(out, h->dbgc.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(h->dbgc.p, 0, 8 * sizeof(unsigned long long));
+  return LQ_OK;
+}
 
 const char* lq_last_error(void) { return g_err.c_str(); }
 const char* lq_version(void) { return "alps-looper_b200 0.1 (sm_100a)"; }

@@ -479,7 +479,10 @@ k_union_global(Dev d, int buf) {
         }
       }
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
-        if (!(a >= lo && a < hi && b >= lo && b < hi)) uf_union(d.parent, a, b);
+        if (!(a >= lo && a < hi && b >= lo && b < hi)) {
+          if (d.dbg & 1) uf_union_count(d.parent, a, b, d.dbgc);
+          else uf_union(d.parent, a, b);
+        }
       });
       p0 = q0; p1 = q1;
     }
@@ -515,12 +518,14 @@ k_compress(Dev d, size_t nwords_cap) {
     pr[k] = (x < nn) ? d.parent[x] : (node_t)x;
   }
   bool any = true;
+  unsigned hops = 0;
   while (any) {
     any = false;
 #pragma unroll
     for (int k = 0; k < LQ_NPT; ++k)
-      if (pr[k] != r[k]) { r[k] = pr[k]; pr[k] = d.parent[r[k]]; any = true; }
+      if (pr[k] != r[k]) { r[k] = pr[k]; pr[k] = d.parent[r[k]]; any = true; ++hops; }
   }
+  if (d.dbg & 1) { atomicAdd(d.dbgc + 4, (unsigned long long)LQ_NPT); atomicAdd(d.dbgc + 5, (unsigned long long)hops); }
 #pragma unroll
   for (int k = 0; k < LQ_NPT; ++k) {
     const size_t x = base + (size_t)k * 256;
@@ -595,6 +600,8 @@ __device__ __forceinline__ void est_global_add(const Dev& d, uint32_t cid, long 
                                                long long c, long long e) {
   if ((long long)cid >= d.nccap) return;  // flagged by k_relabel
   unsigned long long* est = (unsigned long long*)d.est;
+  // one array per field: the four sums of a cluster in ONE 32-byte sector were measured slower
+  // (k_estimate +15 %, k_collect x2: the L2 atomic units serialise per sector)
   if (a) atomicAdd(est + 0 * d.nccap + cid, (unsigned long long)a);
   if (b) atomicAdd(est + 1 * d.nccap + cid, (unsigned long long)b);
   if (c) atomicAdd(est + 2 * d.nccap + cid, (unsigned long long)c);
@@ -663,6 +670,8 @@ k_estimate(Dev d, int buf) {
   __syncthreads();
   const int n = d.pcount[buf][p];
   const int idx0 = d.nbase[p];
+  // (staging the cluster ids of the page's own nodes in shared memory was measured 10 % slower than
+  // gathering them: the gathers already hit L1/L2)
   uint32_t* ginfo = d.info[buf] + p * (size_t)d.cap;
   const double* gtime = d.time[buf] + p * (size_t)d.cap;
   for (int j0 = threadIdx.x; j0 < n; j0 += blockDim.x * LQ_EST_U) {
