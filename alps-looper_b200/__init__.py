@@ -26,7 +26,8 @@ lib = C.CDLL(LIB_PATH)
 class LqLattice(C.Structure):
     _fields_ = [("num_sites", C.c_int32), ("num_bonds", C.c_int32),
                 ("src", C.POINTER(C.c_int32)), ("dst", C.POINTER(C.c_int32)),
-                ("gauge", C.POINTER(C.c_double)), ("dims", C.c_int32 * 3)]
+                ("gauge", C.POINTER(C.c_double)), ("dims", C.c_int32 * 3),
+                ("vector_dim", C.c_int32), ("bond_vectors", C.POINTER(C.c_double))]
 
 
 class LqModel(C.Structure):
@@ -50,7 +51,7 @@ OP_DTYPE = np.dtype([("time", "<f8"), ("loc", "<i4"), ("type", "<i4")])
 
 COLLECTOR_FIELDS = ["nop", "nc", "noc", "ene",
                     "umag0", "usize2", "umag2", "usize4", "umag4", "usize", "umag",
-                    "smag0", "ssize2", "smag2", "ssize4", "smag4", "ssize", "smag", "tlen"]
+                    "smag0", "ssize2", "smag2", "ssize4", "smag4", "ssize", "smag", "tlen", "w2"]
 
 
 class LqCollector(C.Structure):
@@ -135,7 +136,9 @@ def chain_lattice(L):
     src = np.arange(L, dtype=np.int32)
     dst = ((src + 1) % L).astype(np.int32)
     gauge = np.where(np.arange(L) % 2 == 0, 1.0, -1.0)
-    return dict(num_sites=L, src=src, dst=dst, gauge=gauge, dims=(L, 0, 0))
+    vec = np.zeros((L, 3))
+    vec[:, 0] = 1.0
+    return dict(num_sites=L, src=src, dst=dst, gauge=gauge, dims=(L, 0, 0), bond_vectors=vec, vector_dim=1)
 
 
 def hypercubic_lattice(dims):
@@ -149,7 +152,7 @@ def hypercubic_lattice(dims):
     for d in dims:
         coords.append(rem % d)
         rem = rem // d
-    src, dst = [], []
+    src, dst, vecs = [], [], []
     stride = 1
     for k, d in enumerate(dims):
         nxt = idx + stride * (((coords[k] + 1) % d) - coords[k])
@@ -159,6 +162,10 @@ def hypercubic_lattice(dims):
             src.append(idx[keep]); dst.append(nxt[keep])
         else:
             src.append(idx); dst.append(nxt)
+        v = np.zeros((len(src[-1]), 3))   # relative bond vector: +1 along direction k (also across the seam)
+        if k < 3:
+            v[:, k] = 1.0
+        vecs.append(v)
         stride *= d
     src = np.concatenate(src).astype(np.int32)
     dst = np.concatenate(dst).astype(np.int32)
@@ -168,7 +175,8 @@ def hypercubic_lattice(dims):
     bip = all(d % 2 == 0 for d in dims)
     gauge = np.where(parity % 2 == 0, 1.0, -1.0) if bip else np.zeros(n)
     dd = tuple(dims + [0] * (3 - len(dims)))
-    return dict(num_sites=n, src=src, dst=dst, gauge=gauge, dims=dd)
+    return dict(num_sites=n, src=src, dst=dst, gauge=gauge, dims=dd,
+                bond_vectors=np.concatenate(vecs), vector_dim=min(len(dims), 3))
 
 
 def xxz_weights(jxy, jz, a=0.0):
@@ -193,7 +201,8 @@ class Engine:
 
     def __init__(self, lattice, beta, weights=(0.5, 0.0, 0.0, 0.0), energy_offset=None, seed=29833,
                  device=0, tile_sites=0, window_ops=0.0, reserve=0.0, cluster_reserve=0.0,
-                 rank=0, nranks=1, timers=False, bond_weights=None, site_weight=0.0, site_weights=None):
+                 rank=0, nranks=1, timers=False, bond_weights=None, site_weight=0.0, site_weights=None,
+                 stiffness=False):
         self.lattice = lattice
         self.N = int(lattice["num_sites"])
         self._src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
@@ -210,6 +219,18 @@ class Engine:
                      if self._gauge is not None else None)
         dims = tuple(lattice.get("dims", (0, 0, 0)))
         lat.dims = (C.c_int32 * 3)(*dims)
+        # winding-number estimator (stiffness.h): only when asked for and the lattice has vectors
+        self._bvec = None
+        lat.vector_dim = 0
+        lat.bond_vectors = None
+        if stiffness:
+            if lattice.get("bond_vectors") is None:
+                raise ValueError("stiffness needs lattice['bond_vectors'] (B x 3) and lattice['vector_dim']")
+            self._bvec = np.ascontiguousarray(lattice["bond_vectors"], dtype=np.float64).reshape(-1)
+            assert self._bvec.size == 3 * self.B
+            lat.vector_dim = int(lattice.get("vector_dim", 3))
+            lat.bond_vectors = self._bvec.ctypes.data_as(C.POINTER(C.c_double))
+        self.vector_dim = lat.vector_dim
         mod = LqModel()
         self._bw = None
         if bond_weights is not None:
@@ -357,3 +378,8 @@ def observables(coll, beta, num_sites, sse=False):
     o["Transverse Magnetization"] = 0.5 * coll["tlen"]
     o["Transverse Magnetization Density"] = 0.5 * coll["tlen"] / vol
     return o
+
+
+def stiffness(coll, beta, vector_dim):
+    """stiffness.h:131-133: "Stiffness" = w2 / (beta * dim)."""
+    return coll["w2"] / (beta * vector_dim)

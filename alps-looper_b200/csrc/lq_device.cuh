@@ -108,6 +108,9 @@ struct Dev {
   int* est0;       // [4][N]     usize0, umag0, ssize0, smag0 in half units
   uint32_t* flipw; // [nccap/32 + 1] flip decision per cluster id, packed
   uint32_t* openw; // [nccap/32 + 1] cluster is cut by a site operator (has_site only), packed
+  int sdim;              // dimensions of the winding-number estimator (0: stiffness not measured)
+  const short* bond_vec; // [3*B] relative bond vectors in units of 1/1024 (stiffness.h:63-76)
+  int* wind;             // [sdim][nccap] winding of every cluster in those units
   long long ncap;   // operator arena (= P*cap)
   long long nccap;  // cluster arena
   // ---- scalars on device ----

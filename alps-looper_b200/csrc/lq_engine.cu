@@ -269,6 +269,8 @@ struct lq_engine {
   int W = 1, Wl = 1, w0 = 0, cap = 0, tpb = 32, npo = 1, ug = 1;
   int Breal = 0;          // bonds of the caller's lattice; internal bonds Breal.. are site pseudo-bonds
   bool has_site = false;
+  int sdim = 0;                      // dimensions of the winding estimator (0 = off)
+  std::vector<short> bond_vec_e;     // [3 * internal-order-independent external bond] fixed point
   size_t P = 0;
   long long ncap = 0, nccap = 0;
   size_t nwords_cap = 0, device_bytes = 0;
@@ -319,6 +321,8 @@ struct lq_engine {
   DBuf<uint16_t> boff[2];
   DBuf<uint8_t> spinW;
   DBuf<uint32_t> flipw, openw;
+  DBuf<short> bond_vec;
+  DBuf<int> wind;
   DBuf<unsigned long long> dbgc;
   DBuf<long long> est;
   DBuf<int> est0;
@@ -396,6 +400,19 @@ struct lq_engine {
           weights.push_back(0); weights.push_back(0); weights.push_back(0);
         }
     }
+    // relative bond vectors for the winding numbers (stiffness.h:63-76), fixed point 1/1024
+    sdim = 0;
+    bond_vec_e.assign(3 * xsrc.size(), 0);
+    if (L.bond_vectors && L.vector_dim > 0) {
+      sdim = std::min(3, (int)L.vector_dim);   // stiffness.h:68-73 caps at MAX_DIM
+      for (int b = 0; b < L.num_bonds; ++b)
+        for (int x = 0; x < 3; ++x) {
+          const double v = L.bond_vectors[3 * (size_t)b + x] * LQ_WFX;
+          if (!(std::fabs(v) < 32000) || std::fabs(v - std::nearbyint(v)) > 1e-6)
+            fail(LQ_E_UNSUPPORTED, "bond vector is not a multiple of 1/1024 below 31");
+          bond_vec_e[3 * (size_t)b + x] = (short)std::nearbyint(v);
+        }
+    }
     gauge_e.assign(L.num_sites, 0);
     if (L.gauge)
       for (int s = 0; s < L.num_sites; ++s) gauge_e[s] = (signed char)(L.gauge[s] > 0 ? 1 : (L.gauge[s] < 0 ? -1 : 0));
@@ -449,6 +466,12 @@ struct lq_engine {
     bond_p.upload(bp, &device_bytes);
     bond_q.upload(bq, &device_bytes);
     gauge.upload(gi, &device_bytes);
+    {
+      std::vector<short> bv(3 * (size_t)B, 0);
+      for (int i = 0; i < B; ++i)
+        for (int x = 0; x < 3; ++x) bv[3 * (size_t)i + x] = bond_vec_e[3 * (size_t)part.bond_i2e[i] + x];
+      bond_vec.upload(bv, &device_bytes);
+    }
     whalo_cnt.upload(part.whalo_cnt, &device_bytes);
     {
       std::vector<int> tl(B);
@@ -538,6 +561,11 @@ struct lq_engine {
       if (stage_smem > 200 * 1024)
         fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
       const int sm = (int)stage_smem;
+      if (sdim > 0) {
+        const int es = (int)(sizeof(lq::EstHash) + sizeof(lq::WindHash) + 8 * (size_t)part.nbmax + 16);
+        CK(cudaFuncSetAttribute(lq::k_estimate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+        CK(cudaFuncSetAttribute(lq::k_estimate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+      }
       k1_fn = pick_k1();
       CK(cudaFuncSetAttribute(k1_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       // union groups: consecutive windows of a tile unified in one shared-memory union-find
@@ -581,6 +609,8 @@ struct lq_engine {
     est.alloc(4 * (size_t)nccap, tb);
     est0.alloc(4 * (size_t)N, tb);
     flipw.alloc((size_t)nccap / 32 + 2, tb);
+    wind.alloc(sdim > 0 ? (size_t)sdim * (size_t)nccap : 1, tb);
+    CK(cudaMemset(wind.p, 0, wind.n * sizeof(int)));
     openw.alloc(has_site ? (size_t)nccap / 32 + 2 : 1, tb);
     CK(cudaMemset(openw.p, 0, openw.n * sizeof(uint32_t)));
     nblk_collect = std::min<size_t>(((size_t)nccap + 255) / 256, (size_t)sm_count * 8);
@@ -630,7 +660,8 @@ struct lq_engine {
     }
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
-    d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p; d.ncap = ncap; d.nccap = nccap;
+    d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p;
+    d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
     d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
     if (!dbgc.p) { dbgc.alloc(8, nullptr); CK(cudaMemset(dbgc.p, 0, 8 * sizeof(unsigned long long))); }
@@ -722,9 +753,15 @@ struct lq_engine {
     }
     {
       Section s(this, 12);
-      const size_t est_smem = sizeof(lq::EstHash) + 2 * (size_t)part.nbmax + 16;
-      if (flip) lq::k_estimate<true><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
-      else lq::k_estimate<false><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+      const size_t est_smem = sizeof(lq::EstHash) + 2 * (size_t)part.nbmax + 16 +
+                              (sdim > 0 ? sizeof(lq::WindHash) + 6 * (size_t)part.nbmax : 0);
+      if (sdim > 0) {
+        if (flip) lq::k_estimate<true, true><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+        else lq::k_estimate<false, true><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+      } else {
+        if (flip) lq::k_estimate<true, false><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+        else lq::k_estimate<false, false><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+      }
       lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
       launches += 2;
       if (opt.nranks > 1) {
@@ -830,7 +867,7 @@ struct lq_engine {
     c->usize = o[5]; c->umag = o[6];
     c->smag0 = o[7]; c->ssize2 = o[8]; c->smag2 = o[9]; c->ssize4 = o[10]; c->smag4 = o[11];
     c->ssize = o[12]; c->smag = o[13];
-    c->nc = o[14]; c->nop = o[15]; c->noc = o[17]; c->tlen = o[18];
+    c->nc = o[14]; c->nop = o[15]; c->noc = o[17]; c->tlen = o[18]; c->w2 = o[19];
     c->ene = energy_offset - c->nop / beta;  // path_integral.C:851
   }
 

@@ -625,6 +625,27 @@ __device__ __forceinline__ void est_hash_add(const Dev& d, EstHash* h, uint32_t 
   est_global_add(d, cid, a, b, c, e);  // table crowded: go straight to HBM
 }
 
+// winding-number legs (stiffness.h:93-104, source side only): merged in the same hash (three more
+// 32-bit fields per slot), one global atomic per distinct cluster and dimension at the end
+struct WindHash { int w[3][LQ_HASH]; };
+
+__device__ __forceinline__ void wind_add(const Dev& d, EstHash* h, WindHash* wh, uint32_t cid, int sgn,
+                                         const short* vec) {
+  uint32_t slot = (cid * 2654435761u) >> 22;
+  for (int probe = 0; probe < 8; ++probe) {
+    const uint32_t k = atomicCAS(&h->key[slot], 0xffffffffu, cid);
+    if (k == 0xffffffffu || k == cid) {
+      for (int x = 0; x < d.sdim; ++x)
+        if (vec[x]) atomicAdd(&wh->w[x][slot], sgn * (int)vec[x]);
+      return;
+    }
+    slot = (slot + 1) & (LQ_HASH - 1);
+  }
+  if ((long long)cid < d.nccap)
+    for (int x = 0; x < d.sdim; ++x)
+      if (vec[x]) atomicAdd(d.wind + (size_t)x * d.nccap + cid, sgn * (int)vec[x]);
+}
+
 // Bernoulli(1/2) per cluster (path_integral.C:796-799): Philox4x32-10 keyed by (cluster id, rank,
 // step); 32 clusters per thread, one packed word each.  Persistent grid.
 __global__ void __launch_bounds__(256)
@@ -648,16 +669,19 @@ k_flipbits(Dev d, const StepParams* __restrict__ sp) {
 // iff the cluster arriving from below on the source side and the one leaving upwards are flipped
 // differently -- the two cluster ids are already in registers here.
 #define LQ_EST_U 1  /* operators per thread and iteration: independent gathers in flight */
-template <bool FLIP>
+template <bool FLIP, bool STIFF>
 __global__ void __launch_bounds__(256)
 k_estimate(Dev d, int buf) {
   extern __shared__ unsigned char s_raw[];
   EstHash* h = (EstHash*)s_raw;
-  signed char* s_gg = (signed char*)(h + 1);   // [2*nbmax] gauge of the two ends of every own bond
+  WindHash* wh = (WindHash*)(h + 1);           // (STIFF only)
+  short* s_vec = (short*)(wh + 1);             // [3*nbmax] relative vectors of the own bonds (STIFF only)
+  signed char* s_gg = STIFF ? (signed char*)(s_vec + 3 * d.nbmax) : (signed char*)(h + 1);   // [2*nbmax] gauge of the two ends of every own bond
   for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
     h->key[i] = 0xffffffffu;
 #pragma unroll
     for (int f = 0; f < 4; ++f) { h->lo[f][i] = 0u; h->hi[f][i] = 0u; }
+    if (STIFF) { wh->w[0][i] = 0; wh->w[1][i] = 0; wh->w[2][i] = 0; }
   }
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl);
@@ -666,6 +690,7 @@ k_estimate(Dev d, int buf) {
     s_gg[2 * i] = d.gauge[d.bond_s0[b0 + i]];
     const int s1 = d.bond_s1[b0 + i];
     s_gg[2 * i + 1] = s1 >= 0 ? d.gauge[s1] : (signed char)0;
+    if (STIFF) { s_vec[3 * i] = d.bond_vec[3 * (b0 + i)]; s_vec[3 * i + 1] = d.bond_vec[3 * (b0 + i) + 1]; s_vec[3 * i + 2] = d.bond_vec[3 * (b0 + i) + 2]; }
   }
   __syncthreads();
   const int n = d.pcount[buf][p];
@@ -722,6 +747,10 @@ k_estimate(Dev d, int buf) {
         if ((long long)cu0[u] < d.nccap) atomicOr(d.openw + (cu0[u] >> 5), 1u << (cu0[u] & 31u));
         continue;
       }
+      if (STIFF) {   // stiffness.h:93-104: end_bs adds (1-2c) vr below, begin_bs subtracts it above
+        wind_add(d, h, wh, cl0[u], m0, s_vec + 3 * lb);
+        wind_add(d, h, wh, cu0[u], -n0, s_vec + 3 * lb);
+      }
       if (d.npo == 1) {
         // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
         est_hash_add(d, h, cl0[u], 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
@@ -742,6 +771,9 @@ k_estimate(Dev d, int buf) {
 #pragma unroll
       for (int f = 0; f < 4; ++f) v[f] = (long long)(((unsigned long long)h->hi[f][i] << 32) | h->lo[f][i]);
       est_global_add(d, k, v[0], v[1], v[2], v[3]);
+      if (STIFF && (long long)k < d.nccap)
+        for (int x = 0; x < d.sdim; ++x)
+          if (wh->w[x][i]) atomicAdd(d.wind + (size_t)x * d.nccap + k, wh->w[x][i]);
     }
   }
 }
@@ -796,9 +828,10 @@ k_estimate_sites(Dev d) {
 // decision per cluster (path_integral.C:796-799).  Deterministic two-stage reduction
 // (warp shuffles -> per-CTA partials -> one CTA).  The cluster arena is zeroed on the way.
 // ------------------------------------------------------------------------------------------
-#define LQ_NSUM 15   /* 14 susceptibility sums (susceptibility.h:158-160) + transmag length (transmag.h:98) */
+#define LQ_NSUM 16   /* 14 susceptibility sums (susceptibility.h:158-160), transmag length (transmag.h:98), stiffness w2 */
 #define LQ_NSUS 14
-#define LQ_GEST 10   /* int64 fields per global open cluster: 4 sums, 4 tau=0 sums, site-leg count, spare */
+#define LQ_GEST 12   /* int64 fields per global open cluster: 4 sums, 4 tau=0 sums, site-leg count, 3 windings */
+#define LQ_WFX 1024.0 /* fixed-point scale of the relative bond vectors */
 __global__ void __launch_bounds__(256)
 k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
   __shared__ double s_red[8][LQ_NSUM];
@@ -833,6 +866,10 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
     v[12] += ssize * ssize; v[13] += smag * smag;
     // transmag.h:98-101: only clusters cut by a site operator count, with their total length = 2 usize
     if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[14] += 2.0 * usize;
+    for (int x = 0; x < d.sdim; ++x) {   // stiffness.h:125-128: w2 += (winding / 2)^2 per dimension
+      const double w = (0.5 / LQ_WFX) * (double)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
+      v[15] += w * w;
+    }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -874,7 +911,7 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
   if (threadIdx.x < LQ_NSUM) {
     double x = 0;
     for (int w = 0; w < 8; ++w) x += s_red[w][threadIdx.x];
-    out[threadIdx.x < LQ_NSUS ? threadIdx.x : 18] = x;   // slot 18: transmag length
+    out[threadIdx.x < LQ_NSUS ? threadIdx.x : threadIdx.x + 4] = x;   // slot 18: transmag length, 19: stiffness w2
   }
   if (threadIdx.x == 0) {
     out[14] = (double)nc;
@@ -1042,6 +1079,10 @@ __global__ void k_mr_gather(Dev d, MrDev m) {
         if (v) atomicAdd(ge + 4 + f, (unsigned long long)(long long)v);
       }
     if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) atomicAdd(ge + 8, 1ull);
+    for (int x = 0; x < d.sdim; ++x) {
+      const int v = atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
+      if (v) atomicAdd(ge + 9 + x, (unsigned long long)(long long)v);
+    }
     atomicAdd(m.d_g + 1, 1u);
   }
 }
@@ -1092,6 +1133,7 @@ k_mr_gcollect(Dev d, MrDev m) {
     const double ssize0 = 0.5 * i64_to_f64(ge[6]), smag0 = 0.5 * i64_to_f64(ge[7]);
 #pragma unroll
     if (ge[8] > 0) v[14] += 2.0 * usize;
+    for (int x = 0; x < d.sdim; ++x) { const double w = (0.5 / LQ_WFX) * i64_to_f64(ge[9 + x]); v[15] += w * w; }
 #pragma unroll
     for (int f = 0; f < LQ_GEST; ++f) ge[f] = 0;
     const double a = usize0 * usize0, b = umag0 * umag0, e = ssize0 * ssize0, g = smag0 * smag0;
@@ -1119,11 +1161,11 @@ k_mr_gcollect(Dev d, MrDev m) {
 __global__ void k_mr_rankvec(Dev d, MrDev m, const double* slot) {
   const int i = threadIdx.x;
   if (i < LQ_NSUS) m.rankvec[i] = slot[i];
-  if (i == 18) m.rankvec[18] = slot[18];                     // transmag length of the closed clusters
+  if (i == 18 || i == 19) m.rankvec[i] = slot[i];            // transmag length / stiffness w2 of the closed clusters
   if (i == 14) m.rankvec[14] = slot[14] - (double)m.d_g[1];  // closed clusters of this rank
   if (i == 15) m.rankvec[15] = slot[15];                     // operators of this slab
   if (i == 16) m.rankvec[16] = slot[16];                     // error flags
-  if (i > 16 && i < 32 && i != 18) m.rankvec[i] = 0;
+  if (i > 16 && i < 32 && i != 18 && i != 19) m.rankvec[i] = 0;
 }
 
 __global__ void k_mr_final(Dev d, MrDev m, double* slot) {
@@ -1133,6 +1175,7 @@ __global__ void k_mr_final(Dev d, MrDev m, double* slot) {
   for (int r = 0; r < d.nranks; ++r) x += m.allvec[r * 32 + i];
   if (i < LQ_NSUS) x += m.gsum[i];
   if (i == 18) x += m.gsum[14];
+  if (i == 19) x += m.gsum[15];
   if (i == 14) x += (double)m.d_g[0];
   if (i == 17) x = (double)m.d_g[0];  // number of clusters that were open (diagnostic)
   slot[i] = x;

@@ -3,6 +3,7 @@
 // :576-675 virtual graph -- identical to the real graph for S=1/2).  ALPS XML lattice libraries are
 // out of scope; LATTICE selects a built-in generator instead.
 #pragma once
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -15,6 +16,8 @@ struct virtual_graph {
   std::vector<int> src, dst;
   std::vector<double> gauge;
   int dims[3] = {0, 0, 0};
+  std::vector<double> bond_vector_relative;  // 3 per bond (lattice.h bond_vector_relative_t, stiffness.h:63)
+  int dimension = 0;
 };
 
 inline int num_sites(const virtual_graph& g) { return g.nsites; }
@@ -46,6 +49,7 @@ public:
     int n = 1;
     for (int e : ext) { if (e < 2) throw std::invalid_argument("lattice extent < 2"); n *= e; }
     vg_.nsites = n;
+    vg_.dimension = int(std::min<size_t>(ext.size(), 3));
     bipartite_ = true;
     for (size_t k = 0; k < ext.size() && k < 3; ++k) { vg_.dims[k] = ext[k]; if (ext[k] % 2) bipartite_ = false; }
     vg_.gauge.assign(n, 0.0);
@@ -56,6 +60,7 @@ public:
         if (ext[k] == 2 && c == 1) continue;  // a ring of two sites has one bond
         vg_.src.push_back(s);
         vg_.dst.push_back(s + stride * (((c + 1) % ext[k]) - c));
+        for (size_t x = 0; x < 3; ++x) vg_.bond_vector_relative.push_back(x == k ? 1.0 : 0.0);
       }
       stride *= ext[k];
     }

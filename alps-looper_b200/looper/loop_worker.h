@@ -36,6 +36,10 @@ public:
     L.dst = g.dst.data();
     L.gauge = lattice.is_bipartite() ? g.gauge.data() : nullptr;
     for (int k = 0; k < 3; ++k) L.dims[k] = g.dims[k];
+    // MEASURE[Stiffness] (looper/stiffness.h): winding numbers need the relative bond vectors
+    measure_stiffness = p.defined("MEASURE[Stiffness]") && g.dimension > 0;
+    L.vector_dim = measure_stiffness ? g.dimension : 0;
+    L.bond_vectors = measure_stiffness ? g.bond_vector_relative.data() : nullptr;
     lq_model M;
     M.bond_weights = model.bond_weights().data();
     for (int k = 0; k < 4; ++k) M.uniform_weights[k] = 0;
@@ -83,6 +87,7 @@ public:
     energy::commit(obs, coll, beta_, vol);
     susceptibility::commit(obs, coll, beta_, vol, lattice.is_bipartite());
     if (model.site_weight() > 0) transverse_magnetization::commit(obs, coll, vol);
+    if (measure_stiffness) stiffness::commit(obs, coll, beta_, lattice.vg().dimension);
     last_ = coll;
   }
 
@@ -122,6 +127,7 @@ private:
   temperature temp;
   mc_steps mcs;
   bool enable_improved_estimator = true;
+  bool measure_stiffness = false;
   double beta_ = 1;
   lq_handle h_ = nullptr;
   lq_collector last_ = lq_collector();

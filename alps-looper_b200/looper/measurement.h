@@ -128,6 +128,13 @@ struct susceptibility {
   }
 };
 
+// stiffness.h:118-133
+struct stiffness {
+  static void commit(observable_set& m, const lq_collector& c, double beta, int dim, double sign = 1) {
+    if (dim > 0) m["Stiffness"] << sign * c.w2 / (beta * dim);
+  }
+};
+
 // transmag.h:95-110: length of the clusters cut by a site operator
 struct transverse_magnetization {
   static void commit(observable_set& m, const lq_collector& c, double vol, double sign = 1) {

@@ -44,6 +44,11 @@ typedef struct lq_lattice {
   const int32_t* dst;
   const double*  gauge;      /* may be NULL (= not bipartite)                                    */
   int32_t        dims[3];
+  /* optional, for the spin stiffness (looper/stiffness.h:63-76): relative lattice vector of every
+   * bond (bond_vector_relative of the real graph), 3 doubles per bond, multiples of 1/1024;
+   * vector_dim = spatial dimension to measure (stiffness.h MAX_DIM = 3); NULL / 0 = not measured. */
+  int32_t        vector_dim;
+  const double*  bond_vectors;
 } lq_lattice;
 
 /* Model = graph weights per bond, the output of weight_helper (looper/weight_impl.h:349-423):
@@ -90,6 +95,8 @@ typedef struct lq_collector {
   double smag0, ssize2, smag2, ssize4, smag4, ssize, smag;
   double tlen;   /* transverse_magnetization collector length (transmag.h:95-101): total length of
                     the clusters cut by a site operator; "Transverse Magnetization" = tlen / 2   */
+  double w2;     /* stiffness collector (stiffness.h:118-133): sum over clusters and dimensions of
+                    (winding / 2)^2; "Stiffness" = w2 / (beta * vector_dim)                      */
 } lq_collector;
 
 /* Section timers; ids mirror path_integral.C:284-299 (4 init .. 16 measurement). */

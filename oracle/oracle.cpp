@@ -552,6 +552,48 @@ int orc_build_clusters(int nsites, int nbonds, const int32_t* src, const int32_t
   return 0;
 }
 
+// stiffness.h:82-133 improved estimator on the cluster graph of a given configuration: per cluster
+// winding[i] += (1-2c) vr[i] where a leg ends on the SOURCE side of a bond operator (end_bs, :98-102),
+// -= (1-2c) vr[i] where one begins there (begin_bs, :93-97); frozen bond graphs are skipped by the
+// accumulators (path_integral.C:692); site operators do not contribute (:92,:103).
+// Returns w2 = sum over clusters and dimensions of (winding / 2)^2 (:125-128); also the normal
+// estimator (:137-170) of the same configuration in *w2_normal.
+double orc_stiffness(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                     const double* bond_vectors, int dim, const int32_t* spins, const orc_op* ops,
+                     int64_t n, double* w2_normal) {
+  cluster_graph G;
+  if (build_graph(nsites, nbonds, src, dst, spins, ops, n, G) != 0) return -1;
+  std::vector<double> wind(size_t(G.nc) * 3, 0.0);
+  double total[3] = {0, 0, 0};
+  std::vector<int> sc(spins, spins + nsites);
+  for (int64_t k = 0; k < n; ++k) {
+    if (!(ops[k].loc & 1)) {
+      if (ops[k].type & 1) sc[ops[k].loc >> 1] ^= 1;
+      continue;
+    }
+    const int b = ops[k].loc >> 1, s0 = src[b], s1 = dst[b];
+    const int g = ops[k].type >> 2;
+    const double* vr = bond_vectors + 3 * size_t(b);
+    const bool frozen = (g & 2) == 2;
+    for (int i = 0; i < dim; ++i) {
+      if (!frozen) wind[size_t(G.id[G.l0[k]]) * 3 + i] += (1 - 2 * sc[s0]) * vr[i];
+      total[i] += (1 - 2 * sc[s0]) * vr[i];   // normal_estimator: every bond operator (path_integral.C:529-531)
+    }
+    if (ops[k].type & 1) { sc[s0] ^= 1; sc[s1] ^= 1; }
+    for (int i = 0; i < dim; ++i) {
+      if (!frozen) wind[size_t(G.id[G.u0[k]]) * 3 + i] -= (1 - 2 * sc[s0]) * vr[i];
+      total[i] -= (1 - 2 * sc[s0]) * vr[i];
+    }
+  }
+  double w2 = 0;
+  for (double w : wind) w2 += power2(0.5 * w);
+  if (w2_normal) {
+    *w2_normal = 0;
+    for (int i = 0; i < dim; ++i) *w2_normal += power2(0.5 * total[i]);
+  }
+  return w2;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Generic model: path_integral.C:403-864 restated (XXZ bond graphs 0..3 + site graphs), serial.
 // RNG: std::mt19937 + std::exponential_distribution for the gaps (path_integral.C:413-423 uses

@@ -91,6 +91,14 @@ int      orc_model_sweep(orc_model_sim*, orc_collector* out);
 int64_t  orc_model_num_ops(const orc_model_sim*);
 void     orc_model_get_state(const orc_model_sim*, int32_t* spins, orc_op* ops);
 
+/* looper/stiffness.h:82-133 on a given configuration (bond_vectors: 3 doubles per bond, relative
+ * lattice vectors): returns the improved-estimator collector w2 = sum_c sum_i (winding_i / 2)^2
+ * ("Stiffness" = w2 / (beta dim)) and, in *w2_normal, the normal estimator (:137-170); -1 on an
+ * illegal configuration. */
+double   orc_stiffness(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                       const double* bond_vectors, int dim, const int32_t* spins, const orc_op* ops,
+                       int64_t n, double* w2_normal);
+
 /* looper/union_find.h:57-82,145-172,242-284 replayed as test/union_find.C:40-74 does;
  * writes the exact text of test/union_find.op into buf (returns length needed). */
 int      orc_union_find_replay(char* buf, int buflen);

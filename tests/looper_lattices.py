@@ -6,7 +6,9 @@ def chain_lattice(L):
     src = np.arange(L, dtype=np.int32)
     dst = ((src + 1) % L).astype(np.int32)
     gauge = np.where(np.arange(L) % 2 == 0, 1.0, -1.0)
-    return dict(num_sites=L, src=src, dst=dst, gauge=gauge, dims=(L, 0, 0))
+    vec = np.zeros((L, 3))
+    vec[:, 0] = 1.0
+    return dict(num_sites=L, src=src, dst=dst, gauge=gauge, dims=(L, 0, 0), bond_vectors=vec, vector_dim=1)
 
 
 def hypercubic_lattice(dims):
@@ -17,15 +19,20 @@ def hypercubic_lattice(dims):
     for d in dims:
         coords.append(rem % d)
         rem = rem // d
-    src, dst, stride = [], [], 1
+    src, dst, vecs, stride = [], [], [], 1
     for k, d in enumerate(dims):
         nxt = idx + stride * (((coords[k] + 1) % d) - coords[k])
         keep = (coords[k] == 0) if d == 2 else np.ones(n, dtype=bool)
         src.append(idx[keep]); dst.append(nxt[keep])
+        v = np.zeros((int(keep.sum()), 3))
+        if k < 3:
+            v[:, k] = 1.0
+        vecs.append(v)
         stride *= d
     parity = sum(coords)
     bip = all(d % 2 == 0 for d in dims)
     gauge = np.where(parity % 2 == 0, 1.0, -1.0) if bip else np.zeros(n)
     return dict(num_sites=n, src=np.concatenate(src).astype(np.int32),
                 dst=np.concatenate(dst).astype(np.int32), gauge=gauge,
-                dims=tuple(dims + [0] * (3 - len(dims))))
+                dims=tuple(dims + [0] * (3 - len(dims))),
+                bond_vectors=np.concatenate(vecs), vector_dim=min(len(dims), 3))

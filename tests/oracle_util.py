@@ -57,6 +57,9 @@ def lib():
         L.orc_model_num_ops.argtypes = [C.c_void_p]
         L.orc_model_num_ops.restype = C.c_int64
         L.orc_model_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_stiffness.restype = C.c_double
+        L.orc_stiffness.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
         L.orc_union_find_replay.argtypes = [C.c_char_p, C.c_int]
         L.orc_xxz_weights.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -159,6 +162,22 @@ class OracleModelSim:
         ops = np.zeros(n, dtype=OP_DTYPE)
         lib().orc_model_get_state(self.h, spins.ctypes.data, ops.ctypes.data)
         return spins, ops
+
+
+def stiffness(lattice, spins, ops):
+    """orc_stiffness: (w2 improved, w2 normal) of a configuration."""
+    src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
+    dst = np.ascontiguousarray(lattice["dst"], dtype=np.int32)
+    vec = np.ascontiguousarray(lattice["bond_vectors"], dtype=np.float64).reshape(-1)
+    spins = np.ascontiguousarray(spins, dtype=np.int32)
+    ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+    wn = C.c_double(0)
+    w2 = lib().orc_stiffness(int(lattice["num_sites"]), len(src), src.ctypes.data, dst.ctypes.data,
+                             vec.ctypes.data, int(lattice["vector_dim"]), spins.ctypes.data,
+                             ops.ctypes.data, len(ops), C.byref(wn))
+    if w2 < 0:
+        raise ValueError("orc_stiffness: illegal configuration")
+    return w2, wn.value
 
 
 def build_clusters(lattice, spins, ops):

@@ -34,10 +34,10 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import looper_b200 as lq
     assert C.sizeof(lq.LqOp) == 16 and lq.OP_DTYPE.itemsize == 16
-    assert C.sizeof(lq.LqCollector) == 19 * 8 and lq.COLLECTOR_DTYPE.itemsize == 19 * 8
+    assert C.sizeof(lq.LqCollector) == 20 * 8 and lq.COLLECTOR_DTYPE.itemsize == 20 * 8
     assert C.sizeof(lq.LqTimer) == 56
     assert C.sizeof(lq.LqModel) == 8 + 32 + 8 + 8 + 8
-    assert C.sizeof(lq.LqLattice) == 8 + 3 * 8 + 16
+    assert C.sizeof(lq.LqLattice) == 8 + 3 * 8 + 16 + 8
     assert C.sizeof(lq.LqOptions) == 8 + 4 + 4 + 8 * 3 + 4 * 3 + 4
     # compile the header as C and compare sizeof with the compiler's view
     prog = r'''
