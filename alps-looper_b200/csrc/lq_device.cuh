@@ -109,6 +109,7 @@ struct Dev {
   uint32_t* flipw; // [nccap/32 + 1] flip decision per cluster id, packed
   uint32_t* openw; // [nccap/32 + 1] cluster is cut by a site operator (has_site only), packed
   int sdim;              // dimensions of the winding-number estimator (0: stiffness not measured)
+  int gstride;           // int64 fields per global open cluster in the slab exchange
   const short* bond_vec; // [3*B] relative bond vectors in units of 1/1024 (stiffness.h:63-76)
   int* wind;             // [sdim][nccap] winding of every cluster in those units
   long long ncap;   // operator arena (= P*cap)

@@ -269,6 +269,7 @@ struct lq_engine {
   int W = 1, Wl = 1, w0 = 0, cap = 0, tpb = 32, npo = 1, ug = 1;
   int Breal = 0;          // bonds of the caller's lattice; internal bonds Breal.. are site pseudo-bonds
   bool has_site = false;
+  int gstride() const { return 8 + (has_site ? 1 : 0) + sdim; }
   int sdim = 0;                      // dimensions of the winding estimator (0 = off)
   std::vector<short> bond_vec_e;     // [3 * internal-order-independent external bond] fixed point
   size_t P = 0;
@@ -435,7 +436,7 @@ struct lq_engine {
       fail(LQ_E_INVALID, "tile halo has more than 1024 buckets: lower lq_options.tile_sites");
     if (part.T >= (1 << 21)) fail(LQ_E_INVALID, "more than 2^21 tiles: raise lq_options.tile_sites");
     if (part.nksmax > 1024) fail(LQ_E_INVALID, "tile touches more than 1024 sites: lower lq_options.tile_sites");
-    tpb = ((std::max(std::max(part.nbmax + 1, part.hmax), part.nksmax) + 31) / 32) * 32;
+    tpb = ((std::max(std::max(part.nbmax, part.hmax), part.nksmax) + 31) / 32) * 32;   // K1: a thread per own bucket / halo bucket / K-site
 
     // static tables
     const int N = part.N, B = part.B;
@@ -623,7 +624,7 @@ struct lq_engine {
       mr_gparent.alloc(g2, tb);
       mr_gused.alloc(g2, tb);
       mr_gbitmap.alloc(gw, tb); mr_gwcount.alloc(gw, tb); mr_gwbase.alloc(gw + 1, tb);
-      mr_gest.alloc(g2 * LQ_GEST, tb);
+      mr_gest.alloc(g2 * (size_t)gstride(), tb);
       mr_dg.alloc(4, tb);
       mr_rankvec.alloc(32, tb); mr_allvec.alloc(32 * (size_t)opt.nranks, tb); mr_gsum.alloc(16, tb);
       CK(cudaMemset(mr_topmin.p, 0xff, mr_topmin.n * sizeof(uint32_t)));
@@ -661,7 +662,7 @@ struct lq_engine {
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
     d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p;
-    d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.ncap = ncap; d.nccap = nccap;
+    d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.gstride = gstride(); d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
     d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
     if (!dbgc.p) { dbgc.alloc(8, nullptr); CK(cudaMemset(dbgc.p, 0, 8 * sizeof(unsigned long long))); }
@@ -808,8 +809,11 @@ struct lq_engine {
     CK(cudaMemcpyAsync(h_mr, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     const int64_t ngc = h_mr[0];
-    if (ngc > 0) comm_check(comm.all_reduce_i64(comm.ctx, mr.gest, ngc * LQ_GEST, stream), "all_reduce(open-cluster sums)");
-    lq::k_mr_gcollect<<<1, 256, 0, stream>>>(d, mr);
+    if (ngc > 0) comm_check(comm.all_reduce_i64(comm.ctx, mr.gest, ngc * gstride(), stream), "all_reduce(open-cluster sums)");
+    const unsigned gblk = (unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 4);
+    lq::k_mr_gcollect<<<gblk, 256, 0, stream>>>(d, mr, partial.p);   // (partial is free again after k_collect_final)
+    lq::k_mr_gsum<<<1, 32, 0, stream>>>(mr, partial.p, (int)gblk);
+    launches += 1;
     lq::k_mr_rankvec<<<1, 32, 0, stream>>>(d, mr, out_slot);
     launches += 2;
     comm_check(comm.all_gather(comm.ctx, mr.rankvec, mr.allvec, 32 * sizeof(double), stream), "all_gather(collectors)");

@@ -142,7 +142,8 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   const int n_all = n_own + (packed_total & 0xffff), C = packed_total >> 16;
   if (n_all > d.scap || C > d.ccap) {
     if (tid == 0) { atomicOr(d.d_err, n_all > d.scap ? LQ_ERR_PAGE_FULL : LQ_ERR_CAND_FULL); d.pcount[dst][p] = 0; }
-    if (tid <= nb) bo_new[tid] = 0;
+    if (tid < nb) bo_new[tid] = 0;
+    if (tid == 0) bo_new[nb] = 0;
     return;
   }
 
@@ -159,13 +160,22 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
     const uint32_t* gi = d.info[src] + p * (size_t)d.cap;
     for (int j = tid; j < n_own; j += blockDim.x) { S.time[j] = gt[j]; S.info[j] = gi[j]; }
     if (tid < nb) { S.off[tid] = bo[tid]; S.nkb[tid] = 0; S.cbase[tid] = cb; }
-    if (tid == nb) S.cbase[nb] = C;
+    if (tid == 0) S.cbase[nb] = C;
     if (tid < nh) {
       S.off[nb + tid] = n_own + hoff;
-      for (int j = 0; j < hn; ++j) {
-        S.time[n_own + hoff + j] = d.time[src][hbase + j];
-        S.info[n_own + hoff + j] = (d.info[src][hbase + j] & ((1u << LQ_INFO_LBSHIFT) - 1u)) |
-                                   ((uint32_t)(nb + tid) << LQ_INFO_LBSHIFT);
+      // batches of four: all loads of a batch are in flight before the first shared-memory store
+      for (int j0 = 0; j0 < hn; j0 += 4) {
+        double tt[4];
+        uint32_t ii[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < hn) { tt[u] = d.time[src][hbase + j0 + u]; ii[u] = d.info[src][hbase + j0 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < hn) {
+            S.time[n_own + hoff + j0 + u] = tt[u];
+            S.info[n_own + hoff + j0 + u] = (ii[u] & ((1u << LQ_INFO_LBSHIFT) - 1u)) | ((uint32_t)(nb + tid) << LQ_INFO_LBSHIFT);
+          }
       }
     }
     if (tid == 0) { S.off[nb + nh] = n_all; s_cnt[0] = 0; s_cnt[1] = 0; }
@@ -252,11 +262,12 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   const int noff = block_exscan(cnt, &total, s_scan);
   if (total > d.cap) {
     if (tid == 0) { atomicOr(d.d_err, LQ_ERR_PAGE_FULL); d.pcount[dst][p] = 0; }
-    if (tid <= nb) bo_new[tid] = 0;
+    if (tid < nb) bo_new[tid] = 0;
+    if (tid == 0) bo_new[nb] = 0;
     return;
   }
   if (tid < nb) { bo_new[tid] = (uint16_t)noff; S.noff[tid] = noff; }
-  if (tid == nb) { bo_new[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
+  if (tid == 0) { bo_new[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
   __syncthreads();
 
   // ---- 6: scatter into the compacted new page ----------------------------------------------------

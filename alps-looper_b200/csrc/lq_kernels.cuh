@@ -144,12 +144,20 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
     S.off[S.nb + tid] = n_own + hoff;
     S.idx0[S.nb + tid] = r.idx0;
     S.gbond[S.nb + tid] = b2;
-    if (ok)
-      for (int j = 0; j < r.n; ++j) {
-        S.time[n_own + hoff + j] = d.time[buf][r.base + j];
-        // the staged copy carries the LOCAL bucket id of this tile in the bond bits
-        S.info[n_own + hoff + j] = (d.info[buf][r.base + j] & ((1u << LQ_INFO_LBSHIFT) - 1u)) |
-                                   ((uint32_t)(S.nb + tid) << LQ_INFO_LBSHIFT);
+    if (ok)   // batches of four: all loads of a batch are in flight before the first shared-memory store
+      for (int j0 = 0; j0 < r.n; j0 += 4) {
+        double tt[4];
+        uint32_t ii[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < r.n) { tt[u] = d.time[buf][r.base + j0 + u]; ii[u] = d.info[buf][r.base + j0 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < r.n) {
+            S.time[n_own + hoff + j0 + u] = tt[u];
+            // the staged copy carries the LOCAL bucket id of this tile in the bond bits
+            S.info[n_own + hoff + j0 + u] = (ii[u] & ((1u << LQ_INFO_LBSHIFT) - 1u)) | ((uint32_t)(S.nb + tid) << LQ_INFO_LBSHIFT);
+          }
       }
   }
   if (tid == 0) S.off[S.nb + S.nh] = n_own + total;
@@ -830,7 +838,8 @@ k_estimate_sites(Dev d) {
 // ------------------------------------------------------------------------------------------
 #define LQ_NSUM 16   /* 14 susceptibility sums (susceptibility.h:158-160), transmag length (transmag.h:98), stiffness w2 */
 #define LQ_NSUS 14
-#define LQ_GEST 12   /* int64 fields per global open cluster: 4 sums, 4 tau=0 sums, site-leg count, 3 windings */
+#define LQ_GEST_MAX 12   /* int64 fields per global open cluster: 4 sums, 4 tau=0 sums, [site-leg count], [windings];
+                            d.gstride = 8 + has_site + sdim of them travel in the all-reduce */
 #define LQ_WFX 1024.0 /* fixed-point scale of the relative bond vectors */
 __global__ void __launch_bounds__(256)
 k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
@@ -1068,7 +1077,7 @@ __global__ void k_mr_gather(Dev d, MrDev m) {
     if ((long long)c >= d.nccap || m.topmin[c] != (uint32_t)s) continue;  // not the representative
     if (k == 1 && c < ncs) continue;  // bottom-touching clusters are handled through their bottom rep
     const uint32_t gid = global_cid(d, m, open_id(d, m, c));
-    unsigned long long* ge = (unsigned long long*)m.gest + (size_t)gid * LQ_GEST;
+    unsigned long long* ge = (unsigned long long*)m.gest + (size_t)gid * d.gstride;
     for (int f = 0; f < 4; ++f) {
       const long long v = (long long)atomicExch((unsigned long long*)d.est + f * d.nccap + c, 0ull);
       if (v) atomicAdd(ge + f, (unsigned long long)v);
@@ -1081,7 +1090,7 @@ __global__ void k_mr_gather(Dev d, MrDev m) {
     if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) atomicAdd(ge + 8, 1ull);
     for (int x = 0; x < d.sdim; ++x) {
       const int v = atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
-      if (v) atomicAdd(ge + 9 + x, (unsigned long long)(long long)v);
+      if (v) atomicAdd(ge + 8 + d.has_site + x, (unsigned long long)(long long)v);
     }
     atomicAdd(m.d_g + 1, 1u);
   }
@@ -1116,26 +1125,25 @@ __global__ void k_mr_reset_topmin(Dev d, MrDev m) {
   if ((long long)ct < d.nccap) m.topmin[ct] = 0xffffffffu;
 }
 
-// sums over the all-reduced global clusters (one CTA, deterministic order); clears the table
+// sums over the all-reduced global clusters: persistent grid -> per-CTA partials (fixed assignment
+// of clusters to threads, so the result is reproducible), then k_mr_gsum; clears the table
 __global__ void __launch_bounds__(256)
-k_mr_gcollect(Dev d, MrDev m) {
+k_mr_gcollect(Dev d, MrDev m, double* partial) {
   __shared__ double s_red[8][LQ_NSUM];
   const uint32_t ngc = m.d_g[0];
   double v[LQ_NSUM];
 #pragma unroll
   for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;
   const double sc = 0.5 / LQ_FX;
-  for (size_t c = threadIdx.x; c < ngc; c += blockDim.x) {
-    long long* ge = m.gest + c * LQ_GEST;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ngc; c += (size_t)gridDim.x * blockDim.x) {
+    long long* ge = m.gest + c * d.gstride;
     const double usize = sc * i64_to_f64(ge[0]), umag = sc * i64_to_f64(ge[1]);
     const double ssize = sc * i64_to_f64(ge[2]), smag = sc * i64_to_f64(ge[3]);
     const double usize0 = 0.5 * i64_to_f64(ge[4]), umag0 = 0.5 * i64_to_f64(ge[5]);
     const double ssize0 = 0.5 * i64_to_f64(ge[6]), smag0 = 0.5 * i64_to_f64(ge[7]);
-#pragma unroll
-    if (ge[8] > 0) v[14] += 2.0 * usize;
-    for (int x = 0; x < d.sdim; ++x) { const double w = (0.5 / LQ_WFX) * i64_to_f64(ge[9 + x]); v[15] += w * w; }
-#pragma unroll
-    for (int f = 0; f < LQ_GEST; ++f) ge[f] = 0;
+    if (d.has_site && ge[8] > 0) v[14] += 2.0 * usize;
+    for (int x = 0; x < d.sdim; ++x) { const double w = (0.5 / LQ_WFX) * i64_to_f64(ge[8 + d.has_site + x]); v[15] += w * w; }
+    for (int f = 0; f < d.gstride; ++f) ge[f] = 0;
     const double a = usize0 * usize0, b = umag0 * umag0, e = ssize0 * ssize0, g = smag0 * smag0;
     v[0] += umag0; v[1] += a; v[2] += b; v[3] += a * a; v[4] += b * b; v[5] += usize * usize; v[6] += umag * umag;
     v[7] += smag0; v[8] += e; v[9] += g; v[10] += e * e; v[11] += g * g; v[12] += ssize * ssize; v[13] += smag * smag;
@@ -1152,8 +1160,16 @@ k_mr_gcollect(Dev d, MrDev m) {
   if (threadIdx.x < LQ_NSUM) {
     double x = 0;
     for (int w = 0; w < 8; ++w) x += s_red[w][threadIdx.x];
-    m.gsum[threadIdx.x] = x;
+    partial[(size_t)blockIdx.x * LQ_NSUM + threadIdx.x] = x;
   }
+}
+
+__global__ void k_mr_gsum(MrDev m, const double* partial, int nblk) {
+  const int i = threadIdx.x;
+  if (i >= LQ_NSUM) return;
+  double x = 0;
+  for (int k = 0; k < nblk; ++k) x += partial[(size_t)k * LQ_NSUM + i];
+  m.gsum[i] = x;
 }
 
 // rankvec = local closed sums (from k_collect_final's slot) with nc_closed; then after the

@@ -93,6 +93,28 @@ int main() {
     CHECK(s["Magnetization^4"].mean() == 3 * 4 - 2 * 3);
     CHECK(s["Staggered Susceptibility"].mean() == 10.0 * 7 / 16);
   }
+  // --- transverse field (site graphs, weight_impl.h:62-88), transmag and stiffness commits
+  {
+    Parameters p; p["LATTICE"] = "square lattice"; p.set("L", 4); p.set("Jxy", -1.0); p.set("Jz", 0.5); p.set("Gamma", 0.6);
+    lattice_helper lat(p);
+    spinmodel_helper m(p, lat);
+    CHECK(std::abs(m.site_weight() - 0.3) < 1e-15);
+    CHECK(std::abs(m.graph_weight() - (32 * 0.5 + 16 * 0.3)) < 1e-12);     // bonds v0+v1 = 1/2, sites |Hx|/2
+    CHECK(std::abs(m.energy_offset() - (32 * 0.25 + 16 * 0.3)) < 1e-12);   // weight_impl.h:80,187
+    CHECK(lat.vg().dimension == 2 && lat.vg().bond_vector_relative.size() == 3 * 32);
+    CHECK(lat.vg().bond_vector_relative[0] == 1 && lat.vg().bond_vector_relative[3 * 16 + 1] == 1);
+    Parameters q = p; q.set("Jxy", 1.0);   // antiferromagnetic XY coupling + field: sign problem
+    bool threw = false;
+    try { spinmodel_helper bad(q, lat); } catch (const std::invalid_argument&) { threw = true; }
+    CHECK(threw);
+    observable_set s;
+    lq_collector c = lq_collector();
+    c.tlen = 6; c.w2 = 8;
+    transverse_magnetization::commit(s, c, 16.0);
+    stiffness::commit(s, c, 4.0, 2);
+    CHECK(s["Transverse Magnetization"].mean() == 3.0 && s["Transverse Magnetization Density"].mean() == 3.0 / 16);
+    CHECK(s["Stiffness"].mean() == 8.0 / (4.0 * 2));
+  }
   std::cout << "host ok\n";
   return 0;
 }

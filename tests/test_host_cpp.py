@@ -59,3 +59,26 @@ def test_loop_driver_vs_exact_diagonalisation():
     for k, ex in ed.items():
         mean, err = vals[k]
         assert abs(mean - ex) < 4 * err + 1e-9, (k, mean, err, ex)
+
+
+@pytest.mark.gpu
+def test_loop_driver_transverse_field_vs_exact_diagonalisation():
+    """Gamma (site graphs) and MEASURE[Stiffness] through the host worker, against
+    tests/golden/ed_tfi.json row 2 (Jxy = -1, Jz = 0.5, Gamma = 0.6, L = 8, T = 0.4)."""
+    import json
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "alps-looper_b200/looper")])
+    exe = os.path.join(ROOT, "alps-looper_b200/looper/loop")
+    ed = json.load(open(os.path.join(ROOT, "tests/golden/ed_tfi.json")))[2]
+    params = ('LATTICE = "chain lattice"; L = 8; Jxy = -1; Jz = 0.5; Gamma = 0.6; T = 0.4; '
+              'SWEEPS = 32768; VERBOSE = 1; MEASURE[Stiffness] = 1;\n')
+    out = subprocess.run([exe, "-"], input=params, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    vals = {}
+    for ln in out.stdout.splitlines():
+        m = re.match(r"(.+?): (\S+) \+/- (\S+);", ln)
+        if m:
+            vals[m.group(1).strip()] = (float(m.group(2)), float(m.group(3)))
+    for name, key in (("Energy Density", "energy_density"), ("Transverse Magnetization Density", "transmag_density")):
+        mean, err = vals[name]
+        assert abs(mean - ed[key]) < 5 * err + 1e-9, (name, mean, ed[key], err)
+    assert vals["Stiffness"][0] >= 0
