@@ -457,43 +457,55 @@ k_union_local(Dev d, int buf) {
   }
 }
 
+// Only ~0.12 edges per operator leave their group, and every one of them is a chain of dependent
+// random loads (1.5 tree hops, one CAS).  Chasing them where they are found leaves 7 of 8 lanes
+// idle during the latency-bound part, so the CTA first compacts its global edges into a
+// shared-memory queue (coalesced scan of the operators) and then drains the queue with every lane
+// holding an edge; the first hop of the next queue entry is requested while the current one is chased.
+#define LQ_UQ 3072  /* queue entries per CTA (24 KB); more are chased in place */
 __global__ void __launch_bounds__(256)
 k_union_global(Dev d, int buf) {
+  __shared__ uint2 s_q[LQ_UQ];
+  __shared__ int s_qn;
   const int ngw = (d.Wl + d.ug - 1) / d.ug;
   const int t = blockIdx.x / ngw, w_first = (blockIdx.x % ngw) * d.ug;
   const int w_last = min(w_first + d.ug, d.Wl);
   const size_t p_first = (size_t)t * d.Wl + w_first, p_end = (size_t)t * d.Wl + w_last;
   const node_t lo = upper_node(d, d.nbase[p_first], 0), hi = upper_node(d, d.nbase[p_end], 0);
-  const long long nodes_cap = (long long)d.N + (long long)d.npo * d.ncap;
+  if (threadIdx.x == 0) s_qn = 0;
+  __syncthreads();
   for (size_t p = p_first; p < p_end; ++p) {
     const int n = d.pcount[buf][p];
     const int idx0 = d.nbase[p];
     const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
-    // the find of every edge is a chain of dependent loads: the first hop of the NEXT operator's two
-    // lower nodes is requested (L2 prefetch) before the current one is chased
-    int j = threadIdx.x;
-    node_t p0 = 0, p1 = 0;
-    if (j < n) { p0 = d.low0[idx0 + j] & 0x7fffffffu; p1 = d.low1[idx0 + j] & 0x7fffffffu; }
-    for (; j < n; j += blockDim.x) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
       const int idx = idx0 + j;
-      const int jn = j + blockDim.x;
-      node_t q0 = 0, q1 = 0;
-      if (jn < n) {
-        q0 = d.low0[idx0 + jn] & 0x7fffffffu; q1 = d.low1[idx0 + jn] & 0x7fffffffu;
-        if (!(q0 >= lo && q0 < hi && q1 >= lo && q1 < hi)) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + q0));
-          if ((long long)q1 < nodes_cap)   // (low1 of a site operator is never written)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + q1));
-        }
-      }
+      const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
         if (!(a >= lo && a < hi && b >= lo && b < hi)) {
-          if (d.dbg & 1) uf_union_count(d.parent, a, b, d.dbgc);
+          const int slot = atomicAdd(&s_qn, 1);
+          if (slot < LQ_UQ) s_q[slot] = make_uint2(a, b);
           else uf_union(d.parent, a, b);
         }
       });
-      p0 = q0; p1 = q1;
     }
+  }
+  __syncthreads();
+  const int qn = min(s_qn, LQ_UQ);
+  uint2 e = make_uint2(0u, 0u);
+  int i = threadIdx.x;
+  if (i < qn) e = s_q[i];
+  for (; i < qn; i += blockDim.x) {
+    const int in = i + blockDim.x;
+    uint2 en = make_uint2(0u, 0u);
+    if (in < qn) {
+      en = s_q[in];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + en.x));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + en.y));
+    }
+    if (d.dbg & 1) uf_union_count(d.parent, e.x, e.y, d.dbgc);
+    else uf_union(d.parent, e.x, e.y);
+    e = en;
   }
 }
 
