@@ -32,7 +32,6 @@ static const node_t NODE_NONE = 0xffffffffu;
 #define LQ_ERR_CAND_FULL 2
 #define LQ_ERR_NODE_FULL 4
 #define LQ_ERR_CLUSTER_FULL 8
-#define LQ_ERR_NEIGH_FULL 16
 
 // fixed-point scale of imaginary time in the cluster sums (order-independent integer atomics)
 #define LQ_FX 1099511627776.0 /* 2^40 */
@@ -103,6 +102,8 @@ struct Dev {
   uint32_t* bitmap;  // root flags, one bit per node
   uint32_t* wcount;  // roots per bitmap word -> exclusive scan in wbase
   uint32_t* wbase;
+  uint4* rootw;      // [words] {id base, root flags, flip bits of the roots, 0} (serial engines, k_rootflip)
+  int fpack;         // labels carry the flip decision in bit 31 (serial engines)
   // ---- clusters ----
   long long* est;  // [4][nccap] usize, umag, ssize, smag in half units of LQ_FX
   int* est0;       // [4][N]     usize0, umag0, ssize0, smag0 in half units

@@ -269,13 +269,17 @@ struct lq_engine {
   int W = 1, Wl = 1, w0 = 0, cap = 0, tpb = 32, npo = 1, ug = 1;
   int Breal = 0;          // bonds of the caller's lattice; internal bonds Breal.. are site pseudo-bonds
   bool has_site = false;
+  // arena growth after a device-side overflow (the reference's vectors grow on demand,
+  // path_integral.C:240-243 RESERVE_*): multipliers on reserve / candidate slots / cluster_reserve
+  double grow_pages = 1, grow_cand = 1, grow_clusters = 1;
+  int64_t regrows = 0;
   int gstride() const { return 8 + (has_site ? 1 : 0) + sdim; }
   int sdim = 0;                      // dimensions of the winding estimator (0 = off)
   std::vector<short> bond_vec_e;     // [3 * internal-order-independent external bond] fixed point
   size_t P = 0;
   long long ncap = 0, nccap = 0;
   size_t nwords_cap = 0, device_bytes = 0;
-  int sm_count = 0;
+  int sm_count = 0, smem_optin = 0;
   uint32_t mcs = 0;
   int cur = 0;  // live page buffer
   int64_t launches = 0;
@@ -322,6 +326,7 @@ struct lq_engine {
   DBuf<uint16_t> boff[2];
   DBuf<uint8_t> spinW;
   DBuf<uint32_t> flipw, openw;
+  DBuf<uint4> rootw;
   DBuf<short> bond_vec;
   DBuf<int> wind;
   DBuf<unsigned long long> dbgc;
@@ -427,6 +432,7 @@ struct lq_engine {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, opt.device));
     sm_count = prop.multiProcessorCount;
+    smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 
     make_partition(L, (int)xsrc.size(), xsrc.data(), xdst.data(), opt.tile_sites, part);
@@ -531,7 +537,7 @@ struct lq_engine {
       }
       bond_emu.upload(emu, nullptr);
     }
-    const double m = opt.reserve * mu;
+    const double m = opt.reserve * grow_pages * mu;
     long long c = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
     if (c > 65535) fail(LQ_E_INVALID, "page capacity exceeds 65535 operators: lower tile_sites or window_ops");
     cap = (int)c;
@@ -541,7 +547,7 @@ struct lq_engine {
       const double hm = m * ratio;
       scap = cap + (int)std::ceil(hm + 6.0 * std::sqrt(hm) + 16.0);
       const double cm = mu;  // mean candidates per page
-      ccap = (int)std::ceil(cm + 8.0 * std::sqrt(cm) + 32.0);
+      ccap = (int)std::ceil(grow_cand * (cm + 8.0 * std::sqrt(cm) + 32.0));
       if (ccap > 32767 || scap > 65535)
         fail(LQ_E_INVALID, "too many candidates / staged operators per page: lower tile_sites or window_ops");
       fcap = scap + scap / 2;  // off-diagonal legs of the staged operators (checked at run time)
@@ -561,13 +567,16 @@ struct lq_engine {
       }
       stage_smem = lq::k1_smem_bytes(k1_fc, scap, ccap, cap, part.nbmax, part.hmax, part.nksmax);
       walk_smem = lq::stage_bytes(false, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb_walk);
-      if (stage_smem > 200 * 1024)
+      if (stage_smem > (size_t)smem_optin - 2048 || walk_smem > (size_t)smem_optin - 2048 ||
+          (size_t)npo * cap * sizeof(uint32_t) > (size_t)smem_optin - 2048)
         fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
-      const int sm = (int)stage_smem;
+      // The dynamic shared-memory limit is an attribute of the kernel, shared by every engine of the
+      // process: always raise it to the device maximum (the launches pass their own sizes) so that
+      // engines of different shapes can coexist.
+      const int sm = smem_optin - 2048;   // (the limit covers static + dynamic shared memory)
       if (sdim > 0) {
-        const int es = (int)(sizeof(lq::EstHash) + sizeof(lq::WindHash) + 8 * (size_t)part.nbmax + 16);
-        CK(cudaFuncSetAttribute(lq::k_estimate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-        CK(cudaFuncSetAttribute(lq::k_estimate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+        CK(cudaFuncSetAttribute(lq::k_estimate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(lq::k_estimate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       }
       k1_fn = pick_k1();
       CK(cudaFuncSetAttribute(k1_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -579,16 +588,15 @@ struct lq_engine {
       if (getenv("LQ_UG")) ug = std::max(1, atoi(getenv("LQ_UG")));
       ug = (int)std::min<size_t>((size_t)ug, std::max<size_t>(1, (96 * 1024) / ((size_t)npo * cap * sizeof(uint32_t))));
       ug = std::min(ug, Wl);
-      CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)((size_t)ug * npo * cap * sizeof(uint32_t))));
+      CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       walk_fn = pick_walk();
-      CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+      CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     }
     P = (size_t)T * Wl;
     ncap = (long long)P * cap;
     const long long nodes_cap = (long long)N + (long long)npo * ncap;
     if (nodes_cap >= 0x7ffffff0ll) fail(LQ_E_INVALID, "more than 2^31 graph nodes on one GPU: lower lq_options.reserve or split the run over more GPUs");
-    nccap = std::min<long long>(nodes_cap, (long long)N + (long long)std::ceil(opt.cluster_reserve * (double)(npo * ncap)));
+    nccap = std::min<long long>(nodes_cap, (long long)N + (long long)std::ceil(std::min(1.0, opt.cluster_reserve * grow_clusters) * (double)(npo * ncap)));
     nwords_cap = (size_t)((nodes_cap + 31) / 32);
 
     size_t* tb = &device_bytes;
@@ -607,6 +615,7 @@ struct lq_engine {
     bitmap.alloc(nwords_cap + 1, tb);
     wcount.alloc(nwords_cap + 1, tb);
     wbase.alloc(nwords_cap + 1, tb);
+    rootw.alloc(opt.nranks == 1 ? nwords_cap + 1 : 1, tb);
     const size_t scan_n = std::max(nwords_cap, P) + 1;
     scan_tmp.alloc((scan_n + LQ_SCAN_CHUNK - 1) / LQ_SCAN_CHUNK + 1, tb);
     est.alloc(4 * (size_t)nccap, tb);
@@ -663,6 +672,7 @@ struct lq_engine {
     }
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
+    d.rootw = rootw.p; d.fpack = opt.nranks == 1 ? 1 : 0;
     d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p;
     d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.gstride = gstride(); d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
@@ -744,15 +754,21 @@ struct lq_engine {
       Section s(this, 11);
       lq::k_compress<<<grid_for(nwords_cap * 32, 256 * LQ_NPT), 256, 0, stream>>>(d, nwords_cap);
       scan_u32(wcount.p, wbase.p, nwords_cap, wbase.p + nwords_cap, (int*)d_nc.p);
+      if (opt.nranks == 1) {   // flip decision per root (path_integral.C:796-799), packed for k_relabel
+        lq::k_rootflip<<<(unsigned)std::min<size_t>((nwords_cap + 255) / 256, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
+        launches += 1;
+      }
       lq::k_relabel<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d);
       launches += 2;
     }
     if (opt.nranks > 1) merge_open_clusters();
     {
-      Section s(this, 14);  // flip decision per cluster (path_integral.C:796-799)
-      lq::k_flipbits<<<(unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
-      launches += 1;
-      if (opt.nranks > 1) { lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp); launches += 1; }
+      Section s(this, 14);  // flip decision per cluster id (slab engines; serial ones decided per root above)
+      if (opt.nranks > 1) {
+        lq::k_flipbits<<<(unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
+        lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
+        launches += 2;
+      }
     }
     {
       Section s(this, 12);
@@ -882,30 +898,58 @@ struct lq_engine {
     CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
     std::string m = "arena overflow:";
     if (err & LQ_ERR_PAGE_FULL) m += " page full (raise lq_options.reserve);";
-    if (err & LQ_ERR_CAND_FULL) m += " >32 accepted candidates in one bucket (lower window_ops);";
-    if (err & LQ_ERR_NEIGH_FULL) m += " >64 off-diagonal neighbour legs in one window (lower window_ops);";
+    if (err & LQ_ERR_CAND_FULL) m += " too many candidates in one page or bucket (lower window_ops);";
     if (err & LQ_ERR_CLUSTER_FULL) m += " cluster arena full (raise cluster_reserve);";
     if (err & LQ_ERR_NODE_FULL) m += " node arena full;";
     fail(LQ_E_OVERFLOW, m);
   }
 
-  void sweep_many(int count, lq_collector* out) {
+  // A step that overflows an arena leaves the configuration it started from intact: K1 writes the
+  // other page buffer, the labelling works on scratch, and k_flip_spins / every later K1 do nothing
+  // once the error word is set.  The host then rewinds to that step, enlarges the arena that
+  // overflowed (operators travel through lq_get_state / lq_set_state) and runs the remaining steps
+  // again.  Random numbers are keyed by (bond, window, step, draw) and by cluster id, not by slots,
+  // so the trajectory does not depend on the capacities.
+  void sweep_many(int count, lq_collector* out, int depth = 0) {
     if (count <= 0) return;
     if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
     ensure_out((size_t)count);
     stage_params(count, true);
+    const int cur0 = cur;
+    const uint32_t mcs0 = mcs;
     for (int i = 0; i < count; ++i) enqueue_step(d_out.p + (size_t)i * 32, d_params.p + i);
     CK(cudaMemcpyAsync(h_out, d_out.p, (size_t)count * 32 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     d2h_bytes += (int64_t)count * 32 * (int64_t)sizeof(double);
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
     drain_timers();
-    int err = 0;
+    int err = 0, first_bad = count;
     for (int i = 0; i < count; ++i) {
-      if (out) to_collector(h_out + (size_t)i * 32, out + i);
-      err |= (int)h_out[(size_t)i * 32 + 16];
+      const int e = (int)h_out[(size_t)i * 32 + 16];
+      if (e && first_bad == count) first_bad = i;
+      err |= e;
+      if (out && first_bad == count) to_collector(h_out + (size_t)i * 32, out + i);
     }
-    check_err(err);
+    if (!err) return;
+    if (opt.nranks > 1 || depth >= 8) check_err(err);   // slab engines: every rank would have to rewind
+    CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
+    cur = cur0 ^ (first_bad & 1);
+    mcs = mcs0 + (uint32_t)first_bad;
+    if (err & LQ_ERR_PAGE_FULL) grow_pages *= 1.5;
+    if (err & LQ_ERR_CAND_FULL) grow_cand *= 1.5;
+    if (err & LQ_ERR_CLUSTER_FULL) grow_clusters *= 1.5;
+    ++regrows;
+    {
+      int64_t n = 0;
+      get_state(nullptr, nullptr, &n);
+      std::vector<int32_t> spins(part.N);
+      std::vector<lq_op> ops((size_t)n);
+      get_state(spins.data(), ops.data(), &n);
+      size_arenas();
+      clear_state();
+      set_state(spins.data(), ops.data(), n);
+    }
+    sweep_many(count - first_bad, out ? out + first_bad : nullptr, depth + 1);
   }
 
   // -------------------------------------------------------------------------------------------
@@ -1064,6 +1108,7 @@ struct lq_engine {
         if (cid >= minidx.size()) fail(LQ_E_INVALID, "cluster id out of range (internal error)");
         if (minidx[cid] < 0) minidx[cid] = idx;
       };
+      for (auto& v : sl) v &= 0x7fffffffu;   // bit 31 of a label is the flip decision
       for (int se = 0; se < N; ++se) touch(sl[part.site_e2i[se]], se);
       for (size_t k = 0; k < n; ++k) {
         touch(ol[2 * (size_t)v[k].idx], (int32_t)(N + 2 * k));
@@ -1212,6 +1257,7 @@ int lq_enable_timers(lq_handle h, int on) {
 }
 
 int64_t lq_kernel_launches(lq_handle h) { return h ? h->launches : 0; }
+int64_t lq_regrow_count(lq_handle h) { return h ? h->regrows : 0; }
 int64_t lq_h2d_bytes(lq_handle h) { return h ? h->h2d_bytes : 0; }
 int64_t lq_d2h_bytes(lq_handle h) { return h ? h->d2h_bytes : 0; }
 

@@ -95,6 +95,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_scan[34];
   __shared__ int s_cnt[2];
+  if (*d.d_err) return;   // an earlier step of this batch overflowed: leave both page buffers alone
   K1Smem S;
   k1_carve(d, FC, s_raw, S);
   const double beta = sp->beta;

@@ -43,6 +43,11 @@ __device__ __forceinline__ BucketRef bucket_of(const Dev& d, int buf, int b, int
 __device__ __forceinline__ uint32_t flip_of(const Dev& d, uint32_t cid) {
   return ((long long)cid < d.nccap) ? ((d.flipw[cid >> 5] >> (cid & 31u)) & 1u) : 0u;
 }
+// label word written by k_relabel: cluster id (| flip decision << 31 on serial engines)
+#define LQ_CID(v) ((v) & 0x7fffffffu)
+__device__ __forceinline__ uint32_t flip_of_label(const Dev& d, uint32_t v) {
+  return d.fpack ? (v >> 31) : flip_of(d, v);
+}
 
 __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
   return (node_t)d.N + (d.npo == 2 ? (node_t)(2 * (size_t)idx + side) : (node_t)idx);
@@ -568,6 +573,26 @@ __device__ __forceinline__ uint32_t cid_of_root(const Dev& d, node_t r) {
   return d.wbase[r >> 5] + (uint32_t)__popc(d.bitmap[r >> 5] & ((1u << (r & 31)) - 1u));
 }
 
+// Serial engines decide the flips per ROOT before the relabelling: one Philox call yields the 32
+// flip bits of a bitmap word (path_integral.C:796-799, Bernoulli(1/2) per cluster), packed with the
+// word's id base and root flags into one 16-byte record.  k_relabel then needs ONE gather per node
+// and stores cluster id | flip << 31, so the estimator and the spin flip read the decision with the
+// id instead of chasing a second table.  (Slab engines keep the id-indexed table: the flips of open
+// clusters are only known after the exchange.)
+__global__ void __launch_bounds__(256)
+k_rootflip(Dev d, const StepParams* __restrict__ sp) {
+  const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
+  const size_t nwords = (nn + 31) >> 5;
+  const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t bm = d.bitmap[w];
+    uint32_t fl = 0;
+    if (bm) fl = philox4x32_10((uint32_t)w, (uint32_t)(w >> 32), mcs, LQ_STREAM_FLIP, key0, key1).x & bm;
+    d.rootw[w] = make_uint4(d.wbase[w], bm, fl, 0u);
+    if (d.has_site && (long long)(w << 5) < d.nccap + 32) d.openw[w] = 0u;   // see k_flipbits
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_relabel(Dev d) {
   const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
@@ -578,18 +603,30 @@ k_relabel(Dev d) {
     if ((long long)d.d_nc[0] > d.nccap) atomicOr(d.d_err, LQ_ERR_CLUSTER_FULL);
   }
   node_t r[LQ_NPT];
-  uint32_t wb[LQ_NPT], bm[LQ_NPT];
 #pragma unroll
   for (int k = 0; k < LQ_NPT; ++k) {
     const size_t x = base + (size_t)k * 256;
     r[k] = (x < nn) ? d.parent[x] : 0u;
   }
+  if (d.fpack) {
+    uint4 q[LQ_NPT];
 #pragma unroll
-  for (int k = 0; k < LQ_NPT; ++k) { wb[k] = d.wbase[r[k] >> 5]; bm[k] = d.bitmap[r[k] >> 5]; }
+    for (int k = 0; k < LQ_NPT; ++k) q[k] = d.rootw[r[k] >> 5];
 #pragma unroll
-  for (int k = 0; k < LQ_NPT; ++k) {
-    const size_t x = base + (size_t)k * 256;
-    if (x < nn) d.parent[x] = wb[k] + (uint32_t)__popc(bm[k] & ((1u << (r[k] & 31)) - 1u));
+    for (int k = 0; k < LQ_NPT; ++k) {
+      const size_t x = base + (size_t)k * 256;
+      if (x < nn)
+        d.parent[x] = (q[k].x + (uint32_t)__popc(q[k].y & ((1u << (r[k] & 31)) - 1u))) | (((q[k].z >> (r[k] & 31)) & 1u) << 31);
+    }
+  } else {
+    uint32_t wb[LQ_NPT], bm[LQ_NPT];
+#pragma unroll
+    for (int k = 0; k < LQ_NPT; ++k) { wb[k] = d.wbase[r[k] >> 5]; bm[k] = d.bitmap[r[k] >> 5]; }
+#pragma unroll
+    for (int k = 0; k < LQ_NPT; ++k) {
+      const size_t x = base + (size_t)k * 256;
+      if (x < nn) d.parent[x] = wb[k] + (uint32_t)__popc(bm[k] & ((1u << (r[k] & 31)) - 1u));
+    }
   }
 }
 
@@ -715,6 +752,9 @@ k_estimate(Dev d, int buf) {
   __syncthreads();
   const int n = d.pcount[buf][p];
   const int idx0 = d.nbase[p];
+  // an arena overflowed in this batch: the page buffers hold the configuration to rewind to (or
+  // scratch) -- no operator may change type any more (lq_engine.cu sweep_many)
+  const bool dead = FLIP && (*d.d_err != 0);
   // (staging the cluster ids of the page's own nodes in shared memory was measured 10 % slower than
   // gathering them: the gathers already hit L1/L2)
   uint32_t* ginfo = d.info[buf] + p * (size_t)d.cap;
@@ -757,7 +797,9 @@ k_estimate(Dev d, int buf) {
       const int off = (int)(inf[u] & LQ_INFO_OFFDIAG);
       const int m0 = 1 - 2 * c0, m1 = 1 - 2 * c1;              // 2(1/2-c) below
       const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
-      if (FLIP && ((flip_of(d, cl0[u]) ^ flip_of(d, cu0[u])) & 1u)) ginfo[j] = inf[u] ^ LQ_INFO_OFFDIAG;
+      if (FLIP && !dead && ((flip_of_label(d, cl0[u]) ^ flip_of_label(d, cu0[u])) & 1u)) ginfo[j] = inf[u] ^ LQ_INFO_OFFDIAG;
+      cl0[u] = LQ_CID(cl0[u]); cu0[u] = LQ_CID(cu0[u]);
+      if (d.npo == 2) { cl1[u] = LQ_CID(cl1[u]); cu1[u] = LQ_CID(cu1[u]); }
       if (inf[u] & LQ_INFO_SITE) {
         // site operator: end_s below / begin_s above on its one site (path_integral.C:718-726);
         // both clusters are cut open for the transverse magnetisation (transmag.h:72-81)
@@ -830,8 +872,8 @@ k_estimate_sites(Dev d) {
   const int g = d.gauge[s];
   const int c = d.spinW[s];
   const int m = 1 - 2 * c;
-  const uint32_t cb = d.parent[s];
-  const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  const uint32_t cb = LQ_CID(d.parent[s]);
+  const uint32_t ct = LQ_CID(d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
   const long long qlo = time_to_fx(window_lo(d.w0, d.W));
   const long long qhi = (d.w0 + d.Wl >= d.W) ? (1ll << 40) : time_to_fx(window_hi(d.w0 + d.Wl - 1, d.W));
   if (d.rank == 0) site_group_add(d, valid, cb, 1, m, g, g * m, 0, true);
@@ -948,25 +990,12 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
 // flipped differently (loop_0 / loop_1 of graph_impl.h:277-295 in leg form).  The spin carried
 // into every window flips with the cluster of the segment crossing the window start.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_flip(Dev d, int buf) {
-  const size_t p = blockIdx.x;
-  const int n = d.pcount[buf][p];
-  const int idx0 = d.nbase[p];
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const int idx = idx0 + j;
-    const uint32_t cl = d.parent[d.low0[idx] & 0x7fffffffu];
-    const uint32_t cu = d.parent[upper_node(d, idx, 0)];
-    const uint32_t f = (flip_of(d, cl) ^ flip_of(d, cu)) & 1u;
-    if (f) d.info[buf][p * (size_t)d.cap + j] ^= LQ_INFO_OFFDIAG;
-  }
-}
-
 __global__ void k_flip_spins(Dev d) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)(d.Wl + 1) * d.N) return;
+  if (*d.d_err) return;   // an arena overflowed in this step: keep the spins of the configuration it started from
   const uint32_t c = d.parent[d.curW[i]];
-  d.spinW[i] ^= (uint8_t)flip_of(d, c);
+  d.spinW[i] ^= (uint8_t)flip_of_label(d, c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -978,8 +1007,8 @@ __global__ void k_export_labels(Dev d, int buf, uint32_t* out /* [2*ncap-ish], b
   const int idx0 = d.nbase[p];
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int idx = idx0 + j;
-    out[2 * (size_t)idx] = d.parent[upper_node(d, idx, 0)];
-    out[2 * (size_t)idx + 1] = d.parent[upper_node(d, idx, 1)];
+    out[2 * (size_t)idx] = LQ_CID(d.parent[upper_node(d, idx, 0)]);
+    out[2 * (size_t)idx + 1] = LQ_CID(d.parent[upper_node(d, idx, 1)]);
   }
 }
 

@@ -298,6 +298,7 @@ def run_gpu(args):
                        "open_clusters_per_mcs": float(out["noc"].mean()),
                        "thermalisation_mcs": therm, "tile_sites": tile, "windows": info["num_windows"],
                        "page_capacity": info["page_capacity"], "reserve": args.reserve,
+                       "arena_regrows": eng.regrow_count(),
                        "tiles": info["num_tiles"], "device_bytes": info["device_bytes"],
                        "l2_policy": "working set (%.1f GB) larger than L2" % (info["device_bytes"] / 1e9)
                        if info["device_bytes"] > 2.5e8 else "working set comparable to L2",

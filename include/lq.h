@@ -148,6 +148,13 @@ int lq_enable_timers(lq_handle h, int on);
 int lq_get_info(lq_handle h, lq_info* out);
 /* number of kernel launches issued by this handle so far */
 int64_t lq_kernel_launches(lq_handle h);
+/* The arenas are sized at lq_create (lq_options.reserve, cluster_reserve).  When a step overflows
+ * one of them, a serial engine rewinds to the configuration the step started from, enlarges that
+ * arena by 1.5x and repeats the step -- the analogue of the reference's growing vectors
+ * (RESERVE_* only pre-size them, path_integral.C:240-243).  The trajectory does not depend on the
+ * capacities.  This counts those events; LQ_E_OVERFLOW is returned after 8 of them in one call and
+ * by slab engines (nranks > 1), whose configuration is then undefined. */
+int64_t lq_regrow_count(lq_handle h);
 /* bytes copied host->device (per-step inputs, from pinned memory) and device->host (collectors)
  * by lq_sweep / lq_sweep_many so far */
 int64_t lq_h2d_bytes(lq_handle h);

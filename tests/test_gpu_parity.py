@@ -292,3 +292,30 @@ def test_config2_full_size_properties():
     e = out["ene"][-20:].mean() / N
     assert -0.70 < e < -0.60
     eng.close()
+
+
+def test_arena_overflow_rewinds_grows_and_replays():
+    """An undersized page / cluster arena must not change the Markov chain: the engine rewinds to
+    the configuration the failing step started from, grows the arena and replays (the reference's
+    vectors simply grow, path_integral.C:240-243)."""
+    import looper_b200 as lq
+    lat = lq.hypercubic_lattice((12, 12))
+    beta = 6.0
+    small = lq.Engine(lat, beta, seed=99, tile_sites=16, reserve=0.25, cluster_reserve=0.05)
+    ample = lq.Engine(lat, beta, seed=99, tile_sites=16)
+    a = small.sweep_many(25)
+    b = ample.sweep_many(25)
+    assert small.regrow_count() > 0 and ample.regrow_count() == 0
+    assert small.info()["page_capacity"] < ample.info()["page_capacity"] * 2
+    for f in ("nop", "nc"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("ene", "umag2", "smag2", "usize", "smag"):
+        assert np.allclose(a[f], b[f], rtol=1e-12, atol=1e-12), f
+    sa, oa = small.get_state()
+    sb, ob = ample.get_state()
+    assert np.array_equal(sa, sb) and np.array_equal(oa, ob)
+    # one call at a time hits the same path
+    for _ in range(5):
+        ca, cb = small.sweep(), ample.sweep()
+        assert ca["nop"] == cb["nop"] and ca["nc"] == cb["nc"]
+    small.close(); ample.close()

@@ -118,3 +118,38 @@ def test_single_spin_in_a_field():
     assert abs(tm.mean() - sx) < 4.5 * _berr(tm)
     en = out["ene"] / 2
     assert abs(en.mean() + gamma * sx) < 4.5 * _berr(en)
+
+
+def _tfi_chain_energy(jz, gamma, T):
+    """Energy per site of the infinite S=1/2 chain H = Jz sum Sz Sz - Gamma sum Sx (free fermions:
+    eps_k = 2 sqrt(J^2 + h^2 - 2 J h cos k) with J = Jz/4, h = Gamma/2)."""
+    J, h = jz / 4.0, gamma / 2.0
+    k = (np.arange(400000) + 0.5) * np.pi / 400000
+    eps = 2 * np.sqrt(J * J + h * h - 2 * J * h * np.cos(k))
+    return float(-(eps / 2 * np.tanh(eps / (2 * T))).mean())
+
+
+def test_config5_transverse_field_ising_chain_full_size():
+    """BASELINE config 5 (ii) at its full size: chain L = 4096, beta = 256, Jz = 1, Gamma = 0.7.
+    Size-independent checks: the energy against the exact free-fermion value, and the partition /
+    collector of the million-operator configuration against the oracle."""
+    import looper_b200 as lq
+    L, beta, gamma = 4096, 256.0, 0.7
+    lat = lq.chain_lattice(L)
+    v, off, sign = lq.xxz_weights(0.0, 1.0)
+    assert v == [0.0, 0.0, 0.5, 0.0]
+    eng = lq.Engine(lat, beta, weights=tuple(v), site_weight=gamma / 2, seed=5)
+    eng.sweep_many(400, collect=False)
+    out = eng.sweep_many(640)
+    e = out["ene"] / L
+    exact = _tfi_chain_energy(1.0, gamma, 1 / beta)
+    err = _berr(e, nb=16)
+    assert abs(e.mean() - exact) < 5 * err + 2e-5, (e.mean(), exact, err)   # 2e-5: 1/L^2-size corrections
+    spins, ops = eng.get_state()
+    assert len(ops) > 900000 and ((ops["loc"] & 1) == 0).sum() > 300000
+    ref_labels, ref_nc, ref = orc.build_clusters(lat, spins, ops)
+    labels, nc, coll = eng.build_clusters()
+    assert nc == ref_nc and np.array_equal(labels, ref_labels)
+    for f in SUMS:
+        assert coll[f] == pytest.approx(ref[f], rel=1e-7, abs=1e-6), f
+    eng.close()
