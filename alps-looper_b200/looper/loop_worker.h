@@ -23,6 +23,13 @@ public:
 
   explicit loop_worker(const Parameters& p)
       : lattice(p), model(p, lattice), temp(p), mcs(p) {
+    // ALGORITHM (loop.C:25-34, PARAPACK_REGISTER_ALGORITHM path_integral.C:873 / sse.C): both
+    // representations of the loop algorithm sample the same ensemble; this worker always runs the
+    // continuous-time update and reports the path-integral form of the improved estimators
+    // (DESIGN.md section 6 on what "loop; sse" does not get: the fixed-length-string estimators).
+    const std::string alg = p.value_or_default("ALGORITHM", "loop; path integral");
+    if (alg != "loop" && alg != "loop; path integral" && alg != "loop; sse")
+      throw std::invalid_argument("unknown ALGORITHM '" + alg + "' (loop; path integral | loop; sse)");
     if (temp.annealing_steps() > mcs.thermalization())
       throw std::invalid_argument("longer annealing steps than thermalization");  // path_integral.C:213
     enable_improved_estimator = !p.defined("DISABLE_IMPROVED_ESTIMATOR");
