@@ -639,9 +639,15 @@ k_relabel(Dev d) {
 // (at low temperature most legs of a page belong to a handful of long loops), then flushed with
 // one global atomic per distinct key and field.
 // ------------------------------------------------------------------------------------------
-#define LQ_HASH 1024
+// Clusters are numbered in the order of their roots, so the clusters rooted inside a page have
+// CONSECUTIVE ids [cbase, cend): their sums live in a direct-mapped table (slot = id - cbase; no
+// key, no probing, and the flush is one coalesced run of REDs).  Ids outside that range belong to
+// clusters rooted in other pages -- few distinct ones, many legs each -- and go through a small hash.
+#define LQ_LT 1024   /* direct-mapped slots (clusters rooted in this page)          */
+#define LQ_FH 256    /* hashed slots (clusters rooted elsewhere); power of two      */
+#define LQ_HASH (LQ_LT + LQ_FH)
 struct EstHash {
-  uint32_t key[LQ_HASH];
+  uint32_t key[LQ_FH];
   uint32_t lo[4][LQ_HASH];  // 64-bit sums as (lo, hi) pairs: native 32-bit shared atomics with an
   uint32_t hi[4][LQ_HASH];  // explicit carry instead of the CAS loop a 64-bit shared atomicAdd compiles to
 };
@@ -665,42 +671,43 @@ __device__ __forceinline__ void est_global_add(const Dev& d, uint32_t cid, long 
   if (e) atomicAdd(est + 3 * d.nccap + cid, (unsigned long long)e);
 }
 
-__device__ __forceinline__ void est_hash_add(const Dev& d, EstHash* h, uint32_t cid, long long a,
-                                             long long b, long long c, long long e) {
-  uint32_t slot = (cid * 2654435761u) >> 22;  // 10 bits
+// slot of a cluster in the page's table, -1 if the hashed part is crowded
+__device__ __forceinline__ int est_slot(EstHash* h, uint32_t cid, uint32_t cbase, uint32_t nloc) {
+  const uint32_t li = cid - cbase;
+  if (li < nloc) return (int)li;
+  uint32_t s = (cid * 2654435761u) >> 24;  // 8 bits
   for (int probe = 0; probe < 8; ++probe) {
-    const uint32_t k = atomicCAS(&h->key[slot], 0xffffffffu, cid);
-    if (k == 0xffffffffu || k == cid) {
-      if (a) smem_add64(&h->lo[0][slot], &h->hi[0][slot], a);
-      if (b) smem_add64(&h->lo[1][slot], &h->hi[1][slot], b);
-      if (c) smem_add64(&h->lo[2][slot], &h->hi[2][slot], c);
-      if (e) smem_add64(&h->lo[3][slot], &h->hi[3][slot], e);
-      return;
-    }
-    slot = (slot + 1) & (LQ_HASH - 1);
+    const uint32_t k = atomicCAS(&h->key[s], 0xffffffffu, cid);
+    if (k == 0xffffffffu || k == cid) return LQ_LT + (int)s;
+    s = (s + 1) & (LQ_FH - 1);
   }
-  est_global_add(d, cid, a, b, c, e);  // table crowded: go straight to HBM
+  return -1;
 }
 
-// winding-number legs (stiffness.h:93-104, source side only): merged in the same hash (three more
-// 32-bit fields per slot), one global atomic per distinct cluster and dimension at the end
+__device__ __forceinline__ void est_hash_add(const Dev& d, EstHash* h, uint32_t cbase, uint32_t nloc, uint32_t cid,
+                                             long long a, long long b, long long c, long long e) {
+  const int slot = est_slot(h, cid, cbase, nloc);
+  if (slot < 0) { est_global_add(d, cid, a, b, c, e); return; }  // table crowded: go straight to HBM
+  if (a) smem_add64(&h->lo[0][slot], &h->hi[0][slot], a);
+  if (b) smem_add64(&h->lo[1][slot], &h->hi[1][slot], b);
+  if (c) smem_add64(&h->lo[2][slot], &h->hi[2][slot], c);
+  if (e) smem_add64(&h->lo[3][slot], &h->hi[3][slot], e);
+}
+
+// winding-number legs (stiffness.h:93-104, source side only): three more 32-bit fields per slot of
+// the same table, one global atomic per distinct cluster and dimension at the end
 struct WindHash { int w[3][LQ_HASH]; };
 
-__device__ __forceinline__ void wind_add(const Dev& d, EstHash* h, WindHash* wh, uint32_t cid, int sgn,
-                                         const short* vec) {
-  uint32_t slot = (cid * 2654435761u) >> 22;
-  for (int probe = 0; probe < 8; ++probe) {
-    const uint32_t k = atomicCAS(&h->key[slot], 0xffffffffu, cid);
-    if (k == 0xffffffffu || k == cid) {
-      for (int x = 0; x < d.sdim; ++x)
-        if (vec[x]) atomicAdd(&wh->w[x][slot], sgn * (int)vec[x]);
-      return;
-    }
-    slot = (slot + 1) & (LQ_HASH - 1);
-  }
-  if ((long long)cid < d.nccap)
+__device__ __forceinline__ void wind_add(const Dev& d, EstHash* h, WindHash* wh, uint32_t cbase, uint32_t nloc,
+                                         uint32_t cid, int sgn, const short* vec) {
+  const int slot = est_slot(h, cid, cbase, nloc);
+  if (slot >= 0) {
+    for (int x = 0; x < d.sdim; ++x)
+      if (vec[x]) atomicAdd(&wh->w[x][slot], sgn * (int)vec[x]);
+  } else if ((long long)cid < d.nccap) {
     for (int x = 0; x < d.sdim; ++x)
       if (vec[x]) atomicAdd(d.wind + (size_t)x * d.nccap + cid, sgn * (int)vec[x]);
+  }
 }
 
 // Bernoulli(1/2) per cluster (path_integral.C:796-799): Philox4x32-10 keyed by (cluster id, rank,
@@ -735,7 +742,7 @@ k_estimate(Dev d, int buf) {
   short* s_vec = (short*)(wh + 1);             // [3*nbmax] relative vectors of the own bonds (STIFF only)
   signed char* s_gg = STIFF ? (signed char*)(s_vec + 3 * d.nbmax) : (signed char*)(h + 1);   // [2*nbmax] gauge of the two ends of every own bond
   for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
-    h->key[i] = 0xffffffffu;
+    if (i < LQ_FH) h->key[i] = 0xffffffffu;
 #pragma unroll
     for (int f = 0; f < 4; ++f) { h->lo[f][i] = 0u; h->hi[f][i] = 0u; }
     if (STIFF) { wh->w[0][i] = 0; wh->w[1][i] = 0; wh->w[2][i] = 0; }
@@ -755,6 +762,10 @@ k_estimate(Dev d, int buf) {
   // an arena overflowed in this batch: the page buffers hold the configuration to rewind to (or
   // scratch) -- no operator may change type any more (lq_engine.cu sweep_many)
   const bool dead = FLIP && (*d.d_err != 0);
+  // ids of the clusters rooted in this page: [cbase, cbase + nloc) (capped at the table size)
+  const node_t nlo = upper_node(d, idx0, 0), nhi = nlo + (node_t)(d.npo * n);
+  const uint32_t cbase = cid_of_root(d, nlo);
+  const uint32_t nloc = min(cid_of_root(d, nhi) - cbase, (uint32_t)LQ_LT);
   // (staging the cluster ids of the page's own nodes in shared memory was measured 10 % slower than
   // gathering them: the gathers already hit L1/L2)
   uint32_t* ginfo = d.info[buf] + p * (size_t)d.cap;
@@ -803,31 +814,31 @@ k_estimate(Dev d, int buf) {
       if (inf[u] & LQ_INFO_SITE) {
         // site operator: end_s below / begin_s above on its one site (path_integral.C:718-726);
         // both clusters are cut open for the transverse magnetisation (transmag.h:72-81)
-        est_hash_add(d, h, cl0[u], q, q * m0, q * g0, q * g0 * m0);
-        est_hash_add(d, h, cu0[u], -q, -q * n0, -q * g0, -q * g0 * n0);
+        est_hash_add(d, h, cbase, nloc, cl0[u], q, q * m0, q * g0, q * g0 * m0);
+        est_hash_add(d, h, cbase, nloc, cu0[u], -q, -q * n0, -q * g0, -q * g0 * n0);
         if ((long long)cl0[u] < d.nccap) atomicOr(d.openw + (cl0[u] >> 5), 1u << (cl0[u] & 31u));
         if ((long long)cu0[u] < d.nccap) atomicOr(d.openw + (cu0[u] >> 5), 1u << (cu0[u] & 31u));
         continue;
       }
       if (STIFF) {   // stiffness.h:93-104: end_bs adds (1-2c) vr below, begin_bs subtracts it above
-        wind_add(d, h, wh, cl0[u], m0, s_vec + 3 * lb);
-        wind_add(d, h, wh, cu0[u], -n0, s_vec + 3 * lb);
+        wind_add(d, h, wh, cbase, nloc, cl0[u], m0, s_vec + 3 * lb);
+        wind_add(d, h, wh, cbase, nloc, cu0[u], -n0, s_vec + 3 * lb);
       }
       if (d.npo == 1) {
         // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
-        est_hash_add(d, h, cl0[u], 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
-        est_hash_add(d, h, cu0[u], -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
+        est_hash_add(d, h, cbase, nloc, cl0[u], 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
+        est_hash_add(d, h, cbase, nloc, cu0[u], -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
       } else {
-        est_hash_add(d, h, cl0[u], q, q * m0, q * g0, q * g0 * m0);
-        est_hash_add(d, h, cl1[u], q, q * m1, q * g1, q * g1 * m1);
-        est_hash_add(d, h, cu0[u], -q, -q * n0, -q * g0, -q * g0 * n0);
-        est_hash_add(d, h, cu1[u], -q, -q * n1, -q * g1, -q * g1 * n1);
+        est_hash_add(d, h, cbase, nloc, cl0[u], q, q * m0, q * g0, q * g0 * m0);
+        est_hash_add(d, h, cbase, nloc, cl1[u], q, q * m1, q * g1, q * g1 * m1);
+        est_hash_add(d, h, cbase, nloc, cu0[u], -q, -q * n0, -q * g0, -q * g0 * n0);
+        est_hash_add(d, h, cbase, nloc, cu1[u], -q, -q * n1, -q * g1, -q * g1 * n1);
       }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < LQ_HASH; i += blockDim.x) {
-    const uint32_t k = h->key[i];
+    const uint32_t k = (i < LQ_LT) ? ((uint32_t)i < nloc ? cbase + (uint32_t)i : 0xffffffffu) : h->key[i - LQ_LT];
     if (k != 0xffffffffu) {
       long long v[4];
 #pragma unroll
