@@ -86,7 +86,7 @@ class LqComm(C.Structure):
 
 
 # every symbol include/lq.h declares (tests/test_abi.py checks the header against this list)
-EXPORTS = ["lq_create", "lq_destroy", "lq_set_beta", "lq_set_state", "lq_get_state", "lq_sweep",
+EXPORTS = ["lq_create", "lq_destroy", "lq_set_beta", "lq_set_state", "lq_get_state", "lq_get_step", "lq_set_step", "lq_sweep",
            "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_enable_timers", "lq_get_info", "lq_kernel_launches", "lq_regrow_count", "lq_h2d_bytes", "lq_d2h_bytes",
            "lq_set_comm", "lq_stream", "lq_last_error", "lq_version"]
 
@@ -105,6 +105,9 @@ lib.lq_enable_timers.argtypes = [_h, C.c_int]
 lib.lq_get_info.argtypes = [_h, C.POINTER(LqInfo)]
 lib.lq_kernel_launches.argtypes = [_h]
 lib.lq_kernel_launches.restype = C.c_int64
+lib.lq_get_step.argtypes = [_h]
+lib.lq_get_step.restype = C.c_uint32
+lib.lq_set_step.argtypes = [_h, C.c_uint32]
 lib.lq_regrow_count.argtypes = [_h]
 lib.lq_regrow_count.restype = C.c_int64
 lib.lq_h2d_bytes.argtypes = [_h]
@@ -340,6 +343,12 @@ class Engine:
 
     def kernel_launches(self):
         return int(lib.lq_kernel_launches(self._h))
+
+    def get_step(self):
+        return int(lib.lq_get_step(self._h))
+
+    def set_step(self, step):
+        _check(lib.lq_set_step(self._h, int(step)))
 
     def regrow_count(self):
         return int(lib.lq_regrow_count(self._h))

@@ -1196,6 +1196,13 @@ int lq_get_state(lq_handle h, int32_t* spins, lq_op* ops, int64_t* n) {
   LQ_TRY({ CK(cudaSetDevice(h->opt.device)); h->get_state(spins, ops, n); })
 }
 
+uint32_t lq_get_step(lq_handle h) { return h ? h->mcs : 0; }
+int lq_set_step(lq_handle h, uint32_t step) {
+  if (!h) { g_err = "null handle"; return LQ_E_INVALID; }
+  h->mcs = step;
+  return LQ_OK;
+}
+
 int lq_sweep(lq_handle h, lq_collector* out) {
   if (!h) { g_err = "null handle"; return LQ_E_INVALID; }
   LQ_TRY({ CK(cudaSetDevice(h->opt.device)); h->sweep_many(1, out); })

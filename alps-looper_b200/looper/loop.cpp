@@ -1,7 +1,9 @@
 // loop.cpp -- minimal driver around looper::loop_worker (stand-in for loop.C:25-34 +
 // alps::parapack::start): reads "KEY = value" parameters from a file or stdin, or the standalone
 // kernel's flags -l/-t/-n (standalone/options.h:40-63), runs the worker on the GPU and prints the
-// observables.  Usage: loop [-l L] [-t T] [-n sweeps] [--lattice "square lattice"] [params-file]
+// observables.  Usage: loop [-l L] [-t T] [-n sweeps] [--lattice "square lattice"]
+//                    [--checkpoint file] [params-file]
+// --checkpoint: resume from the file if it exists (path_integral.C:111-124 load), write it at the end
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -13,19 +15,29 @@ int main(int argc, char** argv) {
   p.set("L", 8);
   p.set("T", 0.2);
   p.set("SWEEPS", 1u << 16);
+  std::string ckpt;
   try {
     for (int i = 1; i < argc; ++i) {
       if (!std::strcmp(argv[i], "-l") && i + 1 < argc) p["L"] = argv[++i];
       else if (!std::strcmp(argv[i], "-t") && i + 1 < argc) p["T"] = argv[++i];
       else if (!std::strcmp(argv[i], "-n") && i + 1 < argc) p["SWEEPS"] = argv[++i];
       else if (!std::strcmp(argv[i], "--lattice") && i + 1 < argc) p["LATTICE"] = argv[++i];
+      else if (!std::strcmp(argv[i], "--checkpoint") && i + 1 < argc) ckpt = argv[++i];
       else if (!std::strcmp(argv[i], "-")) p.parse(std::cin);
       else { std::ifstream f(argv[i]); if (!f) throw std::invalid_argument(std::string("cannot open ") + argv[i]); p.parse(f); }
     }
     looper::loop_worker w(p);
     looper::observable_set obs;
     w.init_observables(p, obs);
+    if (!ckpt.empty()) {
+      std::ifstream in(ckpt, std::ios::binary);
+      if (in) { w.load(in); std::cout << "resumed at " << w.progress() << " of the run\n"; }
+    }
     while (w.progress() < 1) w.run(obs);
+    if (!ckpt.empty()) {
+      std::ofstream out(ckpt, std::ios::binary | std::ios::trunc);
+      w.save(out);
+    }
     const double N = w.lat().volume(), beta = 1 / obs["Temperature"].mean();
     // the five lines of standalone/loop.C:186-195, from the looper-named observables
     std::cout << "Number of Clusters        = " << obs["Number of Clusters"].mean() << " +- " << obs["Number of Clusters"].error() << "\n"

@@ -5,6 +5,9 @@
 // parameters.h / measurement.h.
 #pragma once
 #include <cmath>
+#include <cstring>
+#include <istream>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -121,11 +124,49 @@ public:
     mcs.set(mcs_in);
   }
 
+  // The same payload as a byte stream, in the reference's field order (path_integral.C:111-124:
+  // `dp << mcs << spins << operators`; operator.h:107,138: type_, loc_, time_ per operator; vectors
+  // as a 32-bit count followed by the elements).  Native little-endian behind an 8-byte tag -- the
+  // XDR container of alps::ODump itself is ALPS's, not reproduced here.
+  void save(std::ostream& os) const {
+    unsigned m = 0;
+    std::vector<int32_t> spins;
+    std::vector<lq_op> ops;
+    save(m, spins, ops);
+    os.write("LQCKPT01", 8);
+    put(os, uint32_t(lq_get_step(h_)));    // the generator state: Philox step counter (include/lq.h)
+    put(os, uint32_t(m));
+    put(os, uint32_t(spins.size()));
+    os.write(reinterpret_cast<const char*>(spins.data()), std::streamsize(spins.size() * sizeof(int32_t)));
+    put(os, uint32_t(ops.size() >> 32));   // operator strings beyond 2^32 entries: count as two words
+    put(os, uint32_t(ops.size()));
+    for (const lq_op& o : ops) { put(os, int32_t(o.type)); put(os, int32_t(o.loc)); put(os, double(o.time)); }
+    if (!os) throw std::runtime_error("checkpoint: write failed");
+  }
+  void load(std::istream& is) {
+    char tag[8];
+    is.read(tag, 8);
+    if (!is || std::memcmp(tag, "LQCKPT01", 8) != 0) throw std::runtime_error("checkpoint: bad tag");
+    const uint32_t step = get<uint32_t>(is);
+    const uint32_t m = get<uint32_t>(is), ns = get<uint32_t>(is);
+    if (ns != uint32_t(num_sites(lattice.vg()))) throw std::runtime_error("checkpoint: lattice size differs");
+    std::vector<int32_t> spins(ns);
+    is.read(reinterpret_cast<char*>(spins.data()), std::streamsize(ns * sizeof(int32_t)));
+    const uint64_t hi = get<uint32_t>(is), lo = get<uint32_t>(is);
+    std::vector<lq_op> ops(size_t((hi << 32) | lo));
+    for (lq_op& o : ops) { o.type = get<int32_t>(is); o.loc = get<int32_t>(is); o.time = get<double>(is); }
+    if (!is) throw std::runtime_error("checkpoint: truncated");
+    load(m, spins, ops);
+    check(lq_set_step(h_, step));
+  }
+
   const lq_collector& last_collector() const { return last_; }
   lq_handle handle() const { return h_; }
   const lattice_helper& lat() const { return lattice; }
 
 private:
+  template <class T> static void put(std::ostream& os, T v) { os.write(reinterpret_cast<const char*>(&v), sizeof v); }
+  template <class T> static T get(std::istream& is) { T v = T(); is.read(reinterpret_cast<char*>(&v), sizeof v); return v; }
   static void check(int rc) {
     if (rc != LQ_OK) throw std::runtime_error(std::string("lq: ") + lq_last_error());
   }

@@ -127,6 +127,12 @@ int lq_set_beta(lq_handle h, double beta);
  * operator string sorted by time.  lq_get_state with ops == NULL only returns *n. */
 int lq_set_state(lq_handle h, const int32_t* spins, const lq_op* ops, int64_t n);
 int lq_get_state(lq_handle h, int32_t* spins, lq_op* ops, int64_t* n);
+/* The random numbers of a step are Philox(seed; bond, window, STEP, draw): the step counter is the
+ * whole generator state (the reference checkpoints its generator with the worker, alps::rng_helper).
+ * Restore it together with the state, the same seed and the same lq_options.tile_sites /
+ * window_ops (the keys use the engine's internal numbering) to continue the same Markov chain. */
+uint32_t lq_get_step(lq_handle h);
+int lq_set_step(lq_handle h, uint32_t step);
 
 /* One Monte Carlo step = the whole of dispatch() (path_integral.C:355-864).  The collector is
  * that of THIS step's clusters; ene = energy_offset - nop/beta (:851). */

@@ -319,3 +319,24 @@ def test_arena_overflow_rewinds_grows_and_replays():
         ca, cb = small.sweep(), ample.sweep()
         assert ca["nop"] == cb["nop"] and ca["nc"] == cb["nc"]
     small.close(); ample.close()
+
+
+def test_restored_engine_continues_the_same_markov_chain():
+    """state + step counter + seed (+ the same tiling: random numbers are keyed by the internal bond
+    and node numbering) = the whole Markov chain (include/lq.h lq_set_step): an engine loaded from a
+    checkpoint reproduces the original engine's next steps exactly."""
+    lq = _lq()
+    lat = lq.hypercubic_lattice((8, 8))
+    a = lq.Engine(lat, 5.0, seed=31, tile_sites=16)
+    a.sweep_many(40, collect=False)
+    spins, ops = a.get_state()
+    b = lq.Engine(lat, 5.0, seed=31, tile_sites=16)
+    b.set_state(spins, ops)
+    b.set_step(a.get_step())
+    assert b.get_step() == 40
+    ca, cb = a.sweep_many(10), b.sweep_many(10)
+    assert np.array_equal(ca["nop"], cb["nop"]) and np.array_equal(ca["nc"], cb["nc"])
+    sa, oa = a.get_state()
+    sb, ob = b.get_state()
+    assert np.array_equal(sa, sb) and np.array_equal(oa, ob)
+    a.close(); b.close()

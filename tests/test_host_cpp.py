@@ -82,3 +82,26 @@ def test_loop_driver_transverse_field_vs_exact_diagonalisation():
         mean, err = vals[name]
         assert abs(mean - ed[key]) < 5 * err + 1e-9, (name, mean, ed[key], err)
     assert vals["Stiffness"][0] >= 0
+
+
+@pytest.mark.gpu
+def test_loop_driver_checkpoint_resume(tmp_path):
+    """save()/load() of the worker (path_integral.C:111-124 field order) through the driver: the second
+    run resumes where the first stopped and its observables are those of the same ensemble."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "alps-looper_b200/looper")])
+    exe = os.path.join(ROOT, "alps-looper_b200/looper/loop")
+    ck = os.path.join(str(tmp_path), "run.ck")
+    first = subprocess.run([exe, "-l", "8", "-t", "0.2", "-n", "8192", "--checkpoint", ck], capture_output=True, text=True)
+    assert first.returncode == 0, first.stderr
+    assert os.path.getsize(ck) > 8 + 4 + 4 + 8 * 4 + 8
+    assert open(ck, "rb").read(8) == b"LQCKPT01"
+    second = subprocess.run([exe, "-l", "8", "-t", "0.2", "-n", "24576", "--checkpoint", ck], capture_output=True, text=True)
+    assert second.returncode == 0, second.stderr
+    assert "resumed at" in second.stdout
+    frac = float(re.search(r"resumed at (\S+)", second.stdout).group(1))
+    assert 0.3 < frac < 0.4            # (1024 + 8192) of (3072 + 24576) steps
+    m = re.search(r"Energy Density\s*=\s*(\S+) \+- (\S+)", second.stdout)
+    mean, err = float(m.group(1)), float(m.group(2))
+    assert abs(mean + 0.441438) < 5 * err + 1e-6
+    bad = subprocess.run([exe, "-l", "10", "-t", "0.2", "-n", "1024", "--checkpoint", ck], capture_output=True, text=True)
+    assert bad.returncode != 0 and "lattice size differs" in bad.stderr
