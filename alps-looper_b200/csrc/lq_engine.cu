@@ -327,6 +327,8 @@ struct lq_engine {
   DBuf<uint8_t> spinW;
   DBuf<uint32_t> flipw, openw;
   DBuf<uint4> rootw;
+  DBuf<uint2> xedge;
+  DBuf<int> xcount;
   DBuf<short> bond_vec;
   DBuf<int> wind;
   DBuf<unsigned long long> dbgc;
@@ -588,7 +590,8 @@ struct lq_engine {
       if (getenv("LQ_UG")) ug = std::max(1, atoi(getenv("LQ_UG")));
       ug = (int)std::min<size_t>((size_t)ug, std::max<size_t>(1, (96 * 1024) / ((size_t)npo * cap * sizeof(uint32_t))));
       ug = std::min(ug, Wl);
-      CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      CK(cudaFuncSetAttribute(lq::k_union_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              sm - (int)(LQ_XCAP * sizeof(uint2)) - 64));   // minus its static edge list
       walk_fn = pick_walk();
       CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     }
@@ -616,6 +619,11 @@ struct lq_engine {
     wcount.alloc(nwords_cap + 1, tb);
     wbase.alloc(nwords_cap + 1, tb);
     rootw.alloc(opt.nranks == 1 ? nwords_cap + 1 : 1, tb);
+    {
+      const size_t ngroups = (size_t)T * ((Wl + ug - 1) / ug);
+      xedge.alloc(ngroups * LQ_XCAP, tb);
+      xcount.alloc(ngroups, tb);
+    }
     const size_t scan_n = std::max(nwords_cap, P) + 1;
     scan_tmp.alloc((scan_n + LQ_SCAN_CHUNK - 1) / LQ_SCAN_CHUNK + 1, tb);
     est.alloc(4 * (size_t)nccap, tb);
@@ -673,6 +681,7 @@ struct lq_engine {
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
     d.rootw = rootw.p; d.fpack = opt.nranks == 1 ? 1 : 0;
+    d.xedge = xedge.p; d.xcount = xcount.p;
     d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p;
     d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.gstride = gstride(); d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;

@@ -406,6 +406,7 @@ __device__ __forceinline__ void sm_union(uint32_t* par, uint32_t a, uint32_t b) 
   }
 }
 
+#define LQ_XCAP 1536  /* external edges per union group kept in the list (12 KB of shared memory) */
 // edges of one operator (graph rules above); site graphs (graph_impl.h:79-86) cut the world line:
 // a new node and no union
 template <class F>
@@ -440,6 +441,11 @@ k_union_local(Dev d, int buf) {
   const int idx_lo = d.nbase[p_first], idx_hi = d.nbase[p_end];
   const int nn = d.npo * (idx_hi - idx_lo);
   const node_t lo = upper_node(d, idx_lo, 0), hi = lo + (node_t)nn;
+  // The edges that leave the group (0.12 per operator) are handed to k_union_global as a compact
+  // list, so that kernel does not read the operators (12 bytes each) a second time.
+  __shared__ uint2 s_x[LQ_XCAP];
+  __shared__ int s_xn;
+  if (threadIdx.x == 0) s_xn = 0;
   for (int i = threadIdx.x; i < nn; i += blockDim.x) s_par[i] = (uint32_t)i;
   __syncthreads();
   for (size_t p = p_first; p < p_end; ++p) {
@@ -451,6 +457,7 @@ k_union_local(Dev d, int buf) {
       const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
         if (a >= lo && a < hi && b >= lo && b < hi) sm_union(s_par, a - lo, b - lo);
+        else { const int slot = atomicAdd(&s_xn, 1); if (slot < LQ_XCAP) s_x[slot] = make_uint2(a, b); }
       });
     }
   }
@@ -460,25 +467,49 @@ k_union_local(Dev d, int buf) {
     while (pr != r) { r = pr; pr = s_par[r]; }
     d.parent[lo + i] = lo + r;
   }
+  const int xn = s_xn;
+  if (threadIdx.x == 0) d.xcount[blockIdx.x] = (xn <= LQ_XCAP) ? xn : -1;   // -1: list overflowed, rescan the group
+  if (xn <= LQ_XCAP) {
+    uint2* xe = d.xedge + (size_t)blockIdx.x * LQ_XCAP;
+    for (int i = threadIdx.x; i < xn; i += blockDim.x) xe[i] = s_x[i];
+  }
 }
 
 // Only ~0.12 edges per operator leave their group, and every one of them is a chain of dependent
 // random loads (1.5 tree hops, one CAS).  Chasing them where they are found leaves 7 of 8 lanes
-// idle during the latency-bound part, so the CTA first compacts its global edges into a
-// shared-memory queue (coalesced scan of the operators) and then drains the queue with every lane
-// holding an edge; the first hop of the next queue entry is requested while the current one is chased.
-#define LQ_UQ 3072  /* queue entries per CTA (24 KB); more are chased in place */
+// idle during the latency-bound part, so k_union_local compacts the external edges of its group
+// into a list (it reads the operators anyway) and k_union_global drains the lists with every lane
+// holding an edge.
 __global__ void __launch_bounds__(256)
 k_union_global(Dev d, int buf) {
-  __shared__ uint2 s_q[LQ_UQ];
-  __shared__ int s_qn;
+  const int xn = d.xcount[blockIdx.x];
+  if (xn >= 0) {
+    // drain the group's list: every lane holds an edge, and the first hop of the next entry is
+    // requested while the current one is chased
+    const uint2* xe = d.xedge + (size_t)blockIdx.x * LQ_XCAP;
+    uint2 e = make_uint2(0u, 0u);
+    int i = threadIdx.x;
+    if (i < xn) e = xe[i];
+    for (; i < xn; i += blockDim.x) {
+      const int in = i + blockDim.x;
+      uint2 en = make_uint2(0u, 0u);
+      if (in < xn) {
+        en = xe[in];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + en.x));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + en.y));
+      }
+      if (d.dbg & 1) uf_union_count(d.parent, e.x, e.y, d.dbgc);
+      else uf_union(d.parent, e.x, e.y);
+      e = en;
+    }
+    return;
+  }
+  // the list overflowed (more than LQ_XCAP external edges in one group): scan the operators again
   const int ngw = (d.Wl + d.ug - 1) / d.ug;
   const int t = blockIdx.x / ngw, w_first = (blockIdx.x % ngw) * d.ug;
   const int w_last = min(w_first + d.ug, d.Wl);
   const size_t p_first = (size_t)t * d.Wl + w_first, p_end = (size_t)t * d.Wl + w_last;
   const node_t lo = upper_node(d, d.nbase[p_first], 0), hi = upper_node(d, d.nbase[p_end], 0);
-  if (threadIdx.x == 0) s_qn = 0;
-  __syncthreads();
   for (size_t p = p_first; p < p_end; ++p) {
     const int n = d.pcount[buf][p];
     const int idx0 = d.nbase[p];
@@ -487,30 +518,9 @@ k_union_global(Dev d, int buf) {
       const int idx = idx0 + j;
       const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
-        if (!(a >= lo && a < hi && b >= lo && b < hi)) {
-          const int slot = atomicAdd(&s_qn, 1);
-          if (slot < LQ_UQ) s_q[slot] = make_uint2(a, b);
-          else uf_union(d.parent, a, b);
-        }
+        if (!(a >= lo && a < hi && b >= lo && b < hi)) uf_union(d.parent, a, b);
       });
     }
-  }
-  __syncthreads();
-  const int qn = min(s_qn, LQ_UQ);
-  uint2 e = make_uint2(0u, 0u);
-  int i = threadIdx.x;
-  if (i < qn) e = s_q[i];
-  for (; i < qn; i += blockDim.x) {
-    const int in = i + blockDim.x;
-    uint2 en = make_uint2(0u, 0u);
-    if (in < qn) {
-      en = s_q[in];
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + en.x));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(d.parent + en.y));
-    }
-    if (d.dbg & 1) uf_union_count(d.parent, e.x, e.y, d.dbgc);
-    else uf_union(d.parent, e.x, e.y);
-    e = en;
   }
 }
 
