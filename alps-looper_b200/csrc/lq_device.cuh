@@ -56,7 +56,6 @@ struct Dev {
   int rank, nranks;
   const int* bond_s0;    // [B] source site
   const int* bond_s1;    // [B] target site
-  const int* bond_tile;  // [B] owning tile
   const int* bond_tl;    // [B] owning tile << 10 | local bond index
   const double* bond_emu;  // [B] exp(-beta * rate / W): P(no candidate in a window)
   const int* whalo_cnt;  // [T] leading halo buckets that touch an own site (walk halo)
@@ -83,7 +82,6 @@ struct Dev {
   const int* sst;         // (local bucket << 1 | side) incident to a K-site
   int hmax;               // max halo buckets per tile
   int nksmax, zmax;       // max K-sites per tile, max coordination number
-  int fcap;               // off-diagonal leg slots in the stage (K1 site lists)
   int scap;               // operators that fit the shared-memory stage (own page + halo)
   int ccap;               // candidates per page that fit the stage (K1)
   // ---- pages (double buffered) ----

@@ -287,11 +287,11 @@ struct lq_engine {
   // device
   lq::Dev d{};
   cudaStream_t stream = nullptr;
-  DBuf<int> bond_s0, bond_s1, bond_tile, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
+  DBuf<int> bond_s0, bond_s1, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
   DBuf<int> whalo_cnt, bond_tl;
   DBuf<double> bond_emu;
   DBuf<int> site_base, halo_off, halo_bond, hsite_off, hsite, tile_class, cls_bs, cls_sso, cls_sst, cls_nks, bs, sst_off, sst;
-  int scap = 0, ccap = 0, fcap = 0;
+  int scap = 0, ccap = 0;
   size_t stage_smem = 0, walk_smem = 0;
   int tpb_walk = 32;
   typedef void (*walk_fn_t)(lq::Dev, int);
@@ -469,7 +469,6 @@ struct lq_engine {
     for (int i = 0; i < N; ++i) gi[i] = gauge_e[part.site_i2e[i]];
     bond_s0.upload(part.bond_s0, &device_bytes);
     bond_s1.upload(part.bond_s1, &device_bytes);
-    bond_tile.upload(part.bond_tile, &device_bytes);
     bond_base.upload(part.bond_base, &device_bytes);
     adj_off.upload(part.adj_off, &device_bytes);
     adj.upload(part.adj, &device_bytes);
@@ -552,7 +551,6 @@ struct lq_engine {
       ccap = (int)std::ceil(grow_cand * (cm + 8.0 * std::sqrt(cm) + 32.0));
       if (ccap > 32767 || scap > 65535)
         fail(LQ_E_INVALID, "too many candidates / staged operators per page: lower tile_sites or window_ops");
-      fcap = scap + scap / 2;  // off-diagonal legs of the staged operators (checked at run time)
       tpb_walk = ((std::max(part.nsmax, part.whmax) + 31) / 32) * 32;
       // width of the fast per-site flip lists of K1: mean legs per site and window ~ 0.6 z window_ops
       {
@@ -568,7 +566,7 @@ struct lq_engine {
         if (getenv("LQ_FC")) k1_fc = atoi(getenv("LQ_FC")) <= 8 ? 8 : (atoi(getenv("LQ_FC")) <= 12 ? 12 : 16);
       }
       stage_smem = lq::k1_smem_bytes(k1_fc, scap, ccap, cap, part.nbmax, part.hmax, part.nksmax);
-      walk_smem = lq::stage_bytes(false, scap, part.nbmax, part.hmax, ccap, fcap, part.nksmax, part.zmax, tpb_walk);
+      walk_smem = lq::stage_bytes(scap, part.nbmax, part.hmax, part.zmax, tpb_walk);
       if (stage_smem > (size_t)smem_optin - 2048 || walk_smem > (size_t)smem_optin - 2048 ||
           (size_t)npo * cap * sizeof(uint32_t) > (size_t)smem_optin - 2048)
         fail(LQ_E_INVALID, "page + halo do not fit shared memory: lower tile_sites or window_ops");
@@ -666,7 +664,7 @@ struct lq_engine {
     d.N = part.N; d.B = part.B; d.T = part.T; d.nbmax = part.nbmax;
     d.W = W; d.w0 = w0; d.Wl = Wl; d.cap = cap; d.npo = npo; d.ug = ug; d.has_site = has_site ? 1 : 0;
     d.rank = opt.rank; d.nranks = opt.nranks;
-    d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_tile = bond_tile.p; d.bond_base = bond_base.p;
+    d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
     d.bond_q = bond_q.p; d.gauge = gauge.p;
     d.whalo_cnt = whalo_cnt.p; d.bond_tl = bond_tl.p; d.bond_emu = bond_emu.p;
@@ -674,7 +672,7 @@ struct lq_engine {
     d.hsite_off = hsite_off.p; d.hsite = hsite.p; d.tile_class = tile_class.p;
     d.cls_bs = cls_bs.p; d.cls_sso = cls_sso.p; d.cls_sst = cls_sst.p; d.cls_nks = cls_nks.p;
     d.bs = bs.p; d.sst_off = sst_off.p; d.sst = sst.p;
-    d.hmax = part.hmax; d.nksmax = part.nksmax; d.zmax = part.zmax; d.scap = scap; d.ccap = ccap; d.fcap = fcap;
+    d.hmax = part.hmax; d.nksmax = part.nksmax; d.zmax = part.zmax; d.scap = scap; d.ccap = ccap;
     for (int k = 0; k < 2; ++k) {
       d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
     }

@@ -16,9 +16,6 @@
 
 namespace lq {
 
-#define LQ_MAXC 32  /* accepted candidates kept per (bond, window) bucket */
-#define LQ_MAXN 64  /* off-diagonal neighbour legs per bond and window    */
-
 struct BucketRef {
   size_t base;  // first slot of the bucket in the page arrays
   int n;        // operators in the bucket
@@ -54,77 +51,41 @@ __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Shared-memory stage of one page and its halo (the "time-slice tile"): the operators of the
+// Shared-memory stage of one page and its walk halo (the "time-slice tile"): the operators of the
 // tile's own buckets are copied as one contiguous stream, the buckets of foreign bonds that touch
-// an end site of an owned bond are gathered behind them.  All neighbour look-ups of K1 and K2
-// then run on shared memory through the static per-class stencils (local bucket ids).
+// an OWN site are gathered behind them.  All neighbour look-ups of the walk then run on shared
+// memory through the static per-class stencils (local bucket ids).  (K1 has its own stage with the
+// larger halo of the far-end sites, lq_k1.cuh.)
 // ------------------------------------------------------------------------------------------
 struct Stage {
   double* time;    // [scap]
-  double* ctime;   // [ccap]   candidate times (K1)
-  double* ftime;   // [fcap]   off-diagonal leg times grouped by K-site (K1)
   uint32_t* info;  // [scap]
   int* off;        // [nloc+1] first staged slot of each local bucket
   int* idx0;       // [nloc]   dense operator index of the first operator of the bucket
   int* gbond;      // [nloc]   global bond id (tie-break order)
-  int* cbase;      // [nbmax+1] first candidate of each own bucket (K1)
-  int* noff;       // [nbmax+1] new bucket offsets (K1)
-  int* foff;       // [nksmax+1] first ftime slot of each K-site (K1)
-  uint16_t* clb;   // [ccap]   owning local bucket of a candidate (K1)
-  uint16_t* head;  // [zmax*blockDim] merge heads of the site walk (K2)
-  uint8_t* cacc;   // [ccap]   accepted bit | graph << 1 (K1)
-  uint8_t* kspin;  // [nksmax] spin of every K-site at the window start (K1)
-  int* fpos;       // [nksmax] fill cursors of the site lists (K1)
-  int* nkb;        // [nbmax]  kept (off-diagonal) operators per own bucket (K1)
-  uint16_t* klist; // [cap]    staged slots of the kept own operators, compacted (K1)
-  uint16_t* alist; // [ccap]   accepted candidates, compacted (K1)
+  uint16_t* head;  // [zmax*blockDim] merge heads of the generic site walk
   int nb, nh;
 };
 
-// FULL = the K1 layout (candidate and site-list arrays); otherwise the lean layout of the walk
-__host__ __device__ inline size_t stage_bytes(bool full, int scap, int nbmax, int hmax, int ccap, int fcap,
-                                              int nksmax, int zmax, int tpb) {
+__host__ __device__ inline size_t stage_bytes(int scap, int nbmax, int hmax, int zmax, int tpb) {
   const size_t nloc = (size_t)nbmax + hmax;
-  if (!full) return (size_t)scap * 12 + (3 * nloc + 1) * 4 + (size_t)zmax * tpb * 2 + 64;
-  return ((size_t)scap + ccap + fcap) * 8 + (size_t)scap * 4 + (3 * nloc + 1) * 4 +
-         3 * ((size_t)nbmax + 1) * 4 + 2 * ((size_t)nksmax + 1) * 4 + ((size_t)ccap * 2 + scap) * 2 +
-         (size_t)ccap + (size_t)nksmax + 64;
+  return (size_t)scap * 12 + (3 * nloc + 1) * 4 + (size_t)zmax * tpb * 2 + 64;
 }
 
-template <bool FULL>
 __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl, unsigned char* smem,
                                            Stage& S, int* s_scan) {
   const int nloc_max = d.nbmax + d.hmax;
   S.time = (double*)smem;
-  if (FULL) {
-    S.ctime = S.time + d.scap;
-    S.ftime = S.ctime + d.ccap;
-    S.info = (uint32_t*)(S.ftime + d.fcap);
-  } else {
-    S.info = (uint32_t*)(S.time + d.scap);
-  }
+  S.info = (uint32_t*)(S.time + d.scap);
   S.off = (int*)(S.info + d.scap);
   S.idx0 = S.off + nloc_max + 1;
   S.gbond = S.idx0 + nloc_max;
-  if (FULL) {
-    S.cbase = S.gbond + nloc_max;
-    S.noff = S.cbase + d.nbmax + 1;
-    S.foff = S.noff + d.nbmax + 1;
-    S.fpos = S.foff + d.nksmax + 1;
-    S.nkb = S.fpos + d.nksmax + 1;
-    S.clb = (uint16_t*)(S.nkb + d.nbmax + 1);
-    S.alist = S.clb + d.ccap;
-    S.klist = S.alist + d.ccap;
-    S.cacc = (uint8_t*)(S.klist + d.scap);
-    S.kspin = S.cacc + d.ccap;
-  } else {
-    S.head = (uint16_t*)(S.gbond + nloc_max);
-  }
+  S.head = (uint16_t*)(S.gbond + nloc_max);
   const size_t p = (size_t)t * d.Wl + wl;
   const int b0 = d.bond_base[t];
   S.nb = d.bond_base[t + 1] - b0;
   const int h0 = d.halo_off[t];
-  S.nh = FULL ? d.halo_off[t + 1] - h0 : d.whalo_cnt[t];  // the walk only needs buckets at own sites
+  S.nh = d.whalo_cnt[t];  // the walk only needs the halo buckets at own sites (they come first)
   const int n_own = d.pcount[buf][p];
   const int base_idx = d.nbase[p];
   const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1);
@@ -158,11 +119,7 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
           if (j0 + u < r.n) { tt[u] = d.time[buf][r.base + j0 + u]; ii[u] = d.info[buf][r.base + j0 + u]; }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (j0 + u < r.n) {
-            S.time[n_own + hoff + j0 + u] = tt[u];
-            // the staged copy carries the LOCAL bucket id of this tile in the bond bits
-            S.info[n_own + hoff + j0 + u] = (ii[u] & ((1u << LQ_INFO_LBSHIFT) - 1u)) | ((uint32_t)(S.nb + tid) << LQ_INFO_LBSHIFT);
-          }
+          if (j0 + u < r.n) { S.time[n_own + hoff + j0 + u] = tt[u]; S.info[n_own + hoff + j0 + u] = ii[u]; }
       }
   }
   if (tid == 0) S.off[S.nb + S.nh] = n_own + total;
@@ -289,7 +246,7 @@ k_walk(Dev d, int buf) {
   const size_t p = blockIdx.x;
   const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl);
   Stage S;
-  const bool staged = stage_page<false>(d, buf, t, wl, s_stage, S, s_scan);
+  const bool staged = stage_page(d, buf, t, wl, s_stage, S, s_scan);
   if (!staged) { if (threadIdx.x == 0) atomicOr(d.d_err, LQ_ERR_PAGE_FULL); return; }
   const int tid = threadIdx.x;
   const int sb = d.site_base[t];
