@@ -93,6 +93,7 @@ struct Dev {
   // ---- per (window, site) carries ----
   uint8_t* spinW;  // [(Wl+1)*N] spin at the start of local window wl
   node_t* curW;    // [(Wl+1)*N] node of the world-line segment crossing the start of window wl
+  uint32_t* firstW;  // [Wl*N] first leg of the site in the window (operator | side << 31), NODE_NONE if none
   // ---- union-find / labels ----
   node_t* parent;  // [N + npo*ncap]; after k_relabel holds the cluster id
   node_t* low0;    // [ncap] node below the operator on the source side

@@ -322,7 +322,7 @@ struct lq_engine {
   DBuf<float4> bond_p;
   DBuf<float> bond_q;
   DBuf<signed char> gauge;
-  DBuf<uint32_t> info[2], parent, low0, low1, bitmap, wcount, wbase, scan_tmp, d_nc, curW, labels;
+  DBuf<uint32_t> info[2], parent, low0, low1, bitmap, wcount, wbase, scan_tmp, d_nc, curW, firstW, labels;
   DBuf<uint16_t> boff[2];
   DBuf<uint8_t> spinW;
   DBuf<uint32_t> flipw, openw;
@@ -610,6 +610,7 @@ struct lq_engine {
     nbase.alloc(P + 1, tb);
     spinW.alloc((size_t)(Wl + 1) * N, tb);
     curW.alloc((size_t)(Wl + 1) * N, tb);
+    firstW.alloc((size_t)Wl * N, tb);
     parent.alloc((size_t)nodes_cap, tb);
     low0.alloc((size_t)ncap, tb);
     low1.alloc((size_t)ncap, tb);
@@ -676,7 +677,7 @@ struct lq_engine {
     for (int k = 0; k < 2; ++k) {
       d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
     }
-    d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.parent = parent.p; d.low0 = low0.p;
+    d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.firstW = firstW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
     d.rootw = rootw.p; d.fpack = opt.nranks == 1 ? 1 : 0;
     d.xedge = xedge.p; d.xcount = xcount.p;
@@ -742,12 +743,13 @@ struct lq_engine {
       Section s(this, 6);
       scan_u32((const uint32_t*)pcount[cur].p, (uint32_t*)nbase.p, P, (uint32_t*)(nbase.p + P), d_ntotal.p);
       lq::k_init_nodes<<<grid_for(N, 256), 256, 0, stream>>>(d);
-      lq::k_carry<<<grid_for(N, 128), 128, 0, stream>>>(d, cur);
-      launches += 2;
+      launches += 1;
     }
     {
       Section s(this, 7);
       walk_fn<<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
+      lq::k_carry_scan<<<grid_for(N, 128), 128, 0, stream>>>(d);   // closes the chain of windows per site
+      launches += 1;
       const unsigned ngroups = (unsigned)((size_t)part.T * ((Wl + ug - 1) / ug));
       lq::k_union_local<<<ngroups, 256, (size_t)ug * npo * cap * sizeof(uint32_t), stream>>>(d, cur);
       lq::k_union_global<<<ngroups, 256, 0, stream>>>(d, cur);

@@ -199,31 +199,28 @@ __global__ void k_init_nodes(Dev d) {  // site nodes; operator nodes are written
 // ------------------------------------------------------------------------------------------
 // K2b: per site, the node of the world-line segment that crosses the start of every window
 // (the reference's current[s], path_integral.C:452, carried through imaginary time).
-// One thread per site, sequential over windows; neighbouring threads read neighbouring buckets.
 // ------------------------------------------------------------------------------------------
-__global__ void k_carry(Dev d, int buf) {
+// The walk below does not know which node enters a window from below (that depends on all earlier
+// windows), so it leaves the FIRST leg of every site open -- firstW[wl][s] = operator | side << 31 --
+// and reports the node leaving the window at the top in curW[wl+1][s] (NODE_NONE if the site has no
+// leg in the window).  This kernel closes the chain: one thread per site runs over the windows,
+// carries the crossing node forward and patches the open first legs.  All its loads are coalesced
+// over the sites and independent of the carried value.  (It replaces a kernel that looked up the
+// last operator of every bucket of every site and window before the walk: 3.3 ms and 12 GB.)
+__global__ void k_carry_scan(Dev d) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= d.N) return;
   node_t cur = (node_t)s;
-  const int a0 = d.adj_off[s], a1 = d.adj_off[s + 1];
+  d.curW[s] = cur;
   for (int wl = 0; wl < d.Wl; ++wl) {
-    d.curW[(size_t)wl * d.N + s] = cur;
-    double bt = -1.0;
-    int bb = -1;
-    for (int a = a0; a < a1; ++a) {
-      const int e = d.adj[a];
-      const int b2 = e >> 1;
-      BucketRef r = bucket_of(d, buf, b2, wl);
-      if (r.n > 0) {
-        const double tt = d.time[buf][r.base + r.n - 1];
-        if (tt > bt || (tt == bt && b2 > bb)) {
-          bt = tt; bb = b2;
-          cur = upper_node(d, r.idx0 + r.n - 1, e & 1);
-        }
-      }
-    }
+    const size_t i = (size_t)wl * d.N + s;
+    const uint32_t f = d.firstW[i];
+    if (f != NODE_NONE && (long long)(f & 0x7fffffffu) < d.ncap)
+      ((f >> 31) ? d.low1 : d.low0)[f & 0x7fffffffu] = cur | ((uint32_t)d.spinW[i] << 31);
+    const node_t nxt = d.curW[i + d.N];
+    if (nxt == NODE_NONE) d.curW[i + d.N] = cur;
+    else cur = nxt;
   }
-  d.curW[(size_t)d.Wl * d.N + s] = cur;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -247,16 +244,22 @@ k_walk(Dev d, int buf) {
   const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl);
   Stage S;
   const bool staged = stage_page(d, buf, t, wl, s_stage, S, s_scan);
-  if (!staged) { if (threadIdx.x == 0) atomicOr(d.d_err, LQ_ERR_PAGE_FULL); return; }
   const int tid = threadIdx.x;
   const int sb = d.site_base[t];
   if (tid >= d.site_base[t + 1] - sb) return;
   const int s = sb + tid;
+  if (!staged) {   // the step is lost (sticky error word); leave nothing for k_carry_scan to patch
+    if (tid == 0) atomicOr(d.d_err, LQ_ERR_PAGE_FULL);
+    d.firstW[(size_t)wl * d.N + s] = NODE_NONE;
+    d.curW[(size_t)(wl + 1) * d.N + s] = NODE_NONE;
+    return;
+  }
   const int cls = d.tile_class[t];
   const int* sso = d.sst_off + d.cls_sso[cls];
   const int* sse = d.sst + d.cls_sst[cls] + sso[tid];
   const int z = sso[tid + 1] - sso[tid];
-  node_t cur = d.curW[(size_t)wl * d.N + s];
+  node_t cur = 0;          // the node entering from below is patched in by k_carry_scan
+  bool have = false;       // a leg of this site has been seen in this window
   uint32_t spin = d.spinW[(size_t)wl * d.N + s];
   if (Z > 0) {
     int hd[Z > 0 ? Z : 1], en[Z > 0 ? Z : 1], gb[Z > 0 ? Z : 1], ix[Z > 0 ? Z : 1], sd[Z > 0 ? Z : 1];
@@ -296,7 +299,9 @@ k_walk(Dev d, int buf) {
         tk[k] = m ? tn : tk[k];
       }
       const int idx = bix + bh;
-      (bsd ? d.low1 : d.low0)[idx] = cur | (spin << 31);
+      if (have) (bsd ? d.low1 : d.low0)[idx] = cur | (spin << 31);
+      else d.firstW[(size_t)wl * d.N + s] = (uint32_t)idx | ((uint32_t)bsd << 31);
+      have = true;
       spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
       cur = upper_node(d, idx, bsd);
     }
@@ -321,11 +326,15 @@ k_walk(Dev d, int buf) {
       head[best * hs] = (uint16_t)(bh + 1);
       const int lid = bent >> 1, side = bent & 1;
       const int idx = S.idx0[lid] + (bh - S.off[lid]);
-      (side ? d.low1 : d.low0)[idx] = cur | (spin << 31);
+      if (have) (side ? d.low1 : d.low0)[idx] = cur | (spin << 31);
+      else d.firstW[(size_t)wl * d.N + s] = (uint32_t)idx | ((uint32_t)side << 31);
+      have = true;
       spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
       cur = upper_node(d, idx, side);
     }
   }
+  if (!have) d.firstW[(size_t)wl * d.N + s] = NODE_NONE;
+  d.curW[(size_t)(wl + 1) * d.N + s] = have ? cur : NODE_NONE;
 }
 
 // ------------------------------------------------------------------------------------------
