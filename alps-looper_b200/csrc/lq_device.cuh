@@ -49,6 +49,7 @@ struct Dev {
   int N, B, T, nbmax;
   int W;            // global number of windows
   int w0, Wl;       // this rank owns windows [w0, w0+Wl)
+  const double* wlo;  // [W+1] window bounds: wlo[w] = window_lo(w, W), wlo[W] = 1 (two f64 divisions less per thread)
   int cap;          // page capacity (operators)
   int npo;          // nodes per operator (1: graphs {0,2,3}; 2: cross graph present)
   int ug;           // windows per union group (k_union_local / k_union_global)

@@ -289,7 +289,7 @@ struct lq_engine {
   cudaStream_t stream = nullptr;
   DBuf<int> bond_s0, bond_s1, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
   DBuf<int> whalo_cnt, bond_tl;
-  DBuf<double> bond_emu;
+  DBuf<double> bond_emu, wlo;
   DBuf<int> site_base, halo_off, halo_bond, hsite_off, hsite, tile_class, cls_bs, cls_sso, cls_sst, cls_nks, bs, sst_off, sst;
   int scap = 0, ccap = 0;
   size_t stage_smem = 0, walk_smem = 0;
@@ -537,6 +537,10 @@ struct lq_engine {
         emu[i] = std::exp(-beta * (v[0] + v[1] + v[2] + v[3]) / W);
       }
       bond_emu.upload(emu, nullptr);
+      std::vector<double> wl(W + 1);
+      for (int w = 0; w < W; ++w) wl[w] = lq::window_lo(w, W);
+      wl[W] = 1.0;   // == window_hi(W - 1, W); window_hi(w, W) == window_lo(w + 1, W) below it
+      wlo.upload(wl, nullptr);
     }
     const double m = opt.reserve * grow_pages * mu;
     long long c = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
@@ -668,7 +672,7 @@ struct lq_engine {
     d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
     d.bond_q = bond_q.p; d.gauge = gauge.p;
-    d.whalo_cnt = whalo_cnt.p; d.bond_tl = bond_tl.p; d.bond_emu = bond_emu.p;
+    d.whalo_cnt = whalo_cnt.p; d.bond_tl = bond_tl.p; d.bond_emu = bond_emu.p; d.wlo = wlo.p;
     d.site_base = site_base.p; d.halo_off = halo_off.p; d.halo_bond = halo_bond.p;
     d.hsite_off = hsite_off.p; d.hsite = hsite.p; d.tile_class = tile_class.p;
     d.cls_bs = cls_bs.p; d.cls_sso = cls_sso.p; d.cls_sst = cls_sst.p; d.cls_nks = cls_nks.p;

@@ -102,7 +102,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
   const int dst = src ^ 1;
   const size_t p = blockIdx.x;
-  const int t = (int)(p / d.Wl), wl = (int)(p - (size_t)t * d.Wl), wg = d.w0 + wl;
+  const int t = (int)(blockIdx.x / (unsigned)d.Wl), wl = (int)(blockIdx.x - (unsigned)t * (unsigned)d.Wl), wg = d.w0 + wl;  // (32-bit division)
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31u;
   const int b0 = d.bond_base[t];
@@ -111,7 +111,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
   const int nh = d.halo_off[t + 1] - h0;
   const int nksp = k1_nksp(d.nksmax);
   uint16_t* bo_new = d.boff[dst] + p * (size_t)(d.nbmax + 1);
-  const double tlo = window_lo(wg, d.W), thi = window_hi(wg, d.W), width = thi - tlo;
+  const double tlo = d.wlo[wg], thi = d.wlo[wg + 1], width = thi - tlo;   // = window_lo / window_hi (host table)
   const int n_own = d.pcount[src][p];
 
   // ---- 1: halo bucket extents and candidate counts, one packed prefix sum ----------------------

@@ -241,7 +241,7 @@ k_walk(Dev d, int buf) {
   extern __shared__ __align__(16) unsigned char s_stage[];
   __shared__ int s_scan[34];
   const size_t p = blockIdx.x;
-  const int t = (int)(p / d.Wl), wl = (int)(p % d.Wl);
+  const int t = (int)(blockIdx.x / (unsigned)d.Wl), wl = (int)(blockIdx.x - (unsigned)t * (unsigned)d.Wl);
   Stage S;
   const bool staged = stage_page(d, buf, t, wl, s_stage, S, s_scan);
   const int tid = threadIdx.x;
@@ -724,7 +724,7 @@ k_estimate(Dev d, int buf) {
     if (STIFF) { wh->w[0][i] = 0; wh->w[1][i] = 0; wh->w[2][i] = 0; }
   }
   const size_t p = blockIdx.x;
-  const int t = (int)(p / d.Wl);
+  const int t = (int)(blockIdx.x / (unsigned)d.Wl);
   const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     s_gg[2 * i] = d.gauge[d.bond_s0[b0 + i]];
