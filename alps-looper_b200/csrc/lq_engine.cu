@@ -579,8 +579,10 @@ struct lq_engine {
       // engines of different shapes can coexist.
       const int sm = smem_optin - 2048;   // (the limit covers static + dynamic shared memory)
       if (sdim > 0) {
-        CK(cudaFuncSetAttribute(lq::k_estimate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        CK(cudaFuncSetAttribute(lq::k_estimate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(lq::k_estimate<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(lq::k_estimate<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(lq::k_estimate<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(lq::k_estimate<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
       }
       k1_fn = pick_k1();
       CK(cudaFuncSetAttribute(k1_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -787,13 +789,12 @@ struct lq_engine {
       Section s(this, 12);
       const size_t est_smem = sizeof(lq::EstHash) + 2 * (size_t)part.nbmax + 16 +
                               (sdim > 0 ? sizeof(lq::WindHash) + 6 * (size_t)part.nbmax : 0);
-      if (sdim > 0) {
-        if (flip) lq::k_estimate<true, true><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
-        else lq::k_estimate<false, true><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
-      } else {
-        if (flip) lq::k_estimate<true, false><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
-        else lq::k_estimate<false, false><<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
-      }
+      typedef void (*est_fn_t)(lq::Dev, int);
+      static const est_fn_t est_fns[8] = {
+          lq::k_estimate<false, false, false>, lq::k_estimate<false, false, true>, lq::k_estimate<false, true, false>,
+          lq::k_estimate<false, true, true>,   lq::k_estimate<true, false, false>, lq::k_estimate<true, false, true>,
+          lq::k_estimate<true, true, false>,   lq::k_estimate<true, true, true>};
+      est_fns[(flip ? 4 : 0) | (sdim > 0 ? 2 : 0) | (npo == 2 ? 1 : 0)]<<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
       lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
       launches += 2;
       if (opt.nranks > 1) {

@@ -709,7 +709,9 @@ k_flipbits(Dev d, const StepParams* __restrict__ sp) {
 // iff the cluster arriving from below on the source side and the one leaving upwards are flipped
 // differently -- the two cluster ids are already in registers here.
 #define LQ_EST_U 1  /* operators per thread and iteration: independent gathers in flight */
-template <bool FLIP, bool STIFF>
+// NPO2: two nodes per operator (models with the cross graph); a template parameter so that the
+// usual one-node instantiation does not carry the four-leg registers
+template <bool FLIP, bool STIFF, bool NPO2>
 __global__ void __launch_bounds__(256)
 k_estimate(Dev d, int buf) {
   extern __shared__ unsigned char s_raw[];
@@ -766,7 +768,7 @@ k_estimate(Dev d, int buf) {
       const int idx = idx0 + (act[u] ? j0 + u * (int)blockDim.x : j0);
       cl0[u] = d.parent[l0[u] & 0x7fffffffu];
       cu0[u] = d.parent[upper_node(d, idx, 0)];
-      if (d.npo == 2 && !(inf[u] & LQ_INFO_SITE)) {   // (low1 of a site operator is never written)
+      if (NPO2 && !(inf[u] & LQ_INFO_SITE)) {   // (low1 of a site operator is never written)
         cl1[u] = d.parent[l1[u] & 0x7fffffffu];
         cu1[u] = d.parent[upper_node(d, idx, 1)];
       }
@@ -786,7 +788,7 @@ k_estimate(Dev d, int buf) {
       const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
       if (FLIP && !dead && ((flip_of_label(d, cl0[u]) ^ flip_of_label(d, cu0[u])) & 1u)) ginfo[j] = inf[u] ^ LQ_INFO_OFFDIAG;
       cl0[u] = LQ_CID(cl0[u]); cu0[u] = LQ_CID(cu0[u]);
-      if (d.npo == 2) { cl1[u] = LQ_CID(cl1[u]); cu1[u] = LQ_CID(cu1[u]); }
+      if (NPO2) { cl1[u] = LQ_CID(cl1[u]); cu1[u] = LQ_CID(cu1[u]); }
       if (inf[u] & LQ_INFO_SITE) {
         // site operator: end_s below / begin_s above on its one site (path_integral.C:718-726);
         // both clusters are cut open for the transverse magnetisation (transmag.h:72-81)
@@ -800,15 +802,30 @@ k_estimate(Dev d, int buf) {
         wind_add(d, h, wh, cbase, nloc, cl0[u], m0, s_vec + 3 * lb);
         wind_add(d, h, wh, cbase, nloc, cu0[u], -n0, s_vec + 3 * lb);
       }
-      if (d.npo == 1) {
-        // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0)
-        est_hash_add(d, h, cbase, nloc, cl0[u], 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
-        est_hash_add(d, h, cbase, nloc, cu0[u], -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
+      if (!NPO2) {
+        // l0 = l1 = cl0, u0 = u1 = cu0 (graph 0).  When the cluster below is the cluster above (most
+        // legs of the long loops) the two contributions are merged: a diagonal operator then adds
+        // nothing at all, an off-diagonal one only its change of magnetisation
+        if (cl0[u] == cu0[u]) {
+          const long long b = q * ((m0 + m1) - (n0 + n1)), e = q * ((g0 * m0 + g1 * m1) - (g0 * n0 + g1 * n1));
+          if (b | e) est_hash_add(d, h, cbase, nloc, cl0[u], 0, b, 0, e);
+        } else {
+          est_hash_add(d, h, cbase, nloc, cl0[u], 2 * q, q * (m0 + m1), q * (g0 + g1), q * (g0 * m0 + g1 * m1));
+          est_hash_add(d, h, cbase, nloc, cu0[u], -2 * q, -q * (n0 + n1), -q * (g0 + g1), -q * (g0 * n0 + g1 * n1));
+        }
       } else {
-        est_hash_add(d, h, cbase, nloc, cl0[u], q, q * m0, q * g0, q * g0 * m0);
-        est_hash_add(d, h, cbase, nloc, cl1[u], q, q * m1, q * g1, q * g1 * m1);
-        est_hash_add(d, h, cbase, nloc, cu0[u], -q, -q * n0, -q * g0, -q * g0 * n0);
-        est_hash_add(d, h, cbase, nloc, cu1[u], -q, -q * n1, -q * g1, -q * g1 * n1);
+        // four legs; legs of the same cluster are merged before they reach the table
+        uint32_t id[4] = {cl0[u], cl1[u], cu0[u], cu1[u]};
+        long long A[4] = {q, q, -q, -q}, B[4] = {q * m0, q * m1, -q * n0, -q * n1};
+        long long C[4] = {q * g0, q * g1, -q * g0, -q * g1}, E[4] = {q * g0 * m0, q * g1 * m1, -q * g0 * n0, -q * g1 * n1};
+#pragma unroll
+        for (int i = 1; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < i; ++j)
+            if (id[i] == id[j]) { A[j] += A[i]; B[j] += B[i]; C[j] += C[i]; E[j] += E[i]; A[i] = B[i] = C[i] = E[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (A[i] | B[i] | C[i] | E[i]) est_hash_add(d, h, cbase, nloc, id[i], A[i], B[i], C[i], E[i]);
       }
     }
   }
