@@ -54,6 +54,9 @@ struct Dev {
   int npo;          // nodes per operator (1: graphs {0,2,3}; 2: cross graph present)
   int ug;           // windows per union group (k_union_local / k_union_global)
   int has_site;     // the model has site graphs: bonds with bond_s1 < 0 are site pseudo-bonds
+  int zero_umag;    // every operator sits on antiparallel spins (graphs 0 and 2 only, no site graphs): clusters
+                    // without a site node have umag == 0 identically
+  int zero_ssize;   // every bond joins sites of opposite gauge (and no site graphs): their ssize == 0 identically
   int rank, nranks;
   const int* bond_s0;    // [B] source site
   const int* bond_s1;    // [B] target site

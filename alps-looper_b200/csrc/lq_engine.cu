@@ -269,6 +269,7 @@ struct lq_engine {
   int W = 1, Wl = 1, w0 = 0, cap = 0, tpb = 32, npo = 1, ug = 1;
   int Breal = 0;          // bonds of the caller's lattice; internal bonds Breal.. are site pseudo-bonds
   bool has_site = false;
+  bool zero_umag = false, zero_ssize = false;   // sums that stay zero for this model (see lq_device.cuh)
   // arena growth after a device-side overflow (the reference's vectors grow on demand,
   // path_integral.C:240-243 RESERVE_*): multipliers on reserve / candidate slots / cluster_reserve
   double grow_pages = 1, grow_cand = 1, grow_clusters = 1;
@@ -467,6 +468,13 @@ struct lq_engine {
     }
     std::vector<signed char> gi(N);
     for (int i = 0; i < N; ++i) gi[i] = gauge_e[part.site_i2e[i]];
+    zero_umag = zero_ssize = !has_site;
+    for (int i = 0; i < B; ++i) {
+      const double* v = &weights[4 * (size_t)part.bond_i2e[i]];
+      if (v[1] > 0 || v[3] > 0) zero_umag = false;                          // graphs on parallel spins
+      if (v[1] > 0) zero_ssize = false;   // cross graph: the two lower legs belong to different clusters
+      if (part.bond_s1[i] >= 0 && gi[part.bond_s0[i]] + gi[part.bond_s1[i]] != 0) zero_ssize = false;
+    }
     bond_s0.upload(part.bond_s0, &device_bytes);
     bond_s1.upload(part.bond_s1, &device_bytes);
     bond_base.upload(part.bond_base, &device_bytes);
@@ -670,6 +678,7 @@ struct lq_engine {
   void fill_dev() {
     d.N = part.N; d.B = part.B; d.T = part.T; d.nbmax = part.nbmax;
     d.W = W; d.w0 = w0; d.Wl = Wl; d.cap = cap; d.npo = npo; d.ug = ug; d.has_site = has_site ? 1 : 0;
+    d.zero_umag = zero_umag ? 1 : 0; d.zero_ssize = zero_ssize ? 1 : 0;
     d.rank = opt.rank; d.nranks = opt.nranks;
     d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;

@@ -422,6 +422,7 @@ k_union_local(Dev d, int buf) {
       const int idx = idx0 + j;
       const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
+        if (a == b) return;   // both legs arrive from the same node (consecutive operators on one bond)
         if (a >= lo && a < hi && b >= lo && b < hi) sm_union(s_par, a - lo, b - lo);
         else { const int slot = atomicAdd(&s_xn, 1); if (slot < LQ_XCAP) s_x[slot] = make_uint2(a, b); }
       });
@@ -484,7 +485,7 @@ k_union_global(Dev d, int buf) {
       const int idx = idx0 + j;
       const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
-        if (!(a >= lo && a < hi && b >= lo && b < hi)) uf_union(d.parent, a, b);
+        if (a != b && !(a >= lo && a < hi && b >= lo && b < hi)) uf_union(d.parent, a, b);
       });
     }
   }
@@ -916,9 +917,12 @@ k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
     // part plain loads of lines last touched by atomics are an order of magnitude slower than
     // atomics on them (measured: 0.11 ms -> 0.03 ms for 1.5e6 clusters, profiles/)
     unsigned long long* e = (unsigned long long*)d.est;
+    // (zero_umag / zero_ssize: sums that the model keeps at zero for every cluster without a site node --
+    // antiparallel legs only, bonds between opposite sublattices only -- are not read at all)
+    const bool site_rooted = c < ncs;
     const double usize = sc * i64_to_f64((long long)atomicExch(e + 0 * d.nccap + c, 0ull));
-    const double umag = sc * i64_to_f64((long long)atomicExch(e + 1 * d.nccap + c, 0ull));
-    const double ssize = sc * i64_to_f64((long long)atomicExch(e + 2 * d.nccap + c, 0ull));
+    const double umag = (d.zero_umag && !site_rooted) ? 0.0 : sc * i64_to_f64((long long)atomicExch(e + 1 * d.nccap + c, 0ull));
+    const double ssize = (d.zero_ssize && !site_rooted) ? 0.0 : sc * i64_to_f64((long long)atomicExch(e + 2 * d.nccap + c, 0ull));
     const double smag = sc * i64_to_f64((long long)atomicExch(e + 3 * d.nccap + c, 0ull));
     double usize0 = 0, umag0 = 0, ssize0 = 0, smag0 = 0;
     if (c < ncs) {
