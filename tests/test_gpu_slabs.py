@@ -100,3 +100,49 @@ def test_slab_sweeps_are_legal_and_physical():
 
     for name, series, ex in [("energy", ene, -0.441438), ("smag", smag, 6.59939), ("ssus", ssus, 2.40159)]:
         assert abs(series.mean() - ex) < 4 * berr(series) + 1e-12, (name, series.mean(), ex, berr(series))
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_slab_merge_with_site_graphs_and_winding_numbers(P):
+    """transverse-field + cross-graph configuration from the oracle's generic sweep, loaded into P
+    slabs: clusters, susceptibility sums, transmag length (transmag.h) and stiffness sum (stiffness.h)
+    of the merged result equal the whole-configuration values -- the open-cluster table of the
+    exchange carries the site-leg count and the windings."""
+    lq, comm = _mods()
+    lat = lq.hypercubic_lattice((6, 6))
+    beta = 4.0
+    v, off, sign = lq.xxz_weights(-1.0, 0.5)
+    sim = orc.OracleModelSim(lat, beta, weights=tuple(v), site_weight=0.3, seed=21)
+    for _ in range(150):
+        sim.sweep()
+    spins, ops = sim.get_state()
+    assert ((ops["loc"] & 1) == 0).any()
+    ref_labels, ref_nc, ref = orc.build_clusters(lat, spins, ops)
+    ref_w2, _ = orc.stiffness(lat, spins, ops)
+    assert ref["tlen"] > 0
+    grp = comm.LoopbackGroup(P)
+
+    def body(r):
+        eng = lq.Engine(lat, beta, weights=tuple(v), site_weight=0.3, rank=r, nranks=P, seed=99, stiffness=True)
+        grp.attach(eng, r)
+        eng.set_state(spins, ops)
+        import ctypes as C
+        nc = C.c_int64(0)
+        c = lq.LqCollector()
+        lq._check(lq.lib.lq_build_clusters(eng._h, None, C.byref(nc), C.byref(c)))
+        d = c.as_dict()
+        # a few steps of the slab engine itself keep the union of the slabs legal
+        eng.sweep_many(10, collect=False)
+        s2, o2 = eng.get_state()
+        eng.close()
+        return nc.value, d, s2, o2
+
+    res = grp.run(body)
+    for nc, d, _, _ in res:
+        assert nc == ref_nc
+        for f in SUMS + ["tlen"]:
+            assert d[f] == pytest.approx(ref[f], rel=1e-8, abs=1e-7), f
+        assert d["w2"] == pytest.approx(ref_w2, rel=1e-10, abs=1e-10)
+    allops = np.concatenate([r[3] for r in res])
+    allops = allops[np.argsort(allops["time"], kind="stable")]
+    orc.build_clusters(lat, res[0][2], allops)     # raises on an illegal configuration
