@@ -1,11 +1,14 @@
 // lq_kernels.cuh -- the sm_100a kernels of one loop-update Monte Carlo step.
 //
-//   K1 k_diag_update   path_integral.C:403-425,484-537 / standalone/loop.C:93-115
-//   K2 k_carry, k_link path_integral.C:539-566,584-588; graph_impl.h:168-177,277-295; union_find.h:242-284
-//   K3 k_compress, k_relabel   union_find.h:325-343 (set_id / copy_id)
-//   K4 k_estimate, k_estimate_sites   path_integral.C:650-737; measurement.h:612-650; susceptibility.h:117-155
-//   K5 k_collect       path_integral.C:774-777,796-799; susceptibility.h:182-198
-//   K6 k_flip, k_flip_spins   path_integral.C:815-823
+//   K1 k_diag_update (lq_k1.cuh)   path_integral.C:403-425,484-537 / standalone/loop.C:93-115
+//   K2 k_walk, k_carry_scan, k_union_local, k_union_global, k_close
+//                      path_integral.C:539-566,584-588; graph_impl.h:67-87,168-177,277-295; union_find.h:242-284
+//   K3 k_compress, k_rootflip, k_relabel   union_find.h:325-343 (set_id / copy_id); path_integral.C:796-799
+//   K4 k_estimate, k_estimate_sites   path_integral.C:650-737; measurement.h:612-650; susceptibility.h:117-155;
+//                      transmag.h:62-117; stiffness.h:82-133; operator flip path_integral.C:815-819
+//   K5 k_collect       path_integral.C:774-777; susceptibility.h:182-198
+//   K6 k_flip_spins    path_integral.C:820-823
+//   k_mr_*             looper/parallel.h:1609-1809 (slab merge, one all-gather + one all-reduce)
 //
 // All kernels are HBM-bound integer/byte work: no tensor-core path.  Pages are processed one CTA
 // per page; node- and cluster-indexed kernels are grid-stride free, sized for the arena capacity
