@@ -279,12 +279,23 @@ k_walk(Dev d, int buf) {
       }
     }
     for (;;) {
-      int best = -1, bb = 0;
-      double bt = 2.0;
+      // earliest head: plain minimum; two buckets of one site holding operators at exactly the same
+      // time (lower bond id first, the order lq_get_state exports) are sorted out on a rare path
+      int best = 0;
+      double bt = tk[0];
 #pragma unroll
-      for (int k = 0; k < Z; ++k)
-        if (tk[k] < bt || (tk[k] == bt && tk[k] < 2.0 && gb[k] < bb)) { best = k; bt = tk[k]; bb = gb[k]; }
-      if (best < 0) break;
+      for (int k = 1; k < Z; ++k)
+        if (tk[k] < bt) { bt = tk[k]; best = k; }
+      if (!(bt < 2.0)) break;
+      int ties = 0;
+#pragma unroll
+      for (int k = 0; k < Z; ++k) ties += (int)(tk[k] == bt);
+      if (ties > 1) {
+        int bb = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < Z; ++k)
+          if (tk[k] == bt && gb[k] < bb) { bb = gb[k]; best = k; }
+      }
       // branch-free head update: select the winner's registers, ONE shared-memory load for the
       // whole warp, then predicated write-back (a load inside `if (k == best)` would serialise
       // the warp Z times)
