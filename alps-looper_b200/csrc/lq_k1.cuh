@@ -285,8 +285,10 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
     for (int j = S.off[lb]; j < o1; ++j)      // kept operators come first on ties
       rank += (int)(S.info[j] & LQ_INFO_OFFDIAG) & (int)(S.time[j] <= tc);
     const int c1 = S.cbase[lb + 1];
-    for (int k = S.cbase[lb]; k < c1; ++k)
-      rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] < tc || (S.ctime[k] == tc && k < c));
+    for (int k = S.cbase[lb]; k < c; ++k)        // equal times: the earlier draw comes first
+      rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] <= tc);
+    for (int k = c + 1; k < c1; ++k)
+      rank += (int)(S.cacc[k] & 1) & (int)(S.ctime[k] < tc);
     const int pos = S.noff[lb] + rank;
     wt[pos] = tc;
     wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((acc >> 1) << LQ_INFO_GSHIFT) |
