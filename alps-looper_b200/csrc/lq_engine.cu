@@ -814,7 +814,7 @@ struct lq_engine {
     }
     {
       Section s(this, 13);
-      lq::k_collect<<<(unsigned)nblk_collect, 256, 0, stream>>>(d, partial.p, sp);
+      lq::k_collect<<<(unsigned)nblk_collect, 256, 0, stream>>>(d, partial.p);
       lq::k_collect_final<<<1, 256, 0, stream>>>(d, partial.p, nblk_collect, out_slot);
       launches += 2;
     }
@@ -979,7 +979,7 @@ struct lq_engine {
   // state import / export (host side, test and checkpoint path)
   // -------------------------------------------------------------------------------------------
   void set_state(const int32_t* spins, const lq_op* ops, int64_t n) {
-    const int N = part.N, B = part.B;
+    const int N = part.N;
     std::vector<std::vector<std::pair<double, uint32_t>>> buckets;  // per (page, lb) for local windows
     const size_t nbk = P * (size_t)part.nbmax;
     buckets.resize(nbk);

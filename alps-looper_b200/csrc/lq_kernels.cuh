@@ -243,7 +243,6 @@ __global__ void __launch_bounds__(MAXT)
 k_walk(Dev d, int buf) {
   extern __shared__ __align__(16) unsigned char s_stage[];
   __shared__ int s_scan[34];
-  const size_t p = blockIdx.x;
   const int t = (int)(blockIdx.x / (unsigned)d.Wl), wl = (int)(blockIdx.x - (unsigned)t * (unsigned)d.Wl);
   Stage S;
   const bool staged = stage_page(d, buf, t, wl, s_stage, S, s_scan);
@@ -915,9 +914,8 @@ k_estimate_sites(Dev d) {
                             d.gstride = 8 + has_site + sdim of them travel in the all-reduce */
 #define LQ_WFX 1024.0 /* fixed-point scale of the relative bond vectors */
 __global__ void __launch_bounds__(256)
-k_collect(Dev d, double* partial, const StepParams* __restrict__ sp) {
+k_collect(Dev d, double* partial) {
   __shared__ double s_red[8][LQ_NSUM];
-  const uint32_t key0 = sp->key0, key1 = sp->key1, mcs = sp->mcs;
   const uint32_t nc = d.d_nc[0], ncs = d.d_nc[1];
   double v[LQ_NSUM];
 #pragma unroll
