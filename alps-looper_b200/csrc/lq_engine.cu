@@ -359,6 +359,8 @@ struct lq_engine {
     if (h_out) cudaFreeHost(h_out);
     if (h_params) cudaFreeHost(h_params);
     if (h_mr) cudaFreeHost(h_mr);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    drop_graphs();
     for (auto& t : tpending) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     if (stream) cudaStreamDestroy(stream);
   }
@@ -437,6 +439,7 @@ struct lq_engine {
     sm_count = prop.multiProcessorCount;
     smem_optin = (int)prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    graphs_off = getenv("LQ_NO_GRAPH") != nullptr;
 
     make_partition(L, (int)xsrc.size(), xsrc.data(), xdst.data(), opt.tile_sites, part);
     if (part.nbmax + 1 > 1024)
@@ -523,6 +526,7 @@ struct lq_engine {
   // (re)size everything that depends on beta
   void size_arenas() {
     const int N = part.N, B = part.B, T = part.T;
+    drop_graphs();   // captured kernels hold the old pointers and grid sizes
     double maxrate = 0;
     std::vector<double> tile_rate(T, 0.0);
     for (int i = 0; i < B; ++i) {
@@ -907,6 +911,69 @@ struct lq_engine {
     ++mcs;
   }
 
+  // ---- CUDA graphs for small systems ---------------------------------------------------------
+  // One executable graph per page-buffer parity holds a whole Monte Carlo step; a batch of steps is
+  // `count` graph launches.  Only serial engines with timers off, and only below LQ_GRAPH_PAGES
+  // pages: above that the launches are hidden behind kernels that run for milliseconds.
+  static constexpr size_t LQ_GRAPH_PAGES = 65536;
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  int64_t glaunches[2] = {0, 0};
+  lq::StepCtl* h_ctl = nullptr;   // pinned
+  DBuf<lq::StepCtl> d_ctl;
+  DBuf<double> d_gout;            // the fixed collector slot of the captured kernels
+  bool graphs_off = false;
+
+  void drop_graphs() {
+    for (int k = 0; k < 2; ++k)
+      if (gexec[k]) { cudaGraphExecDestroy(gexec[k]); gexec[k] = nullptr; }
+  }
+  bool use_graphs() const {
+    return opt.nranks == 1 && !timers_on && !graphs_off && P <= LQ_GRAPH_PAGES;
+  }
+  void capture_graph(int parity) {
+    if (!d_ctl.p) {
+      d_ctl.alloc(1, &device_bytes);
+      d_gout.alloc(32, &device_bytes);
+      CK(cudaMallocHost((void**)&h_ctl, sizeof(lq::StepCtl)));
+    }
+    const int cur_save = cur;
+    const uint32_t mcs_save = mcs;
+    const int64_t l0 = launches;
+    cudaGraph_t g = nullptr;
+    cur = parity;
+    CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_step(d_gout.p, &d_ctl.p->sp);
+    lq::k_step_advance<<<1, 32, 0, stream>>>(d_ctl.p, d_gout.p);
+    launches += 1;
+    const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+    cur = cur_save;
+    mcs = mcs_save;
+    glaunches[parity] = launches - l0;
+    launches = l0;
+    if (ce != cudaSuccess) throw cuda_error{ce, "cudaStreamEndCapture", __FILE__, __LINE__};
+    const cudaError_t ie = cudaGraphInstantiate(&gexec[parity], g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) throw cuda_error{ie, "cudaGraphInstantiate", __FILE__, __LINE__};
+  }
+  void enqueue_batch_graph(int count) {
+    h_ctl->sp.beta = beta;
+    h_ctl->sp.key0 = (uint32_t)opt.seed;
+    h_ctl->sp.key1 = (uint32_t)(opt.seed >> 32);
+    h_ctl->sp.mcs = mcs;
+    h_ctl->sp.pad = 0;
+    h_ctl->slot = 0;
+    h_ctl->pad = 0;
+    h_ctl->ring = d_out.p;
+    CK(cudaMemcpyAsync(d_ctl.p, h_ctl, sizeof(lq::StepCtl), cudaMemcpyHostToDevice, stream));
+    h2d_bytes += (int64_t)sizeof(lq::StepCtl);
+    for (int i = 0; i < count; ++i) {
+      CK(cudaGraphLaunch(gexec[cur], stream));
+      launches += glaunches[cur];
+      cur ^= 1;
+      ++mcs;
+    }
+  }
+
   void to_collector(const double* o, lq_collector* c) const {
     c->umag0 = o[0]; c->usize2 = o[1]; c->umag2 = o[2]; c->usize4 = o[3]; c->umag4 = o[4];
     c->usize = o[5]; c->umag = o[6];
@@ -937,10 +1004,16 @@ struct lq_engine {
     if (count <= 0) return;
     if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
     ensure_out((size_t)count);
-    stage_params(count, true);
     const int cur0 = cur;
     const uint32_t mcs0 = mcs;
-    for (int i = 0; i < count; ++i) enqueue_step(d_out.p + (size_t)i * 32, d_params.p + i);
+    if (use_graphs()) {
+      for (int k = 0; k < 2; ++k)
+        if (!gexec[k]) capture_graph(k);
+      enqueue_batch_graph(count);
+    } else {
+      stage_params(count, true);
+      for (int i = 0; i < count; ++i) enqueue_step(d_out.p + (size_t)i * 32, d_params.p + i);
+    }
     CK(cudaMemcpyAsync(h_out, d_out.p, (size_t)count * 32 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     d2h_bytes += (int64_t)count * 32 * (int64_t)sizeof(double);
     CK(cudaStreamSynchronize(stream));

@@ -1005,6 +1005,26 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Graph-launched steps (small systems, where 20 launches per step are a visible share of a step
+// that takes a few hundred microseconds): the captured kernels read their inputs from ONE fixed
+// record and write the collector to ONE fixed slot; this last node of the graph files the slot in
+// the result ring of the batch and advances the step counter on the device.
+// ------------------------------------------------------------------------------------------
+struct StepCtl {
+  StepParams sp;   // inputs of the step being run
+  int slot;        // next free entry of the result ring
+  int pad;
+  double* ring;    // [slots][32] collectors of the batch
+};
+
+__global__ void k_step_advance(StepCtl* ctl, const double* fixed_out) {
+  double* dst = ctl->ring + (size_t)ctl->slot * 32;
+  dst[threadIdx.x] = fixed_out[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) { ctl->sp.mcs += 1u; ctl->slot += 1; }
+}
+
+// ------------------------------------------------------------------------------------------
 // K6: flip (path_integral.C:815-823).  An operator changes between diagonal and off-diagonal iff
 // the cluster arriving from below on the source side and the one leaving upwards there are
 // flipped differently (loop_0 / loop_1 of graph_impl.h:277-295 in leg form).  The spin carried
