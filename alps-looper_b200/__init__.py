@@ -142,7 +142,7 @@ def chain_lattice(L):
     dst = ((src + 1) % L).astype(np.int32)
     gauge = np.where(np.arange(L) % 2 == 0, 1.0, -1.0)
     vec = np.zeros((L, 3))
-    vec[:, 0] = 1.0
+    vec[:, 0] = 1.0 / L     # ALPS bond_vector_relative: bond vector over the lattice extent
     return dict(num_sites=L, src=src, dst=dst, gauge=gauge, dims=(L, 0, 0), bond_vectors=vec, vector_dim=1)
 
 
@@ -167,9 +167,9 @@ def hypercubic_lattice(dims):
             src.append(idx[keep]); dst.append(nxt[keep])
         else:
             src.append(idx); dst.append(nxt)
-        v = np.zeros((len(src[-1]), 3))   # relative bond vector: +1 along direction k (also across the seam)
+        v = np.zeros((len(src[-1]), 3))   # relative bond vector: 1/extent along direction k (also across the seam)
         if k < 3:
-            v[:, k] = 1.0
+            v[:, k] = 1.0 / d
         vecs.append(v)
         stride *= d
     src = np.concatenate(src).astype(np.int32)

@@ -116,7 +116,8 @@ struct Dev {
   uint32_t* openw; // [nccap/32 + 1] cluster is cut by a site operator (has_site only), packed
   int sdim;              // dimensions of the winding-number estimator (0: stiffness not measured)
   int gstride;           // int64 fields per global open cluster in the slab exchange
-  const short* bond_vec; // [3*B] relative bond vectors in units of 1/1024 (stiffness.h:63-76)
+  const short* bond_vec; // [3*B] relative bond vectors (stiffness.h:63-76) in units of the smallest component
+  double wscale[3];      // half that unit per dimension: (winding / 2) = wscale * integer sum
   int* wind;             // [sdim][nccap] winding of every cluster in those units
   long long ncap;   // operator arena (= P*cap)
   long long nccap;  // cluster arena

@@ -276,7 +276,8 @@ struct lq_engine {
   int64_t regrows = 0;
   int gstride() const { return 8 + (has_site ? 1 : 0) + sdim; }
   int sdim = 0;                      // dimensions of the winding estimator (0 = off)
-  std::vector<short> bond_vec_e;     // [3 * internal-order-independent external bond] fixed point
+  std::vector<short> bond_vec_e;     // [3 * external bond] components in units of wunit[x]
+  double wunit[3] = {0, 0, 0};
   size_t P = 0;
   long long ncap = 0, nccap = 0;
   size_t nwords_cap = 0, device_bytes = 0;
@@ -411,18 +412,29 @@ struct lq_engine {
           weights.push_back(0); weights.push_back(0); weights.push_back(0);
         }
     }
-    // relative bond vectors for the winding numbers (stiffness.h:63-76), fixed point 1/1024
+    // relative bond vectors for the winding numbers (stiffness.h:63-76): every component is stored
+    // as an integer multiple of the smallest non-zero |component| of its dimension (1/L for the ALPS
+    // lattices, where the relative vector is the bond vector over the lattice extent), so the
+    // per-cluster windings are exact integer sums
     sdim = 0;
     bond_vec_e.assign(3 * xsrc.size(), 0);
+    wunit[0] = wunit[1] = wunit[2] = 0;
     if (L.bond_vectors && L.vector_dim > 0) {
       sdim = std::min(3, (int)L.vector_dim);   // stiffness.h:68-73 caps at MAX_DIM
-      for (int b = 0; b < L.num_bonds; ++b)
-        for (int x = 0; x < 3; ++x) {
-          const double v = L.bond_vectors[3 * (size_t)b + x] * LQ_WFX;
-          if (!(std::fabs(v) < 32000) || std::fabs(v - std::nearbyint(v)) > 1e-6)
-            fail(LQ_E_UNSUPPORTED, "bond vector is not a multiple of 1/1024 below 31");
-          bond_vec_e[3 * (size_t)b + x] = (short)std::nearbyint(v);
+      for (int x = 0; x < 3; ++x) {
+        double u = 0;
+        for (int b = 0; b < L.num_bonds; ++b) {
+          const double a = std::fabs(L.bond_vectors[3 * (size_t)b + x]);
+          if (a > 1e-12 && (u == 0 || a < u)) u = a;
         }
+        wunit[x] = u;
+        for (int b = 0; b < L.num_bonds && u > 0; ++b) {
+          const double m = L.bond_vectors[3 * (size_t)b + x] / u;
+          if (!(std::fabs(m) < 32000) || std::fabs(m - std::nearbyint(m)) > 1e-6)
+            fail(LQ_E_UNSUPPORTED, "bond vectors of one dimension are not integer multiples of the smallest one");
+          bond_vec_e[3 * (size_t)b + x] = (short)std::nearbyint(m);
+        }
+      }
     }
     gauge_e.assign(L.num_sites, 0);
     if (L.gauge)
@@ -701,7 +713,9 @@ struct lq_engine {
     d.rootw = rootw.p; d.fpack = opt.nranks == 1 ? 1 : 0;
     d.xedge = xedge.p; d.xcount = xcount.p;
     d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p;
-    d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.gstride = gstride(); d.ncap = ncap; d.nccap = nccap;
+    d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.gstride = gstride();
+    for (int x = 0; x < 3; ++x) d.wscale[x] = 0.5 * wunit[x];   // stiffness.h:127: (winding / 2)^2
+    d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
     d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
     if (!dbgc.p) { dbgc.alloc(8, nullptr); CK(cudaMemset(dbgc.p, 0, 8 * sizeof(unsigned long long))); }

@@ -912,7 +912,6 @@ k_estimate_sites(Dev d) {
 #define LQ_NSUS 14
 #define LQ_GEST_MAX 12   /* int64 fields per global open cluster: 4 sums, 4 tau=0 sums, [site-leg count], [windings];
                             d.gstride = 8 + has_site + sdim of them travel in the all-reduce */
-#define LQ_WFX 1024.0 /* fixed-point scale of the relative bond vectors */
 __global__ void __launch_bounds__(256)
 k_collect(Dev d, double* partial) {
   __shared__ double s_red[8][LQ_NSUM];
@@ -950,7 +949,7 @@ k_collect(Dev d, double* partial) {
     // transmag.h:98-101: only clusters cut by a site operator count, with their total length = 2 usize
     if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[14] += 2.0 * usize;
     for (int x = 0; x < d.sdim; ++x) {   // stiffness.h:125-128: w2 += (winding / 2)^2 per dimension
-      const double w = (0.5 / LQ_WFX) * (double)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
+      const double w = d.wscale[x] * (double)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
       v[15] += w * w;
     }
   }
@@ -1223,7 +1222,7 @@ k_mr_gcollect(Dev d, MrDev m, double* partial) {
     const double usize0 = 0.5 * i64_to_f64(ge[4]), umag0 = 0.5 * i64_to_f64(ge[5]);
     const double ssize0 = 0.5 * i64_to_f64(ge[6]), smag0 = 0.5 * i64_to_f64(ge[7]);
     if (d.has_site && ge[8] > 0) v[14] += 2.0 * usize;
-    for (int x = 0; x < d.sdim; ++x) { const double w = (0.5 / LQ_WFX) * i64_to_f64(ge[8 + d.has_site + x]); v[15] += w * w; }
+    for (int x = 0; x < d.sdim; ++x) { const double w = d.wscale[x] * i64_to_f64(ge[8 + d.has_site + x]); v[15] += w * w; }
     for (int f = 0; f < d.gstride; ++f) ge[f] = 0;
     const double a = usize0 * usize0, b = umag0 * umag0, e = ssize0 * ssize0, g = smag0 * smag0;
     v[0] += umag0; v[1] += a; v[2] += b; v[3] += a * a; v[4] += b * b; v[5] += usize * usize; v[6] += umag * umag;

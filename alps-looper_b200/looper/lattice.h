@@ -60,7 +60,7 @@ public:
         if (ext[k] == 2 && c == 1) continue;  // a ring of two sites has one bond
         vg_.src.push_back(s);
         vg_.dst.push_back(s + stride * (((c + 1) % ext[k]) - c));
-        for (size_t x = 0; x < 3; ++x) vg_.bond_vector_relative.push_back(x == k ? 1.0 : 0.0);
+        for (size_t x = 0; x < 3; ++x) vg_.bond_vector_relative.push_back(x == k ? 1.0 / ext[k] : 0.0);   // over the extent
       }
       stride *= ext[k];
     }

@@ -45,8 +45,10 @@ typedef struct lq_lattice {
   const double*  gauge;      /* may be NULL (= not bipartite)                                    */
   int32_t        dims[3];
   /* optional, for the spin stiffness (looper/stiffness.h:63-76): relative lattice vector of every
-   * bond (bond_vector_relative of the real graph), 3 doubles per bond, multiples of 1/1024;
-   * vector_dim = spatial dimension to measure (stiffness.h MAX_DIM = 3); NULL / 0 = not measured. */
+   * bond (ALPS bond_vector_relative of the real graph: the bond vector over the lattice extent, so
+   * that a world line wrapping once has winding 1), 3 doubles per bond; within one dimension all
+   * components must be integer multiples of the smallest non-zero one.  vector_dim = spatial
+   * dimension to measure (stiffness.h MAX_DIM = 3); NULL / 0 = not measured. */
   int32_t        vector_dim;
   const double*  bond_vectors;
 } lq_lattice;

@@ -102,7 +102,7 @@ int main() {
     CHECK(std::abs(m.graph_weight() - (32 * 0.5 + 16 * 0.3)) < 1e-12);     // bonds v0+v1 = 1/2, sites |Hx|/2
     CHECK(std::abs(m.energy_offset() - (32 * 0.25 + 16 * 0.3)) < 1e-12);   // weight_impl.h:80,187
     CHECK(lat.vg().dimension == 2 && lat.vg().bond_vector_relative.size() == 3 * 32);
-    CHECK(lat.vg().bond_vector_relative[0] == 1 && lat.vg().bond_vector_relative[3 * 16 + 1] == 1);
+    CHECK(lat.vg().bond_vector_relative[0] == 0.25 && lat.vg().bond_vector_relative[3 * 16 + 1] == 0.25);  // 1 / extent
     Parameters q = p; q.set("Jxy", 1.0);   // antiferromagnetic XY coupling + field: sign problem
     bool threw = false;
     try { spinmodel_helper bad(q, lat); } catch (const std::invalid_argument&) { threw = true; }

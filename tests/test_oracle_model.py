@@ -104,16 +104,16 @@ def test_oracle_model_vs_exact_diagonalisation_xxz():
 
 
 def test_stiffness_by_hand_and_improved_vs_normal():
-    """stiffness.h: a single down spin carried once around a 4-ring has winding W = L = 4 in the
-    normal estimator (w2 = (W/2 * 2)^2 / ... = 16 in the collector's units); over a Markov chain the
-    improved and the normal estimator have the same mean."""
+    """stiffness.h: a single down spin carried once around a ring has winding number 1 in the normal
+    estimator (relative bond vectors = 1 / extent, so w2 = 1); over a Markov chain the improved and
+    the normal estimator have the same mean."""
     lat = chain_lattice(4)
     ops = np.zeros(4, dtype=orc.OP_DTYPE)
     ops["time"] = [0.1, 0.3, 0.5, 0.7]
     ops["loc"] = [(0 << 1) | 1, (1 << 1) | 1, (2 << 1) | 1, (3 << 1) | 1]
     ops["type"] = 1
     w2, w2n = orc.stiffness(lat, np.array([1, 0, 0, 0], np.int32), ops)
-    assert w2n == pytest.approx(16.0)
+    assert w2n == pytest.approx(1.0)
     assert w2 >= 0
     from looper_lattices import hypercubic_lattice
     lat = hypercubic_lattice((4, 4))
@@ -127,5 +127,5 @@ def test_stiffness_by_hand_and_improved_vs_normal():
             imp.append(a)
             nrm.append(b)
     err = np.hypot(_berr(imp), _berr(nrm))
-    assert np.mean(imp) > 0.05
+    assert np.mean(imp) > 0.003
     assert abs(np.mean(imp) - np.mean(nrm)) < 4.5 * err, (np.mean(imp), np.mean(nrm), err)
