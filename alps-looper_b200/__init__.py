@@ -64,6 +64,13 @@ class LqCollector(C.Structure):
 COLLECTOR_DTYPE = np.dtype([(f, "<f8") for f in COLLECTOR_FIELDS])
 
 
+class LqTiling(C.Structure):
+    _fields_ = [("num_tiles", C.c_int32), ("num_classes", C.c_int32), ("max_bonds", C.c_int32),
+                ("max_sites", C.c_int32), ("max_halo_buckets", C.c_int32), ("max_walk_halo", C.c_int32),
+                ("max_ksites", C.c_int32), ("max_degree", C.c_int32), ("owned_bonds", C.c_int64),
+                ("halo_buckets", C.c_int64)]
+
+
 class LqTimer(C.Structure):
     _fields_ = [("id", C.c_int32), ("count", C.c_int32), ("seconds", C.c_double),
                 ("label", C.c_char * 40)]
@@ -87,7 +94,7 @@ class LqComm(C.Structure):
 
 # every symbol include/lq.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["lq_create", "lq_destroy", "lq_set_beta", "lq_set_state", "lq_get_state", "lq_get_step", "lq_set_step", "lq_sweep",
-           "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_enable_timers", "lq_get_info", "lq_kernel_launches", "lq_regrow_count", "lq_h2d_bytes", "lq_d2h_bytes",
+           "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_enable_timers", "lq_get_info", "lq_tiling_info", "lq_kernel_launches", "lq_regrow_count", "lq_h2d_bytes", "lq_d2h_bytes",
            "lq_set_comm", "lq_stream", "lq_last_error", "lq_version"]
 
 _h = C.c_void_p
@@ -182,6 +189,24 @@ def hypercubic_lattice(dims):
     dd = tuple(dims + [0] * (3 - len(dims)))
     return dict(num_sites=n, src=src, dst=dst, gauge=gauge, dims=dd,
                 bond_vectors=np.concatenate(vecs), vector_dim=min(len(dims), 3))
+
+
+def tiling_info(lattice, tile_sites=0, with_sites=False):
+    """lq_tiling_info: the host-side spatial tiling of a lattice (runs without a GPU)."""
+    src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
+    dst = np.ascontiguousarray(lattice["dst"], dtype=np.int32)
+    lat = LqLattice()
+    lat.num_sites = int(lattice["num_sites"])
+    lat.num_bonds = len(src)
+    lat.src = src.ctypes.data_as(C.POINTER(C.c_int32))
+    lat.dst = dst.ctypes.data_as(C.POINTER(C.c_int32))
+    lat.gauge = None
+    lat.dims = (C.c_int32 * 3)(*tuple(lattice.get("dims", (0, 0, 0))))
+    lat.vector_dim = 0
+    lat.bond_vectors = None
+    out = LqTiling()
+    _check(lib.lq_tiling_info(C.byref(lat), int(tile_sites), 1 if with_sites else 0, C.byref(out)))
+    return {f: getattr(out, f) for f, _ in LqTiling._fields_}
 
 
 def xxz_weights(jxy, jz, a=0.0):

@@ -1353,6 +1353,32 @@ int lq_timers(lq_handle h, lq_timer* out, int32_t* count) {
   return LQ_OK;
 }
 
+static void tiling_info_impl(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites, lq_tiling* out) {
+  for (int b = 0; b < lat->num_bonds; ++b)
+    if (lat->src[b] < 0 || lat->src[b] >= lat->num_sites || lat->dst[b] < 0 || lat->dst[b] >= lat->num_sites ||
+        lat->src[b] == lat->dst[b])
+      fail(LQ_E_INVALID, "bond endpoint out of range");
+  std::vector<int> xsrc(lat->src, lat->src + lat->num_bonds);
+  std::vector<int> xdst(lat->dst, lat->dst + lat->num_bonds);
+  if (with_sites)
+    for (int s = 0; s < lat->num_sites; ++s) { xsrc.push_back(s); xdst.push_back(-1); }
+  Partition P;
+  make_partition(*lat, (int)xsrc.size(), xsrc.data(), xdst.data(), tile_sites > 0 ? tile_sites : 64, P);
+  out->num_tiles = P.T; out->num_classes = P.nclasses;
+  out->max_bonds = P.nbmax; out->max_sites = P.nsmax;
+  out->max_halo_buckets = P.hmax; out->max_walk_halo = P.whmax; out->max_ksites = P.nksmax; out->max_degree = P.zmax;
+  out->owned_bonds = P.bond_base[P.T];
+  out->halo_buckets = P.halo_off[P.T];
+}
+
+int lq_tiling_info(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites, lq_tiling* out) {
+  if (!lat || !out || lat->num_sites <= 0 || lat->num_bonds < 0 || (lat->num_bonds > 0 && (!lat->src || !lat->dst))) {
+    g_err = "bad argument";
+    return LQ_E_INVALID;
+  }
+  LQ_TRY(tiling_info_impl(lat, tile_sites, with_sites, out))
+}
+
 int lq_get_info(lq_handle h, lq_info* out) {
   if (!h || !out) { g_err = "bad argument"; return LQ_E_INVALID; }
   out->num_tiles = h->part.T;

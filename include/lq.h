@@ -116,6 +116,19 @@ typedef struct lq_info {
   int32_t sm_count, nodes_per_op;
 } lq_info;
 
+/* Host-side spatial tiling of a lattice (no GPU needed; the part of lq_create that replaces the
+ * OpenMP bond ownership of looper/lattice.h:692-787): tiles of neighbouring sites, every bond owned
+ * by the tile of its source site, per-tile halo of the foreign bonds that touch a site of an owned
+ * bond.  with_sites != 0 adds the one-ended pseudo-bond of every site (site graphs).  For tests
+ * and for choosing lq_options.tile_sites. */
+typedef struct lq_tiling {
+  int32_t num_tiles, num_classes;      /* tiles; distinct tile shapes (stencils are shared per shape) */
+  int32_t max_bonds, max_sites;        /* owned by one tile                                        */
+  int32_t max_halo_buckets, max_walk_halo, max_ksites, max_degree;
+  int64_t owned_bonds, halo_buckets;   /* sums over the tiles (owned_bonds == bonds incl. pseudo)  */
+} lq_tiling;
+int lq_tiling_info(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites, lq_tiling* out);
+
 /* Replaces loop_worker::loop_worker (path_integral.C:202-305): builds lattice tables, graph
  * chooser tables, sizes the arenas.  Initial state: all spins up, no operators (:225). */
 int lq_create(lq_handle* out, const lq_lattice* lat, const lq_model* model, double beta,
