@@ -94,6 +94,31 @@ def cpu_arm(L, beta, therm, steps, cores):
     return dict(ops_per_s=sum(per_core), ms_per_step=ms_step, nop=nop, wall=wall)
 
 
+def reference_binary_check():
+    """The unmodified reference binary (oracle/_ref/loop = standalone/loop.C, chains only) and the
+    oracle port on the same chain: operators/s of both, to show that the port used for the 2-D
+    workload is a fair stand-in for the reference's own code.  None if the binary is absent."""
+    import re
+    ref = os.path.join(ROOT, "oracle", "_ref", "loop")
+    port = os.path.join(ROOT, "oracle", "oracle_loop")
+    if not (os.path.exists(ref) and os.path.exists(port)):
+        return None
+    L, T, n = 16384, 0.0625, 48
+    out = {"workload": f"chain L={L} T={T}, {n} MCS + thermalisation, single thread"}
+    try:
+        for name, exe in (("reference", ref), ("port", port)):
+            t0 = time.perf_counter()
+            txt = subprocess.run([exe, "-l", str(L), "-t", str(T), "-n", str(n)], capture_output=True, text=True,
+                                 timeout=120).stdout
+            wall = time.perf_counter() - t0
+            ene = float(re.search(r"Energy Density\s*=\s*(\S+)", txt).group(1))
+            nop = (0.25 - ene) * L / T      # standalone/loop.C:175: E = (B/4 - n/beta) / L
+            out[name + "_operators_per_s"] = nop * (n + (n >> 3)) / wall   # process wall clock, all MCS
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -117,6 +142,9 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    chk = reference_binary_check()
+    if chk is not None:
+        line["reference_binary_check"] = chk
     print(json.dumps(line), flush=True)
 
 
