@@ -109,6 +109,7 @@ struct Dev {
   int fpack;         // labels carry the flip decision in bit 31 (serial engines)
   uint2* xedge;      // [groups][LQ_XCAP] edges that leave their union group (k_union_local -> k_union_global)
   int* xcount;       // [groups] entries of the list, -1 if it overflowed
+  int xcap;          // entries a list may hold (LQ_XCAP; the tests lower it through the LQ_XCAP environment variable)
   // ---- clusters ----
   long long* est;  // [4][nccap] usize, umag, ssize, smag in half units of LQ_FX
   int* est0;       // [4][N]     usize0, umag0, ssize0, smag0 in half units

@@ -712,6 +712,7 @@ struct lq_engine {
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
     d.rootw = rootw.p; d.fpack = opt.nranks == 1 ? 1 : 0;
     d.xedge = xedge.p; d.xcount = xcount.p;
+    d.xcap = getenv("LQ_XCAP") ? std::max(0, std::min(LQ_XCAP, atoi(getenv("LQ_XCAP")))) : LQ_XCAP;
     d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p;
     d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.gstride = gstride();
     for (int x = 0; x < 3; ++x) d.wscale[x] = 0.5 * wunit[x];   // stiffness.h:127: (winding / 2)^2

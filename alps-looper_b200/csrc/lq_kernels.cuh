@@ -437,7 +437,7 @@ k_union_local(Dev d, int buf) {
       op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
         if (a == b) return;   // both legs arrive from the same node (consecutive operators on one bond)
         if (a >= lo && a < hi && b >= lo && b < hi) sm_union(s_par, a - lo, b - lo);
-        else { const int slot = atomicAdd(&s_xn, 1); if (slot < LQ_XCAP) s_x[slot] = make_uint2(a, b); }
+        else { const int slot = atomicAdd(&s_xn, 1); if (slot < d.xcap) s_x[slot] = make_uint2(a, b); }
       });
     }
   }
@@ -448,8 +448,8 @@ k_union_local(Dev d, int buf) {
     d.parent[lo + i] = lo + r;
   }
   const int xn = s_xn;
-  if (threadIdx.x == 0) d.xcount[blockIdx.x] = (xn <= LQ_XCAP) ? xn : -1;   // -1: list overflowed, rescan the group
-  if (xn <= LQ_XCAP) {
+  if (threadIdx.x == 0) d.xcount[blockIdx.x] = (xn <= d.xcap) ? xn : -1;   // -1: list overflowed, rescan the group
+  if (xn <= d.xcap) {
     uint2* xe = d.xedge + (size_t)blockIdx.x * LQ_XCAP;
     for (int i = threadIdx.x; i < xn; i += blockDim.x) xe[i] = s_x[i];
   }
@@ -485,6 +485,7 @@ k_union_global(Dev d, int buf) {
     return;
   }
   // the list overflowed (more than LQ_XCAP external edges in one group): scan the operators again
+  if ((d.dbg & 1) && threadIdx.x == 0) atomicAdd(d.dbgc + 6, 1ull);   // (counted for the tests)
   const int ngw = (d.Wl + d.ug - 1) / d.ug;
   const int t = blockIdx.x / ngw, w_first = (blockIdx.x % ngw) * d.ug;
   const int w_last = min(w_first + d.ug, d.Wl);

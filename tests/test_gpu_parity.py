@@ -340,3 +340,32 @@ def test_restored_engine_continues_the_same_markov_chain():
     sb, ob = b.get_state()
     assert np.array_equal(sa, sb) and np.array_equal(oa, ob)
     a.close(); b.close()
+
+
+def test_external_edge_list_overflow_falls_back_to_a_rescan(monkeypatch):
+    """k_union_local hands the edges that leave a union group to k_union_global as a list of at most
+    LQ_XCAP entries; a group with more must be rescanned instead.  With the capacity lowered to 64 the
+    partition stays bit-exact and the fallback is seen to run (LQ_DBG counters)."""
+    import ctypes as C
+    lq = _lq()
+    monkeypatch.setenv("LQ_DBG", "1")
+    monkeypatch.setenv("LQ_XCAP", "64")
+    lat = lq.hypercubic_lattice((16, 16, 8))
+    beta = 12.0
+    sim = _thermalised_oracle(lat, beta, 30)
+    spins, ops = sim.get_state()
+    ref_labels, ref_nc, ref_coll = orc.build_clusters(lat, spins, ops)
+    eng = lq.Engine(lat, beta, tile_sites=256)
+    assert eng.info()["num_windows"] == 2
+    eng.set_state(spins, ops)
+    buf = (C.c_uint64 * 8)()
+    lq.lib.lq_debug_counters(eng._h, buf)      # clear
+    labels, nc, coll = eng.build_clusters()
+    lq.lib.lq_debug_counters(eng._h, buf)
+    assert buf[6] > 0, "no union group overflowed its edge list: the test does not cover the fallback"
+    assert nc == ref_nc and np.array_equal(labels, ref_labels)
+    for _ in range(5):
+        eng.sweep()
+    s2, o2 = eng.get_state()
+    orc.build_clusters(lat, s2, o2)
+    eng.close()
