@@ -42,6 +42,54 @@ def ed_chain(L, jxy, jz, T):
                 smag2=smag2, ssus_density=ssus / L)
 
 
+def ed_bonds(n, bonds, gauge, jxy, jz, gamma, T):
+    """Same thermal averages as ed_tfi for an arbitrary bond list (n <= 10 sites): used for the 4 x 2
+    ladder, the smallest two-dimensional case of the tests."""
+    dim = 1 << n
+    H = np.zeros((dim, dim))
+    SX = np.zeros((dim, dim))
+    sz = lambda s, i: 0.5 - ((s >> i) & 1)
+    for s in range(dim):
+        for (i, j) in bonds:
+            H[s, s] += jz * sz(s, i) * sz(s, j)
+            if ((s >> i) & 1) != ((s >> j) & 1):
+                H[s ^ (1 << i) ^ (1 << j), s] += 0.5 * jxy
+        for i in range(n):
+            SX[s ^ (1 << i), s] += 0.5
+    H -= gamma * SX
+    E, V = np.linalg.eigh(H)
+    beta = 1.0 / T
+    w = np.exp(-beta * (E - E.min()))
+    Z = w.sum()
+    states = np.arange(dim)
+    mu = sum(0.5 - ((states >> i) & 1) for i in range(n))
+    ms = sum(gauge[i] * (0.5 - ((states >> i) & 1)) for i in range(n))
+    P = V ** 2
+    dE = E[:, None] - E[None, :]
+    wn, wm = w[:, None], w[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        K = np.where(np.abs(dE) > 1e-12, (wm - wn) / dE, beta * wn)
+
+    def kubo(diag):
+        M = V.T @ (diag[:, None] * V)
+        return (M ** 2 * K).sum() / Z
+
+    return dict(n=n, bonds=[list(b) for b in bonds], gauge=list(gauge), jxy=jxy, jz=jz, gamma=gamma, T=T,
+                energy_density=(w * E).sum() / Z / n,
+                transmag_density=(w * np.einsum("sn,st,tn->n", V, SX, V)).sum() / Z / n,
+                umag2=(w * (P * (mu ** 2)[:, None]).sum(0)).sum() / Z,
+                smag2=(w * (P * (ms ** 2)[:, None]).sum(0)).sum() / Z,
+                usus_density=kubo(mu) / n, ssus_density=kubo(ms) / n)
+
+
+def ladder_4x2():
+    """hypercubic_lattice((4, 2)) of tests/looper_lattices.py: x-bonds on both legs, one rung per x."""
+    n = 8
+    bonds = [(s, (s % 4 + 1) % 4 + 4 * (s // 4)) for s in range(8)] + [(x, x + 4) for x in range(4)]
+    gauge = [1.0 if ((s % 4) + (s // 4)) % 2 == 0 else -1.0 for s in range(8)]
+    return n, bonds, gauge
+
+
 def ed_tfi(L, jxy, jz, gamma, T):
     """Transverse field: H = sum_b [Jz Sz Sz + Jxy/2 (S+S- + S-S+)] - Gamma sum_i Sx_i
     (site term of weight_impl.h:62-88: offdiagonal element Hx/2).  Thermal averages of the energy,
@@ -89,6 +137,12 @@ if __name__ == "__main__":
     tfi = [ed_tfi(8, 0.0, 1.0, 0.7, 0.5), ed_tfi(8, 0.0, -1.0, 0.5, 0.4), ed_tfi(8, -1.0, 0.5, 0.6, 0.4),
            ed_tfi(6, -1.0, -1.0, 1.0, 0.25)]   # Jxy <= 0 with a field: no sign problem
     json.dump(tfi, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ed_tfi.json"), "w"), indent=1)
+    n, bonds, gauge = ladder_4x2()
+    lad = [ed_bonds(n, bonds, gauge, 1.0, 1.0, 0.0, 0.3), ed_bonds(n, bonds, gauge, -1.0, 0.5, 0.6, 0.4),
+           ed_bonds(n, bonds, gauge, 0.0, 1.0, 0.8, 0.5)]
+    json.dump(lad, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ed_ladder.json"), "w"), indent=1)
+    for o in lad:
+        print({k: v for k, v in o.items() if k not in ("bonds", "gauge")})
     for o in tfi:
         print(o)
     out = [ed_chain(8, 1.0, 1.0, 0.2), ed_chain(8, 1.0, 0.5, 0.25), ed_chain(8, 1.0, 2.0, 0.5),

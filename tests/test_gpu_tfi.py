@@ -153,3 +153,31 @@ def test_config5_transverse_field_ising_chain_full_size():
     for f in SUMS:
         assert coll[f] == pytest.approx(ref[f], rel=1e-7, abs=1e-6), f
     eng.close()
+
+
+@pytest.mark.parametrize("row", [0, 1, 2])
+def test_ladder_observables_vs_exact_diagonalisation(row):
+    """4 x 2 ladder (the smallest two-dimensional lattice; tests/golden/ed_ladder.json): Heisenberg,
+    XXZ + transverse field, transverse-field Ising against exact diagonalisation."""
+    import looper_b200 as lq
+    ed = json.load(open(os.path.join(HERE, "golden", "ed_ladder.json")))[row]
+    lat = lq.hypercubic_lattice((4, 2))
+    assert sorted(zip(lat["src"].tolist(), lat["dst"].tolist())) == sorted(map(tuple, ed["bonds"]))
+    n, beta = ed["n"], 1 / ed["T"]
+    v, off, sign = lq.xxz_weights(ed["jxy"], ed["jz"])
+    eng = lq.Engine(lat, beta, weights=tuple(v), site_weight=ed["gamma"] / 2, seed=777 + row)
+    eng.sweep_many(3000, collect=False)
+    out = eng.sweep_many(24000)
+    eng.close()
+    series = {
+        "energy_density": out["ene"] / n,
+        "umag2": out["umag2"],
+        "smag2": out["smag2"],
+        "usus_density": beta * out["umag"] / n,
+        "ssus_density": beta * out["smag"] / n,
+    }
+    if v[2] == 0 and v[3] == 0 and ed["gamma"] > 0:
+        series["transmag_density"] = 0.5 * out["tlen"] / n
+    for k, x in series.items():
+        err = _berr(x)
+        assert abs(x.mean() - ed[k]) < 4.5 * err + 1e-10, (k, x.mean(), ed[k], err)

@@ -129,3 +129,32 @@ def test_stiffness_by_hand_and_improved_vs_normal():
     err = np.hypot(_berr(imp), _berr(nrm))
     assert np.mean(imp) > 0.003
     assert abs(np.mean(imp) - np.mean(nrm)) < 4.5 * err, (np.mean(imp), np.mean(nrm), err)
+
+
+@pytest.mark.parametrize("row", [0, 1, 2])
+def test_oracle_model_vs_exact_diagonalisation_ladder(row):
+    """the smallest two-dimensional case (4 x 2 ladder, tests/golden/ed_ladder.json): Heisenberg,
+    XXZ + transverse field, transverse-field Ising."""
+    from looper_lattices import hypercubic_lattice
+    ed = json.load(open(os.path.join(HERE, "golden", "ed_ladder.json")))[row]
+    lat = hypercubic_lattice((4, 2))
+    assert sorted(zip(lat["src"].tolist(), lat["dst"].tolist())) == sorted(map(tuple, ed["bonds"]))
+    n, beta = ed["n"], 1 / ed["T"]
+    v, off, sign = xxz_weights(ed["jxy"], ed["jz"])
+    sim = orc.OracleModelSim(lat, beta, weights=tuple(v), site_weight=ed["gamma"] / 2, seed=101 + row)
+    keep = {k: [] for k in ("energy_density", "transmag_density", "umag2", "smag2", "usus_density", "ssus_density")}
+    for i in range(26000):
+        c = sim.sweep()
+        if i < 2000:
+            continue
+        keep["energy_density"].append(c.ene / n)
+        keep["transmag_density"].append(0.5 * c.tlen / n)
+        keep["umag2"].append(c.umag2)
+        keep["smag2"].append(c.smag2)
+        keep["usus_density"].append(beta * c.umag / n)
+        keep["ssus_density"].append(beta * c.smag / n)
+    for k, x in keep.items():
+        if k == "transmag_density" and (v[2] > 0 or v[3] > 0 or ed["gamma"] == 0):
+            continue   # frozen graphs: see the chain test above; no field: nothing to measure
+        x = np.asarray(x)
+        assert abs(x.mean() - ed[k]) < 4.5 * _berr(x) + 1e-10, (k, x.mean(), ed[k], _berr(x))
