@@ -11,6 +11,11 @@
  *   - test/weight.op XXZ rows      (orc_xxz_weights)
  *   - the reference binary itself  (oracle/_ref/loop, built from /root/reference/standalone/loop.C
  *                                   by oracle/Makefile when the reference tree is present)
+ * The generic-model functions (orc_model_*: XXZ bond graphs + site graphs; orc_stiffness) restate
+ * path_integral.C / graph_impl.h / transmag.h / stiffness.h, which do not compile here (ALPS) and
+ * whose golden outputs depend on the ALPS generator: they are pinned to exact diagonalisation
+ * (tests/golden/ed_*.json, tests/test_oracle_model.py) and, for the stiffness, to the agreement of
+ * the improved with the normal estimator -- "parity unpinned" at the bit level for that part.
  *
  * Every function cites the reference file:line it follows (paths relative to the
  * reference root, wistaria/alps-looper).
