@@ -95,7 +95,7 @@ class LqComm(C.Structure):
 # every symbol include/lq.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["lq_create", "lq_destroy", "lq_set_beta", "lq_set_state", "lq_get_state", "lq_get_step", "lq_set_step", "lq_sweep",
            "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_enable_timers", "lq_get_info", "lq_tiling_info", "lq_kernel_launches", "lq_regrow_count", "lq_h2d_bytes", "lq_d2h_bytes",
-           "lq_set_comm", "lq_stream", "lq_last_error", "lq_version"]
+           "lq_set_comm", "lq_comm_unique_id", "lq_comm_init", "lq_stream", "lq_last_error", "lq_version"]
 
 _h = C.c_void_p
 lib.lq_create.argtypes = [C.POINTER(_h), C.POINTER(LqLattice), C.POINTER(LqModel), C.c_double,
@@ -122,6 +122,8 @@ lib.lq_h2d_bytes.restype = C.c_int64
 lib.lq_d2h_bytes.argtypes = [_h]
 lib.lq_d2h_bytes.restype = C.c_int64
 lib.lq_set_comm.argtypes = [_h, C.POINTER(LqComm)]
+lib.lq_comm_unique_id.argtypes = [C.c_void_p]
+lib.lq_comm_init.argtypes = [_h, C.c_void_p, C.c_int32, C.c_int32]
 lib.lq_stream.argtypes = [_h]
 lib.lq_stream.restype = C.c_void_p
 lib.lq_last_error.restype = C.c_char_p
@@ -384,12 +386,25 @@ class Engine:
     def stream(self):
         return lib.lq_stream(self._h)
 
+    def comm_init(self, unique_id, rank, nranks):
+        """lq_comm_init: the engine's own NCCL communicator (unique_id: 128 bytes from
+        `nccl_unique_id()` on one rank, distributed by the host)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        _check(lib.lq_comm_init(self._h, buf, int(rank), int(nranks)))
+
     def set_comm(self, all_gather, all_reduce_i64):
         ag = ALL_GATHER_FN(all_gather)
         ar = ALL_REDUCE_FN(all_reduce_i64)
         comm = LqComm(ctx=None, all_gather=ag, all_reduce_i64=ar)
         self._comm_keep = (ag, ar, comm)
         _check(lib.lq_set_comm(self._h, C.byref(comm)))
+
+
+def nccl_unique_id():
+    """lq_comm_unique_id: 128 bytes for lq_comm_init, to be created on ONE rank."""
+    buf = (C.c_char * 128)()
+    _check(lib.lq_comm_unique_id(buf))
+    return bytes(buf)
 
 
 def observables(coll, beta, num_sites, sse=False):

@@ -64,6 +64,17 @@ def attach_torch_distributed(engine, device, group=None):
     engine.set_comm(all_gather, all_reduce_i64)
 
 
+def attach_nccl(engine, rank, nranks, group=None):
+    """The engine's own NCCL data plane (lq_comm_init): torch.distributed only carries the 128-byte
+    unique id from rank 0 to the others; every collective of a step is then issued by the engine
+    itself (ncclAllGather / ncclAllReduce on its stream), with no Python in the step."""
+    import torch.distributed as dist
+    import looper_b200 as lq
+    box = [lq.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.comm_init(box[0], rank, nranks)
+
+
 class LoopbackGroup:
     """P engines in one process / one GPU, one thread each; collectives = device copies."""
 

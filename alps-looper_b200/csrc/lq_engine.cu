@@ -7,6 +7,10 @@
 #include "../../include/lq.h"
 #include "lq_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: libnccl.so.2 is bound at run time (dlopen), so the
+                    // library loads and the serial engine runs on a box without NCCL
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -253,6 +257,39 @@ inline int window_of(double t, int W) {
   return w;
 }
 
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time.  In a process that already holds NCCL (torch) dlopen returns that copy.
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.lib) return api;
+  const char* names[] = {getenv("LQ_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names)
+    if (n && *n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!lib) fail(LQ_E_COMM, std::string("cannot load libnccl.so.2 (set LQ_NCCL_LIB): ") + dlerror());
+#define LQ_SYM(f) api.f = (decltype(api.f))dlsym(lib, "nccl" #f); \
+  if (!api.f) fail(LQ_E_COMM, "libnccl lacks nccl" #f)
+  LQ_SYM(GetUniqueId); LQ_SYM(CommInitRank); LQ_SYM(CommDestroy); LQ_SYM(AllGather); LQ_SYM(AllReduce);
+  LQ_SYM(GetErrorString); LQ_SYM(GetVersion);
+#undef LQ_SYM
+  api.lib = lib;
+  return api;
+}
+void nccl_check(ncclResult_t r, const char* what) {
+  if (r != ncclSuccess) fail(LQ_E_COMM, std::string(what) + ": " + nccl_api().GetErrorString(r));
+}
+
 const char* kTimerLabels[17] = {"", "", "", "dispatch", "init", "fill_times(K1 rng)", "init_fragments",
                                 "insert/remove+reconnect", "", "close in tau", "", "assign ids",
                                 "accumulate", "collect", "flip decision", "flip", "measurement"};
@@ -345,6 +382,7 @@ struct lq_engine {
   size_t nblk_collect = 0;
   lq_comm comm{};
   bool has_comm = false;
+  ncclComm_t nccl = nullptr;   // lq_comm_init: the engine's own NCCL communicator (path_integral_mpi.C:75)
   // multi-rank (imaginary-time slabs)
   lq::MrDev mr{};
   DBuf<uint32_t> mr_topmin, mr_sendb, mr_recvb, mr_gparent, mr_gbitmap, mr_gwcount, mr_gwbase, mr_dg;
@@ -361,6 +399,7 @@ struct lq_engine {
     if (h_params) cudaFreeHost(h_params);
     if (h_mr) cudaFreeHost(h_mr);
     if (h_ctl) cudaFreeHost(h_ctl);
+    if (nccl) { cudaStreamSynchronize(stream); nccl_api().CommDestroy(nccl); }
     drop_graphs();
     for (auto& t : tpending) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     if (stream) cudaStreamDestroy(stream);
@@ -378,6 +417,7 @@ struct lq_engine {
     opt = o;
     if (opt.tile_sites <= 0) opt.tile_sites = 64;
     if (!(opt.window_ops > 0)) opt.window_ops = 3.0;
+    if (opt.window_ops > 8.0) fail(LQ_E_INVALID, "window_ops above 8: the candidate draw of one bond and window is capped at 32");
     if (!(opt.reserve > 0)) opt.reserve = 1.7;
     if (!(opt.cluster_reserve > 0)) opt.cluster_reserve = 0.75;
     if (opt.nranks < 1) { opt.nranks = 1; opt.rank = 0; }
@@ -846,6 +886,15 @@ struct lq_engine {
     if (rc != 0) fail(LQ_E_COMM, std::string(what) + " failed in the communicator callback");
   }
 
+  void all_gather(const void* send, void* recv, size_t bytes, const char* what) {
+    if (nccl) nccl_check(nccl_api().AllGather(send, recv, bytes, ncclChar, nccl, stream), what);
+    else comm_check(comm.all_gather(comm.ctx, send, recv, (int64_t)bytes, stream), what);
+  }
+  void all_reduce_i64(void* buf, size_t count, const char* what) {
+    if (nccl) nccl_check(nccl_api().AllReduce(buf, buf, count, ncclInt64, ncclSum, nccl, stream), what);
+    else comm_check(comm.all_reduce_i64(comm.ctx, buf, (int64_t)count, stream), what);
+  }
+
   void merge_open_clusters() {
     Section s(this, 13);
     const int N = part.N;
@@ -853,8 +902,7 @@ struct lq_engine {
     lq::k_mr_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
     lq::k_mr_ids<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
     launches += 2;
-    comm_check(comm.all_gather(comm.ctx, mr.sendb, mr.recvb, (int64_t)(2 * (size_t)N * sizeof(uint32_t)), stream),
-               "all_gather(boundary ids)");
+    all_gather(mr.sendb, mr.recvb, 2 * (size_t)N * sizeof(uint32_t), "all_gather(boundary ids)");
     CK(cudaMemsetAsync(mr.d_g, 0, 4 * sizeof(uint32_t), stream));
     lq::k_mr_ginit<<<grid_for(g2, 256), 256, 0, stream>>>(d, mr);
     lq::k_mr_gunion<<<grid_for(g2 / 2, 256), 256, 0, stream>>>(d, mr);
@@ -869,14 +917,14 @@ struct lq_engine {
     CK(cudaMemcpyAsync(h_mr, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     const int64_t ngc = h_mr[0];
-    if (ngc > 0) comm_check(comm.all_reduce_i64(comm.ctx, mr.gest, ngc * gstride(), stream), "all_reduce(open-cluster sums)");
+    if (ngc > 0) all_reduce_i64(mr.gest, (size_t)ngc * gstride(), "all_reduce(open-cluster sums)");
     const unsigned gblk = (unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 4);
     lq::k_mr_gcollect<<<gblk, 256, 0, stream>>>(d, mr, partial.p);   // (partial is free again after k_collect_final)
     lq::k_mr_gsum<<<1, 32, 0, stream>>>(mr, partial.p, (int)gblk);
     launches += 1;
     lq::k_mr_rankvec<<<1, 32, 0, stream>>>(d, mr, out_slot);
     launches += 2;
-    comm_check(comm.all_gather(comm.ctx, mr.rankvec, mr.allvec, 32 * sizeof(double), stream), "all_gather(collectors)");
+    all_gather(mr.rankvec, mr.allvec, 32 * sizeof(double), "all_gather(collectors)");
     lq::k_mr_final<<<1, 32, 0, stream>>>(d, mr, out_slot);
     launches += 1;
   }
@@ -1017,7 +1065,7 @@ struct lq_engine {
   // so the trajectory does not depend on the capacities.
   void sweep_many(int count, lq_collector* out, int depth = 0) {
     if (count <= 0) return;
-    if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
+    if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
     ensure_out((size_t)count);
     const int cur0 = cur;
     const uint32_t mcs0 = mcs;
@@ -1190,7 +1238,7 @@ struct lq_engine {
 
   void build_clusters(int32_t* labels_out, int64_t* nc_out, lq_collector* coll_out) {
     if (opt.nranks > 1 && labels_out) fail(LQ_E_UNSUPPORTED, "labels are only exported by a serial engine");
-    if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but lq_set_comm was not called");
+    if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
     ensure_out(1);
     stage_params(1, false);
     label_clusters(d_out.p, d_params.p, false);
@@ -1412,6 +1460,31 @@ int lq_set_comm(lq_handle h, const lq_comm* comm) {
   return LQ_OK;
 }
 
+int lq_comm_unique_id(void* id_out) {
+  if (!id_out) { g_err = "bad argument"; return LQ_E_INVALID; }
+  LQ_TRY({
+    static_assert(sizeof(ncclUniqueId) == LQ_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    nccl_check(nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id_out, &id, sizeof id);
+  })
+}
+
+int lq_comm_init(lq_handle h, const void* nccl_unique_id, int32_t rank, int32_t nranks) {
+  if (!h || !nccl_unique_id) { g_err = "bad argument"; return LQ_E_INVALID; }
+  LQ_TRY({
+    if (rank != h->opt.rank || nranks != h->opt.nranks)
+      fail(LQ_E_INVALID, "lq_comm_init: rank / nranks differ from lq_options of this engine");
+    if (nranks < 2) fail(LQ_E_INVALID, "lq_comm_init on a serial engine");
+    if (h->nccl) fail(LQ_E_INVALID, "lq_comm_init called twice");
+    CK(cudaSetDevice(h->opt.device));
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, sizeof id);
+    nccl_check(nccl_api().CommInitRank(&h->nccl, nranks, id, rank), "ncclCommInitRank");
+    h->has_comm = true;
+  })
+}
+
 void* lq_stream(lq_handle h) { return h ? (void*)h->stream : nullptr; }
 
 // experiment counters (LQ_DBG=1; not part of the public header): reads and clears 8 values
@@ -1422,6 +1495,19 @@ int lq_debug_counters(lq_handle h, unsigned long long* out) {
   cudaMemcpy(out, h->dbgc.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
   cudaMemset(h->dbgc.p, 0, 8 * sizeof(unsigned long long));
   return LQ_OK;
+}
+
+// test hook (not part of the public header): histogram of the K1 Poisson draw, see lq_k1.cuh
+int lq_debug_poisson(double mean, long long count, unsigned long long seed, unsigned long long* hist, int nbins) {
+  if (!hist || nbins <= 0 || !(mean > 0)) return LQ_E_INVALID;
+  LQ_TRY({
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, nbins * sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, nbins * sizeof(unsigned long long)));
+    lq::k_debug_poisson<<<592, 256>>>(mean, count, (uint32_t)seed, (uint32_t)(seed >> 32), d, nbins);
+    CK(cudaMemcpy(hist, d, nbins * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaFree(d));
+  })
 }
 
 const char* lq_last_error(void) { return g_err.c_str(); }

@@ -33,6 +33,32 @@ __constant__ double c_rcp[33] = {
     1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
     1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32};
 
+// Number of candidates of one bond in one window: K ~ Poisson(mu) by inversion of the CDF with one
+// 53-bit uniform u in (0,1] (replaces looper/poisson_distribution.h:44-113, whose product method
+// spends K+1 uniforms, and the exponential gaps of path_integral.C:413-423).  emu = exp(-mu).
+// K is capped at 32 (the tail beyond it is < 1e-21 for the means the windows are sized for; the
+// host rejects window_ops above 8); *overflow is raised if the cap was hit.
+__device__ __forceinline__ int k1_poisson(double u, double emu, double mu, bool* overflow) {
+  int K = 0;
+  double pk = emu, cdf = pk;
+  while (u > cdf && K < 32) { ++K; pk *= mu * c_rcp[K]; cdf += pk; }
+  *overflow = (K >= 32 && u > cdf);
+  return K;
+}
+
+// test hook (tests/test_gpu_poisson.py against test/poisson_distribution.op): histogram of
+// k1_poisson over `count` Philox draws
+__global__ void k_debug_poisson(double mean, long long count, uint32_t key0, uint32_t key1,
+                                unsigned long long* hist, int nbins) {
+  const double emu = exp(-mean);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const philox_t x = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, LQ_STREAM_CAND, key0, key1);
+    bool ovf;
+    const int K = k1_poisson(u53(x.x, x.y), emu, mean, &ovf);
+    if (K < nbins) atomicAdd(hist + K, 1ull);
+  }
+}
+
 struct K1Smem {
   double* time;     // [scap]  staged operators (own page first, halo buckets behind)
   double* ctime;    // [ccap]  candidate times
@@ -131,10 +157,9 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp) {
     const double mu = beta * d.bond_rate[b] * width;
     if (mu > 0) {
       const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND, key0, key1);
-      const double u = u53(x.x, x.y);
-      double pk = d.bond_emu[b], cdf = pk;
-      while (u > cdf && K < 32) { ++K; pk *= mu * c_rcp[K]; cdf += pk; }
-      if (K >= 32 && u > cdf) atomicOr(d.d_err, LQ_ERR_CAND_FULL);
+      bool ovf;
+      K = k1_poisson(u53(x.x, x.y), d.bond_emu[b], mu, &ovf);
+      if (ovf) atomicOr(d.d_err, LQ_ERR_CAND_FULL);
     }
   }
   int packed_total;   // both sums stay below 2^16 (scap, ccap <= 65535, checked by the host)

@@ -192,6 +192,17 @@ typedef struct lq_comm {
   int (*all_reduce_i64)(void* ctx, void* buf_dev, int64_t count, void* stream);
 } lq_comm;
 int lq_set_comm(lq_handle h, const lq_comm* comm);
+/* The engine's own data plane: an NCCL communicator over the ranks of the run (the reference hands
+ * the worker a boost::mpi::communicator, path_integral_mpi.C:75,1012, and parallel_cluster_unifier
+ * talks MPI itself, looper/parallel.h:1430-1600).  One rank calls lq_comm_unique_id, the host
+ * distributes the LQ_NCCL_ID_BYTES bytes by whatever means it has (MPI_Bcast, a file, torch), every
+ * rank calls lq_comm_init with its lq_options.rank / nranks; the all-gather and the all-reduce of
+ * every step then run as ncclAllGather / ncclAllReduce on the engine's stream.  libnccl.so.2 is
+ * bound at run time (LQ_NCCL_LIB overrides the name).  lq_set_comm remains for hosts that bring
+ * their own transport. */
+#define LQ_NCCL_ID_BYTES 128
+int lq_comm_unique_id(void* id_out /* LQ_NCCL_ID_BYTES */);
+int lq_comm_init(lq_handle h, const void* nccl_unique_id, int32_t rank, int32_t nranks);
 void* lq_stream(lq_handle h);                                 /* cudaStream_t of the handle      */
 
 const char* lq_last_error(void);

@@ -4,6 +4,8 @@
 // against standalone/loop_mpi.op-P.  TEST INFRASTRUCTURE ONLY (oracle/_ref build).
 #ifndef ORACLE_MPI_SHIM_H
 #define ORACLE_MPI_SHIM_H
+#include <sys/uio.h>
+#include <unistd.h>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -47,7 +49,21 @@ inline int MPI_Barrier(MPI_Comm) {
 inline int MPI_Send(const void* buf, int count, MPI_Datatype dt, int dest, int tag, MPI_Comm) {
   mpi_shim::world& w = mpi_shim::W();
   std::vector<char> msg((size_t)count * dt);
-  if (!msg.empty()) std::memcpy(msg.data(), buf, msg.size());
+  // standalone/parallel.h:240 sends 2N estimates out of a vector that may hold fewer: it reads past
+  // the end of its buffer, which a real MPI survives (the receiver ignores the tail) but a memcpy may
+  // not when the tail crosses an unmapped page.  process_vm_readv on the own process copies what is
+  // readable and stops at the first fault instead of raising SIGSEGV.
+  if (!msg.empty()) {
+    size_t done = 0;
+    while (done < msg.size()) {
+      struct iovec lo = {msg.data() + done, msg.size() - done};
+      struct iovec re = {(char*)const_cast<void*>(buf) + done, msg.size() - done};
+      const ssize_t r = process_vm_readv(getpid(), &lo, 1, &re, 1, 0);
+      if (r <= 0) break;
+      done += (size_t)r;
+    }
+    if (done == 0) std::memcpy(msg.data(), buf, msg.size() < 4096 ? msg.size() : 4096);
+  }
   { std::lock_guard<std::mutex> lk(w.m);
     w.box[std::make_tuple(mpi_shim::rank_ref(), dest, tag)].push_back(std::move(msg)); }
   w.cv.notify_all();

@@ -185,6 +185,7 @@ struct orc_sim {
   std::vector<char> to_flip;
   std::vector<int> built_type;  // operator types as built (pre flip)
   int nc = 0;
+  bool looper_estimators = true;   // orc_set_looper_estimators
   orc_sim(int ns, int nb, const int32_t* s, const int32_t* d, const double* g, double b,
           uint32_t seed)
       : nsites(ns), nbonds(nb), src(s, s + nb), dst(d, d + nb), gauge(ns, 0.0), beta(b),
@@ -200,6 +201,7 @@ orc_sim* orc_create(int nsites, int nbonds, const int32_t* src, const int32_t* d
   return new orc_sim(nsites, nbonds, src, dst, gauge, beta, seed);
 }
 void orc_destroy(orc_sim* s) { delete s; }
+void orc_set_looper_estimators(orc_sim* s, int on) { s->looper_estimators = on != 0; }
 
 // standalone/loop.C:87-167, with left()/right() (common.h:92-93) read from the bond table.
 void orc_sweep(orc_sim* S, orc_collector* out) {
@@ -264,7 +266,7 @@ void orc_sweep(orc_sim* S, orc_collector* out) {
   S->nc = nc;
   S->to_flip.assign(nc, 0);
   std::vector<sa_estimate> estimates(nc);
-  std::vector<lp_estimate> lest(nc);
+  std::vector<lp_estimate> lest(S->looper_estimators ? nc : 0);
 
   // loop.C:141-151
   for (auto& op : operators) {
@@ -280,7 +282,7 @@ void orc_sweep(orc_sim* S, orc_collector* out) {
   }
   // looper estimator on the same graph: path_integral.C:682-734 (accum_i), HAF graph 0:
   // loop_l0 = loop_l1 = loop0, loop_u0 = loop_u1 = loop1 (graph_impl.h:489-494)
-  {
+  if (S->looper_estimators) {
     std::vector<int> sc(spins);  // spins at tau = 0 (== spins after the walk, periodic)
     for (int s = 0; s < nsites; ++s)
       lest[fragments[s].id].start_bottom(S->gauge[s], 0.0, sc[s]);
@@ -824,6 +826,62 @@ void orc_run_chain(int length, double temperature, unsigned sweeps, unsigned the
   out[4] = usus.mean();         out[5] = usus.error();
   out[6] = smag.mean();         out[7] = smag.error();
   out[8] = ssus.mean();         out[9] = ssus.error();
+}
+
+// looper/poisson_distribution.h:44-113 (both branches) driven as test/poisson_distribution.C:33-69
+// does: boost::mt19937 default seed (= std::mt19937 default, 5489), boost::uniform_real<> on a
+// 32-bit engine = eng() / 2^32.  Writes the exact text of test/poisson_distribution.op
+// (setprecision(3) rows "r poisson frequency error") into buf; returns the length needed.
+int orc_poisson_replay(double mean, int count, char* buf, int buflen, int64_t* bins_out, int nbins_out) {
+  std::mt19937 eng;
+  auto rng = [&]() { return eng() / 4294967296.0; };
+  const double exp_mean = std::exp(-mean);                       // poisson_distribution.h:63
+  const bool big = mean >= 16;                                   // THRESHOLD, :45,64
+  const double sqr = big ? std::sqrt(2 * mean) : 0, alxm = big ? std::log(mean) : 0;
+  const double gm = big ? mean * alxm - std::lgamma(mean + 1) : 0;
+  auto draw = [&]() -> int {
+    if (!big) {                                                  // :81-88 O(mean) product method
+      double product = 1;
+      for (int m = 0;; ++m) {
+        product *= rng();
+        if (product <= exp_mean) return m;
+      }
+    }
+    double em, y, t;                                             // :89-101 rejection method
+    do {
+      do {
+        y = std::tan(M_PI * rng());
+        em = sqr * y + mean;
+      } while (em < 0.0);
+      em = std::floor(em);
+      t = 0.9 * (1 + y * y) * std::exp(em * alxm - std::lgamma(em + 1) - gm);
+    } while (rng() > t);
+    return int(em);
+  };
+  std::vector<int> bins(int(5 * mean), 0);                       // poisson_distribution.C:50-55
+  for (int c = 0; c < count; ++c) {
+    int r = draw();
+    if (r < 5 * mean) ++bins[r];
+  }
+  // `std::cout << std::setprecision(3)` (:62-69) prints like printf("%.3g"); formatted with snprintf
+  // because this library is loaded into Python processes that may already hold another libstdc++
+  std::string out;
+  double poi = std::exp(-mean);
+  for (size_t r = 0; r < bins.size(); ++r) {
+    char line[128];
+    std::snprintf(line, sizeof line, "%zu %.3g %.3g %.3g\n", r, poi, (double)bins[r] / count,
+                  std::sqrt((double)bins[r]) / count);
+    out += line;
+    poi *= mean / (r + 1);
+  }
+  if (buf && buflen > 0) {
+    int m = std::min<int>(buflen - 1, int(out.size()));
+    std::memcpy(buf, out.data(), m);
+    buf[m] = 0;
+  }
+  if (bins_out)
+    for (int r = 0; r < nbins_out; ++r) bins_out[r] = r < (int)bins.size() ? bins[r] : 0;
+  return int(out.size());
 }
 
 }  // extern "C"

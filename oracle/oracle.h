@@ -9,6 +9,7 @@
  *   - standalone/loop.op           (bit-for-bit, `oracle_loop` binary, tests/test_oracle.py)
  *   - test/union_find.op           (bit-for-bit, orc_union_find_replay)
  *   - test/weight.op XXZ rows      (orc_xxz_weights)
+ *   - test/poisson_distribution.op (bit-for-bit, orc_poisson_replay)
  *   - the reference binary itself  (oracle/_ref/loop, built from /root/reference/standalone/loop.C
  *                                   by oracle/Makefile when the reference tree is present)
  * The generic-model functions (orc_model_*: XXZ bond graphs + site graphs; orc_stiffness) restate
@@ -57,6 +58,10 @@ typedef struct orc_sim orc_sim;
 orc_sim* orc_create(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
                     const double* gauge, double beta, uint32_t seed);
 void     orc_destroy(orc_sim*);
+/* on = 0: orc_sweep runs the statements of standalone/loop.C only (3 cluster sums, common.h:67-72)
+ * and leaves the 14 looper sums at zero -- the timing configuration of bench.py's CPU legs; the
+ * random numbers drawn do not depend on it.  Default on. */
+void     orc_set_looper_estimators(orc_sim*, int on);
 
 /* One Monte Carlo step, statement-for-statement standalone/loop.C:87-167 (uniform bond choice,
  * weight 1/2 per bond).  Fills the collector from the clusters of this step. */
@@ -115,6 +120,12 @@ void     orc_xxz_weights(double jxy, double jz, double a, double v[4], double* o
  * out = {nc, nc_err, ene, ene_err, usus, usus_err, smag, smag_err, ssus, ssus_err}. */
 void     orc_run_chain(int length, double temperature, unsigned sweeps, unsigned therm,
                        double out[10]);
+
+/* looper/poisson_distribution.h:44-113 replayed as test/poisson_distribution.C:33-69 does (MEAN,
+ * COUNT from test/poisson_distribution.ip); writes the exact text of test/poisson_distribution.op
+ * into buf (returns the length needed) and the raw histogram into bins_out. */
+int      orc_poisson_replay(double mean, int count, char* buf, int buflen, int64_t* bins_out,
+                            int nbins_out);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,8 @@ def lib():
         L.orc_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                  C.c_uint32]
         L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_looper_estimators.argtypes = [C.c_void_p, C.c_int]
+        L.orc_poisson_replay.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_sweep.argtypes = [C.c_void_p, C.POINTER(OrcCollector)]
         L.orc_num_ops.argtypes = [C.c_void_p]
         L.orc_num_ops.restype = C.c_int64
@@ -71,7 +73,7 @@ def lib():
 class OracleSim:
     """standalone/loop.C on an arbitrary bond table."""
 
-    def __init__(self, lattice, beta, seed=29833):
+    def __init__(self, lattice, beta, seed=29833, looper_estimators=True):
         self.N = int(lattice["num_sites"])
         self.src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
         self.dst = np.ascontiguousarray(lattice["dst"], dtype=np.int32)
@@ -81,6 +83,8 @@ class OracleSim:
         self.beta = beta
         self.h = lib().orc_create(self.N, self.B, self.src.ctypes.data, self.dst.ctypes.data,
                                   self.gauge.ctypes.data, beta, seed)
+        if not looper_estimators:     # standalone/loop.C statements only (bench.py CPU legs)
+            lib().orc_set_looper_estimators(self.h, 0)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -117,6 +121,15 @@ class OracleSim:
                                  up.ctypes.data, sid.ctypes.data, C.byref(nc), flip.ctypes.data)
         return dict(spins_before=sb, ops=ops, lower=lo, upper=up, site=sid, nc=nc.value,
                     flip=flip[:nc.value])
+
+
+def poisson_replay(mean=3.0, count=1 << 20, nbins=15):
+    """orc_poisson_replay: (text of test/poisson_distribution.op, histogram)."""
+    n = lib().orc_poisson_replay(mean, count, None, 0, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    bins = np.zeros(nbins, dtype=np.int64)
+    lib().orc_poisson_replay(mean, count, buf, n + 1, bins.ctypes.data, nbins)
+    return buf.value.decode(), bins
 
 
 def xxz_weights(jxy, jz, a=0.0):

@@ -30,3 +30,19 @@ def test_two_gpu_bench_line():
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0
     assert 4.0e6 < line["config"]["operators_per_mcs"] < 6.0e6
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("comm", ["nccl", "torch"])
+def test_slab_parity_over_real_nccl(comm):
+    """tests/mgpu_parity.py on every GPU of the box (up to 8): merged cluster count and sums of an
+    oracle configuration equal the oracle's, slab steps stay legal, collectors identical."""
+    n = min(_ngpu(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29541" if comm == "nccl" else "29542",
+           os.path.join(ROOT, "tests", "mgpu_parity.py"), "--comm", comm]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("MGPU_PARITY ")]
+    assert out.returncode == 0 and lines, (out.stdout[-2000:], out.stderr[-2000:])
+    rep = json.loads(lines[-1][len("MGPU_PARITY "):])
+    assert rep["ok"] and rep["ranks"] == n and all(c["ok"] for c in rep["cases"]), rep

@@ -26,7 +26,24 @@ Uniform Susceptibility    = 0.0800276 +- 0.000536463
 Staggered Magnetization^2 = 6.61901 +- 0.0114392
 Staggered Susceptibility  = 2.4117 +- 0.00442169
 """
+POISSON_OP = """0 0.0498 0.0497 0.000218
+1 0.149 0.149 0.000377
+2 0.224 0.224 0.000462
+3 0.224 0.224 0.000463
+4 0.168 0.168 0.0004
+5 0.101 0.101 0.00031
+6 0.0504 0.0505 0.00022
+7 0.0216 0.0219 0.000145
+8 0.0081 0.00819 8.84e-05
+9 0.0027 0.00261 4.99e-05
+10 0.00081 0.000819 2.8e-05
+11 0.000221 0.000206 1.4e-05
+12 5.52e-05 5.34e-05 7.14e-06
+13 1.27e-05 1.72e-05 4.05e-06
+14 2.73e-06 2.86e-06 1.65e-06
+"""
 SHA = {
+    "test/poisson_distribution.op": "68f1ec97c8acbc760c8da5282b9c365216b68318cf590f20de543e624747f6f2",
     "test/union_find.op": "e7f472e7f249305bf61eec2b55614645c36be1ee1f71f0bac3e7b3af82bfe987",
     "standalone/loop.op": "08b5cb41a9fcac8c2874a42fb3eaa7d21b13b513e0b0aac644192bf3f94a9a91",
     "standalone/loop_mpi.op-1": "d1dbf6c7b20be0a7f3fa5df7aa0d0f9e36134f09fd98ed561e79fc7788f87691",
@@ -169,3 +186,29 @@ def test_observables_vs_exact_diagonalisation_cpu():
     assert abs(out[4] - ed["usus"]) < 5 * out[5]
     assert abs(out[6] - ed["smag"]) < 5 * out[7]
     assert abs(out[8] - ed["ssus"]) < 5 * out[9]
+
+
+def test_oracle_reproduces_poisson_distribution_op():
+    """looper/poisson_distribution.h:44-113 driven as test/poisson_distribution.C does
+    (MEAN = 3, COUNT = 1048576, test/poisson_distribution.ip): bit-for-bit the golden text."""
+    assert sha(POISSON_OP.encode()) == SHA["test/poisson_distribution.op"]
+    txt, bins = orc.poisson_replay(3.0, 1 << 20)
+    assert txt == POISSON_OP
+    assert bins.sum() <= (1 << 20) and bins[3] == round(0.224 * (1 << 20), -3) or bins[3] > 0
+    if os.path.exists(REF):
+        with open(os.path.join(REF, "test/poisson_distribution.op")) as f:
+            assert f.read() == txt
+
+
+def test_standalone_only_mode_draws_the_same_chain():
+    """orc_set_looper_estimators(0) (the timing configuration of bench.py's CPU legs) must not change
+    the Markov chain: same operator counts, cluster counts and standalone sums."""
+    import looper_lattices as ll
+    lat = ll.hypercubic_lattice((8, 8))
+    a = orc.OracleSim(lat, 4.0, 5)
+    b = orc.OracleSim(lat, 4.0, 5, looper_estimators=False)
+    for _ in range(40):
+        ca, cb = a.sweep(), b.sweep()
+        for f in ("nop", "nc", "sa_usus", "sa_smag", "sa_ssus"):
+            assert ca[f] == cb[f]
+    assert cb["usize"] == 0 and ca["usize"] > 0
