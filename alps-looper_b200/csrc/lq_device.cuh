@@ -88,6 +88,8 @@ struct Dev {
   int nksmax, zmax;       // max K-sites per tile, max coordination number
   int scap;               // operators that fit the shared-memory stage (own page + halo)
   int ccap;               // candidates per page that fit the stage (K1)
+  int k1_keyshift;        // LQ_K1_KEYBITS (tests): the 32-bit time keys of K1 are coarsened by this shift
+  int kcap;               // kept (off-diagonal) operators per page that fit the kept list of K1
   // ---- pages (double buffered) ----
   double* time[2];
   uint32_t* info[2];
@@ -260,6 +262,37 @@ __device__ __forceinline__ int block_exscan(int v, int* total, int* smem /* >= 3
   __syncthreads();
   int res = smem[wid] + inc - v;
   *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+// the same for two ints per thread at once
+__device__ __forceinline__ int2 block_exscan2(int2 v, int* total_x, int* total_y, int* smem /* >= 66 ints */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int ix = v.x, iy = v.y;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int nx = __shfl_up_sync(0xffffffffu, ix, o), ny = __shfl_up_sync(0xffffffffu, iy, o);
+    if (lane >= o) { ix += nx; iy += ny; }
+  }
+  if (lane == 31) { smem[wid] = ix; smem[33 + wid] = iy; }
+  __syncthreads();
+  if (wid == 0) {
+    const int wx = (lane < nw) ? smem[lane] : 0, wy = (lane < nw) ? smem[33 + lane] : 0;
+    int sx = wx, sy = wy;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int nx = __shfl_up_sync(0xffffffffu, sx, o), ny = __shfl_up_sync(0xffffffffu, sy, o);
+      if (lane >= o) { sx += nx; sy += ny; }
+    }
+    smem[lane] = sx - wx;
+    smem[33 + lane] = sy - wy;
+    if (lane == 31) { smem[32] = sx; smem[65] = sy; }
+  }
+  __syncthreads();
+  const int2 res = make_int2(smem[wid] + ix - v.x, smem[33 + wid] + iy - v.y);
+  *total_x = smem[32];
+  *total_y = smem[65];
   __syncthreads();
   return res;
 }

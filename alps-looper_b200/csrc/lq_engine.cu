@@ -335,17 +335,22 @@ struct lq_engine {
   int tpb_walk = 32;
   typedef void (*walk_fn_t)(lq::Dev, int);
   walk_fn_t walk_fn = nullptr;
-  typedef void (*k1_fn_t)(lq::Dev, int, const lq::StepParams*);
+  typedef void (*k1_fn_t)(lq::Dev, int, const lq::StepParams*, int);
   k1_fn_t k1_fn = nullptr;
-  int k1_fc = 12;
-  // diagonal update specialised on block size and on the width of the per-site flip lists
+  int k1_fc = 12, k1_nt = 256, k1_chunk = 1, kcap = 0;
+  bool k1_tma = true;
+  double grow_kept = 1;
+  // diagonal update specialised on block size, on the width of the per-site columns and on how the
+  // pages reach shared memory (bulk copy + mbarrier, or plain loads)
   k1_fn_t pick_k1() const {
-#define LQ_PICK1(MT) (k1_fc <= 8 ? lq::k_diag_update<MT, 8> : k1_fc <= 12 ? lq::k_diag_update<MT, 12> : lq::k_diag_update<MT, 16>)
-    if (tpb <= 192) return LQ_PICK1(192);
-    if (tpb <= 320) return LQ_PICK1(320);
-    if (tpb <= 576) return LQ_PICK1(576);
-    return LQ_PICK1(1024);
+#define LQ_PICK2(MT, F) (k1_tma ? lq::k_diag_update<MT, F, true> : lq::k_diag_update<MT, F, false>)
+#define LQ_PICK1(MT) (k1_fc <= 8 ? LQ_PICK2(MT, 8) : k1_fc <= 12 ? LQ_PICK2(MT, 12) : LQ_PICK2(MT, 16))
+    if (k1_nt <= 128) return LQ_PICK1(128);
+    if (k1_nt <= 256) return LQ_PICK1(256);
+    if (k1_nt <= 384) return LQ_PICK1(384);
+    return LQ_PICK1(512);
 #undef LQ_PICK1
+#undef LQ_PICK2
   }
   // world-line walk specialised on block size and coordination number
   walk_fn_t pick_walk() const {
@@ -608,7 +613,8 @@ struct lq_engine {
     }
     const double m = opt.reserve * grow_pages * mu;
     long long c = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
-    if (c > 65535) fail(LQ_E_INVALID, "page capacity exceeds 65535 operators: lower tile_sites or window_ops");
+    c = (c + 3) & ~3ll;   // pages start on 16-byte boundaries (bulk copies of K1)
+    if (c > 65532) fail(LQ_E_INVALID, "page capacity exceeds 65532 operators: lower tile_sites or window_ops");
     cap = (int)c;
     {
       // shared-memory stage: own page + halo buckets (halo/own bucket ratio, 1.5x head room)
@@ -617,23 +623,44 @@ struct lq_engine {
       scap = cap + (int)std::ceil(hm + 6.0 * std::sqrt(hm) + 16.0);
       const double cm = mu;  // mean candidates per page
       ccap = (int)std::ceil(grow_cand * (cm + 8.0 * std::sqrt(cm) + 32.0));
-      if (ccap > 32767 || scap > 65535)
+      if (ccap > 32767 || scap > 65535 || cap > 65532)
         fail(LQ_E_INVALID, "too many candidates / staged operators per page: lower tile_sites or window_ops");
       tpb_walk = ((std::max(part.nsmax, part.whmax) + 31) / 32) * 32;
-      // width of the fast per-site flip lists of K1: mean legs per site and window ~ 0.6 z window_ops
+      // K1 (lq_k1.cuh).  Column width: mean off-diagonal legs per site and window ~ 0.6 z window_ops
       {
-        const double m = 0.6 * part.zmax * opt.window_ops;
-        const double want = m + 2.5 * std::sqrt(m);
-        k1_fc = want <= 8 ? 8 : (want <= 12 ? 12 : 16);
-        // two resident CTAs per SM matter more than a wide list (measured: 74 vs 48 ps/operator);
-        // sites with more legs than the list holds take the slow path of K1
-        const size_t two_ctas = (size_t)(227 * 1024) / 2 - 1024;
-        while (k1_fc > 8 && tpb <= 576 &&
-               lq::k1_smem_bytes(k1_fc, scap, ccap, cap, part.nbmax, part.hmax, part.nksmax) > two_ctas)
-          k1_fc -= 4;
+        const double ml = 0.45 * part.zmax * opt.window_ops;   // (measured: 5.3 on the square-lattice Heisenberg workloads)
+        const double want = ml + 2.5 * std::sqrt(ml);
+        // (a column that overflows sends every candidate on the site through the exact path, 400 warp
+        // instructions at 4 lanes: one step wider than the estimate asks for -- 0.6 % of the sites
+        // overflowed 12 slots at a mean of 5.3 legs, profiles/r02_k1.md)
+        k1_fc = want <= 6 ? 8 : (want <= 9 ? 12 : 16);
         if (getenv("LQ_FC")) k1_fc = atoi(getenv("LQ_FC")) <= 8 ? 8 : (atoi(getenv("LQ_FC")) <= 12 ? 12 : 16);
+        // kept list: the off-diagonal operators of a page (half a page to start with; slab engines,
+        // which cannot rewind, take the whole page)
+        kcap = (int)std::min<double>(cap, std::ceil((opt.nranks > 1 ? 1.0 : 0.55) * grow_kept * cap) + 16);
+        // threads: a thread owns up to LQ_K1_QMAX buckets; one bucket per thread up to 512
+        k1_nt = part.nbmax <= 128 ? 128 : (part.nbmax <= 256 ? 256 : 512);
+        if (getenv("LQ_K1_NT")) k1_nt = atoi(getenv("LQ_K1_NT"));
+        k1_nt = k1_nt <= 128 ? 128 : (k1_nt <= 256 ? 256 : (k1_nt <= 384 ? 384 : 512));
+        while (part.nbmax > LQ_K1_QMAX * k1_nt && k1_nt < 512) k1_nt = k1_nt < 256 ? 256 : (k1_nt < 384 ? 384 : 512);
+        if (part.nbmax > LQ_K1_QMAX * k1_nt) fail(LQ_E_INVALID, "tile owns too many bonds for K1: lower lq_options.tile_sites");
+        k1_tma = !getenv("LQ_K1_NOTMA");
+        // two resident CTAs per SM matter more than wide columns or the bulk-copied page buffer
+        const size_t two_ctas = (size_t)(227 * 1024) / 2 - 1200;
+        auto k1_bytes = [&]() { return lq::k1_smem_bytes(k1_tma, k1_fc, cap, ccap, kcap, part.nbmax, part.hmax, part.nksmax); };
+        while (k1_fc > 8 && k1_bytes() > two_ctas && !getenv("LQ_FC")) k1_fc -= 4;
+        if (k1_bytes() > (size_t)smem_optin - 2048)
+          k1_tma = false;   // page buffer does not fit beside the lists: stream the page with plain loads
+        // windows per persistent CTA: enough CTAs for ~8 waves, at least 4 windows to amortise the tile set-up
+        {
+          const long long want_ctas = 8ll * sm_count * 3;
+          long long nch = std::max<long long>(1, std::min<long long>(Wl, (want_ctas + T - 1) / T));
+          k1_chunk = (int)((Wl + nch - 1) / nch);
+          if (k1_chunk < 4) k1_chunk = std::min(4, Wl);
+          if (getenv("LQ_K1_CHUNK")) k1_chunk = std::max(1, std::min(Wl, atoi(getenv("LQ_K1_CHUNK"))));
+        }
       }
-      stage_smem = lq::k1_smem_bytes(k1_fc, scap, ccap, cap, part.nbmax, part.hmax, part.nksmax);
+      stage_smem = lq::k1_smem_bytes(k1_tma, k1_fc, cap, ccap, kcap, part.nbmax, part.hmax, part.nksmax);
       walk_smem = lq::stage_bytes(scap, part.nbmax, part.hmax, part.zmax, tpb_walk);
       if (stage_smem > (size_t)smem_optin - 2048 || walk_smem > (size_t)smem_optin - 2048 ||
           (size_t)npo * cap * sizeof(uint32_t) > (size_t)smem_optin - 2048)
@@ -744,7 +771,8 @@ struct lq_engine {
     d.hsite_off = hsite_off.p; d.hsite = hsite.p; d.tile_class = tile_class.p;
     d.cls_bs = cls_bs.p; d.cls_sso = cls_sso.p; d.cls_sst = cls_sst.p; d.cls_nks = cls_nks.p;
     d.bs = bs.p; d.sst_off = sst_off.p; d.sst = sst.p;
-    d.hmax = part.hmax; d.nksmax = part.nksmax; d.zmax = part.zmax; d.scap = scap; d.ccap = ccap;
+    d.hmax = part.hmax; d.nksmax = part.nksmax; d.zmax = part.zmax; d.scap = scap; d.ccap = ccap; d.kcap = kcap;
+    d.k1_keyshift = getenv("LQ_K1_KEYBITS") ? std::max(0, std::min(31, 32 - atoi(getenv("LQ_K1_KEYBITS")))) : 0;
     for (int k = 0; k < 2; ++k) {
       d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
     }
@@ -961,7 +989,8 @@ struct lq_engine {
   void enqueue_step(double* out_slot, const lq::StepParams* sp) {
     {
       Section s(this, 5);
-      k1_fn<<<(unsigned)P, tpb, stage_smem, stream>>>(d, cur, sp);
+      const unsigned nch = (unsigned)((Wl + k1_chunk - 1) / k1_chunk);
+      k1_fn<<<(unsigned)part.T * nch, k1_nt, stage_smem, stream>>>(d, cur, sp, k1_chunk);
       launches += 1;
       cur ^= 1;
     }
@@ -1095,7 +1124,7 @@ struct lq_engine {
     cur = cur0 ^ (first_bad & 1);
     mcs = mcs0 + (uint32_t)first_bad;
     if (err & LQ_ERR_PAGE_FULL) grow_pages *= 1.5;
-    if (err & LQ_ERR_CAND_FULL) grow_cand *= 1.5;
+    if (err & LQ_ERR_CAND_FULL) { grow_cand *= 1.5; grow_kept *= 1.6; }
     if (err & LQ_ERR_CLUSTER_FULL) grow_clusters *= 1.5;
     ++regrows;
     {
@@ -1433,7 +1462,7 @@ int lq_get_info(lq_handle h, lq_info* out) {
   out->num_tiles = h->part.T;
   out->num_windows = h->W;
   out->page_capacity = h->cap;
-  out->threads_per_page = h->tpb;
+  out->threads_per_page = h->k1_nt;
   out->op_capacity = h->ncap;
   out->cluster_capacity = h->nccap;
   out->device_bytes = (int64_t)h->device_bytes;
@@ -1498,16 +1527,17 @@ int lq_debug_counters(lq_handle h, unsigned long long* out) {
 }
 
 // test hook (not part of the public header): histogram of the K1 Poisson draw, see lq_k1.cuh
+static void debug_poisson_impl(double mean, long long count, unsigned long long seed, unsigned long long* hist, int nbins) {
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc((void**)&d, nbins * sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, nbins * sizeof(unsigned long long)));
+  lq::k_debug_poisson<<<592, 256>>>(mean, count, (uint32_t)seed, (uint32_t)(seed >> 32), d, nbins);
+  CK(cudaMemcpy(hist, d, nbins * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaFree(d));
+}
 int lq_debug_poisson(double mean, long long count, unsigned long long seed, unsigned long long* hist, int nbins) {
   if (!hist || nbins <= 0 || !(mean > 0)) return LQ_E_INVALID;
-  LQ_TRY({
-    unsigned long long* d = nullptr;
-    CK(cudaMalloc((void**)&d, nbins * sizeof(unsigned long long)));
-    CK(cudaMemset(d, 0, nbins * sizeof(unsigned long long)));
-    lq::k_debug_poisson<<<592, 256>>>(mean, count, (uint32_t)seed, (uint32_t)(seed >> 32), d, nbins);
-    CK(cudaMemcpy(hist, d, nbins * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CK(cudaFree(d));
-  })
+  LQ_TRY(debug_poisson_impl(mean, count, seed, hist, nbins))
 }
 
 const char* lq_last_error(void) { return g_err.c_str(); }

@@ -369,3 +369,27 @@ def test_external_edge_list_overflow_falls_back_to_a_rescan(monkeypatch):
     s2, o2 = eng.get_state()
     orc.build_clusters(lat, s2, o2)
     eng.close()
+
+
+def test_time_key_ties_take_the_exact_path(monkeypatch):
+    """K1 compares 32-bit window-relative keys of the operator times and falls back to the f64 times
+    when a leg and a candidate share a key (csrc/lq_k1.cuh k1_key).  With the keys coarsened to 5 bits
+    (LQ_K1_KEYBITS, a test hook) such ties happen all the time -- and the Markov chain must be exactly
+    the one the full-width keys produce."""
+    lq = _lq()
+    lat = lq.hypercubic_lattice((12, 12))
+    runs = []
+    for bits in (None, "5", "1"):
+        if bits is None:
+            monkeypatch.delenv("LQ_K1_KEYBITS", raising=False)
+        else:
+            monkeypatch.setenv("LQ_K1_KEYBITS", bits)
+        eng = lq.Engine(lat, 6.0, seed=2718, tile_sites=16)
+        out = eng.sweep_many(60)
+        spins, ops = eng.get_state()
+        orc.build_clusters(lat, spins, ops)           # legal
+        runs.append((out, spins, ops))
+        eng.close()
+    for out, spins, ops in runs[1:]:
+        assert np.array_equal(out["nop"], runs[0][0]["nop"]) and np.array_equal(out["nc"], runs[0][0]["nc"])
+        assert np.array_equal(spins, runs[0][1]) and np.array_equal(ops, runs[0][2])
