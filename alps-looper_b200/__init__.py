@@ -40,7 +40,7 @@ class LqOptions(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("device", C.c_int32), ("tile_sites", C.c_int32),
                 ("window_ops", C.c_double), ("reserve", C.c_double),
                 ("cluster_reserve", C.c_double), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("flags", C.c_int32)]
+                ("flags", C.c_int32), ("representation", C.c_int32)]
 
 
 class LqOp(C.Structure):
@@ -234,7 +234,7 @@ class Engine:
     def __init__(self, lattice, beta, weights=(0.5, 0.0, 0.0, 0.0), energy_offset=None, seed=29833,
                  device=0, tile_sites=0, window_ops=0.0, reserve=0.0, cluster_reserve=0.0,
                  rank=0, nranks=1, timers=False, bond_weights=None, site_weight=0.0, site_weights=None,
-                 stiffness=False):
+                 stiffness=False, sse=False):
         self.lattice = lattice
         self.N = int(lattice["num_sites"])
         self._src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
@@ -291,7 +291,8 @@ class Engine:
         self.energy_offset = mod.energy_offset
         opt = LqOptions(seed=seed, device=device, tile_sites=tile_sites, window_ops=window_ops,
                         reserve=reserve, cluster_reserve=cluster_reserve, rank=rank,
-                        nranks=nranks, flags=1 if timers else 0)
+                        nranks=nranks, flags=1 if timers else 0, representation=1 if sse else 0)
+        self.sse = bool(sse)
         self.beta = float(beta)
         self._h = _h()
         _check(lib.lq_create(C.byref(self._h), C.byref(lat), C.byref(mod), self.beta, C.byref(opt)))
@@ -419,15 +420,19 @@ def observables(coll, beta, num_sites, sse=False):
     o["|Magnetization|"] = abs(coll["umag0"])
     o["Magnetization^2"] = coll["umag2"]
     o["Magnetization^4"] = 3 * coll["umag2"] ** 2 - 2 * coll["umag4"]
-    o["Susceptibility"] = beta * coll["umag"] / vol
+    nop = coll["nop"]
+    dip = (lambda x: x / nop if nop > 0 else 0.0)          # divide_if_positive.h
+    # susceptibility.h:213-215: SSE strings carry integer times 0..n-1 and the top n
+    sus = (lambda x, x2: beta * (dip(x) + x2) / (nop + 1) / vol) if sse else (lambda x, x2: beta * x / vol)
+    o["Susceptibility"] = sus(coll["umag"], coll["umag2"])
     o["Generalized Magnetization^2"] = coll["usize2"]
-    o["Generalized Susceptibility"] = beta * coll["usize"] / vol
+    o["Generalized Susceptibility"] = sus(coll["usize"], coll["usize2"])
     o["|Staggered Magnetization|"] = abs(coll["smag0"])
     o["Staggered Magnetization^2"] = coll["smag2"]
     o["Staggered Magnetization^4"] = 3 * coll["smag2"] ** 2 - 2 * coll["smag4"]
-    o["Staggered Susceptibility"] = beta * coll["smag"] / vol
+    o["Staggered Susceptibility"] = sus(coll["smag"], coll["smag2"])
     o["Generalized Staggered Magnetization^2"] = coll["ssize2"]
-    o["Generalized Staggered Susceptibility"] = beta * coll["ssize"] / vol
+    o["Generalized Staggered Susceptibility"] = sus(coll["ssize"], coll["ssize2"])
     # transmag.h:106-109
     o["Transverse Magnetization"] = 0.5 * coll["tlen"]
     o["Transverse Magnetization Density"] = 0.5 * coll["tlen"] / vol

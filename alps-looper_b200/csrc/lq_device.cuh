@@ -108,7 +108,8 @@ struct Dev {
   uint32_t* wcount;  // roots per bitmap word -> exclusive scan in wbase
   uint32_t* wbase;
   uint4* rootw;      // [words] {id base, root flags, flip bits of the roots, 0} (serial engines, k_rootflip)
-  int fpack;         // labels carry the flip decision in bit 31 (serial engines)
+  int fpack;         // labels carry the flip decision in bit 31 when the estimators run
+  int rootflip;      // ... because k_relabel decided it per root (serial engines); slab engines pack it afterwards (k_pack_flips)
   uint2* xedge;      // [groups][LQ_XCAP] edges that leave their union group (k_union_local -> k_union_global)
   int* xcount;       // [groups] entries of the list, -1 if it overflowed
   int xcap;          // entries a list may hold (LQ_XCAP; the tests lower it through the LQ_XCAP environment variable)
@@ -122,6 +123,15 @@ struct Dev {
   const short* bond_vec; // [3*B] relative bond vectors (stiffness.h:63-76) in units of the smallest component
   double wscale[3];      // half that unit per dimension: (winding / 2) = wscale * integer sum
   int* wind;             // [sdim][nccap] winding of every cluster in those units
+  // ---- SSE representation (sse.C): position of every operator in the time-ordered string ----
+  int sse;               // LQ_REPR_SSE: estimator times are string positions, the top is the string length
+  uint32_t* spos;        // [ncap] string position of the operator with dense index idx
+  int nbin;              // time bins per window of the counting sort that produces them
+  uint32_t* bincnt;      // [Wl*nbin + 1] operators per (window, bin); exclusive scan in binbase
+  uint32_t* binbase;
+  uint32_t* binfill;     // [Wl*nbin] scatter cursors
+  double* sorted_time;   // [ncap] operators in (window, bin) order
+  uint2* sorted_id;      // [ncap] {internal bond, dense index}
   long long ncap;   // operator arena (= P*cap)
   long long nccap;  // cluster arena
   // ---- scalars on device ----

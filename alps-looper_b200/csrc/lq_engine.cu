@@ -370,6 +370,11 @@ struct lq_engine {
   DBuf<uint16_t> boff[2];
   DBuf<uint8_t> spinW;
   DBuf<uint32_t> flipw, openw;
+  DBuf<uint32_t> sse_rank, sse_bincnt, sse_binbase, sse_binfill;   // SSE representation (k_sse_*)
+  DBuf<double> sse_time;
+  DBuf<uint2> sse_id;
+  bool sse = false;
+  int nbin = 1;
   DBuf<uint4> rootw;
   DBuf<uint2> xedge;
   DBuf<int> xcount;
@@ -428,6 +433,10 @@ struct lq_engine {
     if (opt.nranks < 1) { opt.nranks = 1; opt.rank = 0; }
     if (opt.rank < 0 || opt.rank >= opt.nranks) fail(LQ_E_INVALID, "rank out of range");
     timers_on = (opt.flags & 1) != 0;
+    if (opt.representation != LQ_REPR_PATH_INTEGRAL && opt.representation != LQ_REPR_SSE)
+      fail(LQ_E_INVALID, "unknown lq_options.representation");
+    sse = opt.representation == LQ_REPR_SSE;
+    if (sse && opt.nranks > 1) fail(LQ_E_UNSUPPORTED, "the SSE representation runs on a serial engine (string positions are global)");
     beta = beta_;
     energy_offset = M.energy_offset;
     weights.resize(4 * (size_t)L.num_bonds);
@@ -720,7 +729,17 @@ struct lq_engine {
       xedge.alloc(ngroups * LQ_XCAP, tb);
       xcount.alloc(ngroups, tb);
     }
-    const size_t scan_n = std::max(nwords_cap, P) + 1;
+    if (sse) {
+      // ~4 operators per time bin at full pages
+      nbin = 1;
+      while ((long long)nbin * 4 < (long long)part.T * cap && nbin < (1 << 24)) nbin <<= 1;
+      const size_t nb = (size_t)Wl * nbin;
+      sse_rank.alloc((size_t)ncap, tb);
+      sse_time.alloc((size_t)ncap, tb);
+      sse_id.alloc((size_t)ncap, tb);
+      sse_bincnt.alloc(nb + 1, tb); sse_binbase.alloc(nb + 2, tb); sse_binfill.alloc(nb + 1, tb);
+    }
+    const size_t scan_n = std::max(std::max(nwords_cap, P), sse ? (size_t)Wl * nbin : (size_t)0) + 1;
     scan_tmp.alloc((scan_n + LQ_SCAN_CHUNK - 1) / LQ_SCAN_CHUNK + 1, tb);
     est.alloc(4 * (size_t)nccap, tb);
     est0.alloc(4 * (size_t)N, tb);
@@ -739,7 +758,7 @@ struct lq_engine {
       mr_gparent.alloc(g2, tb);
       mr_gused.alloc(g2, tb);
       mr_gbitmap.alloc(gw, tb); mr_gwcount.alloc(gw, tb); mr_gwbase.alloc(gw + 1, tb);
-      mr_gest.alloc(g2 * (size_t)gstride(), tb);
+      mr_gest.alloc(g2 * (size_t)gstride() + 32 * (size_t)opt.nranks, tb);   // + the collectors' slots (k_mr_rankvec)
       mr_dg.alloc(4, tb);
       mr_rankvec.alloc(32, tb); mr_allvec.alloc(32 * (size_t)opt.nranks, tb); mr_gsum.alloc(16, tb);
       CK(cudaMemset(mr_topmin.p, 0xff, mr_topmin.n * sizeof(uint32_t)));
@@ -778,12 +797,14 @@ struct lq_engine {
     }
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.firstW = firstW.p; d.parent = parent.p; d.low0 = low0.p;
     d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
-    d.rootw = rootw.p; d.fpack = opt.nranks == 1 ? 1 : 0;
+    d.rootw = rootw.p; d.fpack = 1; d.rootflip = opt.nranks == 1 ? 1 : 0;
     d.xedge = xedge.p; d.xcount = xcount.p;
     d.xcap = getenv("LQ_XCAP") ? std::max(0, std::min(LQ_XCAP, atoi(getenv("LQ_XCAP")))) : LQ_XCAP;
     d.est = est.p; d.est0 = est0.p; d.flipw = flipw.p; d.openw = openw.p;
     d.sdim = sdim; d.bond_vec = bond_vec.p; d.wind = wind.p; d.gstride = gstride();
     for (int x = 0; x < 3; ++x) d.wscale[x] = 0.5 * wunit[x];   // stiffness.h:127: (winding / 2)^2
+    d.sse = sse ? 1 : 0; d.spos = sse_rank.p; d.nbin = nbin; d.bincnt = sse_bincnt.p; d.binbase = sse_binbase.p;
+    d.binfill = sse_binfill.p; d.sorted_time = sse_time.p; d.sorted_id = sse_id.p;
     d.ncap = ncap; d.nccap = nccap;
     d.d_ntotal = d_ntotal.p; d.d_nc = d_nc.p; d.d_err = d_err.p;
     d.dbg = getenv("LQ_DBG") ? atoi(getenv("LQ_DBG")) : 0;
@@ -846,6 +867,16 @@ struct lq_engine {
       scan_u32((const uint32_t*)pcount[cur].p, (uint32_t*)nbase.p, P, (uint32_t*)(nbase.p + P), d_ntotal.p);
       lq::k_init_nodes<<<grid_for(N, 256), 256, 0, stream>>>(d);
       launches += 1;
+      if (sse) {   // string positions of the operators (sse.C: the index t of the sweep over the string)
+        const size_t nb = (size_t)Wl * nbin;
+        CK(cudaMemsetAsync(sse_bincnt.p, 0, (nb + 1) * sizeof(uint32_t), stream));
+        CK(cudaMemsetAsync(sse_binfill.p, 0, (nb + 1) * sizeof(uint32_t), stream));
+        lq::k_sse_hist<<<(unsigned)P, 256, 0, stream>>>(d, cur);
+        scan_u32(sse_bincnt.p, sse_binbase.p, nb + 1, nullptr, nullptr);
+        lq::k_sse_scatter<<<(unsigned)P, 256, 0, stream>>>(d, cur);
+        lq::k_sse_rank<<<grid_for((size_t)ncap, 256), 256, 0, stream>>>(d);
+        launches += 3;
+      }
     }
     {
       Section s(this, 7);
@@ -878,7 +909,8 @@ struct lq_engine {
       if (opt.nranks > 1) {
         lq::k_flipbits<<<(unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
         lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
-        launches += 2;
+        lq::k_pack_flips<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d);
+        launches += 3;
       }
     }
     {
@@ -945,16 +977,15 @@ struct lq_engine {
     CK(cudaMemcpyAsync(h_mr, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     const int64_t ngc = h_mr[0];
-    if (ngc > 0) all_reduce_i64(mr.gest, (size_t)ngc * gstride(), "all_reduce(open-cluster sums)");
+    // one all-reduce carries the open-cluster sums and, in its tail, every rank's collector of its closed clusters
+    double* tail = (double*)(mr.gest + (size_t)ngc * gstride());
+    lq::k_mr_rankvec<<<1, 32, 0, stream>>>(d, mr, out_slot, tail);
+    all_reduce_i64(mr.gest, (size_t)ngc * gstride() + 32 * (size_t)opt.nranks, "all_reduce(open-cluster sums + collectors)");
     const unsigned gblk = (unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 4);
     lq::k_mr_gcollect<<<gblk, 256, 0, stream>>>(d, mr, partial.p);   // (partial is free again after k_collect_final)
     lq::k_mr_gsum<<<1, 32, 0, stream>>>(mr, partial.p, (int)gblk);
-    launches += 1;
-    lq::k_mr_rankvec<<<1, 32, 0, stream>>>(d, mr, out_slot);
-    launches += 2;
-    all_gather(mr.rankvec, mr.allvec, 32 * sizeof(double), "all_gather(collectors)");
-    lq::k_mr_final<<<1, 32, 0, stream>>>(d, mr, out_slot);
-    launches += 1;
+    lq::k_mr_final<<<1, 32, 0, stream>>>(d, mr, tail, out_slot);
+    launches += 4;
   }
 
   void ensure_out(size_t slots) {

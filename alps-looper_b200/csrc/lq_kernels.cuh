@@ -599,7 +599,7 @@ k_relabel(Dev d) {
     const size_t x = base + (size_t)k * 256;
     r[k] = (x < nn) ? d.parent[x] : 0u;
   }
-  if (d.fpack) {
+  if (d.rootflip) {
     uint4 q[LQ_NPT];
 #pragma unroll
     for (int k = 0; k < LQ_NPT; ++k) q[k] = d.rootw[r[k] >> 5];
@@ -720,6 +720,24 @@ k_flipbits(Dev d, const StepParams* __restrict__ sp) {
   }
 }
 
+// Slab engines know the flips of the open clusters only after the exchange (k_mr_openflips); one
+// streaming pass then packs every decision into the labels, so that the estimator and the spin flip
+// read it with the cluster id like on a serial engine instead of gathering the flip table twice per
+// operator (k_estimate ran 30 % slower on slabs).  The table itself is L2-resident.
+__global__ void __launch_bounds__(256)
+k_pack_flips(Dev d) {
+  const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
+  const size_t base = (size_t)blockIdx.x * (256 * LQ_NPT) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < LQ_NPT; ++k) {
+    const size_t x = base + (size_t)k * 256;
+    if (x < nn) {
+      const uint32_t c = d.parent[x];
+      d.parent[x] = c | (flip_of(d, c) << 31);
+    }
+  }
+}
+
 // FLIP: also apply the cluster flip to the operator (K6, path_integral.C:815-819): its type changes
 // iff the cluster arriving from below on the source side and the one leaving upwards are flipped
 // differently -- the two cluster ids are already in registers here.
@@ -794,7 +812,8 @@ k_estimate(Dev d, int buf) {
       const int g = (inf[u] >> LQ_INFO_GSHIFT) & 3;
       if (g & 2) continue;  // frozen graphs: skipped by the estimators (path_integral.C:692), never flip
       const int j = j0 + u * (int)blockDim.x;
-      const long long q = time_to_fx(tt[u]);
+      // path integral: imaginary time in 2^-40 fixed point; SSE: position in the operator string (sse.C:358-361)
+      const long long q = d.sse ? (long long)d.spos[idx0 + j] : time_to_fx(tt[u]);
       const int lb = (int)(inf[u] >> LQ_INFO_LBSHIFT);
       const int g0 = s_gg[2 * lb], g1 = s_gg[2 * lb + 1];
       const int c0 = (int)(l0[u] >> 31), c1 = (int)(l1[u] >> 31);   // spins below (written by the walk)
@@ -893,8 +912,10 @@ k_estimate_sites(Dev d) {
   const int m = 1 - 2 * c;
   const uint32_t cb = LQ_CID(d.parent[s]);
   const uint32_t ct = LQ_CID(d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
-  const long long qlo = time_to_fx(window_lo(d.w0, d.W));
-  const long long qhi = (d.w0 + d.Wl >= d.W) ? (1ll << 40) : time_to_fx(window_hi(d.w0 + d.Wl - 1, d.W));
+  // (SSE: the world lines start at string position 0 and stop at the string length, sse.C:200,283)
+  const long long qlo = d.sse ? 0ll : time_to_fx(window_lo(d.w0, d.W));
+  const long long qhi = d.sse ? (long long)(*d.d_ntotal)
+                              : ((d.w0 + d.Wl >= d.W) ? (1ll << 40) : time_to_fx(window_hi(d.w0 + d.Wl - 1, d.W)));
   if (d.rank == 0) site_group_add(d, valid, cb, 1, m, g, g * m, 0, true);
   if (qlo) site_group_add(d, valid, cb, 1, m, g, g * m, -qlo, false);
   // periodic in imaginary time: the spin at the top of the slab stack equals the one at tau = 0;
@@ -924,7 +945,7 @@ k_collect(Dev d, double* partial) {
   // registers, so the warp-shuffle reduction runs once per thread instead of once per cluster
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc && (long long)c < d.nccap;
        c += (size_t)gridDim.x * blockDim.x) {
-    const double sc = 0.5 / LQ_FX;
+    const double sc = d.sse ? 0.5 : 0.5 / LQ_FX;   // half units of 2^-40 (path integral) / of one string position (SSE)
     // read-and-clear with one L2 atomic per field: the sums were built by RED atomics, and on this
     // part plain loads of lines last touched by atomics are an order of magnitude slower than
     // atomics on them (measured: 0.11 ms -> 0.03 ms for 1.5e6 clusters, profiles/)
@@ -1002,6 +1023,73 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
     out[16] = (double)(*d.d_err);
     out[17] = 0.0;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// SSE representation (sse.C:168-407): the operator string is the time-ordered list of the operators
+// and the estimators use the POSITION of an operator in it as its time (sse.C:251-283: `t`,
+// stop_top(operators.size())).  Positions come from one counting sort over (window, time bin):
+// histogram -> exclusive scan -> scatter -> rank inside the bin by comparing (time, bond) with the
+// handful of operators that share it.  Ties in time are ordered by the internal bond index, the
+// order lq_get_state exports.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sse_bin(const Dev& d, int wl, double t) {
+  const int wg = d.w0 + wl;
+  const double tlo = d.wlo[wg], width = d.wlo[wg + 1] - tlo;
+  int b = (int)((t - tlo) / width * (double)d.nbin);
+  b = b < 0 ? 0 : (b >= d.nbin ? d.nbin - 1 : b);
+  return (uint32_t)wl * (uint32_t)d.nbin + (uint32_t)b;
+}
+
+__global__ void __launch_bounds__(256)
+k_sse_hist(Dev d, int buf) {
+  const size_t p = blockIdx.x;
+  const int wl = (int)(blockIdx.x % (unsigned)d.Wl);
+  const int n = d.pcount[buf][p];
+  const double* gt = d.time[buf] + p * (size_t)d.cap;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) atomicAdd(d.bincnt + sse_bin(d, wl, gt[j]), 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_sse_scatter(Dev d, int buf) {
+  const size_t p = blockIdx.x;
+  const int t = (int)(blockIdx.x / (unsigned)d.Wl), wl = (int)(blockIdx.x - (unsigned)t * (unsigned)d.Wl);
+  const int n = d.pcount[buf][p];
+  const int idx0 = d.nbase[p];
+  const int b0 = d.bond_base[t];
+  const double* gt = d.time[buf] + p * (size_t)d.cap;
+  const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double tt = gt[j];
+    const uint32_t g = sse_bin(d, wl, tt);
+    const uint32_t slot = d.binbase[g] + atomicAdd(d.binfill + g, 1u);
+    d.sorted_time[slot] = tt;
+    d.sorted_id[slot] = make_uint2((uint32_t)(b0 + (int)(gi[j] >> LQ_INFO_LBSHIFT)), (uint32_t)(idx0 + j));
+  }
+}
+
+// one thread per slot of the (window, bin)-ordered list; bins hold a few operators each
+__global__ void __launch_bounds__(256)
+k_sse_rank(Dev d) {
+  const size_t nbins = (size_t)d.Wl * d.nbin;
+  const uint32_t n = (uint32_t)(*d.d_ntotal);
+  // the bin of a slot: every thread walks the bins of its CTA's slot range once (binary search start)
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  size_t lo = 0, hi = nbins;   // last bin with binbase <= s
+  while (hi - lo > 1) {
+    const size_t mid = (lo + hi) >> 1;
+    if (d.binbase[mid] <= s) lo = mid; else hi = mid;
+  }
+  const uint32_t beg = d.binbase[lo], end = d.binbase[lo + 1];
+  const double tt = d.sorted_time[s];
+  const uint2 me = d.sorted_id[s];
+  uint32_t r = beg;
+  for (uint32_t k = beg; k < end; ++k) {
+    const double tk = d.sorted_time[k];
+    r += (tk < tt || (tk == tt && d.sorted_id[k].x < me.x)) ? 1u : 0u;
+  }
+  d.spos[me.y] = r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1150,8 +1238,8 @@ __global__ void k_mr_gather(Dev d, MrDev m) {
   if (s >= d.N) return;
   const uint32_t ncs = d.d_nc[1];
   uint32_t cl[2];
-  cl[0] = d.parent[s];
-  cl[1] = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  cl[0] = LQ_CID(d.parent[s]);   // (runs after k_pack_flips)
+  cl[1] = LQ_CID(d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
   for (int k = 0; k < 2; ++k) {
     const uint32_t c = cl[k];
     if (k == 1 && c == cl[0]) break;
@@ -1200,8 +1288,8 @@ __global__ void k_mr_openflips(Dev d, MrDev m, const StepParams* __restrict__ sp
 __global__ void k_mr_reset_topmin(Dev d, MrDev m) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= d.N) return;
-  const uint32_t cb = d.parent[s];
-  const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  const uint32_t cb = LQ_CID(d.parent[s]);   // (runs after k_pack_flips)
+  const uint32_t ct = LQ_CID(d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
   if ((long long)cb < d.nccap) m.topmin[cb] = 0xffffffffu;
   if ((long long)ct < d.nccap) m.topmin[ct] = 0xffffffffu;
 }
@@ -1253,23 +1341,32 @@ __global__ void k_mr_gsum(MrDev m, const double* partial, int nblk) {
   m.gsum[i] = x;
 }
 
-// rankvec = local closed sums (from k_collect_final's slot) with nc_closed; then after the
-// all-gather: out = sum over ranks (fixed order) + global-cluster sums
-__global__ void k_mr_rankvec(Dev d, MrDev m, const double* slot) {
-  const int i = threadIdx.x;
-  if (i < LQ_NSUS) m.rankvec[i] = slot[i];
-  if (i == 18 || i == 19) m.rankvec[i] = slot[i];            // transmag length / stiffness w2 of the closed clusters
-  if (i == 14) m.rankvec[14] = slot[14] - (double)m.d_g[1];  // closed clusters of this rank
-  if (i == 15) m.rankvec[15] = slot[15];                     // operators of this slab
-  if (i == 16) m.rankvec[16] = slot[16];                     // error flags
-  if (i > 16 && i < 32 && i != 18 && i != 19) m.rankvec[i] = 0;
+// The collectors of the closed clusters travel in the SAME all-reduce as the open-cluster sums: every
+// rank writes its 32 doubles into its own slot of the tail of the table and zeros the other slots, so
+// the integer sum of the bit patterns is the pattern itself (x + 0 + ... + 0) -- one collective less
+// per step.  tail[r * 32 + i]; slot = this rank's k_collect_final output.
+__global__ void k_mr_rankvec(Dev d, MrDev m, const double* slot, double* tail) {
+  const int i = threadIdx.x;   // 32 threads
+  for (int r = 0; r < d.nranks; ++r) {
+    double x = 0;
+    if (r == d.rank) {
+      if (i < LQ_NSUS) x = slot[i];
+      if (i == 18 || i == 19) x = slot[i];              // transmag length / stiffness w2 of the closed clusters
+      if (i == 14) x = slot[14] - (double)m.d_g[1];     // closed clusters of this rank
+      if (i == 15) x = slot[15];                        // operators of this slab
+      if (i == 16) x = slot[16];                        // error flags
+    }
+    tail[r * 32 + i] = x;
+  }
 }
 
-__global__ void k_mr_final(Dev d, MrDev m, double* slot) {
+// after the all-reduce: out = sum over ranks (fixed order) + global-cluster sums.  The tail is
+// zeroed again: the next step's open-cluster table may reach into it.
+__global__ void k_mr_final(Dev d, MrDev m, double* tail, double* slot) {
   const int i = threadIdx.x;
   if (i >= 32) return;
   double x = 0;
-  for (int r = 0; r < d.nranks; ++r) x += m.allvec[r * 32 + i];
+  for (int r = 0; r < d.nranks; ++r) { x += tail[r * 32 + i]; tail[r * 32 + i] = 0.0; }
   if (i < LQ_NSUS) x += m.gsum[i];
   if (i == 18) x += m.gsum[14];
   if (i == 19) x += m.gsum[15];

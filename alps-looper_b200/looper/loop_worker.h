@@ -26,13 +26,14 @@ public:
 
   explicit loop_worker(const Parameters& p)
       : lattice(p), model(p, lattice), temp(p), mcs(p) {
-    // ALGORITHM (loop.C:25-34, PARAPACK_REGISTER_ALGORITHM path_integral.C:873 / sse.C): both
-    // representations of the loop algorithm sample the same ensemble; this worker always runs the
-    // continuous-time update and reports the path-integral form of the improved estimators
-    // (DESIGN.md section 6 on what "loop; sse" does not get: the fixed-length-string estimators).
+    // ALGORITHM (loop.C:25-34; PARAPACK_REGISTER_ALGORITHM path_integral.C:873 "loop; path integral",
+    // sse.C:411 "loop; sse"; plain "loop" is the path integral, loop.C).  Both workers sample the same
+    // ensemble -- an SSE string is the time-ordered operator list of a world-line configuration -- and
+    // the engine reports the estimators of the representation asked for (lq_options.representation).
     const std::string alg = p.value_or_default("ALGORITHM", "loop; path integral");
-    if (alg != "loop" && alg != "loop; path integral" && alg != "loop; sse")
-      throw std::invalid_argument("unknown ALGORITHM '" + alg + "' (loop; path integral | loop; sse)");
+    if (alg == "loop" || alg == "loop; path integral") sse_ = false;
+    else if (alg == "loop; sse") sse_ = true;
+    else throw std::invalid_argument("unknown ALGORITHM '" + alg + "' (loop; path integral | loop; sse)");
     if (temp.annealing_steps() > mcs.thermalization())
       throw std::invalid_argument("longer annealing steps than thermalization");  // path_integral.C:213
     enable_improved_estimator = !p.defined("DISABLE_IMPROVED_ESTIMATOR");
@@ -63,6 +64,7 @@ public:
     o.reserve = p.value_or_default<double>("RESERVE_OPERATORS_FACTOR", 0.0);  // cf. RESERVE_OPERATORS (:241)
     o.cluster_reserve = p.value_or_default<double>("RESERVE_ESTIMATES_FACTOR", 0.0);
     o.flags = p.defined("ENABLE_TIMER") ? 1 : 0;
+    o.representation = sse_ ? LQ_REPR_SSE : LQ_REPR_PATH_INTEGRAL;
     beta_ = 1.0 / temp(0);
     check(lq_create(&h_, &L, &M, beta_, &o));
   }
@@ -86,8 +88,9 @@ public:
     if (b != beta_) { check(lq_set_beta(h_, b)); beta_ = b; }
     lq_collector coll;
     check(lq_sweep(h_, &coll));
-    ++mcs;
-    if (!mcs.is_thermalized()) return;
+    const bool measure = mcs.is_thermalized();   // decided BEFORE the increment: the sweep that completes the
+    ++mcs;                                       // thermalisation is not measured (standalone/loop.C:173)
+    if (!measure) return;
     const double vol = lattice.volume();
     obs["Temperature"] << 1 / beta_;            // path_integral.C:832-836
     obs["Inverse Temperature"] << beta_;
@@ -95,7 +98,7 @@ public:
     obs["Number of Sites"] << double(num_sites(lattice.rg()));
     obs["Number of Clusters"] << coll.nc;
     energy::commit(obs, coll, beta_, vol);
-    susceptibility::commit(obs, coll, beta_, vol, lattice.is_bipartite());
+    susceptibility::commit(obs, coll, beta_, vol, lattice.is_bipartite(), sse_);
     if (model.site_weight() > 0) transverse_magnetization::commit(obs, coll, vol);
     if (measure_stiffness) stiffness::commit(obs, coll, beta_, lattice.vg().dimension);
     last_ = coll;
@@ -176,6 +179,7 @@ private:
   mc_steps mcs;
   bool enable_improved_estimator = true;
   bool measure_stiffness = false;
+  bool sse_ = false;
   double beta_ = 1;
   lq_handle h_ = nullptr;
   lq_collector last_ = lq_collector();

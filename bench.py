@@ -41,12 +41,15 @@ def measured_peaks():
 
 
 def workload(name):
-    """(L, beta, therm sweeps) of the named synthetic workload."""
+    """(lattice extents, beta, thermalisation sweeps, SSE representation) of the named synthetic workload."""
     table = {
-        "square1024_beta1024": (1024, 1024.0, 64),   # stationarity trace: profiles/r02_thermalisation_trace.md
-        "square1024_beta128": (1024, 128.0, 40),
-        "square256_beta64": (256, 64.0, 200),
-        "square64_beta8": (64, 8.0, 100),
+        "square1024_beta1024": ((1024, 1024), 1024.0, 64, False),   # stationarity trace: profiles/r02_thermalisation_trace.md
+        "square1024_beta128": ((1024, 1024), 128.0, 40, False),
+        "square256_beta64": ((256, 256), 64.0, 200, False),
+        "square64_beta8": ((64, 64), 8.0, 100, False),
+        # BASELINE config 4: simple cubic 64^3 near T_N = 0.946 J, SSE representation (sse.C)
+        "cubic64_T0.95_sse": ((64, 64, 64), 1.0 / 0.95, 400, True),
+        "cubic64_T0.95": ((64, 64, 64), 1.0 / 0.95, 400, False),
     }
     return table[name]
 
@@ -247,11 +250,13 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    L, beta, therm = workload(args.workload)
+    dims, beta, therm, sse = workload(args.workload)
+    L = dims[0]
     if args.therm >= 0:
         therm = args.therm
-    lat = lq.hypercubic_lattice((L, L))
-    tile = args.tile_sites or (256 if L >= 512 else 64)
+    lat = lq.hypercubic_lattice(dims)
+    tile = args.tile_sites or (256 if lat["num_sites"] >= 512 * 512 else 64)
+    args.sse = sse
     # parity pre-flight (not timed; the oracle is the checker here, never the thing measured): one
     # oracle configuration through the same engine / communicator, against the reference union-find
     parity = parity_preflight(rank, world, local, args)
@@ -361,8 +366,10 @@ def run_gpu(args):
             "scaling": "strong",   # ONE Markov chain of fixed size, split over the GPUs
             "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "mcs_per_sec": args.steps / (ms * 1e-3),
-            "config": {"workload": args.workload, "lattice": f"square {L}x{L} periodic",
+            "config": {"workload": args.workload, "lattice": ("square " if len(dims) == 2 else "simple cubic ") +
+                       "x".join(str(x) for x in dims) + " periodic",
                        "model": "S=1/2 Heisenberg AF J=1", "beta": beta,
+                       "representation": "sse (sse.C estimators, string positions from a counting sort)" if sse else "path integral",
                        "operators_per_mcs": nop_mean, "clusters_per_mcs": float(out["nc"].mean()),
                        "open_clusters_per_mcs": float(out["noc"].mean()),
                        "thermalisation_mcs": therm, "tile_sites": tile, "windows": info["num_windows"],
@@ -435,7 +442,7 @@ def load_comm():
 def make_engine(lq, lat, beta, tile, local, rank, world, args, timers=False):
     eng = lq.Engine(lat, beta, seed=29833, device=local, tile_sites=tile, timers=timers,
                     window_ops=args.window_ops, reserve=args.reserve,
-                    rank=rank if world > 1 else 0, nranks=world)
+                    rank=rank if world > 1 else 0, nranks=world, sse=getattr(args, "sse", False))
     if world > 1:
         if args.comm == "nccl":
             load_comm().attach_nccl(eng, rank, world)

@@ -77,8 +77,16 @@ typedef struct lq_options {
   double   cluster_reserve;  /* cluster arena / operator arena (0 = default 0.75)                */
   int32_t  rank, nranks;     /* imaginary-time slab of this engine (path_integral_mpi.C:231-232);
                                 nranks <= 1 = serial                                             */
-  int32_t  flags;            /* reserved, 0                                                      */
+  int32_t  flags;            /* bit 0: section timers on (ALPS_ENABLE_TIMER)                     */
+  int32_t  representation;   /* LQ_REPR_PATH_INTEGRAL ("loop; path integral", path_integral.C:873) or
+                                LQ_REPR_SSE ("loop; sse", sse.C:411): the improved estimators are
+                                those of the fixed-length operator string -- the "time" of an
+                                operator is its position in the string and the string length n is the
+                                top (sse.C:251-283,358-361) -- and the collector's sums are in those
+                                units (commit: susceptibility.h:213-215, beta (x/n + x0) / (n+1) / V) */
 } lq_options;
+#define LQ_REPR_PATH_INTEGRAL 0
+#define LQ_REPR_SSE           1
 
 /* looper/operator.h:120-143: {time_, loc_, type_}; loc = pos<<1 | is_bond
  * (location_impl.h:37); type bit0 = offdiagonal, bits >= 2 = graph type (operator.h:62,76). */

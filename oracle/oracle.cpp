@@ -884,4 +884,116 @@ int orc_poisson_replay(double mean, int count, char* buf, int buflen, int64_t* b
   return int(out.size());
 }
 
+// ---------------------------------------------------------------------------------------------
+// SSE worker, sse.C:168-407 restated (serial, XXZ bond graphs 0..3 + site graphs), on the same
+// model tables as orc_model_sim.  The operator string has no times: the "time" of operator k is its
+// position (sse.C:251-283 `t`), the top is the string length (:283).  The string is exported with
+// time = (k + 1/2) / n so that orc_model_get_state / orc_build_clusters see an ordered list; the
+// cluster sums are linear in the time, so the SSE collector is the one of that list with
+// times k/n, scaled by n (sums) and n^2 (squared sums) -- done in orc_sse_collect below.
+// RNG as orc_model_sim (the reference's generator is ALPS's: unpinned).
+// ---------------------------------------------------------------------------------------------
+// collector of a GIVEN string (spins at the bottom + operators in string order), SSE times
+int orc_sse_collect(int nsites, int nbonds, const int32_t* src, const int32_t* dst, const double* gauge,
+                    const int32_t* spins, const orc_op* ops_in, int64_t n, orc_collector* out) {
+  std::vector<orc_op> ops(ops_in, ops_in + n);
+  for (int64_t k = 0; k < n; ++k) ops[k].time = n > 0 ? double(k) / double(n) : 0;   // exact scaling below
+  const int rc = orc_build_clusters(nsites, nbonds, src, dst, gauge, spins, ops.data(), n, nullptr, nullptr, out);
+  if (rc != 0) return rc;
+  const double f = double(n), f2 = f * f;
+  // the "0" sums (tau = 0 magnetisations) and counters do not carry a time
+  out->usize *= f2; out->umag *= f2; out->ssize *= f2; out->smag *= f2;
+  out->sa_ssus *= f2;
+  out->tlen *= f;
+  return 0;
+}
+
+int orc_sse_sweep(orc_model_sim* S, orc_collector* out) {
+  const int nsites = S->nsites;
+  std::vector<orc_op> ops_p;
+  std::swap(ops_p, S->ops);
+  std::vector<int> sc(S->spins);
+  int nop = int(ops_p.size());                                  // sse.C:182
+  const double bw = S->beta * S->total;                         // sse.C:205 beta * model.graph_weight()
+  bool try_gap = true;
+  size_t opi = 0;
+  // sse.C:207-249 (the reconnect / accumulate part, :251-281, is done on the finished string below)
+  while (try_gap || opi != ops_p.size()) {
+    orc_op o;
+    if (try_gap) {
+      if ((nop + 1) * S->uni(S->eng) < bw) {                    // :209
+        const double r = S->uni(S->eng) * S->total;             // :210 model.choose_graph
+        size_t k = size_t(std::upper_bound(S->cum.begin(), S->cum.end(), r) - S->cum.begin());
+        if (k >= S->cum.size()) k = S->cum.size() - 1;
+        const int cg = S->cum_graph[k];
+        bool ok;
+        if (cg & 1) {
+          const int b = cg >> 3, g = (cg >> 1) & 3;
+          ok = ((g & 1) ^ sc[S->src[b]] ^ sc[S->dst[b]]) != 0;  // :211-213, graph_impl.h:257
+          o.loc = (b << 1) | 1;
+          o.type = g << 2;
+        } else {
+          ok = true;                                            // site graph, graph_impl.h:69
+          o.loc = (cg >> 3) << 1;
+          o.type = 0;
+        }
+        if (!ok) { try_gap = false; continue; }                 // :217-219
+        ++nop;                                                  // :215
+      } else {
+        try_gap = false;                                        // :221-223
+        continue;
+      }
+    } else {
+      o = ops_p[opi];
+      if (!(o.type & 1)) {                                      // diagonal
+        if (bw * S->uni(S->eng) < nop) { --nop; ++opi; continue; }   // :226-229 remove
+        if (o.loc & 1) {                                        // :234-237 choose_diagonal (graph_impl.h:307-311)
+          const int b = o.loc >> 1;
+          const double* v = &S->bw[4 * size_t(b)];
+          const int c = 1 ^ sc[S->src[b]] ^ sc[S->dst[b]];      // 0 antiparallel, 1 parallel
+          const double den = c ? v[1] + v[3] : v[0] + v[2];
+          const double pr = den > 1e-10 ? (c ? v[1] : v[0]) / den : 1;
+          o.type = (((S->uni(S->eng) < pr) ? 0 : 2) ^ c) << 2;
+        } else {
+          S->uni(S->eng);                                       // :231-233 (site: graph 0; one number is drawn)
+        }
+      } else if (o.loc & 1) {                                   // :240-244 choose_offdiagonal (graph_impl.h:324-327)
+        const int b = o.loc >> 1;
+        const double v0 = S->bw[4 * size_t(b)], v1 = S->bw[4 * size_t(b) + 1];
+        const double pr = (v0 + v1 > 1e-10) ? v0 / (v0 + v1) : 1;
+        o.type = (((S->uni(S->eng) < pr) ? 0 : 1) << 2) | 1;
+      }
+      ++opi;
+      try_gap = true;
+    }
+    if (o.type & 1) {                                           // :257-261, :270-274 walk the spins
+      if (o.loc & 1) { sc[S->src[o.loc >> 1]] ^= 1; sc[S->dst[o.loc >> 1]] ^= 1; }
+      else sc[o.loc >> 1] ^= 1;
+    }
+    S->ops.push_back(o);
+  }
+  const int64_t n = int64_t(S->ops.size());
+  for (int64_t k = 0; k < n; ++k) S->ops[k].time = (double(k) + 0.5) / double(n);
+  cluster_graph G;
+  const int rc = build_graph(nsites, S->nbonds, S->src.data(), S->dst.data(), S->spins.data(),
+                             S->ops.data(), n, G);
+  if (rc != 0) return rc;
+  if (out) {
+    orc_sse_collect(nsites, S->nbonds, S->src.data(), S->dst.data(), S->gauge.data(), S->spins.data(),
+                    S->ops.data(), n, out);
+    double off = 0;
+    for (double v : S->bw) off += v / 2;
+    for (double v : S->sw) off += v;
+    out->ene = off - double(n) / S->beta;                       // sse.C:398-399
+  }
+  // sse.C:366-381 flip
+  std::vector<char> flip(G.nc);
+  for (int c = 0; c < G.nc; ++c) flip[c] = (2 * S->uni(S->eng) - 1) < 0;
+  for (size_t k = 0; k < S->ops.size(); ++k)
+    if (flip[G.id[G.l0[k]]] ^ flip[G.id[G.u0[k]]]) S->ops[k].type ^= 1;
+  for (int s = 0; s < nsites; ++s)
+    if (flip[G.id[s]]) S->spins[s] ^= 1;
+  return 0;
+}
+
 }  // extern "C"

@@ -101,6 +101,20 @@ int      orc_model_sweep(orc_model_sim*, orc_collector* out);
 int64_t  orc_model_num_ops(const orc_model_sim*);
 void     orc_model_get_state(const orc_model_sim*, int32_t* spins, orc_op* ops);
 
+/* SSE worker, sse.C:168-407 restated on the same model object (orc_model_create): one Monte Carlo
+ * step of the grand-canonical diagonal update (:207-249: insert with (nop+1) u < beta W, remove with
+ * beta W u < nop, choose_diagonal / choose_offdiagonal), cluster construction and flip.  The string
+ * is exported by orc_model_get_state with times (k + 1/2) / n.  The collector carries the SSE sums:
+ * operator k has time k, the top is n (sse.C:251-283,358-361).  Pinned to exact diagonalisation and,
+ * statistically, to the SSE blocks of loop.op (tests/test_oracle_sse.py); "parity unpinned" at the
+ * bit level like the rest of the generic model (ALPS generator). */
+int      orc_sse_sweep(orc_model_sim*, orc_collector* out);
+/* SSE collector of a GIVEN string: spins at the bottom and the operators in string order (their
+ * `time` fields are ignored). */
+int      orc_sse_collect(int nsites, int nbonds, const int32_t* src, const int32_t* dst,
+                         const double* gauge, const int32_t* spins, const orc_op* ops, int64_t n,
+                         orc_collector* out);
+
 /* looper/stiffness.h:82-133 on a given configuration (bond_vectors: 3 doubles per bond, relative
  * lattice vectors): returns the improved-estimator collector w2 = sum_c sum_i (winding_i / 2)^2
  * ("Stiffness" = w2 / (beta dim)) and, in *w2_normal, the normal estimator (:137-170); -1 on an

@@ -56,6 +56,9 @@ def lib():
                                        C.c_void_p, C.c_double, C.c_uint32]
         L.orc_model_destroy.argtypes = [C.c_void_p]
         L.orc_model_sweep.argtypes = [C.c_void_p, C.POINTER(OrcCollector)]
+        L.orc_sse_sweep.argtypes = [C.c_void_p, C.POINTER(OrcCollector)]
+        L.orc_sse_collect.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.POINTER(OrcCollector)]
         L.orc_model_num_ops.argtypes = [C.c_void_p]
         L.orc_model_num_ops.restype = C.c_int64
         L.orc_model_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -169,12 +172,37 @@ class OracleModelSim:
             raise ValueError(f"orc_model_sweep failed with {rc}")
         return c
 
+    def sse_sweep(self):
+        """one step of the SSE worker (sse.C:168-407) on this model"""
+        c = OrcCollector()
+        rc = lib().orc_sse_sweep(self.h, C.byref(c))
+        if rc != 0:
+            raise ValueError(f"orc_sse_sweep failed with {rc}")
+        return c
+
     def get_state(self):
         n = lib().orc_model_num_ops(self.h)
         spins = np.zeros(self.N, dtype=np.int32)
         ops = np.zeros(n, dtype=OP_DTYPE)
         lib().orc_model_get_state(self.h, spins.ctypes.data, ops.ctypes.data)
         return spins, ops
+
+
+def sse_collect(lattice, spins, ops):
+    """orc_sse_collect: SSE collector (string positions as times) of a configuration."""
+    N = int(lattice["num_sites"])
+    src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
+    dst = np.ascontiguousarray(lattice["dst"], dtype=np.int32)
+    g = lattice.get("gauge")
+    gauge = np.ascontiguousarray(g if g is not None else np.zeros(N), dtype=np.float64)
+    spins = np.ascontiguousarray(spins, dtype=np.int32)
+    ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+    c = OrcCollector()
+    rc = lib().orc_sse_collect(N, len(src), src.ctypes.data, dst.ctypes.data, gauge.ctypes.data,
+                               spins.ctypes.data, ops.ctypes.data, len(ops), C.byref(c))
+    if rc != 0:
+        raise ValueError(f"orc_sse_collect failed with {rc}")
+    return c.as_dict()
 
 
 def stiffness(lattice, spins, ops):

@@ -50,9 +50,12 @@ def test_headline_lattice_partition_bit_exact():
     eng.close()
 
 
+# (40 000 sweeps: on 16 x 16 single 12 000-sweep stretches of EITHER code were seen 4 sigma off in the
+# uniform susceptibility while 150 000-sweep runs agree to 0.1 %: GPU 0.05562(9), 0.05559(8); oracle
+# 0.05583(14), 0.05565(12), 0.05557(13), 0.05561(14) -- profiles/r02_parity.md)
 CASES_3SIGMA = [
-    ("square16_beta4", (16, 16), 4.0, 12000),
-    ("cubic8_T0.95", (8, 8, 8), 1 / 0.95, 12000),
+    ("square16_beta4", (16, 16), 4.0, 40000),
+    ("cubic8_T0.95", (8, 8, 8), 1 / 0.95, 20000),
 ]
 
 
@@ -65,11 +68,11 @@ def test_observables_agree_with_reference_cpu_run_within_3_sigma(name, dims, bet
     import looper_b200 as lq
     lat = lq.hypercubic_lattice(dims)
     N, B = lat["num_sites"], len(lat["src"])
-    eng = lq.Engine(lat, beta, seed=20261018)
+    eng = lq.Engine(lat, beta, seed=1)
     eng.sweep_many(sweeps // 8, collect=False)
     g = eng.sweep_many(sweeps)
     eng.close()
-    sim = orc.OracleSim(lat, beta, seed=4711)
+    sim = orc.OracleSim(lat, beta, seed=11)
     for _ in range(sweeps // 8):
         sim.sweep()
     c = [sim.sweep() for _ in range(sweeps)]
