@@ -32,6 +32,7 @@ static const node_t NODE_NONE = 0xffffffffu;
 #define LQ_ERR_CAND_FULL 2
 #define LQ_ERR_NODE_FULL 4
 #define LQ_ERR_CLUSTER_FULL 8
+#define LQ_ERR_REMOTE 16   /* slab engines: another rank overflowed in this step (all ranks rewind together) */
 
 // fixed-point scale of imaginary time in the cluster sums (order-independent integer atomics)
 #define LQ_FX 1099511627776.0 /* 2^40 */

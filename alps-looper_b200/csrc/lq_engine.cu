@@ -317,7 +317,7 @@ struct lq_engine {
   double wunit[3] = {0, 0, 0};
   size_t P = 0;
   long long ncap = 0, nccap = 0;
-  size_t nwords_cap = 0, device_bytes = 0;
+  size_t nwords_cap = 0, device_bytes = 0, static_bytes = 0;
   int sm_count = 0, smem_optin = 0;
   uint32_t mcs = 0;
   int cur = 0;  // live page buffer
@@ -592,6 +592,8 @@ struct lq_engine {
   // (re)size everything that depends on beta
   void size_arenas() {
     const int N = part.N, B = part.B, T = part.T;
+    if (static_bytes == 0) static_bytes = device_bytes;   // lattice tables, sized once in setup()
+    device_bytes = static_bytes;                          // the arenas below are counted afresh
     drop_graphs();   // captured kernels hold the old pointers and grid sizes
     double maxrate = 0;
     std::vector<double> tile_rate(T, 0.0);
@@ -1150,7 +1152,9 @@ struct lq_engine {
       if (out && first_bad == count) to_collector(h_out + (size_t)i * 32, out + i);
     }
     if (!err) return;
-    if (opt.nranks > 1 || depth >= 8) check_err(err);   // slab engines: every rank would have to rewind
+    // (slab engines: every rank sees the OR of all ranks' error bits in the collector and has kept the
+    // configuration of the failing step -- LQ_ERR_REMOTE, k_mr_ids -- so all ranks rewind together)
+    if (depth >= 8) check_err(err);
     CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
     cur = cur0 ^ (first_bad & 1);
     mcs = mcs0 + (uint32_t)first_bad;
@@ -1158,27 +1162,48 @@ struct lq_engine {
     if (err & LQ_ERR_CAND_FULL) { grow_cand *= 1.5; grow_kept *= 1.6; }
     if (err & LQ_ERR_CLUSTER_FULL) grow_clusters *= 1.5;
     ++regrows;
-    {
-      int64_t n = 0;
-      get_state(nullptr, nullptr, &n);
-      std::vector<int32_t> spins(part.N);
-      std::vector<lq_op> ops((size_t)n);
-      get_state(spins.data(), ops.data(), &n);
-      size_arenas();
-      clear_state();
-      set_state(spins.data(), ops.data(), n);
-    }
+    rebucket();
     sweep_many(count - first_bad, out ? out + first_bad : nullptr, depth + 1);
+  }
+
+  // operators and spins of this engine (of its slab, on a slab engine) through new arenas: after a
+  // change of beta or of an arena size
+  void rebucket() {
+    int64_t n = 0;
+    get_state(nullptr, nullptr, &n);
+    std::vector<int32_t> spins(part.N);
+    std::vector<lq_op> ops((size_t)n);
+    get_state(spins.data(), ops.data(), &n);
+    size_arenas();
+    clear_state();
+    set_state(spins.data(), ops.data(), n, opt.nranks > 1);
   }
 
   // -------------------------------------------------------------------------------------------
   // state import / export (host side, test and checkpoint path)
   // -------------------------------------------------------------------------------------------
-  void set_state(const int32_t* spins, const lq_op* ops, int64_t n) {
+  // local = true (slab engines re-bucketing their own slab): `spins` is the state at the start of this
+  // rank's slab and `ops` holds the operators of the slab only
+  void set_state(const int32_t* spins, const lq_op* ops, int64_t n, bool local = false) {
     const int N = part.N;
-    std::vector<std::vector<std::pair<double, uint32_t>>> buckets;  // per (page, lb) for local windows
-    const size_t nbk = P * (size_t)part.nbmax;
-    buckets.resize(nbk);
+    // two passes over the (time-sorted) operators: bucket sizes -> offsets, then placement with the
+    // offsets as cursors -- flat arrays only (a vector per bucket would be 3.6e8 vectors at 1024^2, beta 1024)
+    const size_t nb1 = (size_t)part.nbmax + 1;
+    std::vector<uint16_t> hb(P * nb1, 0);
+    std::vector<int> hc(P, 0);
+    auto locate = [&](const lq_op& o, size_t* pg, int* lbo, uint32_t* info) -> bool {
+      const bool is_site = !(o.loc & 1);
+      const int pos = o.loc >> 1;
+      const int bi = part.bond_e2i[is_site ? Breal + pos : pos];
+      const int w = window_of(o.time, W);
+      if (w < w0 || w >= w0 + Wl) return false;
+      const int tl = part.bond_tile[bi];
+      *lbo = bi - part.bond_base[tl];
+      *pg = (size_t)tl * Wl + (w - w0);
+      *info = ((uint32_t)*lbo << LQ_INFO_LBSHIFT) | ((uint32_t)((o.type >> 2) & 3) << LQ_INFO_GSHIFT) |
+              (uint32_t)(o.type & 1) | (is_site ? LQ_INFO_SITE : 0u);
+      return true;
+    };
     // spin at the start of every global window
     std::vector<uint8_t> par((size_t)(W + 1) * N, 0);
     double tprev = -1;
@@ -1201,13 +1226,25 @@ struct lq_engine {
         par[(size_t)(w + 1) * N + part.bond_s0[bi]] ^= 1;
         if (!is_site) par[(size_t)(w + 1) * N + part.bond_s1[bi]] ^= 1;
       }
-      if (w < w0 || w >= w0 + Wl) continue;
-      const int tl = part.bond_tile[bi];
-      const int lb = bi - part.bond_base[tl];
-      const size_t p = (size_t)tl * Wl + (w - w0);
-      const uint32_t inf = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((uint32_t)g << LQ_INFO_GSHIFT) |
-                           (uint32_t)(ops[k].type & 1) | (is_site ? LQ_INFO_SITE : 0u);
-      buckets[p * part.nbmax + lb].push_back({t, inf});
+      size_t pg; int lb; uint32_t inf;
+      if (!locate(ops[k], &pg, &lb, &inf)) continue;
+      if (++hc[pg] > cap) fail(LQ_E_OVERFLOW, "page full while loading state (raise lq_options.reserve)");
+      hb[pg * nb1 + lb + 1]++;
+    }
+    for (size_t p = 0; p < P; ++p)   // sizes (stored one slot up) -> offsets
+      for (int lb = 0; lb < part.nbmax; ++lb) hb[p * nb1 + lb + 1] = (uint16_t)(hb[p * nb1 + lb + 1] + hb[p * nb1 + lb]);
+    std::vector<double> ht((size_t)ncap, 0.0);
+    std::vector<uint32_t> hi((size_t)ncap, 0u);
+    for (int64_t k = 0; k < n; ++k) {   // placement: hb[lb] is the cursor of bucket lb (ops arrive time-sorted)
+      size_t pg; int lb; uint32_t inf;
+      if (!locate(ops[k], &pg, &lb, &inf)) continue;
+      const size_t at = pg * (size_t)cap + hb[pg * nb1 + lb]++;
+      ht[at] = ops[k].time;
+      hi[at] = inf;
+    }
+    for (size_t p = 0; p < P; ++p) {    // every cursor now holds the END of its bucket: shift back to the starts
+      for (int lb = part.nbmax; lb > 0; --lb) hb[p * nb1 + lb] = hb[p * nb1 + lb - 1];
+      hb[p * nb1] = 0;
     }
     std::vector<uint8_t> sw((size_t)(Wl + 1) * N);
     {
@@ -1218,29 +1255,9 @@ struct lq_engine {
         if (w >= w0 && w <= w0 + Wl)
           std::memcpy(&sw[(size_t)(w - w0) * N], c.data(), N);
       }
-      for (int i = 0; i < N; ++i)
+      for (int i = 0; i < N && !local; ++i)
         if (c[i] != (uint8_t)(spins[part.site_i2e[i]] & 1))
           fail(LQ_E_INVALID, "operator string is not periodic in imaginary time");
-    }
-    std::vector<double> ht((size_t)ncap, 0.0);
-    std::vector<uint32_t> hi((size_t)ncap, 0u);
-    std::vector<uint16_t> hb(P * (size_t)(part.nbmax + 1), 0);
-    std::vector<int> hc(P, 0);
-    for (size_t p = 0; p < P; ++p) {
-      int off = 0;
-      for (int lb = 0; lb < part.nbmax; ++lb) {
-        auto& v = buckets[p * part.nbmax + lb];
-        hb[p * (part.nbmax + 1) + lb] = (uint16_t)off;
-        std::stable_sort(v.begin(), v.end(), [](auto& a, auto& b) { return a.first < b.first; });
-        if (off + (int)v.size() > cap) fail(LQ_E_OVERFLOW, "page full while loading state (raise lq_options.reserve)");
-        for (auto& o : v) {
-          ht[p * (size_t)cap + off] = o.first;
-          hi[p * (size_t)cap + off] = o.second;
-          ++off;
-        }
-      }
-      hb[p * (part.nbmax + 1) + part.nbmax] = (uint16_t)off;
-      hc[p] = off;
     }
     CK(cudaStreamSynchronize(stream));
     cur = 0;
@@ -1259,19 +1276,28 @@ struct lq_engine {
     std::vector<int> hc(P);
     CK(cudaMemcpy(hc.data(), pcount[cur].p, P * sizeof(int), cudaMemcpyDeviceToHost));
     out.clear();
-    std::vector<double> ht(cap);
-    std::vector<uint32_t> hi(cap);
+    {
+      size_t total = 0;
+      for (size_t p = 0; p < P; ++p) total += (size_t)hc[p];
+      out.reserve(total);
+    }
+    // contiguous runs of pages per copy (two copies per 64 MiB of operators instead of two per page)
+    const size_t chunk = std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)cap * 12));
+    std::vector<double> ht(chunk * (size_t)cap);
+    std::vector<uint32_t> hi(chunk * (size_t)cap);
     int idx = 0;
-    for (size_t p = 0; p < P; ++p) {
-      const int n = hc[p];
-      if (n > 0) {
-        CK(cudaMemcpy(ht.data(), time_[cur].p + p * (size_t)cap, n * sizeof(double), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(hi.data(), info[cur].p + p * (size_t)cap, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t p0 = 0; p0 < P; p0 += chunk) {
+      const size_t p1 = std::min(P, p0 + chunk);
+      CK(cudaMemcpy(ht.data(), time_[cur].p + p0 * (size_t)cap, (p1 - p0) * (size_t)cap * sizeof(double), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hi.data(), info[cur].p + p0 * (size_t)cap, (p1 - p0) * (size_t)cap * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      for (size_t p = p0; p < p1; ++p) {
+        const int n = hc[p];
+        const int tl = (int)(p / Wl);
+        const size_t o = (p - p0) * (size_t)cap;
+        for (int j = 0; j < n; ++j)
+          out.push_back({ht[o + j], part.bond_base[tl] + (int)(hi[o + j] >> LQ_INFO_LBSHIFT), hi[o + j], idx + j});
+        idx += n;
       }
-      const int tl = (int)(p / Wl);
-      for (int j = 0; j < n; ++j)
-        out.push_back({ht[j], part.bond_base[tl] + (int)(hi[j] >> LQ_INFO_LBSHIFT), hi[j], idx + j});
-      idx += n;
     }
     std::sort(out.begin(), out.end(), [](const HostOp& a, const HostOp& b) {
       return a.time < b.time || (a.time == b.time && a.bi < b.bi);
@@ -1391,17 +1417,10 @@ int lq_set_beta(lq_handle h, double beta) {
   LQ_TRY({
     if (!(beta > 0)) fail(LQ_E_INVALID, "beta must be positive");
     CK(cudaSetDevice(h->opt.device));
-    std::vector<lq_engine::HostOp> v;
-    if (h->opt.nranks > 1) fail(LQ_E_UNSUPPORTED, "lq_set_beta on a slab engine");
-    int64_t n = 0;
-    h->get_state(nullptr, nullptr, &n);
-    std::vector<int32_t> spins(h->part.N);
-    std::vector<lq_op> ops((size_t)n);
-    h->get_state(spins.data(), ops.data(), &n);
+    // (slab engines: the slab boundaries r / nranks do not move with beta, so every rank re-buckets
+    // its own operators; path_integral_mpi.C anneals the same way, temperature.h:39-80)
     h->beta = beta;
-    h->size_arenas();
-    h->clear_state();
-    h->set_state(spins.data(), ops.data(), n);
+    h->rebucket();
   })
 }
 

@@ -1188,7 +1188,9 @@ __device__ __forceinline__ uint32_t open_id(const Dev& d, const MrDev& m, uint32
 __global__ void k_mr_ids(Dev d, MrDev m) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= d.N) return;
-  m.sendb[s] = d.parent[s];
+  // bit 31 of entry 0 carries "an arena of this rank overflowed in this step": every rank learns it
+  // with the boundary ids, before anything is flipped, so that all ranks rewind together
+  m.sendb[s] = d.parent[s] | ((s == 0 && *d.d_err) ? 0x80000000u : 0u);
   m.sendb[d.N + s] = open_id(d, m, d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
 }
 
@@ -1205,7 +1207,8 @@ __global__ void k_mr_gunion(Dev d, MrDev m) {
   const int r = (int)(i / d.N), s = (int)(i % d.N), rn = (r + 1) % d.nranks;
   const size_t N2 = 2 * (size_t)d.N;
   const uint32_t a = (uint32_t)(r * N2 + m.recvb[r * N2 + d.N + s]);   // top of slab r
-  const uint32_t b = (uint32_t)(rn * N2 + m.recvb[rn * N2 + s]);       // bottom of slab r+1
+  const uint32_t b = (uint32_t)(rn * N2 + (m.recvb[rn * N2 + s] & 0x7fffffffu));       // bottom of slab r+1
+  if (s == 0 && (m.recvb[rn * N2] >> 31)) atomicOr(d.d_err, LQ_ERR_REMOTE);   // (see k_mr_ids)
   m.gused[a] = 1;
   m.gused[b] = 1;
   uf_union(m.gparent, a, b);
@@ -1366,7 +1369,9 @@ __global__ void k_mr_final(Dev d, MrDev m, double* tail, double* slot) {
   const int i = threadIdx.x;
   if (i >= 32) return;
   double x = 0;
-  for (int r = 0; r < d.nranks; ++r) { x += tail[r * 32 + i]; tail[r * 32 + i] = 0.0; }
+  int err = 0;   // slot 16: error bits, OR-ed (not summed) over the ranks
+  for (int r = 0; r < d.nranks; ++r) { x += tail[r * 32 + i]; err |= (int)tail[r * 32 + i]; tail[r * 32 + i] = 0.0; }
+  if (i == 16) x = (double)err;
   if (i < LQ_NSUS) x += m.gsum[i];
   if (i == 18) x += m.gsum[14];
   if (i == 19) x += m.gsum[15];
