@@ -291,7 +291,7 @@ void nccl_check(ncclResult_t r, const char* what) {
 }
 
 const char* kTimerLabels[17] = {"", "", "", "dispatch", "init", "fill_times(K1 rng)", "init_fragments",
-                                "insert/remove+reconnect", "", "close in tau", "", "assign ids",
+                                "insert/remove+reconnect", "", "close in tau", "boundary estimates", "assign ids",
                                 "accumulate", "collect", "flip decision", "flip", "measurement"};
 
 }  // namespace
@@ -902,18 +902,18 @@ struct lq_engine {
         lq::k_rootflip<<<(unsigned)std::min<size_t>((nwords_cap + 255) / 256, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
         launches += 1;
       }
-      lq::k_relabel<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d);
-      launches += 2;
+      if (opt.nranks == 1) { lq::k_relabel<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d); launches += 1; }
+      launches += 1;
     }
-    if (opt.nranks > 1) merge_open_clusters();
-    {
-      Section s(this, 14);  // flip decision per cluster id (slab engines; serial ones decided per root above)
-      if (opt.nranks > 1) {
-        lq::k_flipbits<<<(unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
-        lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
-        lq::k_pack_flips<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d);
-        launches += 3;
-      }
+    if (opt.nranks > 1) {
+      // slab engines: exchange first (on roots), flips of ALL clusters, then the relabelling packs them
+      lq::k_set_ncs<<<1, 1, 0, stream>>>(d);
+      merge_open_clusters();
+      Section s(this, 14);
+      lq::k_flipbits<<<(unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
+      lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
+      lq::k_relabel<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d);
+      launches += 4;
     }
     {
       Section s(this, 12);
@@ -925,10 +925,14 @@ struct lq_engine {
           lq::k_estimate<false, true, true>,   lq::k_estimate<true, false, false>, lq::k_estimate<true, false, true>,
           lq::k_estimate<true, true, false>,   lq::k_estimate<true, true, true>};
       est_fns[(flip ? 4 : 0) | (sdim > 0 ? 2 : 0) | (npo == 2 ? 1 : 0)]<<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+      launches += 1;
+    }
+    {
+      Section s(this, 10);   // world-line ends at the slab boundaries; open-cluster sums into the exchange table
       lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
-      launches += 2;
+      launches += 1;
       if (opt.nranks > 1) {
-        lq::k_mr_gather<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
+        lq::k_mr_gather<<<grid_for(N, 1024), 1024, 0, stream>>>(d, mr);
         lq::k_mr_reset_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
         launches += 2;
       }
@@ -985,7 +989,7 @@ struct lq_engine {
     all_reduce_i64(mr.gest, (size_t)ngc * gstride() + 32 * (size_t)opt.nranks, "all_reduce(open-cluster sums + collectors)");
     const unsigned gblk = (unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 4);
     lq::k_mr_gcollect<<<gblk, 256, 0, stream>>>(d, mr, partial.p);   // (partial is free again after k_collect_final)
-    lq::k_mr_gsum<<<1, 32, 0, stream>>>(mr, partial.p, (int)gblk);
+    lq::k_mr_gsum<<<1, 32 * LQ_NSUM, 0, stream>>>(mr, partial.p, (int)gblk);
     lq::k_mr_final<<<1, 32, 0, stream>>>(d, mr, tail, out_slot);
     launches += 4;
   }

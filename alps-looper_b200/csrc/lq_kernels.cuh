@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(256)
 k_relabel(Dev d) {
   const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
   const size_t base = (size_t)blockIdx.x * (256 * LQ_NPT) + threadIdx.x;
-  if (base == 0) {
+  if (base == 0 && d.rootflip) {   // (slab engines: k_set_ncs, before the exchange)
     // clusters rooted at a site node come first (site ids are the smallest node ids)
     d.d_nc[1] = cid_of_root(d, (node_t)d.N);
     if ((long long)d.d_nc[0] > d.nccap) atomicOr(d.d_err, LQ_ERR_CLUSTER_FULL);
@@ -616,7 +616,10 @@ k_relabel(Dev d) {
 #pragma unroll
     for (int k = 0; k < LQ_NPT; ++k) {
       const size_t x = base + (size_t)k * 256;
-      if (x < nn) d.parent[x] = wb[k] + (uint32_t)__popc(bm[k] & ((1u << (r[k] & 31)) - 1u));
+      if (x < nn) {   // slab engines relabel AFTER the exchange: the flip table is complete (open clusters included)
+        const uint32_t c = wb[k] + (uint32_t)__popc(bm[k] & ((1u << (r[k] & 31)) - 1u));
+        d.parent[x] = c | (flip_of(d, c) << 31);
+      }
     }
   }
 }
@@ -717,24 +720,6 @@ k_flipbits(Dev d, const StepParams* __restrict__ sp) {
     }
     d.flipw[w] = word;
     if (d.has_site) d.openw[w] = 0u;   // "cut by a site operator" flags of this step (transmag.h:72-81)
-  }
-}
-
-// Slab engines know the flips of the open clusters only after the exchange (k_mr_openflips); one
-// streaming pass then packs every decision into the labels, so that the estimator and the spin flip
-// read it with the cluster id like on a serial engine instead of gathering the flip table twice per
-// operator (k_estimate ran 30 % slower on slabs).  The table itself is L2-resident.
-__global__ void __launch_bounds__(256)
-k_pack_flips(Dev d) {
-  const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
-  const size_t base = (size_t)blockIdx.x * (256 * LQ_NPT) + threadIdx.x;
-#pragma unroll
-  for (int k = 0; k < LQ_NPT; ++k) {
-    const size_t x = base + (size_t)k * 256;
-    if (x < nn) {
-      const uint32_t c = d.parent[x];
-      d.parent[x] = c | (flip_of(d, c) << 31);
-    }
   }
 }
 
@@ -1167,11 +1152,21 @@ struct MrDev {
   double* gsum;       // [16] sums over global clusters
 };
 
+// Slab engines run the exchange BEFORE the relabelling (so that k_relabel can pack the flips of the
+// open clusters, known only after the exchange, into the labels like a serial engine does per root):
+// until then parent[] holds roots, and the cluster id of a node is computed from its root.
+__device__ __forceinline__ uint32_t cid_pre(const Dev& d, size_t x) { return cid_of_root(d, d.parent[x]); }
+
+__global__ void k_set_ncs(Dev d) {
+  d.d_nc[1] = cid_of_root(d, (node_t)d.N);   // clusters rooted at a site node come first
+  if ((long long)d.d_nc[0] > d.nccap) atomicOr(d.d_err, LQ_ERR_CLUSTER_FULL);
+}
+
 __global__ void k_mr_topmin(Dev d, MrDev m) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= d.N) return;
-  const uint32_t cb = d.parent[s];
-  const uint32_t ct = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  const uint32_t cb = cid_pre(d, s);
+  const uint32_t ct = cid_pre(d, d.curW[(size_t)d.Wl * d.N + s]);
   // bottom-touching clusters (cid < ncs) are represented by their smallest BOTTOM site,
   // clusters that only touch the top boundary by their smallest top site
   if ((long long)cb < d.nccap) atomicMin(m.topmin + cb, (uint32_t)s);
@@ -1190,8 +1185,8 @@ __global__ void k_mr_ids(Dev d, MrDev m) {
   if (s >= d.N) return;
   // bit 31 of entry 0 carries "an arena of this rank overflowed in this step": every rank learns it
   // with the boundary ids, before anything is flipped, so that all ranks rewind together
-  m.sendb[s] = d.parent[s] | ((s == 0 && *d.d_err) ? 0x80000000u : 0u);
-  m.sendb[d.N + s] = open_id(d, m, d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
+  m.sendb[s] = cid_pre(d, s) | ((s == 0 && *d.d_err) ? 0x80000000u : 0u);
+  m.sendb[d.N + s] = open_id(d, m, cid_pre(d, d.curW[(size_t)d.Wl * d.N + s]));
 }
 
 __global__ void k_mr_ginit(Dev d, MrDev m) {
@@ -1236,35 +1231,87 @@ __device__ __forceinline__ uint32_t global_cid(const Dev& d, const MrDev& m, uin
 
 // representative threads move the partial sums of their open cluster into the global table
 // (collect_estimates, parallel.h:415-427) and clear the local entry
-__global__ void k_mr_gather(Dev d, MrDev m) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= d.N) return;
+// sum of a 64-bit value over the lanes of `grp` (two's complement, mod 2^64): three 24-bit chunks
+// through the integer warp reduction
+__device__ __forceinline__ unsigned long long group_sum64(unsigned grp, unsigned long long v) {
+  const unsigned a = __reduce_add_sync(grp, (unsigned)(v & 0xffffffull));
+  const unsigned b = __reduce_add_sync(grp, (unsigned)((v >> 24) & 0xffffffull));
+  const unsigned c = __reduce_add_sync(grp, (unsigned)(v >> 48));
+  return (unsigned long long)a + ((unsigned long long)b << 24) + ((unsigned long long)c << 48);
+}
+
+// A global loop passes through a slab many times: its local pieces are different local clusters with
+// the SAME global id, and at low temperature one macroscopic loop owns ~1e5 of them per slab.  Their
+// representatives are first combined per warp (match.any on the global id + warp reduction), so one
+// atomic per warp, global cluster and field reaches the table instead of one per piece (the plain
+// version spent 1.1 ms serialised on the few addresses of that loop, profiles/r02_slabs.md).
+#define LQ_GATHER_SLOTS 64
+__global__ void __launch_bounds__(1024)
+k_mr_gather(Dev d, MrDev m) {
+  // second level: the warp leaders of a CTA meet in a small shared-memory table keyed by the global
+  // id (colliding keys go straight to the global table), flushed with one atomic per slot and field
+  __shared__ uint32_t s_key[LQ_GATHER_SLOTS];
+  __shared__ unsigned long long s_val[LQ_GATHER_SLOTS][LQ_GEST_MAX];
+  for (int i = threadIdx.x; i < LQ_GATHER_SLOTS * LQ_GEST_MAX; i += blockDim.x) {
+    if (i < LQ_GATHER_SLOTS) s_key[i] = 0xffffffffu;
+    (&s_val[0][0])[i] = 0ull;
+  }
+  __syncthreads();
+  const int s0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = s0 < d.N;
+  const int s = valid ? s0 : 0;
+  const unsigned lane = threadIdx.x & 31u;
   const uint32_t ncs = d.d_nc[1];
   uint32_t cl[2];
-  cl[0] = LQ_CID(d.parent[s]);   // (runs after k_pack_flips)
+  cl[0] = LQ_CID(d.parent[s]);   // (runs after k_relabel: labels = cluster id | flip << 31)
   cl[1] = LQ_CID(d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
+  unsigned nrep = 0;
   for (int k = 0; k < 2; ++k) {
     const uint32_t c = cl[k];
-    if (k == 1 && c == cl[0]) break;
-    if ((long long)c >= d.nccap || m.topmin[c] != (uint32_t)s) continue;  // not the representative
-    if (k == 1 && c < ncs) continue;  // bottom-touching clusters are handled through their bottom rep
-    const uint32_t gid = global_cid(d, m, open_id(d, m, c));
-    unsigned long long* ge = (unsigned long long*)m.gest + (size_t)gid * d.gstride;
-    for (int f = 0; f < 4; ++f) {
-      const long long v = (long long)atomicExch((unsigned long long*)d.est + f * d.nccap + c, 0ull);
-      if (v) atomicAdd(ge + f, (unsigned long long)v);
-    }
-    if (c < ncs)
-      for (int f = 0; f < 4; ++f) {
-        const int v = atomicExch(d.est0 + f * (size_t)d.N + c, 0);
-        if (v) atomicAdd(ge + 4 + f, (unsigned long long)(long long)v);
+    // representative of its local open cluster?  (bottom-touching clusters go through their bottom site)
+    const bool rep = valid && !(k == 1 && c == cl[0]) && (long long)c < d.nccap && m.topmin[c] == (uint32_t)s &&
+                     !(k == 1 && c < ncs);
+    uint32_t gid = 0xffffffffu;
+    unsigned long long v[LQ_GEST_MAX];
+#pragma unroll
+    for (int f = 0; f < LQ_GEST_MAX; ++f) v[f] = 0ull;
+    if (rep) {
+      gid = global_cid(d, m, open_id(d, m, c));
+#pragma unroll
+      for (int f = 0; f < 4; ++f) v[f] = atomicExch((unsigned long long*)d.est + f * d.nccap + c, 0ull);
+      if (c < ncs) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) v[4 + f] = (unsigned long long)(long long)atomicExch(d.est0 + f * (size_t)d.N + c, 0);
       }
-    if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) atomicAdd(ge + 8, 1ull);
-    for (int x = 0; x < d.sdim; ++x) {
-      const int v = atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
-      if (v) atomicAdd(ge + 8 + d.has_site + x, (unsigned long long)(long long)v);
+      if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[8] = 1ull;
+      for (int x = 0; x < d.sdim; ++x) v[8 + d.has_site + x] = (unsigned long long)(long long)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
+      ++nrep;
     }
-    atomicAdd(m.d_g + 1, 1u);
+    const unsigned grp = __match_any_sync(0xffffffffu, gid);
+    const bool leader = rep && lane == (unsigned)(__ffs(grp) - 1);
+    unsigned long long* ge = (unsigned long long*)m.gest + (size_t)(rep ? gid : 0u) * d.gstride;
+    int slot = -1;
+    if (leader) {
+      const int h = (int)((gid * 2654435761u) >> 26);   // 6 bits
+      const uint32_t old = atomicCAS(&s_key[h], 0xffffffffu, gid);
+      if (old == 0xffffffffu || old == gid) slot = h;
+    }
+    for (int f = 0; f < d.gstride; ++f) {
+      const unsigned long long t = group_sum64(grp, v[f]);
+      if (leader && t) {
+        if (slot >= 0) atomicAdd(&s_val[slot][f], t);
+        else atomicAdd(ge + f, t);
+      }
+    }
+  }
+  nrep = __reduce_add_sync(0xffffffffu, nrep);
+  if (lane == 0 && nrep) atomicAdd(m.d_g + 1, nrep);
+  __syncthreads();
+  for (int i = threadIdx.x; i < LQ_GATHER_SLOTS * d.gstride; i += blockDim.x) {
+    const int slot = i / d.gstride, f = i - slot * d.gstride;
+    const uint32_t gid = s_key[slot];
+    const unsigned long long t = s_val[slot][f];
+    if (gid != 0xffffffffu && t) atomicAdd((unsigned long long*)m.gest + (size_t)gid * d.gstride + f, t);
   }
 }
 
@@ -1274,8 +1321,8 @@ __global__ void k_mr_openflips(Dev d, MrDev m, const StepParams* __restrict__ sp
   if (s >= d.N) return;
   const uint32_t ncs = d.d_nc[1];
   uint32_t cl[2];
-  cl[0] = d.parent[s];
-  cl[1] = d.parent[d.curW[(size_t)d.Wl * d.N + s]];
+  cl[0] = cid_pre(d, s);   // (runs before k_relabel)
+  cl[1] = cid_pre(d, d.curW[(size_t)d.Wl * d.N + s]);
   for (int k = 0; k < 2; ++k) {
     const uint32_t c = cl[k];
     if (k == 1 && c == cl[0]) break;
@@ -1291,7 +1338,7 @@ __global__ void k_mr_openflips(Dev d, MrDev m, const StepParams* __restrict__ sp
 __global__ void k_mr_reset_topmin(Dev d, MrDev m) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= d.N) return;
-  const uint32_t cb = LQ_CID(d.parent[s]);   // (runs after k_pack_flips)
+  const uint32_t cb = LQ_CID(d.parent[s]);   // (runs after k_relabel)
   const uint32_t ct = LQ_CID(d.parent[d.curW[(size_t)d.Wl * d.N + s]]);
   if ((long long)cb < d.nccap) m.topmin[cb] = 0xffffffffu;
   if ((long long)ct < d.nccap) m.topmin[ct] = 0xffffffffu;
@@ -1336,12 +1383,13 @@ k_mr_gcollect(Dev d, MrDev m, double* partial) {
   }
 }
 
-__global__ void k_mr_gsum(MrDev m, const double* partial, int nblk) {
-  const int i = threadIdx.x;
-  if (i >= LQ_NSUM) return;
+__global__ void k_mr_gsum(MrDev m, const double* partial, int nblk) {   // LQ_NSUM warps: one sum each, fixed order
+  const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double x = 0;
-  for (int k = 0; k < nblk; ++k) x += partial[(size_t)k * LQ_NSUM + i];
-  m.gsum[i] = x;
+  for (int k = lane; k < nblk; k += 32) x += partial[(size_t)k * LQ_NSUM + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+  if (lane == 0) m.gsum[i] = x;
 }
 
 // The collectors of the closed clusters travel in the SAME all-reduce as the open-cluster sums: every
