@@ -308,6 +308,33 @@ __device__ __forceinline__ int2 block_exscan2(int2 v, int* total_x, int* total_y
   return res;
 }
 
+// One-barrier variant for kernels that scan several times per iteration (K1): every warp scans the
+// warp totals itself, and two shared-memory buffers alternate (`par`), so the buffer a call writes was
+// last read two calls -- hence at least one barrier -- ago.
+__device__ __forceinline__ int2 block_exscan2_1b(int2 v, int* total_x, int* total_y, int (*buf)[2][32], int& par) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int ix = v.x, iy = v.y;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int nx = __shfl_up_sync(0xffffffffu, ix, o), ny = __shfl_up_sync(0xffffffffu, iy, o);
+    if (lane >= o) { ix += nx; iy += ny; }
+  }
+  if (lane == 31) { buf[par][0][wid] = ix; buf[par][1][wid] = iy; }
+  __syncthreads();
+  const int wx = (lane < nw) ? buf[par][0][lane] : 0, wy = (lane < nw) ? buf[par][1][lane] : 0;
+  int sx = wx, sy = wy;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int nx = __shfl_up_sync(0xffffffffu, sx, o), ny = __shfl_up_sync(0xffffffffu, sy, o);
+    if (lane >= o) { sx += nx; sy += ny; }
+  }
+  const int bx = __shfl_sync(0xffffffffu, sx - wx, wid), by = __shfl_sync(0xffffffffu, sy - wy, wid);
+  *total_x = __shfl_sync(0xffffffffu, sx, 31);
+  *total_y = __shfl_sync(0xffffffffu, sy, 31);
+  par ^= 1;
+  return make_int2(bx + ix - v.x, by + iy - v.y);
+}
+
 // 64-bit integer <-> double without the (very slow on sm_100) I2F.F64.S64 / F2I.S64.F64 paths
 __device__ __forceinline__ double i64_to_f64(long long v) {
   return __int2double_rn((int)(v >> 32)) * 4294967296.0 + __uint2double_rn((unsigned)v);

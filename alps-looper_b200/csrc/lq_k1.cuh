@@ -193,7 +193,8 @@ template <int NT, int FC, bool TMA>
 __global__ void __launch_bounds__(NT, (NT <= 256 ? 3 : 2))
 k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ int s_scan[66];
+  __shared__ int s_scanb[2][2][32];   // block_exscan2_1b
+  int scan_par = 0;
   __shared__ int s_misc[4];                 // [0] error word at entry
   __shared__ __align__(8) uint64_t s_mbar;
   K1Smem S;
@@ -334,7 +335,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
     for (int j = j_lo + (int)lane; j < j_hi; j += 32) wcnt += (int)(pi[j] & LQ_INFO_OFFDIAG);
     wcnt = __reduce_add_sync(0xffffffffu, wcnt);
     int C, nkept;
-    int2 ex = block_exscan2(make_int2(ksum, lane == 0 ? wcnt : 0), &C, &nkept, s_scan);
+    int2 ex = block_exscan2_1b(make_int2(ksum, lane == 0 ? wcnt : 0), &C, &nkept, s_scanb, scan_par);
     // (every thread has left the previous window by now: its lists may be rewritten from here on)
     if (C > d.ccap || nkept > d.kcap) { bail(LQ_ERR_CAND_FULL); return; }
     for (int k = tid; k < nks; k += NT) S.kspin[k] = d.spinW[(size_t)wl * d.N + S.ksite[k]];
@@ -447,8 +448,8 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
       const uint32_t se = S.kse[lb];
       cnt += n + (int)(se >> 16) - (int)(se & 0xffffu);
     }
-    int total;
-    int run = block_exscan(cnt, &total, s_scan);
+    int total, unused;
+    int run = block_exscan2_1b(make_int2(cnt, 0), &total, &unused, s_scanb, scan_par).x;
     if (total > d.cap) { bail(LQ_ERR_PAGE_FULL); return; }
     if (tid == 0) { bo_new[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
 

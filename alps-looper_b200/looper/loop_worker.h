@@ -4,8 +4,12 @@
 // parameters), minus the ALPS base classes: Parameters / observable_set are the stand-ins of
 // parameters.h / measurement.h.
 #pragma once
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <fstream>
+#include <thread>
 #include <istream>
 #include <ostream>
 #include <stdexcept>
@@ -20,12 +24,27 @@
 
 namespace looper {
 
+// Stand-in for the boost::mpi::communicator the parallel worker receives (path_integral_mpi.C:75):
+// rank / size of the imaginary-time slabs, one process and one GPU per rank.  The ranks only have to
+// agree on 128 bytes once -- the NCCL unique id, created by rank 0 and passed through `id_file` (a
+// path all ranks can read; an MPI host would MPI_Bcast it instead); every collective of a step is
+// then issued by the engine itself (lq_comm_init, include/lq.h).
+struct communicator {
+  int rank_ = 0, size_ = 1;
+  std::string id_file;
+  int rank() const { return rank_; }
+  int size() const { return size_; }
+};
+
 class loop_worker {
 public:
   typedef double weight_parameter_type;
 
-  explicit loop_worker(const Parameters& p)
-      : lattice(p), model(p, lattice), temp(p), mcs(p) {
+  // parallel flavour (path_integral_mpi.C:75, PARAPACK_REGISTER_PARALLEL_ALGORITHM :1012)
+  loop_worker(const communicator& c, const Parameters& p) : loop_worker(p, c) {}
+
+  explicit loop_worker(const Parameters& p, const communicator& c = communicator())
+      : lattice(p), model(p, lattice), temp(p), mcs(p), comm_(c) {
     // ALGORITHM (loop.C:25-34; PARAPACK_REGISTER_ALGORITHM path_integral.C:873 "loop; path integral",
     // sse.C:411 "loop; sse"; plain "loop" is the path integral, loop.C).  Both workers sample the same
     // ensemble -- an SSE string is the time-ordered operator list of a world-line configuration -- and
@@ -59,14 +78,19 @@ public:
     M.uniform_site_weight = model.site_weight();
     lq_options o = lq_options();
     o.seed = p.value_or_default<unsigned long long>("WORKER_SEED", p.value_or_default<unsigned long long>("SEED", 29833ull));
-    o.device = p.value_or_default<int>("DEVICE", 0);
+    seed_ = o.seed;
+    o.device = p.value_or_default<int>("DEVICE", comm_.size() > 1 ? comm_.rank() : 0);
+    o.rank = comm_.rank();
+    o.nranks = comm_.size();
     o.tile_sites = p.value_or_default<int>("TILE_SITES", 0);
+    tile_sites_ = o.tile_sites;
     o.reserve = p.value_or_default<double>("RESERVE_OPERATORS_FACTOR", 0.0);  // cf. RESERVE_OPERATORS (:241)
     o.cluster_reserve = p.value_or_default<double>("RESERVE_ESTIMATES_FACTOR", 0.0);
     o.flags = p.defined("ENABLE_TIMER") ? 1 : 0;
     o.representation = sse_ ? LQ_REPR_SSE : LQ_REPR_PATH_INTEGRAL;
     beta_ = 1.0 / temp(0);
     check(lq_create(&h_, &L, &M, beta_, &o));
+    if (comm_.size() > 1) connect();
   }
   ~loop_worker() { lq_destroy(h_); }
   loop_worker(const loop_worker&) = delete;
@@ -136,7 +160,16 @@ public:
     std::vector<int32_t> spins;
     std::vector<lq_op> ops;
     save(m, spins, ops);
-    os.write("LQCKPT01", 8);
+    os.write("LQCKPT02", 8);
+    // what the chain depends on besides the configuration: seed, tiling (the Philox keys use the engine's
+    // internal numbering) and temperature -- validated on load, a resume with other settings would silently
+    // continue a different chain
+    lq_info info;
+    check(lq_get_info(h_, &info));
+    put(os, uint64_t(seed_));
+    put(os, int32_t(tile_sites_));
+    put(os, int32_t(info.num_tiles));
+    put(os, double(beta_));
     put(os, uint32_t(lq_get_step(h_)));    // the generator state: Philox step counter (include/lq.h)
     put(os, uint32_t(m));
     put(os, uint32_t(spins.size()));
@@ -149,7 +182,14 @@ public:
   void load(std::istream& is) {
     char tag[8];
     is.read(tag, 8);
-    if (!is || std::memcmp(tag, "LQCKPT01", 8) != 0) throw std::runtime_error("checkpoint: bad tag");
+    if (!is || std::memcmp(tag, "LQCKPT02", 8) != 0) throw std::runtime_error("checkpoint: bad tag");
+    lq_info info;
+    check(lq_get_info(h_, &info));
+    const uint64_t seed = get<uint64_t>(is);
+    const int32_t tile = get<int32_t>(is), ntiles = get<int32_t>(is);
+    const double beta = get<double>(is);
+    if (seed != seed_ || tile != tile_sites_ || ntiles != info.num_tiles)
+      throw std::runtime_error("checkpoint: seed or tiling differ from this run (the chain would not continue)");
     const uint32_t step = get<uint32_t>(is);
     const uint32_t m = get<uint32_t>(is), ns = get<uint32_t>(is);
     if (ns != uint32_t(num_sites(lattice.vg()))) throw std::runtime_error("checkpoint: lattice size differs");
@@ -159,6 +199,9 @@ public:
     std::vector<lq_op> ops(size_t((hi << 32) | lo));
     for (lq_op& o : ops) { o.type = get<int32_t>(is); o.loc = get<int32_t>(is); o.time = get<double>(is); }
     if (!is) throw std::runtime_error("checkpoint: truncated");
+    // the pages are sized for the temperature: go to the checkpoint's before the operators come in
+    // (a run that was annealing starts hot, with pages too small for a late configuration)
+    if (beta != beta_) { check(lq_set_beta(h_, beta)); beta_ = beta; }
     load(m, spins, ops);
     check(lq_set_step(h_, step));
   }
@@ -168,6 +211,26 @@ public:
   const lattice_helper& lat() const { return lattice; }
 
 private:
+  // NCCL rendezvous through a file: rank 0 writes the unique id (tmp + rename), the others wait for it
+  void connect() {
+    unsigned char id[LQ_NCCL_ID_BYTES];
+    if (comm_.id_file.empty()) throw std::invalid_argument("communicator without an id_file");
+    if (comm_.rank() == 0) {
+      check(lq_comm_unique_id(id));
+      const std::string tmp = comm_.id_file + ".tmp";
+      { std::ofstream f(tmp, std::ios::binary | std::ios::trunc); f.write(reinterpret_cast<const char*>(id), sizeof id); }
+      if (std::rename(tmp.c_str(), comm_.id_file.c_str()) != 0) throw std::runtime_error("cannot publish the NCCL id");
+    } else {
+      bool ok = false;
+      for (int tries = 0; tries < 1200 && !ok; ++tries) {   // up to two minutes
+        std::ifstream f(comm_.id_file, std::ios::binary);
+        if (f && f.read(reinterpret_cast<char*>(id), sizeof id) && f.gcount() == (std::streamsize)sizeof id) ok = true;
+        else std::this_thread::sleep_for(std::chrono::milliseconds(100));
+      }
+      if (!ok) throw std::runtime_error("timed out waiting for the NCCL id of rank 0");
+    }
+    check(lq_comm_init(h_, id, comm_.rank(), comm_.size()));
+  }
   template <class T> static void put(std::ostream& os, T v) { os.write(reinterpret_cast<const char*>(&v), sizeof v); }
   template <class T> static T get(std::istream& is) { T v = T(); is.read(reinterpret_cast<char*>(&v), sizeof v); return v; }
   static void check(int rc) {
@@ -180,6 +243,9 @@ private:
   bool enable_improved_estimator = true;
   bool measure_stiffness = false;
   bool sse_ = false;
+  communicator comm_;
+  unsigned long long seed_ = 0;
+  int tile_sites_ = 0;
   double beta_ = 1;
   lq_handle h_ = nullptr;
   lq_collector last_ = lq_collector();

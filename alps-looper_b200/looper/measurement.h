@@ -7,6 +7,8 @@
 // (csrc/lq_kernels.cuh k_estimate / k_collect); lq_collector carries the 14 collector sums.
 #pragma once
 #include <cmath>
+#include <cstdint>
+#include <istream>
 #include <map>
 #include <ostream>
 #include <string>
@@ -42,6 +44,34 @@ public:
     for (const level& L : lv_) if (L.n >= 32) e = std::max(e, err(L));
     return e > 0 ? e : naive_error();
   }
+  // checkpoint payload: the whole binning state (the ALPS scheduler dumps its ObservableSet with the worker)
+  void save(std::ostream& os) const {
+    const uint64_t nl = lv_.size();
+    os.write(reinterpret_cast<const char*>(&n_), sizeof n_);
+    os.write(reinterpret_cast<const char*>(&sum_), sizeof sum_);
+    os.write(reinterpret_cast<const char*>(&nl), sizeof nl);
+    for (const level& L : lv_) {
+      const double v[3] = {L.s, L.s2, L.pend};
+      const uint64_t m[2] = {L.n, L.have ? 1u : 0u};
+      os.write(reinterpret_cast<const char*>(v), sizeof v);
+      os.write(reinterpret_cast<const char*>(m), sizeof m);
+    }
+  }
+  void load(std::istream& is) {
+    uint64_t nl = 0;
+    is.read(reinterpret_cast<char*>(&n_), sizeof n_);
+    is.read(reinterpret_cast<char*>(&sum_), sizeof sum_);
+    is.read(reinterpret_cast<char*>(&nl), sizeof nl);
+    if (!is || nl > 64) { is.setstate(std::ios::failbit); return; }
+    lv_.assign(nl, level());
+    for (level& L : lv_) {
+      double v[3];
+      uint64_t m[2];
+      is.read(reinterpret_cast<char*>(v), sizeof v);
+      is.read(reinterpret_cast<char*>(m), sizeof m);
+      L.s = v[0]; L.s2 = v[1]; L.pend = v[2]; L.n = m[0]; L.have = m[1] != 0;
+    }
+  }
   double tau() const {  // integrated autocorrelation time estimate
     const double e0 = naive_error(), e = error();
     return e0 > 0 ? 0.5 * (power2(e / e0) - 1) : 0.0;
@@ -68,6 +98,28 @@ public:
   bool has(const std::string& name) const { return obs_.count(name) != 0; }
   const observable& at(const std::string& name) const { return obs_.at(name); }
   const std::vector<std::string>& names() const { return order_; }
+  void save(std::ostream& os) const {
+    const uint64_t n = order_.size();
+    os.write(reinterpret_cast<const char*>(&n), sizeof n);
+    for (const std::string& name : order_) {
+      const uint64_t len = name.size();
+      os.write(reinterpret_cast<const char*>(&len), sizeof len);
+      os.write(name.data(), std::streamsize(len));
+      obs_.at(name).save(os);
+    }
+  }
+  void load(std::istream& is) {
+    uint64_t n = 0;
+    is.read(reinterpret_cast<char*>(&n), sizeof n);
+    for (uint64_t k = 0; is && k < n && n < 4096; ++k) {
+      uint64_t len = 0;
+      is.read(reinterpret_cast<char*>(&len), sizeof len);
+      if (!is || len > 256) { is.setstate(std::ios::failbit); return; }
+      std::string name(size_t(len), ' ');
+      is.read(&name[0], std::streamsize(len));
+      (*this)[name].load(is);
+    }
+  }
   void print(std::ostream& os) const {
     for (const std::string& n : order_) {
       const observable& o = obs_.at(n);

@@ -94,7 +94,7 @@ def test_loop_driver_checkpoint_resume(tmp_path):
     first = subprocess.run([exe, "-l", "8", "-t", "0.2", "-n", "8192", "--checkpoint", ck], capture_output=True, text=True)
     assert first.returncode == 0, first.stderr
     assert os.path.getsize(ck) > 8 + 4 + 4 + 8 * 4 + 8
-    assert open(ck, "rb").read(8) == b"LQCKPT01"
+    assert open(ck, "rb").read(8) == b"LQCKPT02"
     second = subprocess.run([exe, "-l", "8", "-t", "0.2", "-n", "24576", "--checkpoint", ck], capture_output=True, text=True)
     assert second.returncode == 0, second.stderr
     assert "resumed at" in second.stdout
@@ -104,4 +104,31 @@ def test_loop_driver_checkpoint_resume(tmp_path):
     mean, err = float(m.group(1)), float(m.group(2))
     assert abs(mean + 0.441438) < 5 * err + 1e-6
     bad = subprocess.run([exe, "-l", "10", "-t", "0.2", "-n", "1024", "--checkpoint", ck], capture_output=True, text=True)
-    assert bad.returncode != 0 and "lattice size differs" in bad.stderr
+    assert bad.returncode != 0 and ("lattice size differs" in bad.stderr or "tiling differ" in bad.stderr)
+    # a finished run resumed again measures nothing more and says so instead of printing nan
+    third = subprocess.run([exe, "-l", "8", "-t", "0.2", "-n", "24576", "--checkpoint", ck], capture_output=True, text=True)
+    assert third.returncode == 0 and "nan" not in third.stdout
+    m3 = re.search(r"Energy Density\s*=\s*(\S+) \+- (\S+)", third.stdout)
+    assert m3 and float(m3.group(1)) == pytest.approx(mean, rel=1e-12)      # the observables travel with the checkpoint
+
+
+@pytest.mark.gpu
+def test_loop_driver_sse_algorithm(tmp_path):
+    """ALGORITHM = "loop; sse" (sse.C:411) through the host mirror: the SSE forms of the estimators
+    (susceptibility.h:213-215) against exact diagonalisation (chain L = 8, T = 0.2)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "alps-looper_b200/looper")])
+    exe = os.path.join(ROOT, "alps-looper_b200/looper/loop")
+    par = os.path.join(str(tmp_path), "sse.ip")
+    open(par, "w").write('ALGORITHM = "loop; sse"\nLATTICE = "chain lattice"\nL = 8\nT = 0.2\nSWEEPS = 32768\n')
+    out = subprocess.run([exe, par], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    vals = {}
+    for ln in out.stdout.splitlines():
+        m = re.match(r"(.+?)\s*=\s*(\S+) \+- (\S+)", ln)
+        if m:
+            vals[m.group(1).strip()] = (float(m.group(2)), float(m.group(3)))
+    for name, ex in (("Energy Density", -0.441438), ("Staggered Susceptibility", 2.40159), ("Staggered Magnetization^2", 6.59939)):
+        mean, err = vals[name]
+        assert abs(mean - ex) < 5 * err + 1e-9, (name, mean, ex, err)
+    bad = subprocess.run([exe, "-"], input='ALGORITHM = "loop; worm"\n', capture_output=True, text=True)
+    assert bad.returncode != 0 and "unknown ALGORITHM" in bad.stderr
