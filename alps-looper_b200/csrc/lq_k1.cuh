@@ -26,10 +26,9 @@
 //      table; graph by the model's weights (graph_impl.h:679).  Site-graph candidates
 //      (graph_impl.h:67-87) are always accepted.
 //   3  per bucket: new size = kept + accepted -> CTA prefix sum -> new bucket offsets
-//   4  per bucket: the (few) candidate times are sorted in place (rejected ones carry a time beyond
-//      the window and sink to the end), then merged with the bucket's slice of the kept list straight
-//      into the new page.  (Ranking every accepted candidate against its bucket in a flat loop cost
-//      a quarter of the kernel's instructions at 12 of 32 lanes -- profiles/r02_k1.md.)
+//   4  per accepted candidate / kept operator (flat): rank inside the new bucket = kept operators
+//      before it (the kept list is sorted) + accepted candidates before it (rejected ones carry a time
+//      beyond the window and never count) -> scatter into the compacted new page
 #pragma once
 #include "lq_device.cuh"
 
@@ -453,55 +452,58 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
     if (total > d.cap) { bail(LQ_ERR_PAGE_FULL); return; }
     if (tid == 0) { bo_new[nb] = (uint16_t)total; d.pcount[dst][p] = total; }
 
-    // ---- 4: per bucket, sort the candidates in place and merge them with the kept operators --------
-    double* wt = d.time[dst] + p * (size_t)d.cap;
-    uint32_t* wi = d.info[dst] + p * (size_t)d.cap;
     for (int q = 0; q < Q; ++q) {
       const int lb = tid * Q + q;
       if (lb >= nb) break;
-      bo_new[lb] = (uint16_t)run;
       const int K = (int)((kpack >> (6 * q)) & 63u), nacc = (int)((npack >> (6 * q)) & 63u);
-      const int c0 = S.cbase[lb];
-      // insertion sort (stable: equal times keep the order of the draws); rejected candidates (4.0) sink
-      for (int i = 1; i < K; ++i) {
-        const double x = S.ctime[c0 + i];
-        const uint16_t xm = S.cmeta[c0 + i];
-        int j = i - 1;
-        while (j >= 0 && S.ctime[c0 + j] > x) { S.ctime[c0 + j + 1] = S.ctime[c0 + j]; S.cmeta[c0 + j + 1] = S.cmeta[c0 + j]; --j; }
-        S.ctime[c0 + j + 1] = x;
-        S.cmeta[c0 + j + 1] = xm;
-      }
       const uint32_t se = S.kse[lb];
-      const int ks = (int)(se & 0xffffu), ke = (int)(se >> 16);
-      int i = ks, j = c0;
-      const int je = c0 + nacc;
+      (void)K;
+      S.noff[lb] = (uint16_t)run;
+      bo_new[lb] = (uint16_t)run;
+      run += nacc + (int)(se >> 16) - (int)(se & 0xffffu);
+    }
+    __syncthreads();
+
+    // ---- 4: rank inside the new bucket -> scatter into the compacted new page ----------------------
+    // flat, one element per thread, with three-instruction loop bodies: a rejected candidate carries
+    // the time 4.0 and never counts.  (A sort + merge per bucket thread ran at 10 of 32 lanes and took
+    // 29 % of the kernel's instructions, profiles/r02_k1.md.)
+    double* wt = d.time[dst] + p * (size_t)d.cap;
+    uint32_t* wi = d.info[dst] + p * (size_t)d.cap;
+    for (int c = tid; c < C; c += NT) {
+      const double tc = S.ctime[c];
+      if (tc > 3.0) continue;
+      const uint32_t mt = S.cmeta[c];
+      const int lb = (int)(mt & 0x3ff);
+      const int c0 = S.cbase[lb], c1 = S.cbase[lb + 1];
+      const uint32_t se = S.kse[lb];
+      int rank = 0;
+      for (int k = c0; k < c; ++k) rank += (int)(S.ctime[k] <= tc);        // equal times: the earlier draw first
+      for (int k = c + 1; k < c1; ++k) rank += (int)(S.ctime[k] < tc);
+      for (int i = (int)(se & 0xffffu); i < (int)(se >> 16); ++i) rank += (int)(S.ktime[i] <= tc);   // kept operators first on ties
+      const int pos = S.noff[lb] + rank;
+      wt[pos] = tc;
+      wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (((mt >> 11) & 3u) << LQ_INFO_GSHIFT) |
+                ((d.has_site && (S.bs2[lb] >> 16) == LQ_K1_NONE) ? LQ_INFO_SITE : 0u);
+    }
+    for (int i = tid; i < nkept; i += NT) {
+      const uint32_t kl = S.klb[i];
+      const int lb = (int)(kl & 0x3ff);
+      const double tt = S.ktime[i];
+      const int r0 = i - (int)(S.kse[lb] & 0xffffu);
+      int rank = r0;
+      const int c1 = S.cbase[lb + 1];
+      for (int k = S.cbase[lb]; k < c1; ++k) rank += (int)(S.ctime[k] < tt);
+      uint32_t g = 0;
       const int b = b0 + lb;
-      const uint32_t site_flag = (d.has_site && (S.bs2[lb] >> 16) == LQ_K1_NONE) ? LQ_INFO_SITE : 0u;
       const float q0 = d.bond_q[b];
-      double tk = i < ke ? S.ktime[i] : 8.0, tcn = j < je ? S.ctime[j] : 8.0;
-      while (i < ke || j < je) {
-        double tw;
-        uint32_t iw;
-        if (tk <= tcn) {   // kept operators come first on ties
-          uint32_t g = 0;
-          if (q0 < 1.0f) {  // graph_impl.h:324-327 choose_offdiagonal
-            const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)(i - ks), key0, key1);
-            g = (u24(x.x) < q0) ? 0u : 1u;
-          }
-          tw = tk;
-          iw = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG | ((S.klb[i] & 0x8000u) ? LQ_INFO_SITE : 0u);
-          ++i;
-          tk = i < ke ? S.ktime[i] : 8.0;
-        } else {
-          tw = tcn;
-          iw = ((uint32_t)lb << LQ_INFO_LBSHIFT) | ((((uint32_t)S.cmeta[j] >> 11) & 3u) << LQ_INFO_GSHIFT) | site_flag;
-          ++j;
-          tcn = j < je ? S.ctime[j] : 8.0;
-        }
-        wt[run] = tw;
-        wi[run] = iw;
-        ++run;
+      if (q0 < 1.0f) {  // graph_impl.h:324-327 choose_offdiagonal
+        const philox_t x = philox4x32_10((uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)r0, key0, key1);
+        g = (u24(x.x) < q0) ? 0u : 1u;
       }
+      const int pos = S.noff[lb] + rank;
+      wt[pos] = tt;
+      wi[pos] = ((uint32_t)lb << LQ_INFO_LBSHIFT) | (g << LQ_INFO_GSHIFT) | LQ_INFO_OFFDIAG | ((kl & 0x8000u) ? LQ_INFO_SITE : 0u);
     }
     // (no barrier here: the next window touches the columns -- cleared before the prefix sum above --
     // and its own registers only until its first prefix sum, whose barriers every thread reaches
