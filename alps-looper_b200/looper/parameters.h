@@ -8,6 +8,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace looper {
 
@@ -49,9 +50,15 @@ public:
       if (c != std::string::npos) line.erase(c);
       c = line.find("//");
       if (c != std::string::npos) line.erase(c);
-      std::istringstream ls(line);
-      std::string stmt;
-      while (std::getline(ls, stmt, ';')) {
+      // statements end at ';' -- outside quotes: ALGORITHM = "loop; sse" is one value (loop.op:334)
+      std::vector<std::string> stmts(1);
+      bool quoted = false;
+      for (char ch : line) {
+        if (ch == '"') quoted = !quoted;
+        if (ch == ';' && !quoted) stmts.emplace_back();
+        else stmts.back().push_back(ch);
+      }
+      for (const std::string& stmt : stmts) {
         auto eq = stmt.find('=');
         if (eq == std::string::npos) continue;
         std::string k = trim(stmt.substr(0, eq)), v = trim(stmt.substr(eq + 1));
