@@ -40,7 +40,7 @@ class LqOptions(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("device", C.c_int32), ("tile_sites", C.c_int32),
                 ("window_ops", C.c_double), ("reserve", C.c_double),
                 ("cluster_reserve", C.c_double), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("flags", C.c_int32), ("representation", C.c_int32)]
+                ("flags", C.c_int32), ("representation", C.c_int32), ("cut", C.c_int32)]
 
 
 class LqOp(C.Structure):
@@ -85,11 +85,13 @@ class LqInfo(C.Structure):
 
 ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 ALL_REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+SEND_RECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                           C.c_void_p)
 
 
 class LqComm(C.Structure):
     _fields_ = [("ctx", C.c_void_p), ("all_gather", ALL_GATHER_FN),
-                ("all_reduce_i64", ALL_REDUCE_FN)]
+                ("all_reduce_i64", ALL_REDUCE_FN), ("send_recv", SEND_RECV_FN)]
 
 
 # every symbol include/lq.h declares (tests/test_abi.py checks the header against this list)
@@ -234,7 +236,7 @@ class Engine:
     def __init__(self, lattice, beta, weights=(0.5, 0.0, 0.0, 0.0), energy_offset=None, seed=29833,
                  device=0, tile_sites=0, window_ops=0.0, reserve=0.0, cluster_reserve=0.0,
                  rank=0, nranks=1, timers=False, bond_weights=None, site_weight=0.0, site_weights=None,
-                 stiffness=False, sse=False):
+                 stiffness=False, sse=False, cut="time"):
         self.lattice = lattice
         self.N = int(lattice["num_sites"])
         self._src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
@@ -291,7 +293,8 @@ class Engine:
         self.energy_offset = mod.energy_offset
         opt = LqOptions(seed=seed, device=device, tile_sites=tile_sites, window_ops=window_ops,
                         reserve=reserve, cluster_reserve=cluster_reserve, rank=rank,
-                        nranks=nranks, flags=1 if timers else 0, representation=1 if sse else 0)
+                        nranks=nranks, flags=1 if timers else 0, representation=1 if sse else 0,
+                        cut={"time": 0, "space": 1}[cut])
         self.sse = bool(sse)
         self.beta = float(beta)
         self._h = _h()
@@ -393,11 +396,12 @@ class Engine:
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         _check(lib.lq_comm_init(self._h, buf, int(rank), int(nranks)))
 
-    def set_comm(self, all_gather, all_reduce_i64):
+    def set_comm(self, all_gather, all_reduce_i64, send_recv=None):
         ag = ALL_GATHER_FN(all_gather)
         ar = ALL_REDUCE_FN(all_reduce_i64)
-        comm = LqComm(ctx=None, all_gather=ag, all_reduce_i64=ar)
-        self._comm_keep = (ag, ar, comm)
+        sr = SEND_RECV_FN(send_recv) if send_recv is not None else SEND_RECV_FN()   # (NULL: imaginary-time slabs only)
+        comm = LqComm(ctx=None, all_gather=ag, all_reduce_i64=ar, send_recv=sr)
+        self._comm_keep = (ag, ar, sr, comm)
         _check(lib.lq_set_comm(self._h, C.byref(comm)))
 
 

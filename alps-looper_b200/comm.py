@@ -28,7 +28,7 @@ def device_tensor(ptr, nbytes, device):
     key = (int(ptr), int(nbytes), str(device))
     t = _tensor_cache.get(key)
     if t is None:
-        if len(_tensor_cache) > 64:
+        if len(_tensor_cache) > 4096:
             _tensor_cache.clear()
         t = torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
         _tensor_cache[key] = t
@@ -61,7 +61,23 @@ def attach_torch_distributed(engine, device, group=None):
             print("lq comm all_reduce failed:", e, flush=True)
             return 1
 
-    engine.set_comm(all_gather, all_reduce_i64)
+    def send_recv(ctx, send, sbytes, dst, recv, rbytes, src, strm):
+        try:
+            with torch.cuda.stream(stream):
+                ops = []
+                if sbytes:
+                    ops.append(dist.P2POp(dist.isend, device_tensor(send, sbytes, dev), dst, group))
+                if rbytes:
+                    ops.append(dist.P2POp(dist.irecv, device_tensor(recv, rbytes, dev), src, group))
+                if ops:
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+            return 0
+        except Exception as e:  # noqa: BLE001
+            print("lq comm send_recv failed:", e, flush=True)
+            return 1
+
+    engine.set_comm(all_gather, all_reduce_i64, send_recv)
 
 
 def attach_nccl(engine, rank, nranks, group=None):
@@ -83,6 +99,7 @@ class LoopbackGroup:
         self.dev = torch.device("cuda", device)
         self.barrier = threading.Barrier(nranks)
         self.slots = [None] * nranks
+        self.p2p = {}
         self.lock = threading.Lock()
 
     def attach(self, engine, rank):
@@ -124,7 +141,25 @@ class LoopbackGroup:
                 print("loopback all_reduce failed:", e, flush=True)
                 return 1
 
-        engine.set_comm(all_gather, all_reduce_i64)
+        def send_recv(ctx, send, sbytes, dst, recv, rbytes, src, strm):
+            # (spatial cut: halo pages and ghost spins; every rank makes the same sequence of calls)
+            try:
+                stream.synchronize()
+                self.p2p[(rank, dst)] = (send, sbytes)
+                self.barrier.wait()
+                ptr, nbytes = self.p2p[(src, rank)]
+                assert nbytes == rbytes, (rank, src, nbytes, rbytes)
+                if rbytes:
+                    with torch.cuda.stream(stream):
+                        device_tensor(recv, rbytes, self.dev).copy_(device_tensor(ptr, rbytes, self.dev))
+                stream.synchronize()
+                self.barrier.wait()
+                return 0
+            except Exception as e:  # noqa: BLE001
+                print("loopback send_recv failed:", repr(e), flush=True)
+                return 1
+
+        engine.set_comm(all_gather, all_reduce_i64, send_recv)
 
     def run(self, fn):
         """fn(rank) in one thread per rank; returns the list of results (re-raises errors)."""

@@ -15,6 +15,7 @@ namespace lq {
 
 typedef uint32_t node_t;
 static const node_t NODE_NONE = 0xffffffffu;
+static const node_t NODE_JUNK = 0xfffffffeu;   // spatial cut: ghost node nobody on this rank refers to (no cluster of its own)
 
 // info word of an operator (mirrors looper/operator.h type_ in the low bits)
 //   bit 0      offdiagonal            (local_operator_type::offdiagonal, operator.h:44)
@@ -33,6 +34,7 @@ static const node_t NODE_NONE = 0xffffffffu;
 #define LQ_ERR_NODE_FULL 4
 #define LQ_ERR_CLUSTER_FULL 8
 #define LQ_ERR_REMOTE 16   /* slab engines: another rank overflowed in this step (all ranks rewind together) */
+#define LQ_ERR_BOUNDARY 32 /* spatial cut: the two copies of a boundary page disagree (internal error) */
 
 // fixed-point scale of imaginary time in the cluster sums (order-independent integer atomics)
 #define LQ_FX 1099511627776.0 /* 2^40 */
@@ -59,6 +61,14 @@ struct Dev {
                     // without a site node have umag == 0 identically
   int zero_ssize;   // every bond joins sites of opposite gauge (and no site graphs): their ssize == 0 identically
   int rank, nranks;
+  // spatial cut (lq_space.cuh): the sites / pages this rank OWNS come first, then the ghost copies.
+  // Serial and slab engines: Nown = Nwalk = N, Pown = all pages, space = 0.
+  int space;        // LQ_CUT_SPACE engine
+  int Nown;         // owned sites [0, Nown)
+  int Nwalk;        // sites whose world lines are walked here [0, Nwalk): owned + W ghost tiles
+  int Pown;         // owned pages [0, Pown)
+  const uint32_t* bond_key;   // spatial cut: rank-independent id of a bond for the Philox counters (the internal
+                              // numbering differs from rank to rank); NULL: the internal bond id itself
   const int* bond_s0;    // [B] source site
   const int* bond_s1;    // [B] target site
   const int* bond_tl;    // [B] owning tile << 10 | local bond index

@@ -6,6 +6,7 @@
 // device and fails with LQ_E_CUDA otherwise.
 #include "../../include/lq.h"
 #include "lq_kernels.cuh"
+#include "lq_space.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: libnccl.so.2 is bound at run time (dlopen), so the
@@ -84,7 +85,10 @@ struct Partition {
 
 // src/dst: end sites of the B internal "bonds"; dst < 0 marks the pseudo-bond that carries the site
 // operators of src (graph_impl.h:67-87): it has one end only.
-void make_partition(const lq_lattice& L, int B, const int* Lsrc, const int* Ldst, int tile_sites, Partition& P) {
+// tile_relabel (spatial cut): a permutation of the tile ids -- every engine numbers its own tiles first,
+// then its ghost tiles, so that the pages it holds are the first ones (see SpacePlan below)
+void make_partition(const lq_lattice& L, int B, const int* Lsrc, const int* Ldst, int tile_sites, Partition& P,
+                    const std::vector<int>* tile_relabel = nullptr) {
   const int N = L.num_sites;
   P.N = N;
   P.B = B;
@@ -117,6 +121,19 @@ void make_partition(const lq_lattice& L, int B, const int* Lsrc, const int* Ldst
     T = (N + S - 1) / S;
     for (int s = 0; s < N; ++s) tile_of[s] = s / S;
   }
+  // drop empty tiles (ragged shapes) by compacting tile ids in ascending order
+  {
+    std::vector<int> tmap(T, 0);
+    for (int s = 0; s < N; ++s) tmap[tile_of[s]] = 1;
+    int Tc = 0;
+    for (int t = 0; t < T; ++t) tmap[t] = tmap[t] ? Tc++ : -1;
+    for (int s = 0; s < N; ++s) tile_of[s] = tmap[tile_of[s]];
+    P.T = T = Tc;
+  }
+  if (tile_relabel) {
+    if ((int)tile_relabel->size() != T) fail(LQ_E_INVALID, "tile relabelling of the wrong size (internal error)");
+    for (int s = 0; s < N; ++s) tile_of[s] = (*tile_relabel)[tile_of[s]];
+  }
   // sites
   P.site_i2e.resize(N);
   std::iota(P.site_i2e.begin(), P.site_i2e.end(), 0);
@@ -124,15 +141,6 @@ void make_partition(const lq_lattice& L, int B, const int* Lsrc, const int* Ldst
                    [&](int a, int b) { return tile_of[a] < tile_of[b]; });
   P.site_e2i.resize(N);
   for (int i = 0; i < N; ++i) P.site_e2i[P.site_i2e[i]] = i;
-  // drop empty tiles (ragged shapes) by compacting tile ids
-  std::vector<int> tmap(T, -1);
-  int Tc = 0;
-  for (int i = 0; i < N; ++i) {
-    int t = tile_of[P.site_i2e[i]];
-    if (tmap[t] < 0) tmap[t] = Tc++;
-  }
-  for (int s = 0; s < N; ++s) tile_of[s] = tmap[tile_of[s]];
-  P.T = T = Tc;
   // bonds
   P.bond_i2e.resize(B);
   std::iota(P.bond_i2e.begin(), P.bond_i2e.end(), 0);
@@ -248,6 +256,115 @@ void make_partition(const lq_lattice& L, int B, const int* Lsrc, const int* Ldst
   P.nclasses = (int)classes.size();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spatial cut (lq_options.cut = LQ_CUT_SPACE): rank q owns the contiguous range of tiles
+// [T q / P, T (q+1) / P) of the GLOBAL tiling G (the same on every rank) over the whole imaginary-time
+// axis -- the bond ownership of looper/lattice.h:692-787 taken across GPUs.  It also holds ghost
+// copies of the foreign tiles its kernels read:
+//   W tiles  hold the far-end sites of its owned bonds; their world lines are walked here too, so
+//            that every leg of an OWNED operator gets its lower node locally (no reverse exchange),
+//   H tiles  own the foreign bonds that touch one of its K-sites (halo buckets of K1 and of the walk)
+//            or a site of a W tile from outside (walk halo of the W tiles).
+// Every engine renumbers the tiles [owned | W | H | rest], so that the pages it holds are the first
+// ones and the kernels run unchanged on a prefix of the tiles.
+// Clusters that cross a cut are merged through BOUNDARY SEGMENTS: for every ordered pair
+// (owner q, user r) the sites of q that are far-end K-sites of r and the bonds of q that touch a
+// K-site of r, in a canonical order both sides agree on.  The user holds exact copies of the pages of
+// those bonds, so entry i of the segment is the same physical node on both sides.
+// ---------------------------------------------------------------------------------------------
+struct SpaceSeg {
+  int owner = 0, user = 0;
+  std::vector<int> sites, bonds;   // EXTERNAL site ids / internal-bond order key -> stored as external ids
+  long long off_owner = 0, off_user = 0, cap = 0, opcap = 0;   // (sized with beta, size_space())
+};
+struct SpaceRun { int peer, tile0, ntiles, walked; };   // tile0 in THIS rank's numbering
+struct SpacePlan {
+  int nranks = 1, rank = 0;
+  int To = 0, Tw = 0, Tloc = 0;
+  std::vector<int> relabel;                      // global tile -> this rank's tile id
+  std::vector<std::vector<SpaceRun>> send_runs, recv_runs;   // [delta]: to (rank+delta)%P / from (rank-delta+P)%P
+  std::vector<int> rounds;                       // [delta] messages every rank issues in that round (0: skipped)
+  std::vector<SpaceSeg> segs;                    // all segments of the run, canonical order
+};
+
+// external ids of the two ends of an internal bond b of partition G: pseudo-bonds (site graphs) are
+// identified by Breal + site
+void plan_space(const Partition& G, int nranks, int rank, SpacePlan& S) {
+  const int T = G.T, P = nranks;
+  if (T < P) fail(LQ_E_INVALID, "spatial cut: fewer tiles than ranks (lower lq_options.tile_sites)");
+  S.nranks = P; S.rank = rank;
+  auto owner = [&](int t) { return (int)(((long long)t * P) / T); };
+  std::vector<int> site_tile(G.N);
+  for (int t = 0; t < T; ++t)
+    for (int s = G.site_base[t]; s < G.site_base[t + 1]; ++s) site_tile[s] = t;
+  // per rank: far-end sites F, halo bonds HB, tile sets
+  std::vector<std::vector<int>> F(P), HB(P), local(P);
+  std::vector<std::vector<int>> relabel(P, std::vector<int>(T, -1));
+  std::vector<std::vector<char>> is_w(P, std::vector<char>(T, 0));
+  std::vector<int> nown(P, 0), nw(P, 0), nloc(P, 0);
+  for (int q = 0; q < P; ++q) {
+    std::vector<char> in_w(T, 0), in_h(T, 0);
+    for (int t = 0; t < T; ++t) {
+      if (owner(t) != q) continue;
+      for (int k = G.hsite_off[t]; k < G.hsite_off[t + 1]; ++k)
+        if (owner(site_tile[G.hsite[k]]) != q) F[q].push_back(G.hsite[k]);
+      for (int k = G.halo_off[t]; k < G.halo_off[t + 1]; ++k)
+        if (owner(G.bond_tile[G.halo_bond[k]]) != q) HB[q].push_back(G.halo_bond[k]);
+    }
+    for (auto* v : {&F[q], &HB[q]}) { std::sort(v->begin(), v->end()); v->erase(std::unique(v->begin(), v->end()), v->end()); }
+    for (int s : F[q]) in_w[site_tile[s]] = 1;
+    for (int b : HB[q]) in_h[G.bond_tile[b]] = 1;
+    for (int t = 0; t < T; ++t)   // walk halo of the W tiles: the leading whalo_cnt halo buckets
+      if (in_w[t])
+        for (int k = 0; k < G.whalo_cnt[t]; ++k) {
+          const int t2 = G.bond_tile[G.halo_bond[G.halo_off[t] + k]];
+          if (owner(t2) != q) in_h[t2] = 1;
+        }
+    int next = 0;
+    for (int t = 0; t < T; ++t) if (owner(t) == q) relabel[q][t] = next++;
+    nown[q] = next;
+    if (next == 0) fail(LQ_E_INVALID, "spatial cut: a rank owns no tile");
+    for (int t = 0; t < T; ++t) if (owner(t) != q && in_w[t]) { relabel[q][t] = next++; is_w[q][t] = 1; }
+    nw[q] = next - nown[q];
+    for (int t = 0; t < T; ++t) if (owner(t) != q && !in_w[t] && in_h[t]) relabel[q][t] = next++;
+    nloc[q] = next;
+    for (int t = 0; t < T; ++t) if (relabel[q][t] < 0) relabel[q][t] = next++;
+  }
+  S.To = nown[rank]; S.Tw = nw[rank]; S.Tloc = nloc[rank];
+  S.relabel = relabel[rank];
+  // page runs between owner q and holder r: maximal stretches that are contiguous on both sides
+  auto runs_of = [&](int q, int r, bool for_owner) {
+    std::vector<SpaceRun> out;
+    int pq = -2, pr = -2, pw = -1;
+    for (int t = 0; t < T; ++t) {
+      if (owner(t) != q || relabel[r][t] >= nloc[r]) continue;
+      const int a = relabel[q][t], b = relabel[r][t], w = is_w[r][t];
+      if (!out.empty() && a == pq + 1 && b == pr + 1 && w == pw) out.back().ntiles++;
+      else out.push_back({for_owner ? r : q, for_owner ? a : b, 1, w});
+      pq = a; pr = b; pw = w;
+    }
+    return out;
+  };
+  S.send_runs.assign(P, {}); S.recv_runs.assign(P, {}); S.rounds.assign(P, 0);
+  for (int dl = 1; dl < P; ++dl) {
+    for (int q = 0; q < P; ++q) S.rounds[dl] = std::max(S.rounds[dl], (int)runs_of(q, (q + dl) % P, true).size());
+    S.send_runs[dl] = runs_of(rank, (rank + dl) % P, true);
+    S.recv_runs[dl] = runs_of((rank - dl + P) % P, rank, false);
+  }
+  // boundary segments, canonical order (owner, user); ids leave as EXTERNAL site ids / external bond ids
+  // (pseudo-bond of site s: Breal + s, the convention of Partition::bond_i2e)
+  S.segs.clear();
+  for (int q = 0; q < P; ++q)
+    for (int r = 0; r < P; ++r) {
+      if (q == r) continue;
+      SpaceSeg g;
+      g.owner = q; g.user = r;
+      for (int s : F[r]) if (owner(site_tile[s]) == q) g.sites.push_back(G.site_i2e[s]);
+      for (int b : HB[r]) if (owner(G.bond_tile[b]) == q) g.bonds.push_back(G.bond_i2e[b]);
+      if (!g.sites.empty() || !g.bonds.empty()) S.segs.push_back(std::move(g));
+    }
+}
+
 inline int window_of(double t, int W) {
   int w = (int)(t * W);
   if (w >= W) w = W - 1;
@@ -267,6 +384,10 @@ struct NcclApi {
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   decltype(&ncclGetVersion) GetVersion = nullptr;
 };
@@ -281,7 +402,7 @@ NcclApi& nccl_api() {
 #define LQ_SYM(f) api.f = (decltype(api.f))dlsym(lib, "nccl" #f); \
   if (!api.f) fail(LQ_E_COMM, "libnccl lacks nccl" #f)
   LQ_SYM(GetUniqueId); LQ_SYM(CommInitRank); LQ_SYM(CommDestroy); LQ_SYM(AllGather); LQ_SYM(AllReduce);
-  LQ_SYM(GetErrorString); LQ_SYM(GetVersion);
+  LQ_SYM(GetErrorString); LQ_SYM(GetVersion); LQ_SYM(Send); LQ_SYM(Recv); LQ_SYM(GroupStart); LQ_SYM(GroupEnd);
 #undef LQ_SYM
   api.lib = lib;
   return api;
@@ -291,7 +412,7 @@ void nccl_check(ncclResult_t r, const char* what) {
 }
 
 const char* kTimerLabels[17] = {"", "", "", "dispatch", "init", "fill_times(K1 rng)", "init_fragments",
-                                "insert/remove+reconnect", "", "close in tau", "boundary estimates", "assign ids",
+                                "insert/remove+reconnect", "halo exchange (spatial cut)", "close in tau", "boundary estimates", "assign ids",
                                 "accumulate", "collect", "flip decision", "flip", "measurement"};
 
 }  // namespace
@@ -311,6 +432,22 @@ struct lq_engine {
   // path_integral.C:240-243 RESERVE_*): multipliers on reserve / candidate slots / cluster_reserve
   double grow_pages = 1, grow_cand = 1, grow_clusters = 1;
   int64_t regrows = 0;
+  // spatial cut (LQ_CUT_SPACE): tiles / sites / pages this engine holds; serial and slab engines hold everything
+  bool space = false;
+  SpacePlan plan;
+  int Tl = 0, To = 0, Tw = 0;       // local tiles (owned + ghosts), owned, walked ghost tiles
+  int Ns = 0, Nown = 0, Nwalk = 0;  // local sites, owned, walked
+  size_t Pown = 0;                  // owned pages
+  lq::SpDev spd{};
+  std::vector<lq::SpSeg> sp_segs_h;        // this rank's segments (host copy; offsets follow beta)
+  std::vector<int> sp_seg_index;           // their indices in plan.segs
+  DBuf<lq::SpSeg> sp_seg;
+  DBuf<lq::SpGSeg> sp_gseg;
+  DBuf<int> sp_site, sp_sseg, sp_bond, sp_bseg;
+  DBuf<uint32_t> sp_cnt, sp_base, sp_bnode;
+  DBuf<uint8_t> sp_spin_send, sp_spin_recv;
+  DBuf<uint32_t> sp_bond_key;
+  long long sp_maxcap = 0;
   int gstride() const { return 8 + (has_site ? 1 : 0) + sdim; }
   int sdim = 0;                      // dimensions of the winding estimator (0 = off)
   std::vector<short> bond_vec_e;     // [3 * external bond] components in units of wunit[x]
@@ -437,6 +574,8 @@ struct lq_engine {
       fail(LQ_E_INVALID, "unknown lq_options.representation");
     sse = opt.representation == LQ_REPR_SSE;
     if (sse && opt.nranks > 1) fail(LQ_E_UNSUPPORTED, "the SSE representation runs on a serial engine (string positions are global)");
+    if (opt.cut != LQ_CUT_TIME && opt.cut != LQ_CUT_SPACE) fail(LQ_E_INVALID, "unknown lq_options.cut");
+    space = opt.cut == LQ_CUT_SPACE && opt.nranks > 1;
     beta = beta_;
     energy_offset = M.energy_offset;
     weights.resize(4 * (size_t)L.num_bonds);
@@ -507,7 +646,20 @@ struct lq_engine {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     graphs_off = getenv("LQ_NO_GRAPH") != nullptr;
 
-    make_partition(L, (int)xsrc.size(), xsrc.data(), xdst.data(), opt.tile_sites, part);
+    if (space) {
+      // the global tiling (the same on every rank) decides who owns what; this engine then numbers
+      // its own tiles first and its ghost tiles behind them
+      Partition G;
+      make_partition(L, (int)xsrc.size(), xsrc.data(), xdst.data(), opt.tile_sites, G);
+      plan_space(G, opt.nranks, opt.rank, plan);
+      make_partition(L, (int)xsrc.size(), xsrc.data(), xdst.data(), opt.tile_sites, part, &plan.relabel);
+      Tl = plan.Tloc; To = plan.To; Tw = plan.Tw;
+      Ns = part.site_base[Tl]; Nown = part.site_base[To]; Nwalk = part.site_base[To + Tw];
+    } else {
+      make_partition(L, (int)xsrc.size(), xsrc.data(), xdst.data(), opt.tile_sites, part);
+      Tl = To = part.T; Tw = 0;
+      Ns = Nown = Nwalk = part.N;
+    }
     if (part.nbmax + 1 > 1024)
       fail(LQ_E_INVALID, "tile owns more than 1023 bonds: lower lq_options.tile_sites");
     if (part.hmax > 1024)
@@ -578,6 +730,38 @@ struct lq_engine {
     bs.upload(part.bs, &device_bytes);
     sst_off.upload(part.sst_off, &device_bytes);
     sst.upload(part.sst, &device_bytes);
+    if (space) {
+      // boundary segments this rank takes part in: site / bond entries in the rank's own numbering
+      std::vector<int> hs, hss, hb, hbs;
+      for (size_t k = 0; k < plan.segs.size(); ++k) {
+        const SpaceSeg& g = plan.segs[k];
+        if (g.owner != opt.rank && g.user != opt.rank) continue;
+        lq::SpSeg x{};
+        x.ns = (int)g.sites.size(); x.nb = (int)g.bonds.size();
+        x.site0 = (int)hs.size(); x.bond0 = (int)hb.size();
+        x.user_side = g.user == opt.rank ? 1 : 0;
+        for (int se : g.sites) { hs.push_back(part.site_e2i[se]); hss.push_back((int)sp_segs_h.size()); }
+        for (int be : g.bonds) { hb.push_back(part.bond_e2i[be]); hbs.push_back((int)sp_segs_h.size()); }
+        for (size_t i = (size_t)x.site0; i < hs.size(); ++i)
+          if (hs[i] >= Ns) fail(LQ_E_INVALID, "spatial cut: boundary site outside the local tiles (internal error)");
+        for (size_t i = (size_t)x.bond0; i < hb.size(); ++i)
+          if (part.bond_tile[hb[i]] >= Tl) fail(LQ_E_INVALID, "spatial cut: boundary bond outside the local tiles (internal error)");
+        sp_segs_h.push_back(x);
+        sp_seg_index.push_back((int)k);
+      }
+      if (hs.empty()) hs.push_back(0), hss.push_back(0);
+      if (hb.empty()) hb.push_back(0), hbs.push_back(0);
+      spd.nseg = (int)sp_segs_h.size();
+      spd.nst = 0; spd.nbt = 0;
+      for (const auto& x : sp_segs_h) { spd.nst += x.ns; spd.nbt += x.nb; }
+      sp_site.upload(hs, &device_bytes); sp_sseg.upload(hss, &device_bytes);
+      sp_bond.upload(hb, &device_bytes); sp_bseg.upload(hbs, &device_bytes);
+      // Philox counters of K1: the bond id every rank agrees on (two ranks must not draw the same
+      // stream for their bonds number 0, 1, ...)
+      std::vector<uint32_t> key(part.B);
+      for (int i = 0; i < part.B; ++i) key[i] = (uint32_t)part.bond_i2e[i];
+      sp_bond_key.upload(key, &device_bytes);
+    }
     d_ntotal.alloc(1, &device_bytes);
     d_err.alloc(1, &device_bytes);
     d_nc.alloc(2, &device_bytes);
@@ -605,9 +789,12 @@ struct lq_engine {
     }
     W = (int)std::ceil(beta * maxrate / opt.window_ops);
     if (W < 1) W = 1;
-    W = ((W + opt.nranks - 1) / opt.nranks) * opt.nranks;
-    Wl = W / opt.nranks;
-    w0 = opt.rank * Wl;
+    if (space) { Wl = W; w0 = 0; }   // every rank holds the whole imaginary-time axis of its tiles
+    else {
+      W = ((W + opt.nranks - 1) / opt.nranks) * opt.nranks;
+      Wl = W / opt.nranks;
+      w0 = opt.rank * Wl;
+    }
     double mu = 0;
     for (int t = 0; t < T; ++t) mu = std::max(mu, tile_rate[t] * beta / W);
     {
@@ -701,11 +888,12 @@ struct lq_engine {
       walk_fn = pick_walk();
       CK(cudaFuncSetAttribute(walk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     }
-    P = (size_t)T * Wl;
+    P = (size_t)Tl * Wl;
+    Pown = (size_t)To * Wl;
     ncap = (long long)P * cap;
-    const long long nodes_cap = (long long)N + (long long)npo * ncap;
+    const long long nodes_cap = (long long)Ns + (long long)npo * ncap;
     if (nodes_cap >= 0x7ffffff0ll) fail(LQ_E_INVALID, "more than 2^31 graph nodes on one GPU: lower lq_options.reserve or split the run over more GPUs");
-    nccap = std::min<long long>(nodes_cap, (long long)N + (long long)std::ceil(std::min(1.0, opt.cluster_reserve * grow_clusters) * (double)(npo * ncap)));
+    nccap = std::min<long long>(nodes_cap, (long long)Ns + (long long)std::ceil(std::min(1.0, opt.cluster_reserve * grow_clusters) * (double)(npo * ncap)));
     nwords_cap = (size_t)((nodes_cap + 31) / 32);
 
     size_t* tb = &device_bytes;
@@ -716,9 +904,9 @@ struct lq_engine {
       pcount[k].alloc(P, tb);
     }
     nbase.alloc(P + 1, tb);
-    spinW.alloc((size_t)(Wl + 1) * N, tb);
-    curW.alloc((size_t)(Wl + 1) * N, tb);
-    firstW.alloc((size_t)Wl * N, tb);
+    spinW.alloc((size_t)(Wl + 1) * Ns, tb);
+    curW.alloc((size_t)(Wl + 1) * Ns, tb);
+    firstW.alloc((size_t)Wl * Ns, tb);
     parent.alloc((size_t)nodes_cap, tb);
     low0.alloc((size_t)ncap, tb);
     low1.alloc((size_t)ncap, tb);
@@ -727,7 +915,7 @@ struct lq_engine {
     wbase.alloc(nwords_cap + 1, tb);
     rootw.alloc(opt.nranks == 1 ? nwords_cap + 1 : 1, tb);
     {
-      const size_t ngroups = (size_t)T * ((Wl + ug - 1) / ug);
+      const size_t ngroups = (size_t)To * ((Wl + ug - 1) / ug);
       xedge.alloc(ngroups * LQ_XCAP, tb);
       xcount.alloc(ngroups, tb);
     }
@@ -741,10 +929,12 @@ struct lq_engine {
       sse_id.alloc((size_t)ncap, tb);
       sse_bincnt.alloc(nb + 1, tb); sse_binbase.alloc(nb + 2, tb); sse_binfill.alloc(nb + 1, tb);
     }
-    const size_t scan_n = std::max(std::max(nwords_cap, P), sse ? (size_t)Wl * nbin : (size_t)0) + 1;
+    if (space) size_space();
+    const size_t scan_n = std::max(std::max(std::max(nwords_cap, P), sse ? (size_t)Wl * nbin : (size_t)0),
+                                   space ? std::max((size_t)spd.nbt * Wl + 2, (size_t)(opt.nranks * spd.stride) / 32 + 2) : (size_t)0) + 1;
     scan_tmp.alloc((scan_n + LQ_SCAN_CHUNK - 1) / LQ_SCAN_CHUNK + 1, tb);
     est.alloc(4 * (size_t)nccap, tb);
-    est0.alloc(4 * (size_t)N, tb);
+    est0.alloc(4 * (size_t)Ns, tb);
     flipw.alloc((size_t)nccap / 32 + 2, tb);
     wind.alloc(sdim > 0 ? (size_t)sdim * (size_t)nccap : 1, tb);
     CK(cudaMemset(wind.p, 0, wind.n * sizeof(int)));
@@ -753,14 +943,18 @@ struct lq_engine {
     nblk_collect = std::min<size_t>(((size_t)nccap + 255) / 256, (size_t)sm_count * 8);
     partial.alloc(nblk_collect * LQ_NSUM, tb);
     if (opt.nranks > 1) {
-      const size_t g2 = (size_t)opt.nranks * 2 * N, gw = (g2 + 31) / 32 + 1;
+      // gathered boundary forest: slabs 2N nodes per rank (bottom + top of every world line); spatial
+      // cut `stride` words per rank (header + the entries of its boundary segments)
+      const size_t per_rank = space ? (size_t)spd.stride : 2 * (size_t)N;
+      const size_t g2 = (size_t)opt.nranks * per_rank, gw = (g2 + 31) / 32 + 1;
       mr_topmin.alloc((size_t)nccap, tb);
-      mr_sendb.alloc(2 * (size_t)N, tb);
+      mr_sendb.alloc(per_rank, tb);
       mr_recvb.alloc(g2, tb);
       mr_gparent.alloc(g2, tb);
       mr_gused.alloc(g2, tb);
       mr_gbitmap.alloc(gw, tb); mr_gwcount.alloc(gw, tb); mr_gwbase.alloc(gw + 1, tb);
-      mr_gest.alloc(g2 * (size_t)gstride() + 32 * (size_t)opt.nranks, tb);   // + the collectors' slots (k_mr_rankvec)
+      // (spatial cut: every global open cluster has at least two entries, one per side of a cut)
+      mr_gest.alloc((space ? g2 / 2 + 1 : g2) * (size_t)gstride() + 32 * (size_t)opt.nranks, tb);   // + the collectors' slots (k_mr_rankvec)
       mr_dg.alloc(4, tb);
       mr_rankvec.alloc(32, tb); mr_allvec.alloc(32 * (size_t)opt.nranks, tb); mr_gsum.alloc(16, tb);
       CK(cudaMemset(mr_topmin.p, 0xff, mr_topmin.n * sizeof(uint32_t)));
@@ -771,6 +965,25 @@ struct lq_engine {
       mr.gused = mr_gused.p; mr.gbitmap = mr_gbitmap.p; mr.gwcount = mr_gwcount.p; mr.gwbase = mr_gwbase.p;
       mr.gest = mr_gest.p; mr.d_g = mr_dg.p; mr.rankvec = mr_rankvec.p; mr.allvec = mr_allvec.p;
       mr.gsum = mr_gsum.p;
+      mr.gn = g2;
+      mr.gbase = space ? (size_t)opt.rank * per_rank + LQ_SP_HDR : (size_t)opt.rank * per_rank;
+      if (space) {
+        sp_cnt.alloc((size_t)spd.nbt * Wl + 2, tb);
+        sp_base.alloc((size_t)spd.nbt * Wl + 3, tb);
+        sp_bnode.alloc((size_t)std::max<long long>(spd.cbmax, 1), tb);
+        CK(cudaMemset(sp_cnt.p, 0, sp_cnt.n * sizeof(uint32_t)));
+        spd.cnt = sp_cnt.p; spd.base = sp_base.p; spd.bnode = sp_bnode.p;
+        spd.site = sp_site.p; spd.sseg = sp_sseg.p; spd.bond = sp_bond.p; spd.bseg = sp_bseg.p;
+        spd.seg = sp_seg.p; spd.gseg = sp_gseg.p;
+        // staging of the ghost spins: (Wl + 1) rows per exchanged run of tiles
+        size_t ssend = 0, srecv = 0;
+        for (int dl = 1; dl < opt.nranks; ++dl) {
+          for (const auto& r : plan.send_runs[dl]) if (r.walked) ssend += (size_t)(part.site_base[r.tile0 + r.ntiles] - part.site_base[r.tile0]);
+          for (const auto& r : plan.recv_runs[dl]) if (r.walked) srecv += (size_t)(part.site_base[r.tile0 + r.ntiles] - part.site_base[r.tile0]);
+        }
+        sp_spin_send.alloc(std::max<size_t>(1, ssend * (size_t)(Wl + 1)), tb);
+        sp_spin_recv.alloc(std::max<size_t>(1, srecv * (size_t)(Wl + 1)), tb);
+      }
     }
     CK(cudaMemset(est.p, 0, est.n * sizeof(long long)));
     CK(cudaMemset(est0.p, 0, est0.n * sizeof(int)));
@@ -779,8 +992,44 @@ struct lq_engine {
     fill_dev();
   }
 
+  // boundary segments of the spatial cut: capacities follow beta (like the pages), offsets follow the
+  // capacities; every rank computes the layout of ALL ranks' buffers (the merge is redundant)
+  void size_space() {
+    std::vector<long long> fill(opt.nranks, 0);
+    std::vector<lq::SpGSeg> gs;
+    sp_maxcap = 0;
+    for (auto& g : plan.segs) {
+      double rate = 0;
+      for (int be : g.bonds) { const double* v = &weights[4 * (size_t)be]; rate += v[0] + v[1] + v[2] + v[3]; }
+      const double m = opt.reserve * grow_pages * beta * rate;
+      g.opcap = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
+      g.cap = (long long)g.sites.size() + (long long)npo * g.opcap;
+      g.off_owner = fill[g.owner]; fill[g.owner] += g.cap;
+      g.off_user = fill[g.user]; fill[g.user] += g.cap;
+      gs.push_back({g.owner, g.user, g.off_owner, g.off_user, g.cap});
+      sp_maxcap = std::max(sp_maxcap, g.cap);
+    }
+    spd.cb = fill[opt.rank];
+    spd.cbmax = *std::max_element(fill.begin(), fill.end());
+    spd.stride = LQ_SP_HDR + spd.cbmax;
+    if ((long long)opt.nranks * spd.stride >= 0x7ffffff0ll) fail(LQ_E_INVALID, "spatial cut: boundary too large");
+    spd.ngseg = (int)gs.size();
+    if (gs.empty()) gs.push_back({0, 0, 0, 0, 0});
+    for (size_t i = 0; i < sp_segs_h.size(); ++i) {
+      const SpaceSeg& g = plan.segs[sp_seg_index[i]];
+      sp_segs_h[i].off = sp_segs_h[i].user_side ? g.off_user : g.off_owner;
+      sp_segs_h[i].opcap = g.opcap;
+    }
+    std::vector<lq::SpSeg> hseg = sp_segs_h;
+    if (hseg.empty()) hseg.push_back(lq::SpSeg{});
+    sp_seg.upload(hseg, nullptr);
+    sp_gseg.upload(gs, nullptr);
+  }
+
   void fill_dev() {
-    d.N = part.N; d.B = part.B; d.T = part.T; d.nbmax = part.nbmax;
+    d.N = Ns; d.B = part.B; d.T = Tl; d.nbmax = part.nbmax;
+    d.bond_key = space ? sp_bond_key.p : nullptr;
+    d.space = space ? 1 : 0; d.Nown = Nown; d.Nwalk = Nwalk; d.Pown = (int)Pown;
     d.W = W; d.w0 = w0; d.Wl = Wl; d.cap = cap; d.npo = npo; d.ug = ug; d.has_site = has_site ? 1 : 0;
     d.zero_umag = zero_umag ? 1 : 0; d.zero_ssize = zero_ssize ? 1 : 0;
     d.rank = opt.rank; d.nranks = opt.nranks;
@@ -861,8 +1110,9 @@ struct lq_engine {
   static unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
   // K2 + K3 on the live buffer (+ K4/K5 sums); used by the step and by lq_build_clusters
-  void label_clusters(double* out_slot, const lq::StepParams* sp, bool flip) {
-    const int N = part.N;
+  void label_clusters(double* out_slot, const lq::StepParams* sp_in, bool flip) {
+    const lq::StepParams* sp = sp_in;   // (`sp` the member is the spatial-cut table)
+    const int N = Ns;
     const size_t nodes_cap = (size_t)N + (size_t)npo * (size_t)ncap;
     {
       Section s(this, 6);
@@ -879,20 +1129,31 @@ struct lq_engine {
         lq::k_sse_rank<<<grid_for((size_t)ncap, 256), 256, 0, stream>>>(d);
         launches += 3;
       }
+      if (space) {
+        // ghost nodes: junk unless they sit in a boundary segment; the segments' entries in (bond, window, slot) order
+        const size_t nghost = (size_t)npo * (size_t)(P - Pown) * (size_t)cap;
+        const size_t ncnt = (size_t)spd.nbt * Wl;
+        if (nghost) lq::k_sp_init_ghost<<<grid_for(nghost, 256), 256, 0, stream>>>(d);
+        if (ncnt) lq::k_sp_count<<<grid_for(ncnt, 256), 256, 0, stream>>>(d, spd, cur);
+        scan_u32(sp_cnt.p, sp_base.p, ncnt + 1, nullptr, nullptr);
+        CK(cudaMemsetAsync(sp_bnode.p, 0xff, sp_bnode.n * sizeof(uint32_t), stream));
+        lq::k_sp_fill<<<grid_for(std::max<size_t>(std::max(ncnt, (size_t)spd.nst), 1), 256), 256, 0, stream>>>(d, spd, cur);
+        launches += 3;
+      }
     }
     {
       Section s(this, 7);
-      walk_fn<<<(unsigned)P, tpb_walk, walk_smem, stream>>>(d, cur);
-      lq::k_carry_scan<<<grid_for(N, 128), 128, 0, stream>>>(d);   // closes the chain of windows per site
+      walk_fn<<<(unsigned)((size_t)(To + Tw) * Wl), tpb_walk, walk_smem, stream>>>(d, cur);
+      lq::k_carry_scan<<<grid_for(Nwalk, 128), 128, 0, stream>>>(d);   // closes the chain of windows per site
       launches += 1;
-      const unsigned ngroups = (unsigned)((size_t)part.T * ((Wl + ug - 1) / ug));
+      const unsigned ngroups = (unsigned)((size_t)To * ((Wl + ug - 1) / ug));
       lq::k_union_local<<<ngroups, 256, (size_t)ug * npo * cap * sizeof(uint32_t), stream>>>(d, cur);
       lq::k_union_global<<<ngroups, 256, 0, stream>>>(d, cur);
       launches += 3;
     }
     {
-      Section s(this, 9);
-      if (opt.nranks == 1) { lq::k_close<<<grid_for(N, 128), 128, 0, stream>>>(d); launches += 1; }
+      Section s(this, 9);   // (slab engines: the top boundary is merged by the exchange instead)
+      if (opt.nranks == 1 || space) { lq::k_close<<<grid_for(Nown, 128), 128, 0, stream>>>(d); launches += 1; }
     }
     {
       Section s(this, 11);
@@ -906,12 +1167,13 @@ struct lq_engine {
       launches += 1;
     }
     if (opt.nranks > 1) {
-      // slab engines: exchange first (on roots), flips of ALL clusters, then the relabelling packs them
+      // multi-rank engines: exchange first (on roots), flips of ALL clusters, then the relabelling packs them
       lq::k_set_ncs<<<1, 1, 0, stream>>>(d);
       merge_open_clusters();
       Section s(this, 14);
       lq::k_flipbits<<<(unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
-      lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
+      if (space) lq::k_sp_openflips<<<grid_for(std::max<size_t>((size_t)spd.cb, 1), 256), 256, 0, stream>>>(d, spd, mr, sp);
+      else lq::k_mr_openflips<<<grid_for(N, 128), 128, 0, stream>>>(d, mr, sp);
       lq::k_relabel<<<grid_for(nodes_cap, 256 * LQ_NPT), 256, 0, stream>>>(d);
       launches += 4;
     }
@@ -924,14 +1186,19 @@ struct lq_engine {
           lq::k_estimate<false, false, false>, lq::k_estimate<false, false, true>, lq::k_estimate<false, true, false>,
           lq::k_estimate<false, true, true>,   lq::k_estimate<true, false, false>, lq::k_estimate<true, false, true>,
           lq::k_estimate<true, true, false>,   lq::k_estimate<true, true, true>};
-      est_fns[(flip ? 4 : 0) | (sdim > 0 ? 2 : 0) | (npo == 2 ? 1 : 0)]<<<(unsigned)P, 256, est_smem, stream>>>(d, cur);
+      est_fns[(flip ? 4 : 0) | (sdim > 0 ? 2 : 0) | (npo == 2 ? 1 : 0)]<<<(unsigned)Pown, 256, est_smem, stream>>>(d, cur);
       launches += 1;
     }
     {
       Section s(this, 10);   // world-line ends at the slab boundaries; open-cluster sums into the exchange table
-      lq::k_estimate_sites<<<grid_for(N, 128), 128, 0, stream>>>(d);
+      lq::k_estimate_sites<<<grid_for(Nown, 128), 128, 0, stream>>>(d);
       launches += 1;
-      if (opt.nranks > 1) {
+      if (space) {
+        const size_t cb = std::max<size_t>((size_t)spd.cb, 1);
+        lq::k_sp_gather<<<grid_for(cb, 1024), 1024, 0, stream>>>(d, spd, mr);
+        lq::k_sp_reset<<<grid_for(cb, 256), 256, 0, stream>>>(d, spd, mr);
+        launches += 2;
+      } else if (opt.nranks > 1) {
         lq::k_mr_gather<<<grid_for(N, 1024), 1024, 0, stream>>>(d, mr);
         lq::k_mr_reset_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
         launches += 2;
@@ -963,6 +1230,21 @@ struct lq_engine {
 
   void merge_open_clusters() {
     Section s(this, 13);
+    if (space) {
+      const size_t cb = std::max<size_t>((size_t)spd.cb, 1), g2 = mr.gn;
+      lq::k_sp_topmin<<<grid_for(cb, 256), 256, 0, stream>>>(d, spd, mr);
+      lq::k_sp_ids<<<grid_for(std::max<size_t>((size_t)spd.cbmax, LQ_SP_HDR), 256), 256, 0, stream>>>(d, spd, mr);
+      launches += 2;
+      all_gather(mr.sendb, mr.recvb, (size_t)spd.stride * sizeof(uint32_t), "all_gather(boundary entries)");
+      CK(cudaMemsetAsync(mr.d_g, 0, 4 * sizeof(uint32_t), stream));
+      lq::k_sp_ginit<<<grid_for(g2, 256), 256, 0, stream>>>(d, spd, mr);
+      if (spd.ngseg > 0 && sp_maxcap > 0)
+        lq::k_sp_gunion<<<dim3(grid_for((size_t)sp_maxcap, 256), (unsigned)spd.ngseg), 256, 0, stream>>>(d, spd, mr);
+      lq::k_mr_gcompress<<<grid_for(((g2 + 31) / 32) * 32, 256), 256, 0, stream>>>(d, mr);
+      launches += 3;
+      scan_u32(mr.gwcount, mr.gwbase, (g2 + 31) / 32, mr.gwbase + (g2 + 31) / 32, (int*)mr.d_g);
+      return;
+    }
     const int N = part.N;
     const size_t g2 = (size_t)opt.nranks * 2 * N;
     lq::k_mr_topmin<<<grid_for(N, 128), 128, 0, stream>>>(d, mr);
@@ -975,6 +1257,70 @@ struct lq_engine {
     lq::k_mr_gcompress<<<grid_for(((g2 + 31) / 32) * 32, 256), 256, 0, stream>>>(d, mr);
     launches += 3;
     scan_u32(mr.gwcount, mr.gwbase, (g2 + 31) / 32, mr.gwbase + (g2 + 31) / 32, (int*)mr.d_g);
+  }
+
+  // ---- spatial cut: ghost pages and ghost spins (SpacePlan) ----------------------------------------
+  // `full`: whole pages (times, info words, bucket offsets, counts) -- after K1 has written new pages;
+  // else only the info words -- before K1, which has to see the operator flips of the previous step
+  // on its halo buckets -- and, with `spins`, the spins of the walked ghost sites.
+  struct XMsg { const void* s; size_t sb; void* r; size_t rb; };
+  void xchg_round(int dl, const std::vector<XMsg>& msgs) {
+    const int Pn = opt.nranks, dst = (opt.rank + dl) % Pn, src = (opt.rank - dl + Pn) % Pn;
+    if (nccl) {
+      NcclApi& a = nccl_api();
+      nccl_check(a.GroupStart(), "ncclGroupStart");
+      for (const XMsg& m : msgs) {
+        if (m.sb) nccl_check(a.Send(m.s, m.sb, ncclChar, dst, nccl, stream), "ncclSend(ghost pages)");
+        if (m.rb) nccl_check(a.Recv(m.r, m.rb, ncclChar, src, nccl, stream), "ncclRecv(ghost pages)");
+      }
+      nccl_check(a.GroupEnd(), "ncclGroupEnd");
+    } else {
+      if (!comm.send_recv) fail(LQ_E_COMM, "the spatial cut needs lq_comm.send_recv (or lq_comm_init)");
+      for (const XMsg& m : msgs)
+        comm_check(comm.send_recv(comm.ctx, m.s, (int64_t)m.sb, dst, m.r, (int64_t)m.rb, src, stream), "send_recv(ghost pages)");
+    }
+  }
+  void exchange_ghosts(int buf, bool full, bool spins) {
+    Section s(this, 8);
+    size_t so = 0, ro = 0;
+    std::vector<XMsg> msgs;
+    struct Unpack { size_t off, len; int site0; };
+    std::vector<Unpack> unpack;
+    const size_t nb1 = (size_t)part.nbmax + 1;
+    for (int dl = 1; dl < opt.nranks; ++dl) {
+      if (!plan.rounds[dl]) continue;
+      msgs.clear();
+      unpack.clear();
+      const auto& sr = plan.send_runs[dl];
+      const auto& rr = plan.recv_runs[dl];
+      for (int k = 0; k < plan.rounds[dl]; ++k) {
+        const SpaceRun* a = k < (int)sr.size() ? &sr[k] : nullptr;
+        const SpaceRun* b = k < (int)rr.size() ? &rr[k] : nullptr;
+        const size_t pa = a ? (size_t)a->ntiles * Wl : 0, pb = b ? (size_t)b->ntiles * Wl : 0;
+        const size_t a0 = a ? (size_t)a->tile0 * Wl : 0, b0 = b ? (size_t)b->tile0 * Wl : 0;
+        msgs.push_back({info[buf].p + a0 * cap, pa * cap * sizeof(uint32_t), info[buf].p + b0 * cap, pb * cap * sizeof(uint32_t)});
+        if (full) {
+          msgs.push_back({time_[buf].p + a0 * cap, pa * cap * sizeof(double), time_[buf].p + b0 * cap, pb * cap * sizeof(double)});
+          msgs.push_back({boff[buf].p + a0 * nb1, pa * nb1 * sizeof(uint16_t), boff[buf].p + b0 * nb1, pb * nb1 * sizeof(uint16_t)});
+          msgs.push_back({pcount[buf].p + a0, pa * sizeof(int), pcount[buf].p + b0, pb * sizeof(int)});
+        }
+        if (spins) {
+          const size_t la = (a && a->walked) ? (size_t)(part.site_base[a->tile0 + a->ntiles] - part.site_base[a->tile0]) : 0;
+          const size_t lb = (b && b->walked) ? (size_t)(part.site_base[b->tile0 + b->ntiles] - part.site_base[b->tile0]) : 0;
+          const size_t rows = (size_t)Wl + 1;
+          if (la) CK(cudaMemcpy2DAsync(sp_spin_send.p + so, la, spinW.p + part.site_base[a->tile0], (size_t)Ns, la, rows,
+                                       cudaMemcpyDeviceToDevice, stream));
+          msgs.push_back({sp_spin_send.p + so, la * rows, sp_spin_recv.p + ro, lb * rows});
+          if (lb) unpack.push_back({ro, lb, part.site_base[b->tile0]});
+          so += la * rows;
+          ro += lb * rows;
+        }
+      }
+      xchg_round(dl, msgs);
+      for (const Unpack& u : unpack)
+        CK(cudaMemcpy2DAsync(spinW.p + u.site0, (size_t)Ns, sp_spin_recv.p + u.off, u.len, u.len, (size_t)Wl + 1,
+                             cudaMemcpyDeviceToDevice, stream));
+    }
   }
 
   void finish_open_clusters(double* out_slot, const lq::StepParams* sp) {
@@ -1024,17 +1370,19 @@ struct lq_engine {
   }
 
   void enqueue_step(double* out_slot, const lq::StepParams* sp) {
+    if (space) exchange_ghosts(cur, false, true);   // the flips of the previous step: types of the ghost operators, ghost spins
     {
       Section s(this, 5);
       const unsigned nch = (unsigned)((Wl + k1_chunk - 1) / k1_chunk);
-      k1_fn<<<(unsigned)part.T * nch, k1_nt, stage_smem, stream>>>(d, cur, sp, k1_chunk);
+      k1_fn<<<(unsigned)To * nch, k1_nt, stage_smem, stream>>>(d, cur, sp, k1_chunk);
       launches += 1;
       cur ^= 1;
     }
+    if (space) exchange_ghosts(cur, true, false);   // the new pages of the ghost tiles
     label_clusters(out_slot, sp, true);   // includes the flip of the operators (fused into K4)
     {
       Section s(this, 15);
-      lq::k_flip_spins<<<grid_for((size_t)(Wl + 1) * part.N, 256), 256, 0, stream>>>(d);
+      lq::k_flip_spins<<<grid_for((size_t)(Wl + 1) * Ns, 256), 256, 0, stream>>>(d);
       launches += 1;
     }
     ++mcs;
@@ -1119,7 +1467,8 @@ struct lq_engine {
     if (err & LQ_ERR_PAGE_FULL) m += " page full (raise lq_options.reserve);";
     if (err & LQ_ERR_CAND_FULL) m += " too many candidates in one page or bucket (lower window_ops);";
     if (err & LQ_ERR_CLUSTER_FULL) m += " cluster arena full (raise cluster_reserve);";
-    if (err & LQ_ERR_NODE_FULL) m += " node arena full;";
+    if (err & LQ_ERR_NODE_FULL) m += " node arena / boundary segment full;";
+    if (err & LQ_ERR_BOUNDARY) m += " the two copies of a boundary page disagree (internal error);";
     fail(LQ_E_OVERFLOW, m);
   }
 
@@ -1158,11 +1507,13 @@ struct lq_engine {
     if (!err) return;
     // (slab engines: every rank sees the OR of all ranks' error bits in the collector and has kept the
     // configuration of the failing step -- LQ_ERR_REMOTE, k_mr_ids -- so all ranks rewind together)
-    if (depth >= 8) check_err(err);
+    // (a boundary mismatch next to an overflow is a consequence of the lost step, alone it is a bug)
+    if (depth >= 8 || ((err & LQ_ERR_BOUNDARY) && !(err & (LQ_ERR_PAGE_FULL | LQ_ERR_CAND_FULL | LQ_ERR_NODE_FULL | LQ_ERR_CLUSTER_FULL))))
+      check_err(err);
     CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
     cur = cur0 ^ (first_bad & 1);
     mcs = mcs0 + (uint32_t)first_bad;
-    if (err & LQ_ERR_PAGE_FULL) grow_pages *= 1.5;
+    if (err & (LQ_ERR_PAGE_FULL | LQ_ERR_NODE_FULL)) grow_pages *= 1.5;   // (boundary segments are sized like the pages)
     if (err & LQ_ERR_CAND_FULL) { grow_cand *= 1.5; grow_kept *= 1.6; }
     if (err & LQ_ERR_CLUSTER_FULL) grow_clusters *= 1.5;
     ++regrows;
@@ -1173,11 +1524,19 @@ struct lq_engine {
   // operators and spins of this engine (of its slab, on a slab engine) through new arenas: after a
   // change of beta or of an arena size
   void rebucket() {
+    // (spatial cut: all ranks come here together -- lq_set_beta is collective, and an overflow makes
+    // every rank rewind.  The ghost pages still carry the operator types of before the last flip:
+    // refresh them, then move owned AND ghost operators, so that the spins at the new window
+    // boundaries can be recomputed for every site this rank reads.)
+    if (space) {
+      if (!has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
+      exchange_ghosts(cur, false, true);
+    }
     int64_t n = 0;
-    get_state(nullptr, nullptr, &n);
+    get_state(nullptr, nullptr, &n, true);
     std::vector<int32_t> spins(part.N);
     std::vector<lq_op> ops((size_t)n);
-    get_state(spins.data(), ops.data(), &n);
+    get_state(spins.data(), ops.data(), &n, true);
     size_arenas();
     clear_state();
     set_state(spins.data(), ops.data(), n, opt.nranks > 1);
@@ -1202,6 +1561,7 @@ struct lq_engine {
       const int w = window_of(o.time, W);
       if (w < w0 || w >= w0 + Wl) return false;
       const int tl = part.bond_tile[bi];
+      if (tl >= Tl) return false;   // spatial cut: a tile this rank neither owns nor mirrors
       *lbo = bi - part.bond_base[tl];
       *pg = (size_t)tl * Wl + (w - w0);
       *info = ((uint32_t)*lbo << LQ_INFO_LBSHIFT) | ((uint32_t)((o.type >> 2) & 3) << LQ_INFO_GSHIFT) |
@@ -1250,16 +1610,18 @@ struct lq_engine {
       for (int lb = part.nbmax; lb > 0; --lb) hb[p * nb1 + lb] = hb[p * nb1 + lb - 1];
       hb[p * nb1] = 0;
     }
-    std::vector<uint8_t> sw((size_t)(Wl + 1) * N);
+    // (spatial cut: the device rows hold the Ns local sites, which come first in the numbering; the
+    // spins of the sites beyond the walked ones are never read)
+    std::vector<uint8_t> sw((size_t)(Wl + 1) * Ns);
     {
       std::vector<uint8_t> c(N);
       for (int i = 0; i < N; ++i) c[i] = (uint8_t)(spins[part.site_i2e[i]] & 1);
       for (int w = 0; w <= W; ++w) {
         for (int i = 0; i < N; ++i) c[i] ^= par[(size_t)w * N + i];
         if (w >= w0 && w <= w0 + Wl)
-          std::memcpy(&sw[(size_t)(w - w0) * N], c.data(), N);
+          std::memcpy(&sw[(size_t)(w - w0) * Ns], c.data(), Ns);
       }
-      for (int i = 0; i < N && !local; ++i)
+      for (int i = 0; i < (space ? Nown : N) && !local; ++i)
         if (c[i] != (uint8_t)(spins[part.site_i2e[i]] & 1))
           fail(LQ_E_INVALID, "operator string is not periodic in imaginary time");
     }
@@ -1275,8 +1637,10 @@ struct lq_engine {
   struct HostOp { double time; int bi; uint32_t info; int idx; };
 
   // all local operators sorted by (time, internal bond); idx = dense device index
-  void fetch_ops(std::vector<HostOp>& out) {
+  // (spatial cut: the owned pages only, unless `with_ghosts`; idx counts the pages that are listed)
+  void fetch_ops(std::vector<HostOp>& out, bool with_ghosts = false) {
     CK(cudaStreamSynchronize(stream));
+    const size_t P = with_ghosts ? this->P : Pown;
     std::vector<int> hc(P);
     CK(cudaMemcpy(hc.data(), pcount[cur].p, P * sizeof(int), cudaMemcpyDeviceToHost));
     out.clear();
@@ -1308,9 +1672,11 @@ struct lq_engine {
     });
   }
 
-  void get_state(int32_t* spins, lq_op* ops, int64_t* n) {
+  // (spatial cut: the operators this rank owns and the spins of its own sites, -1 elsewhere; with
+  // `with_ghosts` also the ghost copies and the spins of the walked ghost sites -- rebucket())
+  void get_state(int32_t* spins, lq_op* ops, int64_t* n, bool with_ghosts = false) {
     std::vector<HostOp> v;
-    fetch_ops(v);
+    fetch_ops(v, with_ghosts);
     if (n) *n = (int64_t)v.size();
     if (ops)
       for (size_t k = 0; k < v.size(); ++k) {
@@ -1320,9 +1686,10 @@ struct lq_engine {
         ops[k].type = (int32_t)(v[k].info & 0xf) & ~2;  // offdiag bit + graph bits
       }
     if (spins) {
-      std::vector<uint8_t> sw(part.N);
-      CK(cudaMemcpy(sw.data(), spinW.p, part.N, cudaMemcpyDeviceToHost));
-      for (int i = 0; i < part.N; ++i) spins[part.site_i2e[i]] = sw[i];
+      std::vector<uint8_t> sw(Ns);
+      CK(cudaMemcpy(sw.data(), spinW.p, Ns, cudaMemcpyDeviceToHost));
+      const int nvalid = with_ghosts ? Nwalk : Nown;
+      for (int i = 0; i < part.N; ++i) spins[part.site_i2e[i]] = i < nvalid ? (int32_t)sw[i] : -1;
     }
   }
 
@@ -1331,6 +1698,7 @@ struct lq_engine {
     if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
     ensure_out(1);
     stage_params(1, false);
+    if (space) exchange_ghosts(cur, false, true);
     label_clusters(d_out.p, d_params.p, false);
     labels.alloc(2 * (size_t)std::max<long long>(ncap, 1), nullptr);
     lq::k_export_labels<<<(unsigned)P, 256, 0, stream>>>(d, cur, labels.p);

@@ -196,7 +196,7 @@ k_scan_final(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t
 // ------------------------------------------------------------------------------------------
 __global__ void k_init_nodes(Dev d) {  // site nodes; operator nodes are written by k_union_local
   const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (x < (size_t)d.N) d.parent[x] = (node_t)x;
+  if (x < (size_t)d.N) d.parent[x] = (x < (size_t)d.Nown) ? (node_t)x : NODE_JUNK;   // (ghost sites: lq_space.cuh)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -212,7 +212,7 @@ __global__ void k_init_nodes(Dev d) {  // site nodes; operator nodes are written
 // last operator of every bucket of every site and window before the walk: 3.3 ms and 12 GB.)
 __global__ void k_carry_scan(Dev d) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= d.N) return;
+  if (s >= d.Nwalk) return;
   node_t cur = (node_t)s;
   d.curW[s] = cur;
   for (int wl = 0; wl < d.Wl; ++wl) {
@@ -509,7 +509,7 @@ k_union_global(Dev d, int buf) {
 // with several slabs the top boundary is merged by the exchange step instead.
 __global__ void k_close(Dev d) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= d.N) return;
+  if (s >= d.Nown) return;
   uf_union(d.parent, (node_t)s, d.curW[(size_t)d.Wl * d.N + s]);
 }
 
@@ -527,11 +527,13 @@ k_compress(Dev d, size_t nwords_cap) {
   // all unions are done: plain (L1-allocating) loads are safe here and neighbouring nodes mostly
   // chase to the same few roots
   node_t r[LQ_NPT], pr[LQ_NPT];
+  unsigned junk = 0;
 #pragma unroll
   for (int k = 0; k < LQ_NPT; ++k) {
     const size_t x = base + (size_t)k * 256;
     r[k] = (node_t)x;
     pr[k] = (x < nn) ? d.parent[x] : (node_t)x;
+    if (pr[k] == NODE_JUNK) { pr[k] = (node_t)x; junk |= 1u << k; }   // spatial cut: unreferenced ghost node
   }
   bool any = true;
   unsigned hops = 0;
@@ -550,7 +552,7 @@ k_compress(Dev d, size_t nwords_cap) {
     bool isroot = false;
     if (x < nn) {
       if (r[k] != (node_t)x) d.parent[x] = r[k];
-      isroot = (r[k] == (node_t)x);
+      isroot = (r[k] == (node_t)x) && !((junk >> k) & 1u);
     }
     const uint32_t word = __ballot_sync(0xffffffffu, isroot);
     if ((threadIdx.x & 31) == 0) {   // words beyond the live nodes are cleared: the scan input stays clean
@@ -612,7 +614,10 @@ k_relabel(Dev d) {
   } else {
     uint32_t wb[LQ_NPT], bm[LQ_NPT];
 #pragma unroll
-    for (int k = 0; k < LQ_NPT; ++k) { wb[k] = d.wbase[r[k] >> 5]; bm[k] = d.bitmap[r[k] >> 5]; }
+    for (int k = 0; k < LQ_NPT; ++k) {
+      if (r[k] == NODE_JUNK) r[k] = 0u;   // (its label is never read)
+      wb[k] = d.wbase[r[k] >> 5]; bm[k] = d.bitmap[r[k] >> 5];
+    }
 #pragma unroll
     for (int k = 0; k < LQ_NPT; ++k) {
       const size_t x = base + (size_t)k * 256;
@@ -890,7 +895,7 @@ __device__ __forceinline__ void site_group_add(const Dev& d, bool valid, uint32_
 __global__ void __launch_bounds__(128)
 k_estimate_sites(Dev d) {
   const int s0 = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = s0 < d.N;
+  const bool valid = s0 < d.Nown;
   const int s = valid ? s0 : 0;
   const int g = d.gauge[s];
   const int c = d.spinW[s];
@@ -901,7 +906,7 @@ k_estimate_sites(Dev d) {
   const long long qlo = d.sse ? 0ll : time_to_fx(window_lo(d.w0, d.W));
   const long long qhi = d.sse ? (long long)(*d.d_ntotal)
                               : ((d.w0 + d.Wl >= d.W) ? (1ll << 40) : time_to_fx(window_hi(d.w0 + d.Wl - 1, d.W)));
-  if (d.rank == 0) site_group_add(d, valid, cb, 1, m, g, g * m, 0, true);
+  if (d.rank == 0 || d.space) site_group_add(d, valid, cb, 1, m, g, g * m, 0, true);   // (tau = 0 lies in rank 0's slab)
   if (qlo) site_group_add(d, valid, cb, 1, m, g, g * m, -qlo, false);
   // periodic in imaginary time: the spin at the top of the slab stack equals the one at tau = 0;
   // inside a slab it is the spin at the start of the next slab = spinW[Wl]
@@ -1004,7 +1009,7 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
   }
   if (threadIdx.x == 0) {
     out[14] = (double)nc;
-    out[15] = (double)(*d.d_ntotal);
+    out[15] = (double)d.nbase[d.Pown];   // operators this rank owns (all of them on a serial engine)
     out[16] = (double)(*d.d_err);
     out[17] = 0.0;
   }
@@ -1106,6 +1111,7 @@ __global__ void k_step_advance(StepCtl* ctl, const double* fixed_out) {
 __global__ void k_flip_spins(Dev d) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)(d.Wl + 1) * d.N) return;
+  if (d.space && (int)(i % (size_t)d.N) >= d.Nown) return;   // ghost sites: their owners send the spins
   if (*d.d_err) return;   // an arena overflowed in this step: keep the spins of the configuration it started from
   const uint32_t c = d.parent[d.curW[i]];
   d.spinW[i] ^= (uint8_t)flip_of_label(d, c);
@@ -1150,6 +1156,8 @@ struct MrDev {
   double* rankvec;    // [32] this rank's closed-cluster sums
   double* allvec;     // [P*32]
   double* gsum;       // [16] sums over global clusters
+  size_t gn;          // nodes of the gathered boundary forest (slabs: P*2N; spatial cut: P*stride)
+  size_t gbase;       // first node of this rank in it
 };
 
 // Slab engines run the exchange BEFORE the relabelling (so that k_relabel can pack the flips of the
@@ -1211,7 +1219,7 @@ __global__ void k_mr_gunion(Dev d, MrDev m) {
 
 __global__ void k_mr_gcompress(Dev d, MrDev m) {
   const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nn = (size_t)d.nranks * 2 * d.N;
+  const size_t nn = m.gn;
   if ((x >> 5) >= ((nn + 31) >> 5)) return;
   bool isroot = false;
   if (x < nn) {
@@ -1225,7 +1233,7 @@ __global__ void k_mr_gcompress(Dev d, MrDev m) {
 }
 
 __device__ __forceinline__ uint32_t global_cid(const Dev& d, const MrDev& m, uint32_t oid) {
-  const uint32_t r = m.gparent[(size_t)d.rank * 2 * d.N + oid];
+  const uint32_t r = m.gparent[m.gbase + oid];
   return m.gwbase[r >> 5] + (uint32_t)__popc(m.gbitmap[r >> 5] & ((1u << (r & 31)) - 1u));
 }
 

@@ -84,9 +84,18 @@ typedef struct lq_options {
                                 operator is its position in the string and the string length n is the
                                 top (sse.C:251-283,358-361) -- and the collector's sums are in those
                                 units (commit: susceptibility.h:213-215, beta (x/n + x0) / (n+1) / V) */
+  int32_t  cut;              /* nranks > 1: how the configuration is shared among the engines.
+                                LQ_CUT_TIME: imaginary-time slabs (path_integral_mpi.C:231-232,
+                                looper/parallel.h); LQ_CUT_SPACE: every engine owns a contiguous range of
+                                spatial tiles over the whole imaginary-time axis (the bond ownership of
+                                looper/lattice.h:692-787 taken across GPUs), keeps ghost copies of the
+                                neighbouring tiles and merges the clusters that cross a cut through the
+                                same all-gather + all-reduce pair                                   */
 } lq_options;
 #define LQ_REPR_PATH_INTEGRAL 0
 #define LQ_REPR_SSE           1
+#define LQ_CUT_TIME           0
+#define LQ_CUT_SPACE          1
 
 /* looper/operator.h:120-143: {time_, loc_, type_}; loc = pos<<1 | is_bond
  * (location_impl.h:37); type bit0 = offdiagonal, bits >= 2 = graph type (operator.h:62,76). */
@@ -189,7 +198,7 @@ int64_t lq_regrow_count(lq_handle h);
 int64_t lq_h2d_bytes(lq_handle h);
 int64_t lq_d2h_bytes(lq_handle h);
 
-/* Multi-GPU (imaginary-time slabs, one engine per GPU; replaces
+/* Multi-GPU (imaginary-time slabs or spatial strips, one engine per GPU; replaces
  * parallel_cluster_unifier::unify, looper/parallel.h:1609-1809): the engine calls
  * exchange(ctx, ...) between the local labelling and the flip.  See INTEGRATION.md. */
 typedef struct lq_comm {
@@ -198,6 +207,11 @@ typedef struct lq_comm {
   int (*all_gather)(void* ctx, const void* send_dev, void* recv_dev, int64_t bytes, void* stream);
   /* in-place sum all-reduce of `count` int64 values (device pointer) */
   int (*all_reduce_i64)(void* ctx, void* buf_dev, int64_t count, void* stream);
+  /* LQ_CUT_SPACE only (may be NULL otherwise): send `send_bytes` to rank dst and receive `recv_bytes`
+   * from rank src in one step (MPI_Sendrecv; the halo pages and spins of the ghost tiles).  Every rank
+   * makes the same sequence of calls; either size may be 0. */
+  int (*send_recv)(void* ctx, const void* send_dev, int64_t send_bytes, int32_t dst,
+                   void* recv_dev, int64_t recv_bytes, int32_t src, void* stream);
 } lq_comm;
 int lq_set_comm(lq_handle h, const lq_comm* comm);
 /* The engine's own data plane: an NCCL communicator over the ranks of the run (the reference hands

@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(lq.LqTimer) == 56
     assert C.sizeof(lq.LqModel) == 8 + 32 + 8 + 8 + 8
     assert C.sizeof(lq.LqLattice) == 8 + 3 * 8 + 16 + 8
-    assert C.sizeof(lq.LqOptions) == 8 + 4 + 4 + 8 * 3 + 4 * 4   # seed, device, tile_sites, 3 doubles, rank..representation
+    assert C.sizeof(lq.LqOptions) == 8 + 4 + 4 + 8 * 3 + 4 * 5 + 4   # seed, device, tile_sites, 3 doubles, rank..cut, tail padding
     # compile the header as C and compare sizeof with the compiler's view
     prog = r'''
     #include <stdio.h>
