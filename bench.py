@@ -401,7 +401,7 @@ def parity_preflight(rank, world, local, args):
     try:
         if world > 1:
             import mgpu_parity
-            return mgpu_parity.preflight(rank, world, local, args.comm, steps=6)
+            return mgpu_parity.preflight(rank, world, local, args.comm, steps=6, cut=args.cut)
         import numpy as np
         import looper_b200 as lq
         import oracle_util as orc
@@ -425,6 +425,12 @@ def parity_preflight(rank, world, local, args):
 def multi_gpu_mode(args, world):
     if world == 1:
         return "single GPU"
+    if args.cut == "space":
+        return ("spatial strips: %d ranks, every rank owns a contiguous range of tiles over the whole imaginary-time "
+                "axis + ghost copies of the neighbouring tile rows (halo pages and spins by ncclSend/ncclRecv twice per "
+                "step), boundary segments all-gathered and open-cluster sums all-reduced with NCCL every step (one "
+                "Markov chain over all GPUs); issued by %s"
+                % (world, "the engine (lq_comm_init)" if args.comm == "nccl" else "torch.distributed callbacks (lq_set_comm)"))
     return ("imaginary-time slabs: %d ranks, boundary cluster ids all-gathered and open-cluster sums "
             "all-reduced with NCCL every step (one Markov chain over all GPUs); collectives issued by %s"
             % (world, "the engine (lq_comm_init, ncclAllGather/ncclAllReduce on its stream)" if args.comm == "nccl"
@@ -442,7 +448,8 @@ def load_comm():
 def make_engine(lq, lat, beta, tile, local, rank, world, args, timers=False):
     eng = lq.Engine(lat, beta, seed=29833, device=local, tile_sites=tile, timers=timers,
                     window_ops=args.window_ops, reserve=args.reserve,
-                    rank=rank if world > 1 else 0, nranks=world, sse=getattr(args, "sse", False))
+                    rank=rank if world > 1 else 0, nranks=world, sse=getattr(args, "sse", False),
+                    cut=args.cut if world > 1 else "time")
     if world > 1:
         if args.comm == "nccl":
             load_comm().attach_nccl(eng, rank, world)
@@ -468,6 +475,9 @@ def main():
     ap.add_argument("--comm", default="nccl", choices=["nccl", "torch"],
                     help="multi-GPU data plane: the engine's own NCCL communicator (lq_comm_init) or "
                          "torch.distributed callbacks (lq_set_comm)")
+    ap.add_argument("--cut", default=os.environ.get("LQ_BENCH_CUT", "time"), choices=["time", "space"],
+                    help="multi-GPU decomposition of the one Markov chain: imaginary-time slabs (looper/parallel.h) "
+                         "or spatial strips (BASELINE config 3 wording; lq_options.cut)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -46,7 +46,7 @@ def attach(eng, local, rank, world, comm):
         m.attach_nccl(eng, rank, world)
 
 
-def preflight(rank, world, local, comm="nccl", cases=None, steps=12):
+def preflight(rank, world, local, comm="nccl", cases=None, steps=12, cut="time"):
     """returns a dict (identical on all ranks): {"ok": bool, "cases": [...]}; raises nothing."""
     import torch
     import torch.distributed as dist
@@ -54,9 +54,10 @@ def preflight(rank, world, local, comm="nccl", cases=None, steps=12):
     import oracle_util as orc
 
     if cases is None:
-        cases = [("chain64_b16", lq.chain_lattice(64), 16.0, 120, 0),
+        # (spatial cut: at least one tile per rank)
+        cases = [("chain64_b16", lq.chain_lattice(64), 16.0, 120, 4 if cut == "space" else 0),
                  ("square32_b8", lq.hypercubic_lattice((32, 32)), 8.0, 60, 16)]
-    report = {"ok": True, "ranks": world, "comm": comm, "cases": []}
+    report = {"ok": True, "ranks": world, "comm": comm, "cut": cut, "cases": []}
     for name, lat, beta, therm, tile in cases:
         rec = {"name": name}
         try:
@@ -65,7 +66,7 @@ def preflight(rank, world, local, comm="nccl", cases=None, steps=12):
                 sim.sweep()
             spins, ops = sim.get_state()
             _, ref_nc, ref = orc.build_clusters(lat, spins, ops)
-            eng = lq.Engine(lat, beta, seed=99, device=local, tile_sites=tile, rank=rank, nranks=world)
+            eng = lq.Engine(lat, beta, seed=99, device=local, tile_sites=tile, rank=rank, nranks=world, cut=cut)
             attach(eng, local, rank, world, comm)
             eng.set_state(spins, ops)
             nloc = eng.num_ops()
@@ -93,11 +94,16 @@ def preflight(rank, world, local, comm="nccl", cases=None, steps=12):
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             same = bool(torch.equal(lo, hi))
             gathered = [None] * world
-            dist.all_gather_object(gathered, (o2.tobytes(), s2.tobytes() if rank == 0 else b""))
+            dist.all_gather_object(gathered, (o2.tobytes(), s2.tobytes() if (rank == 0 or cut == "space") else b""))
             legal = True
             if rank == 0:
                 allops = np.concatenate([np.frombuffer(g[0], dtype=lq.OP_DTYPE) for g in gathered])
                 order = np.argsort(allops["time"], kind="stable")
+                if cut == "space":   # every rank reports the spins of its own sites, -1 elsewhere
+                    s2 = np.full(lat["num_sites"], -1, dtype=np.int32)
+                    for g in gathered:
+                        sg = np.frombuffer(g[1], dtype=np.int32)
+                        s2[sg >= 0] = sg[sg >= 0]
                 try:
                     orc.build_clusters(lat, s2, allops[order])
                     legal = len(allops) == int(out["nop"][-1])
@@ -119,13 +125,14 @@ def main():
     import torch.distributed as dist
     ap = argparse.ArgumentParser()
     ap.add_argument("--comm", default="nccl", choices=["nccl", "torch"])
+    ap.add_argument("--cut", default="time", choices=["time", "space"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rep = preflight(rank, world, local, args.comm)
+    rep = preflight(rank, world, local, args.comm, cut=args.cut)
     if rank == 0:
         print("MGPU_PARITY " + json.dumps(rep), flush=True)
     dist.barrier()

@@ -46,3 +46,19 @@ def test_slab_parity_over_real_nccl(comm):
     assert out.returncode == 0 and lines, (out.stdout[-2000:], out.stderr[-2000:])
     rep = json.loads(lines[-1][len("MGPU_PARITY "):])
     assert rep["ok"] and rep["ranks"] == n and all(c["ok"] for c in rep["cases"]), rep
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("comm", ["nccl", "torch"])
+def test_space_parity_over_real_nccl(comm):
+    """the same check for the SPATIAL cut (lq_options.cut = LQ_CUT_SPACE): halo pages and spins travel
+    by ncclSend/ncclRecv (or torch.distributed P2P), boundary segments through the all-gather."""
+    n = min(_ngpu(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29543" if comm == "nccl" else "29544",
+           os.path.join(ROOT, "tests", "mgpu_parity.py"), "--comm", comm, "--cut", "space"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("MGPU_PARITY ")]
+    assert out.returncode == 0 and lines, (out.stdout[-2000:], out.stderr[-2000:])
+    rep = json.loads(lines[-1][len("MGPU_PARITY "):])
+    assert rep["ok"] and rep["ranks"] == n and rep["cut"] == "space" and all(c["ok"] for c in rep["cases"]), rep
