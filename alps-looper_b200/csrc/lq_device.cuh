@@ -34,6 +34,7 @@ static const node_t NODE_JUNK = 0xfffffffeu;   // spatial cut: ghost node nobody
 #define LQ_ERR_NODE_FULL 4
 #define LQ_ERR_CLUSTER_FULL 8
 #define LQ_ERR_REMOTE 16   /* slab engines: another rank overflowed in this step (all ranks rewind together) */
+#define LQ_ERR_OPEN_FULL 64 /* multi-rank: more open clusters than this step's all-reduce carries (replayed with the exact count) */
 #define LQ_ERR_BOUNDARY 32 /* spatial cut: the two copies of a boundary page disagree (internal error) */
 
 // fixed-point scale of imaginary time in the cluster sums (order-independent integer atomics)

@@ -4,6 +4,7 @@
 // Build: alps-looper_b200/csrc/Makefile  (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo)
 // There is deliberately no CPU path in this file: every entry point that computes needs a CUDA
 // device and fails with LQ_E_CUDA otherwise.
+#include <chrono>
 #include "../../include/lq.h"
 #include "lq_kernels.cuh"
 #include "lq_space.cuh"
@@ -536,15 +537,25 @@ struct lq_engine {
   DBuf<uint8_t> mr_gused;
   DBuf<long long> mr_gest;
   DBuf<double> mr_rankvec, mr_allvec, mr_gsum;
-  uint32_t* h_mr = nullptr;  // pinned: ngc read-back
+  uint32_t* h_mr = nullptr;  // pinned: ngc read-back, a ring of 4 steps x 4 words
+  cudaEvent_t mr_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t mr_step = 0;      // labellings since the arenas were sized / a state was loaded
+  size_t mr_gslots = 0;      // open-cluster slots the table can hold
   // timers
   struct TimerAcc { double sec = 0; int count = 0; } tacc[17];
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> tpending;
 
   ~lq_engine() {
+    if (host_timers) {
+      std::string m = "lq host enqueue ms per call, rank " + std::to_string(opt.rank) + ":";
+      for (int i = 0; i < 17; ++i)
+        if (hcnt[i]) m += " [" + std::to_string(i) + "] " + std::to_string(1e3 * hacc[i] / hcnt[i]) + " x" + std::to_string(hcnt[i]);
+      std::fprintf(stderr, "%s\n", m.c_str());
+    }
     if (h_out) cudaFreeHost(h_out);
     if (h_params) cudaFreeHost(h_params);
     if (h_mr) cudaFreeHost(h_mr);
+    for (auto& e : mr_ev) if (e) cudaEventDestroy(e);
     if (h_ctl) cudaFreeHost(h_ctl);
     if (nccl) { cudaStreamSynchronize(stream); nccl_api().CommDestroy(nccl); }
     drop_graphs();
@@ -852,7 +863,8 @@ struct lq_engine {
         // windows per persistent CTA: enough CTAs for ~8 waves, at least 4 windows to amortise the tile set-up
         {
           const long long want_ctas = 8ll * sm_count * 3;
-          long long nch = std::max<long long>(1, std::min<long long>(Wl, (want_ctas + T - 1) / T));
+          const int Tk = To;   // (the tiles K1 runs on: the owned ones)
+          long long nch = std::max<long long>(1, std::min<long long>(Wl, (want_ctas + Tk - 1) / Tk));
           k1_chunk = (int)((Wl + nch - 1) / nch);
           if (k1_chunk < 4) k1_chunk = std::min(4, Wl);
           if (getenv("LQ_K1_CHUNK")) k1_chunk = std::max(1, std::min(Wl, atoi(getenv("LQ_K1_CHUNK"))));
@@ -954,16 +966,19 @@ struct lq_engine {
       mr_gused.alloc(g2, tb);
       mr_gbitmap.alloc(gw, tb); mr_gwcount.alloc(gw, tb); mr_gwbase.alloc(gw + 1, tb);
       // (spatial cut: every global open cluster has at least two entries, one per side of a cut)
-      mr_gest.alloc((space ? g2 / 2 + 1 : g2) * (size_t)gstride() + 32 * (size_t)opt.nranks, tb);   // + the collectors' slots (k_mr_rankvec)
+      mr_gslots = space ? g2 / 2 + 1 : g2;
+      mr_gest.alloc(mr_gslots * (size_t)gstride() + 32 * (size_t)opt.nranks, tb);   // the collectors' slots (k_mr_rankvec) come first
       mr_dg.alloc(4, tb);
       mr_rankvec.alloc(32, tb); mr_allvec.alloc(32 * (size_t)opt.nranks, tb); mr_gsum.alloc(16, tb);
       CK(cudaMemset(mr_topmin.p, 0xff, mr_topmin.n * sizeof(uint32_t)));
       CK(cudaMemset(mr_gest.p, 0, mr_gest.n * sizeof(long long)));
       CK(cudaMemset(mr_dg.p, 0, 4 * sizeof(uint32_t)));
-      if (!h_mr) CK(cudaMallocHost((void**)&h_mr, 4 * sizeof(uint32_t)));
+      if (!h_mr) CK(cudaMallocHost((void**)&h_mr, 16 * sizeof(uint32_t)));
+      for (auto& e : mr_ev) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      mr_step = 0;
       mr.topmin = mr_topmin.p; mr.sendb = mr_sendb.p; mr.recvb = mr_recvb.p; mr.gparent = mr_gparent.p;
       mr.gused = mr_gused.p; mr.gbitmap = mr_gbitmap.p; mr.gwcount = mr_gwcount.p; mr.gwbase = mr_gwbase.p;
-      mr.gest = mr_gest.p; mr.d_g = mr_dg.p; mr.rankvec = mr_rankvec.p; mr.allvec = mr_allvec.p;
+      mr.gest = mr_gest.p + 32 * (size_t)opt.nranks; mr.d_g = mr_dg.p; mr.rankvec = mr_rankvec.p; mr.allvec = mr_allvec.p;
       mr.gsum = mr_gsum.p;
       mr.gn = g2;
       mr.gbase = space ? (size_t)opt.rank * per_rank + LQ_SP_HDR : (size_t)opt.rank * per_rank;
@@ -1078,13 +1093,20 @@ struct lq_engine {
   // timers (ids of path_integral.C:284-299); device time between two events on the stream
   struct Section {
     lq_engine* e; int id; cudaEvent_t a = nullptr, b = nullptr;
+    std::chrono::steady_clock::time_point h0;
     Section(lq_engine* e_, int id_) : e(e_), id(id_) {
       if (e->timers_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, e->stream); }
+      if (e->host_timers) h0 = std::chrono::steady_clock::now();
     }
     ~Section() {
       if (e->timers_on) { cudaEventRecord(b, e->stream); e->tpending.push_back({id, {a, b}}); }
+      if (e->host_timers) { e->hacc[id] += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count(); e->hcnt[id]++; }
     }
   };
+  // LQ_HOST_TIMERS=1 (diagnostic): host time spent ENQUEUEING every section, printed when the engine is destroyed
+  bool host_timers = getenv("LQ_HOST_TIMERS") != nullptr;
+  double hacc[17] = {0};
+  long hcnt[17] = {0};
   void drain_timers() {
     for (auto& t : tpending) {
       float ms = 0;
@@ -1243,6 +1265,7 @@ struct lq_engine {
       lq::k_mr_gcompress<<<grid_for(((g2 + 31) / 32) * 32, 256), 256, 0, stream>>>(d, mr);
       launches += 3;
       scan_u32(mr.gwcount, mr.gwbase, (g2 + 31) / 32, mr.gwbase + (g2 + 31) / 32, (int*)mr.d_g);
+      size_open_cluster_table();
       return;
     }
     const int N = part.N;
@@ -1257,6 +1280,31 @@ struct lq_engine {
     lq::k_mr_gcompress<<<grid_for(((g2 + 31) / 32) * 32, 256), 256, 0, stream>>>(d, mr);
     launches += 3;
     scan_u32(mr.gwcount, mr.gwbase, (g2 + 31) / 32, mr.gwbase + (g2 + 31) / 32, (int*)mr.d_g);
+    size_open_cluster_table();
+  }
+
+  // The all-reduce of the open-cluster sums needs its length on the HOST.  Reading the number of
+  // global open clusters back every step made the host wait for the GPU and then the GPU wait for the
+  // host to enqueue the next step.  The count is therefore taken from TWO steps
+  // ago (+25 %; the same number on every rank, which the collective needs), whose read-back has long
+  // arrived; a step with more open clusters than that raises the error word and is replayed like any
+  // other arena overflow.  The first two labellings after (re)sizing wait for the exact count.
+  void size_open_cluster_table() {
+    const int slot = (int)(mr_step & 3);
+    CK(cudaMemcpyAsync(h_mr + 4 * slot, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(mr_ev[slot], stream));
+    uint64_t want;
+    if (mr_step >= 2 && !getenv("LQ_MR_SYNC")) {
+      const int old = (int)((mr_step - 2) & 3);
+      CK(cudaEventSynchronize(mr_ev[old]));
+      const uint64_t n = h_mr[4 * old];
+      want = std::max<uint64_t>(1024, n + n / 4 + 256);
+    } else {
+      CK(cudaEventSynchronize(mr_ev[slot]));
+      want = std::max<uint64_t>(1, h_mr[4 * slot]);
+    }
+    mr.gcap = (uint32_t)std::min<uint64_t>(want, mr_gslots);
+    ++mr_step;
   }
 
   // ---- spatial cut: ghost pages and ghost spins (SpacePlan) ----------------------------------------
@@ -1264,16 +1312,15 @@ struct lq_engine {
   // else only the info words -- before K1, which has to see the operator flips of the previous step
   // on its halo buckets -- and, with `spins`, the spins of the walked ghost sites.
   struct XMsg { const void* s; size_t sb; void* r; size_t rb; };
+  bool in_group = false;
   void xchg_round(int dl, const std::vector<XMsg>& msgs) {
     const int Pn = opt.nranks, dst = (opt.rank + dl) % Pn, src = (opt.rank - dl + Pn) % Pn;
     if (nccl) {
       NcclApi& a = nccl_api();
-      nccl_check(a.GroupStart(), "ncclGroupStart");
       for (const XMsg& m : msgs) {
         if (m.sb) nccl_check(a.Send(m.s, m.sb, ncclChar, dst, nccl, stream), "ncclSend(ghost pages)");
         if (m.rb) nccl_check(a.Recv(m.r, m.rb, ncclChar, src, nccl, stream), "ncclRecv(ghost pages)");
       }
-      nccl_check(a.GroupEnd(), "ncclGroupEnd");
     } else {
       if (!comm.send_recv) fail(LQ_E_COMM, "the spatial cut needs lq_comm.send_recv (or lq_comm_init)");
       for (const XMsg& m : msgs)
@@ -1287,10 +1334,11 @@ struct lq_engine {
     struct Unpack { size_t off, len; int site0; };
     std::vector<Unpack> unpack;
     const size_t nb1 = (size_t)part.nbmax + 1;
+    // (engine-owned NCCL: ONE group for all rounds, so that the transfers to and from both neighbours overlap)
+    if (nccl) nccl_check(nccl_api().GroupStart(), "ncclGroupStart");
     for (int dl = 1; dl < opt.nranks; ++dl) {
       if (!plan.rounds[dl]) continue;
       msgs.clear();
-      unpack.clear();
       const auto& sr = plan.send_runs[dl];
       const auto& rr = plan.recv_runs[dl];
       for (int k = 0; k < plan.rounds[dl]; ++k) {
@@ -1317,22 +1365,19 @@ struct lq_engine {
         }
       }
       xchg_round(dl, msgs);
-      for (const Unpack& u : unpack)
-        CK(cudaMemcpy2DAsync(spinW.p + u.site0, (size_t)Ns, sp_spin_recv.p + u.off, u.len, u.len, (size_t)Wl + 1,
-                             cudaMemcpyDeviceToDevice, stream));
     }
+    if (nccl) nccl_check(nccl_api().GroupEnd(), "ncclGroupEnd");
+    for (const Unpack& u : unpack)
+      CK(cudaMemcpy2DAsync(spinW.p + u.site0, (size_t)Ns, sp_spin_recv.p + u.off, u.len, u.len, (size_t)Wl + 1,
+                           cudaMemcpyDeviceToDevice, stream));
   }
 
   void finish_open_clusters(double* out_slot, const lq::StepParams* sp) {
     Section s(this, 13);
-    // the all-reduce length is the number of global open clusters: one 16-byte read-back
-    CK(cudaMemcpyAsync(h_mr, mr.d_g, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    const int64_t ngc = h_mr[0];
-    // one all-reduce carries the open-cluster sums and, in its tail, every rank's collector of its closed clusters
-    double* tail = (double*)(mr.gest + (size_t)ngc * gstride());
+    // one all-reduce carries, in front, every rank's collector of its closed clusters and then the open-cluster sums
+    double* tail = (double*)mr_gest.p;
     lq::k_mr_rankvec<<<1, 32, 0, stream>>>(d, mr, out_slot, tail);
-    all_reduce_i64(mr.gest, (size_t)ngc * gstride() + 32 * (size_t)opt.nranks, "all_reduce(open-cluster sums + collectors)");
+    all_reduce_i64(mr_gest.p, 32 * (size_t)opt.nranks + (size_t)mr.gcap * gstride(), "all_reduce(collectors + open-cluster sums)");
     const unsigned gblk = (unsigned)std::min<size_t>(nblk_collect, (size_t)sm_count * 4);
     lq::k_mr_gcollect<<<gblk, 256, 0, stream>>>(d, mr, partial.p);   // (partial is free again after k_collect_final)
     lq::k_mr_gsum<<<1, 32 * LQ_NSUM, 0, stream>>>(mr, partial.p, (int)gblk);
@@ -1468,6 +1513,7 @@ struct lq_engine {
     if (err & LQ_ERR_CAND_FULL) m += " too many candidates in one page or bucket (lower window_ops);";
     if (err & LQ_ERR_CLUSTER_FULL) m += " cluster arena full (raise cluster_reserve);";
     if (err & LQ_ERR_NODE_FULL) m += " node arena / boundary segment full;";
+    if (err & LQ_ERR_OPEN_FULL) m += " open-cluster table of the exchange full;";
     if (err & LQ_ERR_BOUNDARY) m += " the two copies of a boundary page disagree (internal error);";
     fail(LQ_E_OVERFLOW, m);
   }
@@ -1513,11 +1559,17 @@ struct lq_engine {
     CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
     cur = cur0 ^ (first_bad & 1);
     mcs = mcs0 + (uint32_t)first_bad;
-    if (err & (LQ_ERR_PAGE_FULL | LQ_ERR_NODE_FULL)) grow_pages *= 1.5;   // (boundary segments are sized like the pages)
-    if (err & LQ_ERR_CAND_FULL) { grow_cand *= 1.5; grow_kept *= 1.6; }
-    if (err & LQ_ERR_CLUSTER_FULL) grow_clusters *= 1.5;
-    ++regrows;
-    rebucket();
+    if (!(err & ~(LQ_ERR_OPEN_FULL | LQ_ERR_REMOTE))) {
+      // only the open-cluster table of the all-reduce was short (size_open_cluster_table): nothing to
+      // grow, the configuration the step started from is intact -- run it again with the exact count
+      mr_step = 0;
+    } else {
+      if (err & (LQ_ERR_PAGE_FULL | LQ_ERR_NODE_FULL)) grow_pages *= 1.5;   // (boundary segments are sized like the pages)
+      if (err & LQ_ERR_CAND_FULL) { grow_cand *= 1.5; grow_kept *= 1.6; }
+      if (err & LQ_ERR_CLUSTER_FULL) grow_clusters *= 1.5;
+      ++regrows;
+      rebucket();
+    }
     sweep_many(count - first_bad, out ? out + first_bad : nullptr, depth + 1);
   }
 
@@ -1627,6 +1679,7 @@ struct lq_engine {
     }
     CK(cudaStreamSynchronize(stream));
     cur = 0;
+    mr_step = 0;   // (the open-cluster count of the old configuration says nothing about the new one)
     CK(cudaMemcpy(time_[0].p, ht.data(), ht.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(info[0].p, hi.data(), hi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(boff[0].p, hb.data(), hb.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));

@@ -1156,6 +1156,8 @@ struct MrDev {
   double* rankvec;    // [32] this rank's closed-cluster sums
   double* allvec;     // [P*32]
   double* gsum;       // [16] sums over global clusters
+  uint32_t gcap;      // open-cluster slots that travel in this step's all-reduce (the host sizes it from the
+                      // count of two steps ago, so that no step waits for a read-back; see merge_open_clusters)
   size_t gn;          // nodes of the gathered boundary forest (slabs: P*2N; spatial cut: P*stride)
   size_t gbase;       // first node of this rank in it
 };
@@ -1294,6 +1296,12 @@ k_mr_gather(Dev d, MrDev m) {
       if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[8] = 1ull;
       for (int x = 0; x < d.sdim; ++x) v[8 + d.has_site + x] = (unsigned long long)(long long)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
       ++nrep;
+      if (gid >= m.gcap) {   // more open clusters than the all-reduce of this step carries: the step is lost
+        atomicOr(d.d_err, LQ_ERR_OPEN_FULL);
+        gid = 0u;
+#pragma unroll
+        for (int f = 0; f < LQ_GEST_MAX; ++f) v[f] = 0ull;
+      }
     }
     const unsigned grp = __match_any_sync(0xffffffffu, gid);
     const bool leader = rep && lane == (unsigned)(__ffs(grp) - 1);
@@ -1357,7 +1365,7 @@ __global__ void k_mr_reset_topmin(Dev d, MrDev m) {
 __global__ void __launch_bounds__(256)
 k_mr_gcollect(Dev d, MrDev m, double* partial) {
   __shared__ double s_red[8][LQ_NSUM];
-  const uint32_t ngc = m.d_g[0];
+  const uint32_t ngc = min(m.d_g[0], m.gcap);
   double v[LQ_NSUM];
 #pragma unroll
   for (int i = 0; i < LQ_NSUM; ++i) v[i] = 0;

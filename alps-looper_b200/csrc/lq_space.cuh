@@ -192,6 +192,12 @@ k_sp_gather(Dev d, SpDev sp, MrDev m) {
     }
     if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[8] = 1ull;
     for (int x = 0; x < d.sdim; ++x) v[8 + d.has_site + x] = (unsigned long long)(long long)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
+    if (gid >= m.gcap) {   // (see k_mr_gather)
+      atomicOr(d.d_err, LQ_ERR_OPEN_FULL);
+      gid = 0u;
+#pragma unroll
+      for (int f = 0; f < LQ_GEST_MAX; ++f) v[f] = 0ull;
+    }
   }
   const unsigned grp = __match_any_sync(0xffffffffu, gid);
   const bool leader = rep && lane == (unsigned)(__ffs(grp) - 1);
