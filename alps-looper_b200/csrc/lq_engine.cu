@@ -549,7 +549,7 @@ struct lq_engine {
     if (host_timers) {
       std::string m = "lq host enqueue ms per call, rank " + std::to_string(opt.rank) + ":";
       for (int i = 0; i < 17; ++i)
-        if (hcnt[i]) m += " [" + std::to_string(i) + "] " + std::to_string(1e3 * hacc[i] / hcnt[i]) + " x" + std::to_string(hcnt[i]);
+        if (hcnt[i] > 40) m += " [" + std::to_string(i) + "] " + std::to_string(1e3 * hacc[i] / (hcnt[i] - 40)) + " x" + std::to_string(hcnt[i]);
       std::fprintf(stderr, "%s\n", m.c_str());
     }
     if (h_out) cudaFreeHost(h_out);
@@ -1100,7 +1100,10 @@ struct lq_engine {
     }
     ~Section() {
       if (e->timers_on) { cudaEventRecord(b, e->stream); e->tpending.push_back({id, {a, b}}); }
-      if (e->host_timers) { e->hacc[id] += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count(); e->hcnt[id]++; }
+      if (e->host_timers) {   // (steady state: the first 40 calls -- connection set-up, first launches -- are left out)
+        if (e->hcnt[id] >= 40) e->hacc[id] += std::chrono::duration<double>(std::chrono::steady_clock::now() - h0).count();
+        e->hcnt[id]++;
+      }
     }
   };
   // LQ_HOST_TIMERS=1 (diagnostic): host time spent ENQUEUEING every section, printed when the engine is destroyed

@@ -321,14 +321,15 @@ def run_gpu(args):
         if eng_t is not None:
             eng_t.enable_timers(True)
             before = {x["id"]: (x["seconds"], x["count"]) for x in eng_t.timers()}
-            o2 = eng_t.sweep_many(max(3, min(args.steps, 10)))
+            nt = max(3, min(args.steps, 10))
+            o2 = eng_t.sweep_many(nt)
             after = {x["id"]: (x["seconds"], x["count"]) for x in eng_t.timers()}
             nop_t = float(o2["nop"].mean())
             phases = {}
             for pid, (sec, cnt) in after.items():
                 s0, c0 = before.get(pid, (0.0, 0))
                 if cnt > c0:
-                    phases[pid] = (sec - s0) / (cnt - c0)
+                    phases[pid] = (sec - s0) / nt   # per STEP (a multi-rank step enters phases 8 and 13 more than once)
             tot = sum(phases.values())
             dom = max((p for p in phases if p in PHASE_BYTES), key=lambda p: phases[p])
             kname, bpo = PHASE_BYTES[dom]
