@@ -266,6 +266,9 @@ void make_partition(const lq_lattice& L, int B, const int* Lsrc, const int* Ldst
 //            that every leg of an OWNED operator gets its lower node locally (no reverse exchange),
 //   H tiles  own the foreign bonds that touch one of its K-sites (halo buckets of K1 and of the walk)
 //            or a site of a W tile from outside (walk halo of the W tiles).
+// A ghost page only holds the buckets of the bonds that touch a K-site of this rank (the bond lists of
+// the boundary segments below): their owners send them as dense streams twice per step -- after K1
+// (new operators) and before it (the flips of the previous step) -- and k_sp_unpack rebuilds the pages.
 // Every engine renumbers the tiles [owned | W | H | rest], so that the pages it holds are the first
 // ones and the kernels run unchanged on a prefix of the tiles.
 // Clusters that cross a cut are merged through BOUNDARY SEGMENTS: for every ordered pair
@@ -278,13 +281,11 @@ struct SpaceSeg {
   std::vector<int> sites, bonds;   // EXTERNAL site ids / internal-bond order key -> stored as external ids
   long long off_owner = 0, off_user = 0, cap = 0, opcap = 0;   // (sized with beta, size_space())
 };
-struct SpaceRun { int peer, tile0, ntiles, walked; };   // tile0 in THIS rank's numbering
 struct SpacePlan {
   int nranks = 1, rank = 0;
   int To = 0, Tw = 0, Tloc = 0;
   std::vector<int> relabel;                      // global tile -> this rank's tile id
-  std::vector<std::vector<SpaceRun>> send_runs, recv_runs;   // [delta]: to (rank+delta)%P / from (rank-delta+P)%P
-  std::vector<int> rounds;                       // [delta] messages every rank issues in that round (0: skipped)
+  std::vector<int> rounds;                       // [delta] some rank q has a segment for rank (q+delta)%P: the round exists
   std::vector<SpaceSeg> segs;                    // all segments of the run, canonical order
 };
 
@@ -333,25 +334,6 @@ void plan_space(const Partition& G, int nranks, int rank, SpacePlan& S) {
   }
   S.To = nown[rank]; S.Tw = nw[rank]; S.Tloc = nloc[rank];
   S.relabel = relabel[rank];
-  // page runs between owner q and holder r: maximal stretches that are contiguous on both sides
-  auto runs_of = [&](int q, int r, bool for_owner) {
-    std::vector<SpaceRun> out;
-    int pq = -2, pr = -2, pw = -1;
-    for (int t = 0; t < T; ++t) {
-      if (owner(t) != q || relabel[r][t] >= nloc[r]) continue;
-      const int a = relabel[q][t], b = relabel[r][t], w = is_w[r][t];
-      if (!out.empty() && a == pq + 1 && b == pr + 1 && w == pw) out.back().ntiles++;
-      else out.push_back({for_owner ? r : q, for_owner ? a : b, 1, w});
-      pq = a; pr = b; pw = w;
-    }
-    return out;
-  };
-  S.send_runs.assign(P, {}); S.recv_runs.assign(P, {}); S.rounds.assign(P, 0);
-  for (int dl = 1; dl < P; ++dl) {
-    for (int q = 0; q < P; ++q) S.rounds[dl] = std::max(S.rounds[dl], (int)runs_of(q, (q + dl) % P, true).size());
-    S.send_runs[dl] = runs_of(rank, (rank + dl) % P, true);
-    S.recv_runs[dl] = runs_of((rank - dl + P) % P, rank, false);
-  }
   // boundary segments, canonical order (owner, user); ids leave as EXTERNAL site ids / external bond ids
   // (pseudo-bond of site s: Breal + s, the convention of Partition::bond_i2e)
   S.segs.clear();
@@ -364,6 +346,10 @@ void plan_space(const Partition& G, int nranks, int rank, SpacePlan& S) {
       for (int b : HB[r]) if (owner(G.bond_tile[b]) == q) g.bonds.push_back(G.bond_i2e[b]);
       if (!g.sites.empty() || !g.bonds.empty()) S.segs.push_back(std::move(g));
     }
+  // halo rounds: in round delta every rank sends the stream of its segment for rank+delta and receives
+  // the one of rank-delta (every rank makes the same calls, MPI_Sendrecv style)
+  S.rounds.assign(P, 0);
+  for (const SpaceSeg& g : S.segs) S.rounds[(g.user - g.owner + P) % P] = 1;
 }
 
 inline int window_of(double t, int W) {
@@ -446,7 +432,10 @@ struct lq_engine {
   DBuf<lq::SpGSeg> sp_gseg;
   DBuf<int> sp_site, sp_sseg, sp_bond, sp_bseg;
   DBuf<uint32_t> sp_cnt, sp_base, sp_bnode;
-  DBuf<uint8_t> sp_spin_send, sp_spin_recv;
+  DBuf<uint8_t> sp_pk_spin;
+  DBuf<double> sp_pk_time;
+  DBuf<uint32_t> sp_pk_info;
+  DBuf<int> sp_gt_off, sp_gt_lb, sp_gt_j;
   DBuf<uint32_t> sp_bond_key;
   long long sp_maxcap = 0;
   int gstride() const { return 8 + (has_site ? 1 : 0) + sdim; }
@@ -767,6 +756,26 @@ struct lq_engine {
       for (const auto& x : sp_segs_h) { spd.nst += x.ns; spd.nbt += x.nb; }
       sp_site.upload(hs, &device_bytes); sp_sseg.upload(hss, &device_bytes);
       sp_bond.upload(hb, &device_bytes); sp_bseg.upload(hbs, &device_bytes);
+      {
+        // per ghost tile: the buckets its owner sends (bonds of the user-side segments), ascending
+        std::vector<std::vector<std::pair<int, int>>> need((size_t)std::max(0, Tl - To));
+        for (size_t i = 0; i < sp_segs_h.size(); ++i) {
+          if (!sp_segs_h[i].user_side) continue;
+          for (int j = sp_segs_h[i].bond0; j < sp_segs_h[i].bond0 + sp_segs_h[i].nb; ++j) {
+            const int t = part.bond_tile[hb[j]];
+            if (t < To) fail(LQ_E_INVALID, "spatial cut: ghost bond in an owned tile (internal error)");
+            need[t - To].push_back({hb[j] - part.bond_base[t], j});
+          }
+        }
+        std::vector<int> go(1, 0), glb, gj;
+        for (auto& v : need) {
+          std::sort(v.begin(), v.end());
+          for (auto& x : v) { glb.push_back(x.first); gj.push_back(x.second); }
+          go.push_back((int)glb.size());
+        }
+        if (glb.empty()) { glb.push_back(0); gj.push_back(0); }
+        sp_gt_off.upload(go, &device_bytes); sp_gt_lb.upload(glb, &device_bytes); sp_gt_j.upload(gj, &device_bytes);
+      }
       // Philox counters of K1: the bond id every rank agrees on (two ranks must not draw the same
       // stream for their bonds number 0, 1, ...)
       std::vector<uint32_t> key(part.B);
@@ -990,14 +999,14 @@ struct lq_engine {
         spd.cnt = sp_cnt.p; spd.base = sp_base.p; spd.bnode = sp_bnode.p;
         spd.site = sp_site.p; spd.sseg = sp_sseg.p; spd.bond = sp_bond.p; spd.bseg = sp_bseg.p;
         spd.seg = sp_seg.p; spd.gseg = sp_gseg.p;
-        // staging of the ghost spins: (Wl + 1) rows per exchanged run of tiles
-        size_t ssend = 0, srecv = 0;
-        for (int dl = 1; dl < opt.nranks; ++dl) {
-          for (const auto& r : plan.send_runs[dl]) if (r.walked) ssend += (size_t)(part.site_base[r.tile0 + r.ntiles] - part.site_base[r.tile0]);
-          for (const auto& r : plan.recv_runs[dl]) if (r.walked) srecv += (size_t)(part.site_base[r.tile0 + r.ntiles] - part.site_base[r.tile0]);
-        }
-        sp_spin_send.alloc(std::max<size_t>(1, ssend * (size_t)(Wl + 1)), tb);
-        sp_spin_recv.alloc(std::max<size_t>(1, srecv * (size_t)(Wl + 1)), tb);
+        // halo streams (k_sp_pack / k_sp_unpack): operators and spins of this rank's segments
+        long long pk = 0, spb = 0;
+        for (auto& x : sp_segs_h) { pk += x.opcap; spb += (long long)x.ns * (Wl + 1); }
+        sp_pk_time.alloc((size_t)std::max<long long>(pk, 1), tb);
+        sp_pk_info.alloc((size_t)std::max<long long>(pk, 1), tb);
+        sp_pk_spin.alloc((size_t)std::max<long long>(spb, 1), tb);
+        spd.pk_time = sp_pk_time.p; spd.pk_info = sp_pk_info.p; spd.pk_spin = sp_pk_spin.p;
+        spd.gt_off = sp_gt_off.p; spd.gt_lb = sp_gt_lb.p; spd.gt_j = sp_gt_j.p;
       }
     }
     CK(cudaMemset(est.p, 0, est.n * sizeof(long long)));
@@ -1030,10 +1039,13 @@ struct lq_engine {
     if ((long long)opt.nranks * spd.stride >= 0x7ffffff0ll) fail(LQ_E_INVALID, "spatial cut: boundary too large");
     spd.ngseg = (int)gs.size();
     if (gs.empty()) gs.push_back({0, 0, 0, 0, 0});
+    long long pk = 0, spb = 0;
     for (size_t i = 0; i < sp_segs_h.size(); ++i) {
       const SpaceSeg& g = plan.segs[sp_seg_index[i]];
       sp_segs_h[i].off = sp_segs_h[i].user_side ? g.off_user : g.off_owner;
       sp_segs_h[i].opcap = g.opcap;
+      sp_segs_h[i].pk0 = pk; pk += g.opcap;
+      sp_segs_h[i].sp0 = spb; spb += (long long)sp_segs_h[i].ns * (Wl + 1);
     }
     std::vector<lq::SpSeg> hseg = sp_segs_h;
     if (hseg.empty()) hseg.push_back(lq::SpSeg{});
@@ -1159,11 +1171,10 @@ struct lq_engine {
         const size_t nghost = (size_t)npo * (size_t)(P - Pown) * (size_t)cap;
         const size_t ncnt = (size_t)spd.nbt * Wl;
         if (nghost) lq::k_sp_init_ghost<<<grid_for(nghost, 256), 256, 0, stream>>>(d);
-        if (ncnt) lq::k_sp_count<<<grid_for(ncnt, 256), 256, 0, stream>>>(d, spd, cur);
-        scan_u32(sp_cnt.p, sp_base.p, ncnt + 1, nullptr, nullptr);
+        // (bucket sizes and offsets of the segments: left by the halo exchange that precedes every labelling)
         CK(cudaMemsetAsync(sp_bnode.p, 0xff, sp_bnode.n * sizeof(uint32_t), stream));
         lq::k_sp_fill<<<grid_for(std::max<size_t>(std::max(ncnt, (size_t)spd.nst), 1), 256), 256, 0, stream>>>(d, spd, cur);
-        launches += 3;
+        launches += 2;
       }
     }
     {
@@ -1310,69 +1321,64 @@ struct lq_engine {
     ++mr_step;
   }
 
-  // ---- spatial cut: ghost pages and ghost spins (SpacePlan) ----------------------------------------
-  // `full`: whole pages (times, info words, bucket offsets, counts) -- after K1 has written new pages;
-  // else only the info words -- before K1, which has to see the operator flips of the previous step
-  // on its halo buckets -- and, with `spins`, the spins of the walked ghost sites.
+  // ---- spatial cut: halo exchange (SpacePlan) ---------------------------------------------------
+  // Every owner packs the buckets of its segments' bonds into a dense stream (k_sp_pack), the streams
+  // travel by ncclSend/ncclRecv (one group: both neighbours at once) or lq_comm.send_recv, and the user
+  // rebuilds its ghost pages from them (k_sp_unpack).  Twice per step: before K1 -- the flips of the
+  // previous step changed operator types and spins -- and after it, for the new operators.
   struct XMsg { const void* s; size_t sb; void* r; size_t rb; };
-  bool in_group = false;
   void xchg_round(int dl, const std::vector<XMsg>& msgs) {
     const int Pn = opt.nranks, dst = (opt.rank + dl) % Pn, src = (opt.rank - dl + Pn) % Pn;
     if (nccl) {
       NcclApi& a = nccl_api();
       for (const XMsg& m : msgs) {
-        if (m.sb) nccl_check(a.Send(m.s, m.sb, ncclChar, dst, nccl, stream), "ncclSend(ghost pages)");
-        if (m.rb) nccl_check(a.Recv(m.r, m.rb, ncclChar, src, nccl, stream), "ncclRecv(ghost pages)");
+        if (m.sb) nccl_check(a.Send(m.s, m.sb, ncclChar, dst, nccl, stream), "ncclSend(halo stream)");
+        if (m.rb) nccl_check(a.Recv(m.r, m.rb, ncclChar, src, nccl, stream), "ncclRecv(halo stream)");
       }
     } else {
       if (!comm.send_recv) fail(LQ_E_COMM, "the spatial cut needs lq_comm.send_recv (or lq_comm_init)");
       for (const XMsg& m : msgs)
-        comm_check(comm.send_recv(comm.ctx, m.s, (int64_t)m.sb, dst, m.r, (int64_t)m.rb, src, stream), "send_recv(ghost pages)");
+        comm_check(comm.send_recv(comm.ctx, m.s, (int64_t)m.sb, dst, m.r, (int64_t)m.rb, src, stream), "send_recv(halo stream)");
     }
   }
-  void exchange_ghosts(int buf, bool full, bool spins) {
+  void exchange_ghosts(int buf, bool spins) {
     Section s(this, 8);
-    size_t so = 0, ro = 0;
+    const size_t ncnt = (size_t)spd.nbt * Wl, nspin = spins ? (size_t)spd.nst * (size_t)(Wl + 1) : 0;
+    // owner side: bucket sizes -> dense offsets -> stream
+    if (ncnt) lq::k_sp_count<<<grid_for(ncnt, 256), 256, 0, stream>>>(d, spd, buf);
+    scan_u32(sp_cnt.p, sp_base.p, ncnt + 1, nullptr, nullptr);
+    lq::k_sp_pack<<<grid_for(std::max<size_t>(std::max(ncnt, nspin), 1), 256), 256, 0, stream>>>(d, spd, buf, spins ? 1 : 0);
+    launches += 5;
     std::vector<XMsg> msgs;
-    struct Unpack { size_t off, len; int site0; };
-    std::vector<Unpack> unpack;
-    const size_t nb1 = (size_t)part.nbmax + 1;
-    // (engine-owned NCCL: ONE group for all rounds, so that the transfers to and from both neighbours overlap)
     if (nccl) nccl_check(nccl_api().GroupStart(), "ncclGroupStart");
     for (int dl = 1; dl < opt.nranks; ++dl) {
       if (!plan.rounds[dl]) continue;
-      msgs.clear();
-      const auto& sr = plan.send_runs[dl];
-      const auto& rr = plan.recv_runs[dl];
-      for (int k = 0; k < plan.rounds[dl]; ++k) {
-        const SpaceRun* a = k < (int)sr.size() ? &sr[k] : nullptr;
-        const SpaceRun* b = k < (int)rr.size() ? &rr[k] : nullptr;
-        const size_t pa = a ? (size_t)a->ntiles * Wl : 0, pb = b ? (size_t)b->ntiles * Wl : 0;
-        const size_t a0 = a ? (size_t)a->tile0 * Wl : 0, b0 = b ? (size_t)b->tile0 * Wl : 0;
-        msgs.push_back({info[buf].p + a0 * cap, pa * cap * sizeof(uint32_t), info[buf].p + b0 * cap, pb * cap * sizeof(uint32_t)});
-        if (full) {
-          msgs.push_back({time_[buf].p + a0 * cap, pa * cap * sizeof(double), time_[buf].p + b0 * cap, pb * cap * sizeof(double)});
-          msgs.push_back({boff[buf].p + a0 * nb1, pa * nb1 * sizeof(uint16_t), boff[buf].p + b0 * nb1, pb * nb1 * sizeof(uint16_t)});
-          msgs.push_back({pcount[buf].p + a0, pa * sizeof(int), pcount[buf].p + b0, pb * sizeof(int)});
-        }
-        if (spins) {
-          const size_t la = (a && a->walked) ? (size_t)(part.site_base[a->tile0 + a->ntiles] - part.site_base[a->tile0]) : 0;
-          const size_t lb = (b && b->walked) ? (size_t)(part.site_base[b->tile0 + b->ntiles] - part.site_base[b->tile0]) : 0;
-          const size_t rows = (size_t)Wl + 1;
-          if (la) CK(cudaMemcpy2DAsync(sp_spin_send.p + so, la, spinW.p + part.site_base[a->tile0], (size_t)Ns, la, rows,
-                                       cudaMemcpyDeviceToDevice, stream));
-          msgs.push_back({sp_spin_send.p + so, la * rows, sp_spin_recv.p + ro, lb * rows});
-          if (lb) unpack.push_back({ro, lb, part.site_base[b->tile0]});
-          so += la * rows;
-          ro += lb * rows;
-        }
+      const int dst = (opt.rank + dl) % opt.nranks, src = (opt.rank - dl + opt.nranks) % opt.nranks;
+      const lq::SpSeg* a = nullptr; const lq::SpSeg* b = nullptr;   // my segment for dst / src's segment for me
+      for (size_t i = 0; i < sp_segs_h.size(); ++i) {
+        const SpaceSeg& g = plan.segs[sp_seg_index[i]];
+        if (g.owner == opt.rank && g.user == dst) a = &sp_segs_h[i];
+        if (g.user == opt.rank && g.owner == src) b = &sp_segs_h[i];
       }
+      msgs.clear();
+      auto add = [&](auto* base, auto off_of, auto len_of) {
+        typedef std::remove_pointer_t<decltype(base)> T;
+        msgs.push_back({a ? (const void*)(base + off_of(*a)) : nullptr, a ? len_of(*a) * sizeof(T) : 0,
+                        b ? (void*)(base + off_of(*b)) : nullptr, b ? len_of(*b) * sizeof(T) : 0});
+      };
+      add(sp_cnt.p, [&](const lq::SpSeg& x) { return (size_t)x.bond0 * Wl; }, [&](const lq::SpSeg& x) { return (size_t)x.nb * Wl; });
+      add(sp_pk_time.p, [&](const lq::SpSeg& x) { return (size_t)x.pk0; }, [&](const lq::SpSeg& x) { return (size_t)x.opcap; });
+      add(sp_pk_info.p, [&](const lq::SpSeg& x) { return (size_t)x.pk0; }, [&](const lq::SpSeg& x) { return (size_t)x.opcap; });
+      if (spins)
+        add(sp_pk_spin.p, [&](const lq::SpSeg& x) { return (size_t)x.sp0; }, [&](const lq::SpSeg& x) { return (size_t)x.ns * (size_t)(Wl + 1); });
       xchg_round(dl, msgs);
     }
     if (nccl) nccl_check(nccl_api().GroupEnd(), "ncclGroupEnd");
-    for (const Unpack& u : unpack)
-      CK(cudaMemcpy2DAsync(spinW.p + u.site0, (size_t)Ns, sp_spin_recv.p + u.off, u.len, u.len, (size_t)Wl + 1,
-                           cudaMemcpyDeviceToDevice, stream));
+    // user side: the received bucket sizes complete the count table -> offsets -> ghost pages
+    scan_u32(sp_cnt.p, sp_base.p, ncnt + 1, nullptr, nullptr);
+    const size_t nghost = (size_t)(Tl - To) * Wl;
+    if (nghost) lq::k_sp_unpack<<<(unsigned)nghost, 256, 0, stream>>>(d, spd, buf, spins ? 1 : 0);
+    launches += 4;
   }
 
   void finish_open_clusters(double* out_slot, const lq::StepParams* sp) {
@@ -1418,7 +1424,7 @@ struct lq_engine {
   }
 
   void enqueue_step(double* out_slot, const lq::StepParams* sp) {
-    if (space) exchange_ghosts(cur, false, true);   // the flips of the previous step: types of the ghost operators, ghost spins
+    if (space) exchange_ghosts(cur, true);   // the flips of the previous step: types of the ghost operators, ghost spins
     {
       Section s(this, 5);
       const unsigned nch = (unsigned)((Wl + k1_chunk - 1) / k1_chunk);
@@ -1426,7 +1432,7 @@ struct lq_engine {
       launches += 1;
       cur ^= 1;
     }
-    if (space) exchange_ghosts(cur, true, false);   // the new pages of the ghost tiles
+    if (space) exchange_ghosts(cur, false);   // the new operators on the halo bonds
     label_clusters(out_slot, sp, true);   // includes the flip of the operators (fused into K4)
     {
       Section s(this, 15);
@@ -1585,7 +1591,7 @@ struct lq_engine {
     // boundaries can be recomputed for every site this rank reads.)
     if (space) {
       if (!has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
-      exchange_ghosts(cur, false, true);
+      exchange_ghosts(cur, true);
     }
     int64_t n = 0;
     get_state(nullptr, nullptr, &n, true);
@@ -1754,7 +1760,7 @@ struct lq_engine {
     if (opt.nranks > 1 && !has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
     ensure_out(1);
     stage_params(1, false);
-    if (space) exchange_ghosts(cur, false, true);
+    if (space) exchange_ghosts(cur, true);
     label_clusters(d_out.p, d_params.p, false);
     labels.alloc(2 * (size_t)std::max<long long>(ncap, 1), nullptr);
     lq::k_export_labels<<<(unsigned)P, 256, 0, stream>>>(d, cur, labels.p);

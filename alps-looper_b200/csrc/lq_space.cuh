@@ -30,6 +30,8 @@ struct SpSeg {          // a boundary segment this rank takes part in
   int site0, bond0;     // first entry in the site / bond tables
   int user_side;        // this rank holds the GHOST copies of the segment's nodes
   int pad;
+  long long pk0;        // first operator slot of the segment in the packed halo stream (pk_time / pk_info)
+  long long sp0;        // first byte of the segment in the packed spin stream
 };
 struct SpGSeg { int owner, user; long long off_owner, off_user, cap; };
 
@@ -47,6 +49,14 @@ struct SpDev {
   uint32_t* base;       // [nbt*Wl + 2] exclusive scan
   node_t* bnode;        // [cbmax] local node of every entry (NODE_NONE: unused)
   const SpGSeg* gseg;   // [ngseg] all segments of the run
+  // halo stream: the operators of the segments' bonds, dense in (bond, window, slot) order -- what the
+  // owner sends instead of whole pages; the user rebuilds its ghost pages from it
+  double* pk_time;      // [sum of opcap over this rank's segments]
+  uint32_t* pk_info;
+  uint8_t* pk_spin;     // [(Wl+1) * ns per segment] spins of the segments' sites at every window start
+  const int* gt_off;    // [ghost tiles + 1] needed buckets of a ghost tile ...
+  const int* gt_lb;     //   local bucket in the tile (ascending)
+  const int* gt_j;      //   its bond entry (index into bond / bseg)
 };
 
 // Ghost nodes nobody here refers to must not become clusters: they start as NODE_JUNK (k_compress and
@@ -89,6 +99,91 @@ __global__ void k_sp_fill(Dev d, SpDev sp, int buf) {
       if (fits) sp.bnode[g.off + g.ns + (long long)d.npo * (rel + k) + side] = x;
       if (g.user_side) d.parent[x] = x;
     }
+}
+
+// owner side: the buckets of the segments' bonds -> dense stream (same order as the boundary entries)
+__global__ void k_sp_pack(Dev d, SpDev sp, int buf, int with_spins) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (with_spins && i < (size_t)sp.nst * (size_t)(d.Wl + 1)) {   // spins of the segments' sites, row w = window start w
+    const size_t e = i % (size_t)sp.nst, w = i / (size_t)sp.nst;
+    const SpSeg g = sp.seg[sp.sseg[e]];
+    if (!g.user_side) sp.pk_spin[g.sp0 + (long long)w * g.ns + ((long long)e - g.site0)] = d.spinW[w * (size_t)d.N + sp.site[e]];
+  }
+  if (i >= (size_t)sp.nbt * d.Wl) return;
+  const int j = (int)(i / d.Wl), wl = (int)(i - (size_t)j * d.Wl);
+  const SpSeg g = sp.seg[sp.bseg[j]];
+  if (g.user_side) return;
+  const long long rel = (long long)sp.base[i] - (long long)sp.base[(size_t)g.bond0 * d.Wl];
+  const BucketRef r = bucket_of(d, buf, sp.bond[j], wl);
+  if (rel + r.n > g.opcap) { atomicOr(d.d_err, LQ_ERR_NODE_FULL); return; }   // (the user sees the same counts and skips the bucket too)
+  for (int k = 0; k < r.n; ++k) {
+    sp.pk_time[g.pk0 + rel + k] = d.time[buf][r.base + k];
+    sp.pk_info[g.pk0 + rel + k] = d.info[buf][r.base + k];
+  }
+}
+
+// user side: one CTA per ghost page rebuilds it from the stream -- the needed buckets of the tile in
+// ascending bucket order, all other buckets empty
+__global__ void __launch_bounds__(256)
+k_sp_unpack(Dev d, SpDev sp, int buf, int with_spins) {
+  __shared__ int s_scan[34];
+  __shared__ int s_carry;
+  if (with_spins) {   // (grid-stride over the received spins; every CTA takes its share)
+    const size_t total = (size_t)sp.nst * (size_t)(d.Wl + 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+      const size_t e = i % (size_t)sp.nst, w = i / (size_t)sp.nst;
+      const SpSeg g = sp.seg[sp.sseg[e]];
+      if (g.user_side) d.spinW[w * (size_t)d.N + sp.site[e]] = sp.pk_spin[g.sp0 + (long long)w * g.ns + ((long long)e - g.site0)];
+    }
+  }
+  const int gt = (int)(blockIdx.x / (unsigned)d.Wl), wl = (int)(blockIdx.x - (unsigned)gt * (unsigned)d.Wl);
+  const int t = d.Pown / d.Wl + gt;   // ghost tiles follow the owned ones
+  const size_t p = (size_t)t * d.Wl + wl;
+  const int nb = d.bond_base[t + 1] - d.bond_base[t];
+  uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1);
+  double* pt = d.time[buf] + p * (size_t)d.cap;
+  uint32_t* pi = d.info[buf] + p * (size_t)d.cap;
+  const int e0 = sp.gt_off[gt], ne = sp.gt_off[gt + 1] - e0;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int nchunks = max(1, (ne + (int)blockDim.x - 1) / (int)blockDim.x);
+  for (int c = 0; c < nchunks; ++c) {
+    const int e = c * (int)blockDim.x + (int)threadIdx.x;
+    int n = 0, lb = 0;
+    long long src = 0;
+    if (e < ne) {
+      lb = sp.gt_lb[e0 + e];
+      const int j = sp.gt_j[e0 + e];
+      const SpSeg g = sp.seg[sp.bseg[j]];
+      const size_t ci = (size_t)j * d.Wl + wl;
+      const long long rel = (long long)sp.base[ci] - (long long)sp.base[(size_t)g.bond0 * d.Wl];
+      n = (int)sp.cnt[ci];
+      if (rel + n > g.opcap) { atomicOr(d.d_err, LQ_ERR_NODE_FULL); n = 0; }   // (the owner did not pack it either)
+      src = g.pk0 + rel;
+    }
+    int total;
+    const int ex = block_exscan(n, &total, s_scan);
+    const int carry = s_carry;
+    int off = carry + ex;
+    if (carry + total > d.cap) {   // cannot happen with identical page capacities; never write beyond the page
+      if (threadIdx.x == 0) atomicOr(d.d_err, LQ_ERR_PAGE_FULL);
+      n = 0;
+      off = min(off, d.cap);
+    }
+    if (e < ne) {
+      // the buckets after the previous needed one up to this one all start where this one starts
+      const int lb_prev = (e == 0) ? -1 : sp.gt_lb[e0 + e - 1];
+      for (int b = lb_prev + 1; b <= lb; ++b) bo[b] = (uint16_t)off;
+      for (int k = 0; k < n; ++k) { pt[off + k] = sp.pk_time[src + k]; pi[off + k] = sp.pk_info[src + k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = min(carry + total, d.cap);
+    __syncthreads();
+  }
+  const int tot = s_carry;
+  const int lb_last = ne > 0 ? sp.gt_lb[e0 + ne - 1] : -1;
+  for (int b = lb_last + 1 + (int)threadIdx.x; b <= nb; b += blockDim.x) bo[b] = (uint16_t)tot;
+  if (threadIdx.x == 0) d.pcount[buf][p] = tot;
 }
 
 __global__ void k_sp_topmin(Dev d, SpDev sp, MrDev m) {
