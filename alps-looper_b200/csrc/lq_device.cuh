@@ -68,8 +68,9 @@ struct Dev {
   int Nown;         // owned sites [0, Nown)
   int Nwalk;        // sites whose world lines are walked here [0, Nwalk): owned + W ghost tiles
   int Pown;         // owned pages [0, Pown)
-  const uint32_t* bond_key;   // spatial cut: rank-independent id of a bond for the Philox counters (the internal
-                              // numbering differs from rank to rank); NULL: the internal bond id itself
+  const uint32_t* tile_key;   // spatial cut: rank-independent id of a tile; the Philox counters of K1 use
+                              // tile_key << 10 | local bond (the internal bond numbering differs from rank to
+                              // rank: two ranks must not draw the same stream); NULL: the internal bond id
   const int* bond_s0;    // [B] source site
   const int* bond_s1;    // [B] target site
   const int* bond_tl;    // [B] owning tile << 10 | local bond index

@@ -776,10 +776,10 @@ struct lq_engine {
         if (glb.empty()) { glb.push_back(0); gj.push_back(0); }
         sp_gt_off.upload(go, &device_bytes); sp_gt_lb.upload(glb, &device_bytes); sp_gt_j.upload(gj, &device_bytes);
       }
-      // Philox counters of K1: the bond id every rank agrees on (two ranks must not draw the same
-      // stream for their bonds number 0, 1, ...)
-      std::vector<uint32_t> key(part.B);
-      for (int i = 0; i < part.B; ++i) key[i] = (uint32_t)part.bond_i2e[i];
+      // Philox counters of K1: a tile id every rank agrees on (two ranks must not draw the same
+      // stream for their tiles number 0, 1, ...): the tile's id in the global tiling
+      std::vector<uint32_t> key(part.T);
+      for (int t = 0; t < part.T; ++t) key[plan.relabel[t]] = (uint32_t)t;
       sp_bond_key.upload(key, &device_bytes);
     }
     d_ntotal.alloc(1, &device_bytes);
@@ -1055,7 +1055,7 @@ struct lq_engine {
 
   void fill_dev() {
     d.N = Ns; d.B = part.B; d.T = Tl; d.nbmax = part.nbmax;
-    d.bond_key = space ? sp_bond_key.p : nullptr;
+    d.tile_key = space ? sp_bond_key.p : nullptr;
     d.space = space ? 1 : 0; d.Nown = Nown; d.Nwalk = Nwalk; d.Pown = (int)Pown;
     d.W = W; d.w0 = w0; d.Wl = Wl; d.cap = cap; d.npo = npo; d.ug = ug; d.has_site = has_site ? 1 : 0;
     d.zero_umag = zero_umag ? 1 : 0; d.zero_ssize = zero_ssize ? 1 : 0;

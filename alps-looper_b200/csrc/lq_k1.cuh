@@ -213,6 +213,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
 
   // ---- per-tile constants -----------------------------------------------------------------------
   const int b0 = d.bond_base[t], nb = d.bond_base[t + 1] - b0;
+  const uint32_t kbase = d.tile_key ? (d.tile_key[t] << 10) : (uint32_t)b0;   // Philox counter of bucket lb: kbase + lb
   const int h0 = d.halo_off[t], nh = d.halo_off[t + 1] - h0;
   const int cls = d.tile_class[t];
   const int nks = d.cls_nks[cls];
@@ -312,7 +313,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
         const double mu = beta * d.bond_rate[b] * width;
         int K = 0;
         if (mu > 0) {
-          const philox_t x = philox4x32_10(d.bond_key ? d.bond_key[b] : (uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND, key0, key1);
+          const philox_t x = philox4x32_10(kbase + (uint32_t)lb, (uint32_t)wg, mcs, LQ_STREAM_CAND, key0, key1);
           bool ovf;
           K = k1_poisson(u53(x.x, x.y), d.bond_emu[b], mu, &ovf);
           if (ovf) atomicOr(d.d_err, LQ_ERR_CAND_FULL);
@@ -392,7 +393,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
       const int lb = S.cmeta[c];
       const int i = c - S.cbase[lb];
       const int b = b0 + lb;
-      const philox_t x = philox4x32_10(d.bond_key ? d.bond_key[b] : (uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_CAND + 1u + (uint32_t)i, key0, key1);
+      const philox_t x = philox4x32_10(kbase + (uint32_t)lb, (uint32_t)wg, mcs, LQ_STREAM_CAND + 1u + (uint32_t)i, key0, key1);
       // 53 uniform bits, (x.x << 32 | x.y) >> 11, converted in two exact 32-bit halves
       const double frac = __uint2double_rn(x.x >> 11) * (1.0 / 2097152.0) +
                           __uint2double_rn((x.x << 21) | (x.y >> 11)) * (1.0 / 9007199254740992.0);
@@ -498,7 +499,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
       const int b = b0 + lb;
       const float q0 = d.bond_q[b];
       if (q0 < 1.0f) {  // graph_impl.h:324-327 choose_offdiagonal
-        const philox_t x = philox4x32_10(d.bond_key ? d.bond_key[b] : (uint32_t)b, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)r0, key0, key1);
+        const philox_t x = philox4x32_10(kbase + (uint32_t)lb, (uint32_t)wg, mcs, LQ_STREAM_OFFD + (uint32_t)r0, key0, key1);
         g = (u24(x.x) < q0) ? 0u : 1u;
       }
       const int pos = S.noff[lb] + rank;
