@@ -922,8 +922,15 @@ k_estimate_sites(Dev d) {
 // ------------------------------------------------------------------------------------------
 #define LQ_NSUM 16   /* 14 susceptibility sums (susceptibility.h:158-160), transmag length (transmag.h:98), stiffness w2 */
 #define LQ_NSUS 14
-#define LQ_GEST_MAX 12   /* int64 fields per global open cluster: 4 sums, 4 tau=0 sums, [site-leg count], [windings];
-                            d.gstride = 8 + has_site + sdim of them travel in the all-reduce */
+#define LQ_GEST_MAX 10   /* int64 fields per global open cluster: 4 sums, the 4 tau=0 sums packed in 2, [site-leg count],
+                            [windings]; d.gstride = 6 + has_site + sdim of them travel in the all-reduce */
+// two int32 sums in one int64 field, additive: x = hi * 2^32 + lo as INTEGERS (not bit fields), so the
+// sum of packed values is the packed pair of sums as long as both stay inside int32
+__device__ __forceinline__ unsigned long long pack2_i32(int hi, int lo) {
+  return (unsigned long long)((long long)hi * 4294967296ll + (long long)lo);
+}
+__device__ __forceinline__ int unpack2_lo(long long x) { return (int)(unsigned)(unsigned long long)x; }
+__device__ __forceinline__ int unpack2_hi(long long x, int lo) { return (int)((x - (long long)lo) >> 32); }
 __global__ void __launch_bounds__(256)
 k_collect(Dev d, double* partial) {
   __shared__ double s_red[8][LQ_NSUM];
@@ -1290,11 +1297,14 @@ k_mr_gather(Dev d, MrDev m) {
 #pragma unroll
       for (int f = 0; f < 4; ++f) v[f] = atomicExch((unsigned long long*)d.est + f * d.nccap + c, 0ull);
       if (c < ncs) {
+        int z[4];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) v[4 + f] = (unsigned long long)(long long)atomicExch(d.est0 + f * (size_t)d.N + c, 0);
+        for (int f = 0; f < 4; ++f) z[f] = atomicExch(d.est0 + f * (size_t)d.N + c, 0);
+        v[4] = pack2_i32(z[0], z[1]);   // the four tau = 0 sums (|x| <= N) travel as two fields
+        v[5] = pack2_i32(z[2], z[3]);
       }
-      if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[8] = 1ull;
-      for (int x = 0; x < d.sdim; ++x) v[8 + d.has_site + x] = (unsigned long long)(long long)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
+      if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[6] = 1ull;
+      for (int x = 0; x < d.sdim; ++x) v[6 + d.has_site + x] = (unsigned long long)(long long)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
       ++nrep;
       if (gid >= m.gcap) {   // more open clusters than the all-reduce of this step carries: the step is lost
         atomicOr(d.d_err, LQ_ERR_OPEN_FULL);
@@ -1374,10 +1384,11 @@ k_mr_gcollect(Dev d, MrDev m, double* partial) {
     long long* ge = m.gest + c * d.gstride;
     const double usize = sc * i64_to_f64(ge[0]), umag = sc * i64_to_f64(ge[1]);
     const double ssize = sc * i64_to_f64(ge[2]), smag = sc * i64_to_f64(ge[3]);
-    const double usize0 = 0.5 * i64_to_f64(ge[4]), umag0 = 0.5 * i64_to_f64(ge[5]);
-    const double ssize0 = 0.5 * i64_to_f64(ge[6]), smag0 = 0.5 * i64_to_f64(ge[7]);
-    if (d.has_site && ge[8] > 0) v[14] += 2.0 * usize;
-    for (int x = 0; x < d.sdim; ++x) { const double w = d.wscale[x] * i64_to_f64(ge[8 + d.has_site + x]); v[15] += w * w; }
+    const int u0 = unpack2_lo(ge[4]), u1 = unpack2_lo(ge[5]);
+    const double usize0 = 0.5 * (double)unpack2_hi(ge[4], u0), umag0 = 0.5 * (double)u0;
+    const double ssize0 = 0.5 * (double)unpack2_hi(ge[5], u1), smag0 = 0.5 * (double)u1;
+    if (d.has_site && ge[6] > 0) v[14] += 2.0 * usize;
+    for (int x = 0; x < d.sdim; ++x) { const double w = d.wscale[x] * i64_to_f64(ge[6 + d.has_site + x]); v[15] += w * w; }
     for (int f = 0; f < d.gstride; ++f) ge[f] = 0;
     const double a = usize0 * usize0, b = umag0 * umag0, e = ssize0 * ssize0, g = smag0 * smag0;
     v[0] += umag0; v[1] += a; v[2] += b; v[3] += a * a; v[4] += b * b; v[5] += usize * usize; v[6] += umag * umag;

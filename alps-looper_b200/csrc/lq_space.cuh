@@ -282,11 +282,14 @@ k_sp_gather(Dev d, SpDev sp, MrDev m) {
 #pragma unroll
     for (int f = 0; f < 4; ++f) v[f] = atomicExch((unsigned long long*)d.est + f * d.nccap + c, 0ull);
     if (c < d.d_nc[1]) {
+      int z[4];
 #pragma unroll
-      for (int f = 0; f < 4; ++f) v[4 + f] = (unsigned long long)(long long)atomicExch(d.est0 + f * (size_t)d.N + c, 0);
+      for (int f = 0; f < 4; ++f) z[f] = atomicExch(d.est0 + f * (size_t)d.N + c, 0);
+      v[4] = pack2_i32(z[0], z[1]);   // the four tau = 0 sums (|x| <= N) travel as two fields
+      v[5] = pack2_i32(z[2], z[3]);
     }
-    if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[8] = 1ull;
-    for (int x = 0; x < d.sdim; ++x) v[8 + d.has_site + x] = (unsigned long long)(long long)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
+    if (d.has_site && ((d.openw[c >> 5] >> (c & 31u)) & 1u)) v[6] = 1ull;
+    for (int x = 0; x < d.sdim; ++x) v[6 + d.has_site + x] = (unsigned long long)(long long)atomicExch(d.wind + (size_t)x * d.nccap + c, 0);
     if (gid >= m.gcap) {   // (see k_mr_gather)
       atomicOr(d.d_err, LQ_ERR_OPEN_FULL);
       gid = 0u;
