@@ -88,6 +88,13 @@ public:
     o.cluster_reserve = p.value_or_default<double>("RESERVE_ESTIMATES_FACTOR", 0.0);
     o.flags = p.defined("ENABLE_TIMER") ? 1 : 0;
     o.representation = sse_ ? LQ_REPR_SSE : LQ_REPR_PATH_INTEGRAL;
+    {
+      // how the ranks share the configuration: "time" = imaginary-time slabs (path_integral_mpi.C:231-232),
+      // "space" = strips of tiles (the lattice sharing of looper/lattice.h:692-787 taken across GPUs)
+      const std::string cut = p.value_or_default<std::string>("PARTITION", "time");
+      if (cut != "time" && cut != "space") throw std::invalid_argument("PARTITION must be \"time\" or \"space\"");
+      o.cut = cut == "space" ? LQ_CUT_SPACE : LQ_CUT_TIME;
+    }
     beta_ = 1.0 / temp(0);
     check(lq_create(&h_, &L, &M, beta_, &o));
     if (comm_.size() > 1) connect();

@@ -62,3 +62,27 @@ def test_space_parity_over_real_nccl(comm):
     assert out.returncode == 0 and lines, (out.stdout[-2000:], out.stderr[-2000:])
     rep = json.loads(lines[-1][len("MGPU_PARITY "):])
     assert rep["ok"] and rep["ranks"] == n and rep["cut"] == "space" and all(c["ok"] for c in rep["cases"]), rep
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("partition", ["time", "space"])
+def test_cpp_driver_two_ranks_vs_exact_diagonalisation(partition):
+    """the C++ host mirror (looper::loop_worker with a communicator, path_integral_mpi.C:75) over two GPUs,
+    no Python in the run: `loop --nranks 2` forks one process per GPU, the NCCL id travels through a file,
+    PARTITION picks the cut; observables against exact diagonalisation of the L = 8 chain at T = 0.2."""
+    import re
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "alps-looper_b200/looper")])
+    exe = os.path.join(ROOT, "alps-looper_b200/looper/loop")
+    params = ('LATTICE = "chain lattice"; L = 8; T = 0.2; SWEEPS = 16384; TILE_SITES = 2; '
+              'PARTITION = "%s";\n' % partition)
+    out = subprocess.run([exe, "--nranks", "2", "-"], input=params, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    vals = {}
+    for ln in out.stdout.splitlines():
+        m = re.match(r"(.+?)\s*=\s*(\S+) \+- (\S+)", ln)
+        if m:
+            vals[m.group(1).strip()] = (float(m.group(2)), float(m.group(3)))
+    ed = {"Energy Density": -0.441438, "Staggered Magnetization^2": 6.59939, "Staggered Susceptibility": 2.40159}
+    for k, ex in ed.items():
+        mean, err = vals[k]
+        assert abs(mean - ex) < 4 * err + 1e-9, (k, mean, err, ex)
