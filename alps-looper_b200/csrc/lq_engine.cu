@@ -8,6 +8,7 @@
 #include "../../include/lq.h"
 #include "lq_kernels.cuh"
 #include "lq_space.cuh"
+#include "lq_rebucket.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: libnccl.so.2 is bound at run time (dlopen), so the
@@ -58,6 +59,7 @@ struct DBuf {  // device array
     p = nullptr;
     n = 0;
   }
+  void take(DBuf& o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
   ~DBuf() { release(); }
 };
 
@@ -1584,11 +1586,70 @@ struct lq_engine {
 
   // operators and spins of this engine (of its slab, on a slab engine) through new arenas: after a
   // change of beta or of an arena size
+  // Everything size_arenas() allocates, freed up front so that a re-size peaks at (old live pages + new
+  // arenas) instead of (all old + all new).
+  void release_arenas() {
+    for (int k = 0; k < 2; ++k) { time_[k].release(); info[k].release(); boff[k].release(); pcount[k].release(); }
+    nbase.release(); spinW.release(); curW.release(); firstW.release(); parent.release(); low0.release(); low1.release();
+    bitmap.release(); wcount.release(); wbase.release(); rootw.release(); xedge.release(); xcount.release();
+    sse_rank.release(); sse_time.release(); sse_id.release(); sse_bincnt.release(); sse_binbase.release(); sse_binfill.release();
+    scan_tmp.release(); est.release(); est0.release(); flipw.release(); wind.release(); openw.release(); partial.release();
+    mr_topmin.release(); mr_sendb.release(); mr_recvb.release(); mr_gparent.release(); mr_gused.release();
+    mr_gbitmap.release(); mr_gwcount.release(); mr_gwbase.release(); mr_gest.release();
+    sp_cnt.release(); sp_base.release(); sp_bnode.release(); sp_pk_time.release(); sp_pk_info.release(); sp_pk_spin.release();
+  }
+
+  // operators and spins of this engine (of its slab / its tiles on a multi-rank engine) into new arenas:
+  // after a change of beta or of an arena size.  On the device (lq_rebucket.cuh): every (tile, bond)
+  // column is already time-ordered and only has to be re-cut at the new window boundaries.
   void rebucket() {
-    // (spatial cut: all ranks come here together -- lq_set_beta is collective, and an overflow makes
-    // every rank rewind.  The ghost pages still carry the operator types of before the last flip:
-    // refresh them, then move owned AND ghost operators, so that the spins at the new window
-    // boundaries can be recomputed for every site this rank reads.)
+    if (getenv("LQ_REBUCKET_HOST")) { rebucket_host(); return; }
+    // (spatial cut: all ranks come here together -- lq_set_beta is collective, and an overflow makes every
+    // rank rewind.  The ghost pages still carry the operator types of before the last flip: refresh them,
+    // the spins at the new window starts are recomputed from the off-diagonal legs of owned AND ghost operators.)
+    if (space) {
+      if (!has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
+      exchange_ghosts(cur, true);
+    }
+    CK(cudaStreamSynchronize(stream));
+    DBuf<double> otime;
+    DBuf<uint32_t> oinfo;
+    DBuf<uint16_t> oboff;
+    DBuf<uint8_t> ospin;
+    otime.take(time_[cur]); oinfo.take(info[cur]); oboff.take(boff[cur]);
+    ospin.alloc((size_t)Ns, nullptr);
+    CK(cudaMemcpy(ospin.p, spinW.p, (size_t)Ns, cudaMemcpyDeviceToDevice));
+    const lq::OldPages o{otime.p, oinfo.p, oboff.p, W, Wl, w0, cap};
+    release_arenas();
+    const int nbl = part.bond_base[Tl];
+    for (int attempt = 0;; ++attempt) {
+      size_arenas();
+      clear_state();
+      CK(cudaDeviceSynchronize());   // (the memsets above ran on the default stream)
+      CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
+      if (nbl) lq::k_rb_columns<0><<<grid_for(nbl, 128), 128, 0, stream>>>(d, o, nbl);
+      lq::k_rb_offsets<<<(unsigned)P, 128, 0, stream>>>(d);
+      int err = 0;
+      CK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      launches += 2;
+      if (!err) break;
+      CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), stream));
+      if ((err & LQ_ERR_BOUNDARY) || space || attempt >= 6)   // (spatial cut: the page capacity is part of the exchange format)
+        fail(LQ_E_OVERFLOW, "the configuration does not fit the new pages (raise lq_options.reserve)");
+      grow_pages *= 1.5;   // a page of the new layout is fuller than its capacity allows: larger pages, again
+      release_arenas();
+    }
+    if (nbl) lq::k_rb_columns<1><<<grid_for(nbl, 128), 128, 0, stream>>>(d, o, nbl);
+    lq::k_rb_spin_parity<<<grid_for((size_t)Wl * Ns, 256), 256, 0, stream>>>(d, Tl);
+    lq::k_rb_spin_scan<<<grid_for(Ns, 128), 128, 0, stream>>>(d, ospin.p);
+    launches += 3;
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+  }
+
+  // the same through the host (lq_get_state -> lq_set_state); kept for LQ_REBUCKET_HOST=1 as a cross-check
+  void rebucket_host() {
     if (space) {
       if (!has_comm) fail(LQ_E_COMM, "nranks > 1 but neither lq_comm_init nor lq_set_comm was called");
       exchange_ghosts(cur, true);

@@ -216,6 +216,40 @@ def test_set_beta_keeps_the_configuration():
     eng.close()
 
 
+def test_set_beta_rebuckets_on_the_device(monkeypatch):
+    """lq_set_beta / the rewind after an overflow must not move the configuration
+    through the host.  The device path (csrc/lq_rebucket.cuh: every (tile, bond) column re-cut at the new
+    window boundaries) against the host path (lq_get_state -> lq_set_state, LQ_REBUCKET_HOST=1) on a
+    4e6-operator configuration: identical pages, spins at every window start and Markov chain afterwards."""
+    import time
+    lq = _lq()
+    lat = lq.hypercubic_lattice((256, 256))
+
+    def run(host):
+        if host:
+            monkeypatch.setenv("LQ_REBUCKET_HOST", "1")
+        else:
+            monkeypatch.delenv("LQ_REBUCKET_HOST", raising=False)
+        eng = lq.Engine(lat, 48.0, seed=17, tile_sites=256)
+        eng.sweep_many(12, collect=False)
+        t0 = time.perf_counter()
+        eng.set_beta(64.0)
+        dt = time.perf_counter() - t0
+        out = eng.sweep_many(3)
+        st = eng.get_state()
+        eng.close()
+        return dt, out, st
+
+    t_dev, out_dev, (s_dev, o_dev) = run(False)
+    t_host, out_host, (s_host, o_host) = run(True)
+    assert len(o_dev) > 3_000_000
+    for f in ("nop", "nc", "usize", "umag2"):
+        assert np.array_equal(out_dev[f], out_host[f]), f
+    assert np.array_equal(s_dev, s_host) and np.array_equal(o_dev, o_host)
+    print(f"set_beta on {len(o_dev)} operators: device {t_dev:.3f} s, through the host {t_host:.3f} s")
+    assert t_dev < t_host
+
+
 def test_checkpoint_roundtrip_continues_identically():
     """save/load payload (path_integral.C:111-124): a second engine loaded with (spins, operators)
     and the same step counter... the step counter is internal, so compare the loaded state itself
