@@ -71,6 +71,14 @@ class LqTiling(C.Structure):
                 ("halo_buckets", C.c_int64)]
 
 
+class LqSpacePlan(C.Structure):
+    _fields_ = [("owned_tiles", C.c_int32), ("walked_ghost_tiles", C.c_int32), ("ghost_tiles", C.c_int32),
+                ("owned_sites", C.c_int32), ("walked_sites", C.c_int32), ("local_sites", C.c_int32),
+                ("segments", C.c_int32), ("neighbours", C.c_int32),
+                ("owner_bonds", C.c_int64), ("owner_sites", C.c_int64), ("user_bonds", C.c_int64),
+                ("user_sites", C.c_int64), ("checksum_owner", C.c_int64), ("checksum_user", C.c_int64)]
+
+
 class LqTimer(C.Structure):
     _fields_ = [("id", C.c_int32), ("count", C.c_int32), ("seconds", C.c_double),
                 ("label", C.c_char * 40)]
@@ -96,7 +104,7 @@ class LqComm(C.Structure):
 
 # every symbol include/lq.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = ["lq_create", "lq_destroy", "lq_set_beta", "lq_set_state", "lq_get_state", "lq_get_step", "lq_set_step", "lq_sweep",
-           "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_enable_timers", "lq_get_info", "lq_tiling_info", "lq_kernel_launches", "lq_regrow_count", "lq_h2d_bytes", "lq_d2h_bytes",
+           "lq_sweep_many", "lq_build_clusters", "lq_timers", "lq_enable_timers", "lq_get_info", "lq_tiling_info", "lq_space_plan_info", "lq_kernel_launches", "lq_regrow_count", "lq_h2d_bytes", "lq_d2h_bytes",
            "lq_set_comm", "lq_comm_unique_id", "lq_comm_init", "lq_stream", "lq_last_error", "lq_version"]
 
 _h = C.c_void_p
@@ -211,6 +219,27 @@ def tiling_info(lattice, tile_sites=0, with_sites=False):
     out = LqTiling()
     _check(lib.lq_tiling_info(C.byref(lat), int(tile_sites), 1 if with_sites else 0, C.byref(out)))
     return {f: getattr(out, f) for f, _ in LqTiling._fields_}
+
+
+def space_plan_info(lattice, nranks, rank, tile_sites=0, with_sites=False, peer=-1):
+    """lq_space_plan_info: what rank `rank` of `nranks` owns and mirrors under the spatial cut (no GPU)."""
+    src = np.ascontiguousarray(lattice["src"], dtype=np.int32)
+    dst = np.ascontiguousarray(lattice["dst"], dtype=np.int32)
+    lat = LqLattice()
+    lat.num_sites = int(lattice["num_sites"])
+    lat.num_bonds = len(src)
+    lat.src = src.ctypes.data_as(C.POINTER(C.c_int32))
+    lat.dst = dst.ctypes.data_as(C.POINTER(C.c_int32))
+    lat.gauge = None
+    lat.dims = (C.c_int32 * 3)(*tuple(lattice.get("dims", (0, 0, 0))))
+    lat.vector_dim = 0
+    lat.bond_vectors = None
+    out = LqSpacePlan()
+    lib.lq_space_plan_info.argtypes = [C.POINTER(LqLattice), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.POINTER(LqSpacePlan)]
+    _check(lib.lq_space_plan_info(C.byref(lat), int(tile_sites), 1 if with_sites else 0, int(nranks), int(rank),
+                                  int(peer), C.byref(out)))
+    return {f: getattr(out, f) for f, _ in LqSpacePlan._fields_}
 
 
 def xxz_weights(jxy, jz, a=0.0):

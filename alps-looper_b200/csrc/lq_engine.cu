@@ -1195,7 +1195,8 @@ struct lq_engine {
     }
     {
       Section s(this, 11);
-      lq::k_compress<<<grid_for(nwords_cap * 32, 256 * LQ_NPT), 256, 0, stream>>>(d, nwords_cap);
+      if (space) lq::k_compress<true><<<grid_for(nwords_cap * 32, 256 * LQ_NPT), 256, 0, stream>>>(d, nwords_cap);
+      else lq::k_compress<false><<<grid_for(nwords_cap * 32, 256 * LQ_NPT), 256, 0, stream>>>(d, nwords_cap);
       scan_u32(wcount.p, wbase.p, nwords_cap, wbase.p + nwords_cap, (int*)d_nc.p);
       if (opt.nranks == 1) {   // flip decision per root (path_integral.C:796-799), packed for k_relabel
         lq::k_rootflip<<<(unsigned)std::min<size_t>((nwords_cap + 255) / 256, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);
@@ -2000,6 +2001,58 @@ int lq_tiling_info(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites
     return LQ_E_INVALID;
   }
   LQ_TRY(tiling_info_impl(lat, tile_sites, with_sites, out))
+}
+
+// peer >= 0: the checksums cover only the segments shared with that rank (so that the two sides can be compared)
+static void space_plan_impl(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites, int32_t nranks, int32_t rank,
+                            int32_t peer, lq_space_plan* out) {
+  if (nranks < 2 || rank < 0 || rank >= nranks || peer >= nranks) fail(LQ_E_INVALID, "bad rank / nranks");
+  for (int b = 0; b < lat->num_bonds; ++b)
+    if (lat->src[b] < 0 || lat->src[b] >= lat->num_sites || lat->dst[b] < 0 || lat->dst[b] >= lat->num_sites ||
+        lat->src[b] == lat->dst[b])
+      fail(LQ_E_INVALID, "bond endpoint out of range");
+  std::vector<int> xsrc(lat->src, lat->src + lat->num_bonds);
+  std::vector<int> xdst(lat->dst, lat->dst + lat->num_bonds);
+  if (with_sites)
+    for (int s = 0; s < lat->num_sites; ++s) { xsrc.push_back(s); xdst.push_back(-1); }
+  const int ts = tile_sites > 0 ? tile_sites : 64;
+  Partition G, L;
+  make_partition(*lat, (int)xsrc.size(), xsrc.data(), xdst.data(), ts, G);
+  SpacePlan S;
+  plan_space(G, nranks, rank, S);
+  make_partition(*lat, (int)xsrc.size(), xsrc.data(), xdst.data(), ts, L, &S.relabel);
+  *out = lq_space_plan{};
+  out->owned_tiles = S.To; out->walked_ghost_tiles = S.Tw; out->ghost_tiles = S.Tloc - S.To;
+  out->owned_sites = L.site_base[S.To]; out->walked_sites = L.site_base[S.To + S.Tw]; out->local_sites = L.site_base[S.Tloc];
+  std::vector<char> nb(nranks, 0);
+  auto mix = [](int64_t h, int64_t v) { return (int64_t)(((uint64_t)h * 1099511628211ull) ^ (uint64_t)(v + 0x9e3779b97f4a7c15ull)); };
+  for (const SpaceSeg& g : S.segs) {
+    if (g.owner != rank && g.user != rank) continue;
+    const int other = g.owner == rank ? g.user : g.owner;
+    out->segments++;
+    nb[other] = 1;
+    const bool counted = peer < 0 || other == peer;
+    int64_t& sum = g.owner == rank ? out->checksum_owner : out->checksum_user;
+    if (g.owner == rank) { out->owner_bonds += (int64_t)g.bonds.size(); out->owner_sites += (int64_t)g.sites.size(); }
+    else { out->user_bonds += (int64_t)g.bonds.size(); out->user_sites += (int64_t)g.sites.size(); }
+    if (counted) {
+      for (int s2 : g.sites) sum = mix(sum, s2);
+      for (int b2 : g.bonds) sum = mix(sum, (int64_t)b2 + ((int64_t)1 << 40));
+    }
+    // every listed bond / site must lie in a tile this rank holds
+    for (int s2 : g.sites) if (L.site_e2i[s2] >= out->local_sites) fail(LQ_E_INVALID, "boundary site outside the local tiles (internal error)");
+    for (int b2 : g.bonds) if (L.bond_tile[L.bond_e2i[b2]] >= S.Tloc) fail(LQ_E_INVALID, "boundary bond outside the local tiles (internal error)");
+  }
+  for (int r = 0; r < nranks; ++r) out->neighbours += nb[r];
+}
+
+int lq_space_plan_info(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites, int32_t nranks, int32_t rank,
+                       int32_t peer, lq_space_plan* out) {
+  if (!lat || !out || lat->num_sites <= 0 || lat->num_bonds < 0 || (lat->num_bonds > 0 && (!lat->src || !lat->dst))) {
+    g_err = "bad argument";
+    return LQ_E_INVALID;
+  }
+  LQ_TRY(space_plan_impl(lat, tile_sites, with_sites, nranks, rank, peer, out))
 }
 
 int lq_get_info(lq_handle h, lq_info* out) {

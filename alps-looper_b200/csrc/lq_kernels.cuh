@@ -519,6 +519,9 @@ __global__ void k_close(Dev d) {
 // copy_id (:338-343) becomes one gather per node.  parent[] ends up holding the cluster id.
 // ------------------------------------------------------------------------------------------
 #define LQ_NPT 4  /* nodes per thread: independent pointer chases in flight */
+// SPACE: engines of the spatial cut hold ghost nodes marked NODE_JUNK (lq_space.cuh); a template parameter so
+// that the serial kernel does not carry the test
+template <bool SPACE>
 __global__ void __launch_bounds__(256)
 k_compress(Dev d, size_t nwords_cap) {
   const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
@@ -533,7 +536,7 @@ k_compress(Dev d, size_t nwords_cap) {
     const size_t x = base + (size_t)k * 256;
     r[k] = (node_t)x;
     pr[k] = (x < nn) ? d.parent[x] : (node_t)x;
-    if (pr[k] == NODE_JUNK) { pr[k] = (node_t)x; junk |= 1u << k; }   // spatial cut: unreferenced ghost node
+    if (SPACE && pr[k] == NODE_JUNK) { pr[k] = (node_t)x; junk |= 1u << k; }   // unreferenced ghost node
   }
   bool any = true;
   unsigned hops = 0;
@@ -552,7 +555,7 @@ k_compress(Dev d, size_t nwords_cap) {
     bool isroot = false;
     if (x < nn) {
       if (r[k] != (node_t)x) d.parent[x] = r[k];
-      isroot = (r[k] == (node_t)x) && !((junk >> k) & 1u);
+      isroot = (r[k] == (node_t)x) && !(SPACE && ((junk >> k) & 1u));
     }
     const uint32_t word = __ballot_sync(0xffffffffu, isroot);
     if ((threadIdx.x & 31) == 0) {   // words beyond the live nodes are cleared: the scan input stays clean

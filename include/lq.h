@@ -146,6 +146,23 @@ typedef struct lq_tiling {
 } lq_tiling;
 int lq_tiling_info(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites, lq_tiling* out);
 
+/* Host-side plan of the spatial cut (lq_options.cut = LQ_CUT_SPACE; no GPU needed): what rank `rank` of
+ * `nranks` owns and mirrors.  The part of lq_create that takes the lattice sharing of
+ * looper/lattice.h:692-787 across GPUs.  For tests and for sizing. */
+typedef struct lq_space_plan {
+  int32_t owned_tiles, walked_ghost_tiles, ghost_tiles;   /* ghost_tiles includes the walked ones          */
+  int32_t owned_sites, walked_sites, local_sites;         /* local = owned + sites of all ghost tiles     */
+  int32_t segments;                                       /* boundary segments this rank takes part in    */
+  int32_t neighbours;                                     /* ranks it exchanges halo streams with         */
+  int64_t owner_bonds, owner_sites;                       /* entries of the segments it OWNS (sends)      */
+  int64_t user_bonds, user_sites;                         /* ... of the segments it uses (receives)       */
+  int64_t checksum_owner, checksum_user;                  /* order-dependent hash of the owner / user side
+                                                             lists (external ids): the user side of rank r
+                                                             for owner q equals q's owner side for r      */
+} lq_space_plan;
+int lq_space_plan_info(const lq_lattice* lat, int32_t tile_sites, int32_t with_sites, int32_t nranks,
+                       int32_t rank, int32_t peer, lq_space_plan* out);
+
 /* Replaces loop_worker::loop_worker (path_integral.C:202-305): builds lattice tables, graph
  * chooser tables, sizes the arenas.  Initial state: all spins up, no operators (:225). */
 int lq_create(lq_handle* out, const lq_lattice* lat, const lq_model* model, double beta,
