@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblq.so")
+LIB_PATH = os.environ.get("LQ_LIB") or os.path.join(_HERE, "liblq.so")   # (LQ_LIB: A/B builds of the kernels, experiments only)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

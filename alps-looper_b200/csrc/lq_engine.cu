@@ -1195,8 +1195,14 @@ struct lq_engine {
     }
     {
       Section s(this, 11);
-      if (space) lq::k_compress<true><<<grid_for(nwords_cap * 32, 256 * LQ_NPT), 256, 0, stream>>>(d, nwords_cap);
-      else lq::k_compress<false><<<grid_for(nwords_cap * 32, 256 * LQ_NPT), 256, 0, stream>>>(d, nwords_cap);
+      {
+        const unsigned g = grid_for(nwords_cap * 32, 256 * LQ_NPT);
+        if (d.dbg & 1) {
+          if (space) lq::k_compress<true, true><<<g, 256, 0, stream>>>(d, nwords_cap);
+          else lq::k_compress<false, true><<<g, 256, 0, stream>>>(d, nwords_cap);
+        } else if (space) lq::k_compress<true, false><<<g, 256, 0, stream>>>(d, nwords_cap);
+        else lq::k_compress<false, false><<<g, 256, 0, stream>>>(d, nwords_cap);
+      }
       scan_u32(wcount.p, wbase.p, nwords_cap, wbase.p + nwords_cap, (int*)d_nc.p);
       if (opt.nranks == 1) {   // flip decision per root (path_integral.C:796-799), packed for k_relabel
         lq::k_rootflip<<<(unsigned)std::min<size_t>((nwords_cap + 255) / 256, (size_t)sm_count * 8), 256, 0, stream>>>(d, sp);

@@ -59,10 +59,16 @@ __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
 // an OWN site are gathered behind them.  All neighbour look-ups of the walk then run on shared
 // memory through the static per-class stencils (local bucket ids).  (K1 has its own stage with the
 // larger halo of the far-end sites, lq_k1.cuh.)
+// The walk only needs the ORDER of the operators at a site and their off-diagonal bit, so an operator
+// is staged as ONE 32-bit word: the window-relative time key of K1 (k1_key, monotone in the time)
+// cut to 28 bits, the off-diagonal bit below it, and three zero bits that take the number of the merge
+// head.  4 bytes per operator instead of 12 (three times as many resident CTAs), integer compares
+// instead of f64 ones; two heads whose keys agree in the 28 time bits (2^-28 of a window apart, ~60
+// pairs per step at the headline size) are ordered on their f64 times in global memory.
 // ------------------------------------------------------------------------------------------
+#define LQ_WKEY_END 0xfffffff0u   /* exhausted merge head (real keys stay below 2^32 - 256) */
 struct Stage {
-  double* time;    // [scap]
-  uint32_t* info;  // [scap]
+  uint32_t* key;   // [scap+1] time key << 4 | offdiagonal << 3
   int* off;        // [nloc+1] first staged slot of each local bucket
   int* idx0;       // [nloc]   dense operator index of the first operator of the bucket
   int* gbond;      // [nloc]   global bond id (tie-break order)
@@ -72,15 +78,18 @@ struct Stage {
 
 __host__ __device__ inline size_t stage_bytes(int scap, int nbmax, int hmax, int zmax, int tpb) {
   const size_t nloc = (size_t)nbmax + hmax;
-  return (size_t)scap * 12 + (3 * nloc + 1) * 4 + (size_t)zmax * tpb * 2 + 64;
+  return ((size_t)scap + 1) * 4 + (3 * nloc + 1) * 4 + (size_t)zmax * tpb * 2 + 64;
+}
+
+__device__ __forceinline__ uint32_t walk_key(double t, uint32_t inf, double tlo, double kscale, int shift) {
+  return (((k1_key(t, tlo, kscale, 0) >> 4) >> shift) << 4) | ((inf & LQ_INFO_OFFDIAG) << 3);
 }
 
 __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl, unsigned char* smem,
                                            Stage& S, int* s_scan) {
   const int nloc_max = d.nbmax + d.hmax;
-  S.time = (double*)smem;
-  S.info = (uint32_t*)(S.time + d.scap);
-  S.off = (int*)(S.info + d.scap);
+  S.key = (uint32_t*)smem;
+  S.off = (int*)(S.key + d.scap + 1);
   S.idx0 = S.off + nloc_max + 1;
   S.gbond = S.idx0 + nloc_max;
   S.head = (uint16_t*)(S.gbond + nloc_max);
@@ -93,6 +102,9 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   const int base_idx = d.nbase[p];
   const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1);
   const int tid = threadIdx.x;
+  const int wg = d.w0 + wl;
+  const double tlo = d.wlo[wg], kscale = 4294967040.0 / (d.wlo[wg + 1] - tlo);
+  const int kshift = d.k1_keyshift;
   for (int i = tid; i < S.nb; i += blockDim.x) {
     const int o = bo[i];
     S.off[i] = o;
@@ -101,7 +113,24 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   }
   const double* gt = d.time[buf] + p * (size_t)d.cap;
   const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
-  for (int j = tid; j < n_own; j += blockDim.x) { S.time[j] = gt[j]; S.info[j] = gi[j]; }
+  {
+    // four operators per thread and round: all loads are in flight before the first conversion
+    const int step = 4 * (int)blockDim.x;
+    for (int j0 = tid; j0 < n_own; j0 += step) {
+      double tt[4];
+      uint32_t ii[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * (int)blockDim.x;
+        if (j < n_own) { tt[u] = gt[j]; ii[u] = gi[j]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * (int)blockDim.x;
+        if (j < n_own) S.key[j] = walk_key(tt[u], ii[u], tlo, kscale, kshift);
+      }
+    }
+  }
   // halo buckets
   BucketRef r; r.base = 0; r.n = 0; r.idx0 = 0;
   int b2 = 0;
@@ -122,12 +151,21 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
           if (j0 + u < r.n) { tt[u] = d.time[buf][r.base + j0 + u]; ii[u] = d.info[buf][r.base + j0 + u]; }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (j0 + u < r.n) { S.time[n_own + hoff + j0 + u] = tt[u]; S.info[n_own + hoff + j0 + u] = ii[u]; }
+          if (j0 + u < r.n) S.key[n_own + hoff + j0 + u] = walk_key(tt[u], ii[u], tlo, kscale, kshift);
       }
   }
   if (tid == 0) S.off[S.nb + S.nh] = n_own + total;
   __syncthreads();
   return ok;
+}
+
+// f64 time of the operator in slot `slot` of the bucket of bond b (rare path of the walk: key ties)
+__device__ __noinline__ double walk_exact_time(const int* __restrict__ bond_tl, const uint16_t* __restrict__ boff,
+                                               const double* __restrict__ time, int Wl, int nbmax, int cap,
+                                               int b, int wl, int slot) {
+  const int tl = bond_tl[b];
+  const size_t p = (size_t)(tl >> 10) * Wl + wl;
+  return time[p * (size_t)cap + boff[p * (size_t)(nbmax + 1) + (tl & 1023)] + slot];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -234,12 +272,18 @@ __global__ void k_carry_scan(Dev d) {
 // Each leg of the page is visited exactly once -- O(legs x z) instead of one neighbourhood scan
 // per operator.  low0/low1[idx] = node below on the source/target side | spin << 31.
 // ------------------------------------------------------------------------------------------
-// Z = compile-time bound on the coordination number: the merge heads (position, end, time, bond
-// of the next unread operator of every incident bucket) live in registers; every step compares Z
-// register values and reloads only the head that advanced.  Z == 0: generic version with the head
-// positions in shared memory.
+// Z = compile-time bound on the coordination number: the merge heads live in registers -- per head the
+// key of its next unread operator with the head's number in the low three bits (so the minimum over
+// the heads names the winner), its staged position and end packed in one word, and the offset from
+// staged position to dense operator index; every step is an integer minimum over Z registers and
+// reloads only the head that advanced.  Z == 0: generic version with the head positions in shared
+// memory.  Heads that agree in the 28 time bits of the key are ordered on the f64 times (then by bond
+// id: two operators of one site at exactly the same time keep the order lq_get_state exports).
+#ifndef LQ_WALK_MINB
+#define LQ_WALK_MINB 6   /* resident 256-thread CTAs per SM the square-lattice walk is compiled for (40 registers) */
+#endif
 template <int MAXT, int Z>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256 && Z > 2 && Z <= 4) ? LQ_WALK_MINB : 1)
 k_walk(Dev d, int buf) {
   extern __shared__ __align__(16) unsigned char s_stage[];
   __shared__ int s_scan[34];
@@ -263,86 +307,115 @@ k_walk(Dev d, int buf) {
   node_t cur = 0;          // the node entering from below is patched in by k_carry_scan
   bool have = false;       // a leg of this site has been seen in this window
   uint32_t spin = d.spinW[(size_t)wl * d.N + s];
+  const node_t nmul = (node_t)d.npo, nside = (node_t)(d.npo >> 1);   // nodes per operator: 1 or 2
   if (Z > 0) {
-    int hd[Z > 0 ? Z : 1], en[Z > 0 ? Z : 1], gb[Z > 0 ? Z : 1], ix[Z > 0 ? Z : 1], sd[Z > 0 ? Z : 1];
-    double tk[Z > 0 ? Z : 1];
+    constexpr int ZZ = Z > 0 ? Z : 1;
+    uint32_t tk[ZZ], he[ZZ];   // key | head number; staged position | end << 16
+    int ix[ZZ];                // dense index = ix + staged position
+    uint32_t sdm = 0;          // side of the site on the bond of head k, one bit each
 #pragma unroll
     for (int k = 0; k < Z; ++k) {
-      hd[k] = 0; en[k] = 0; gb[k] = 0; ix[k] = 0; sd[k] = 0; tk[k] = 2.0;
+      tk[k] = LQ_WKEY_END | (uint32_t)k; he[k] = 0; ix[k] = 0;
       if (k < z) {
         const int ent = sse[k], lid = ent >> 1;
-        hd[k] = S.off[lid]; en[k] = S.off[lid + 1]; gb[k] = S.gbond[lid];
-        ix[k] = S.idx0[lid] - hd[k];   // dense index = ix + slot
-        sd[k] = ent & 1;
-        if (hd[k] < en[k]) tk[k] = S.time[hd[k]];
+        const int h = S.off[lid], e = S.off[lid + 1];
+        he[k] = (uint32_t)h | ((uint32_t)e << 16);
+        ix[k] = S.idx0[lid] - h;
+        sdm |= (uint32_t)(ent & 1) << k;
+        if (h < e) tk[k] = S.key[h] | (uint32_t)k;
       }
     }
     for (;;) {
-      // earliest head: plain minimum; two buckets of one site holding operators at exactly the same
-      // time (lower bond id first, the order lq_get_state exports) are sorted out on a rare path
-      int best = 0;
-      double bt = tk[0];
+      uint32_t m = tk[0];
 #pragma unroll
-      for (int k = 1; k < Z; ++k)
-        if (tk[k] < bt) { bt = tk[k]; best = k; }
-      if (!(bt < 2.0)) break;
-      int ties = 0;
+      for (int k = 1; k < Z; ++k) m = min(m, tk[k]);
+      if (m >= LQ_WKEY_END) break;
+      // another head within 16 of the minimum shares its time key (or sits on the next one): rare
+      uint32_t dmin = 0xffffffffu;
+      const uint32_t nm = ~m;   // tk - m - 1: the winner itself wraps to 0xffffffff
 #pragma unroll
-      for (int k = 0; k < Z; ++k) ties += (int)(tk[k] == bt);
-      if (ties > 1) {
+      for (int k = 0; k < Z; ++k) dmin = min(dmin, tk[k] + nm);
+      if (dmin < 15u) {
+        const uint32_t mh = m >> 4;
+        double bt = 4.0;
         int bb = 0x7fffffff;
 #pragma unroll
         for (int k = 0; k < Z; ++k)
-          if (tk[k] == bt && gb[k] < bb) { bb = gb[k]; best = k; }
+          if ((tk[k] >> 4) == mh) {
+            const int lid = sse[k] >> 1, gb = S.gbond[lid];
+            const double t2 = walk_exact_time(d.bond_tl, d.boff[buf], d.time[buf], d.Wl, d.nbmax, d.cap, gb, wl,
+                                              (int)(he[k] & 0xffffu) - S.off[lid]);
+            if (t2 < bt || (t2 == bt && gb < bb)) { bt = t2; bb = gb; m = tk[k]; }
+          }
       }
+      const int best = (int)(m & 7u);
       // branch-free head update: select the winner's registers, ONE shared-memory load for the
-      // whole warp, then predicated write-back (a load inside `if (k == best)` would serialise
-      // the warp Z times)
-      int bh = 0, bix = 0, bsd = 0, ben = 0;
+      // whole warp, then predicated write-back
+      uint32_t bhe = 0;
+      int bix = 0;
 #pragma unroll
       for (int k = 0; k < Z; ++k) {
-        const bool m = (k == best);
-        bh = m ? hd[k] : bh; bix = m ? ix[k] : bix; bsd = m ? sd[k] : bsd; ben = m ? en[k] : ben;
+        const bool w = (k == best);
+        bhe = w ? he[k] : bhe; bix = w ? ix[k] : bix;
       }
-      const double tn = (bh + 1 < ben) ? S.time[bh + 1] : 2.0;
+      const int bh = (int)(bhe & 0xffffu), ben = (int)(bhe >> 16);
+      const uint32_t kn = S.key[bh + 1];   // (the stage has one spare word behind the last operator)
+      const uint32_t tn = ((bh + 1 < ben) ? kn : LQ_WKEY_END) | (uint32_t)best;
 #pragma unroll
       for (int k = 0; k < Z; ++k) {
-        const bool m = (k == best);
-        hd[k] = m ? bh + 1 : hd[k];
-        tk[k] = m ? tn : tk[k];
+        const bool w = (k == best);
+        he[k] = w ? bhe + 1u : he[k];
+        tk[k] = w ? tn : tk[k];
       }
+      const int bsd = (int)((sdm >> best) & 1u);
       const int idx = bix + bh;
       if (have) (bsd ? d.low1 : d.low0)[idx] = cur | (spin << 31);
       else d.firstW[(size_t)wl * d.N + s] = (uint32_t)idx | ((uint32_t)bsd << 31);
       have = true;
-      spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
-      cur = upper_node(d, idx, bsd);
+      spin ^= (m >> 3) & 1u;
+      cur = (node_t)d.N + (node_t)idx * nmul + ((node_t)bsd & nside);   // = upper_node(d, idx, bsd)
     }
   } else {
     uint16_t* head = S.head + tid;
     const int hs = blockDim.x;
     for (int k = 0; k < z; ++k) head[k * hs] = (uint16_t)S.off[sse[k] >> 1];
     for (;;) {
-      int best = -1, bh = 0, bent = 0, bb = 0;
-      double bt = 0;
+      int best = -1, bh = 0, bent = 0;
+      uint32_t bk = 0;
+      bool tie = false;
       for (int k = 0; k < z; ++k) {
         const int ent = sse[k];
         const int lid = ent >> 1;
         const int h = head[k * hs];
         if (h < S.off[lid + 1]) {
-          const double t2 = S.time[h];
-          const int b2 = S.gbond[lid];
-          if (best < 0 || t2 < bt || (t2 == bt && b2 < bb)) { best = k; bt = t2; bb = b2; bh = h; bent = ent; }
+          const uint32_t k2 = S.key[h];
+          if (best < 0 || (k2 >> 4) < (bk >> 4)) { best = k; bk = k2; bh = h; bent = ent; tie = false; }
+          else if ((k2 >> 4) == (bk >> 4)) tie = true;
         }
       }
       if (best < 0) break;
+      if (tie) {   // heads with the same time key: f64 times, then bond ids
+        const uint32_t mh = bk >> 4;
+        double bt = 4.0;
+        int bb = 0x7fffffff;
+        for (int k = 0; k < z; ++k) {
+          const int ent = sse[k];
+          const int lid = ent >> 1;
+          const int h = head[k * hs];
+          if (h < S.off[lid + 1] && (S.key[h] >> 4) == mh) {
+            const int gb = S.gbond[lid];
+            const double t2 = walk_exact_time(d.bond_tl, d.boff[buf], d.time[buf], d.Wl, d.nbmax, d.cap, gb, wl, h - S.off[lid]);
+            if (t2 < bt || (t2 == bt && gb < bb)) { bt = t2; bb = gb; best = k; bk = S.key[h]; bh = h; bent = ent; }
+          }
+        }
+      }
       head[best * hs] = (uint16_t)(bh + 1);
       const int lid = bent >> 1, side = bent & 1;
       const int idx = S.idx0[lid] + (bh - S.off[lid]);
       if (have) (side ? d.low1 : d.low0)[idx] = cur | (spin << 31);
       else d.firstW[(size_t)wl * d.N + s] = (uint32_t)idx | ((uint32_t)side << 31);
       have = true;
-      spin ^= S.info[bh] & LQ_INFO_OFFDIAG;
+      spin ^= (bk >> 3) & 1u;
       cur = upper_node(d, idx, side);
     }
   }
@@ -431,14 +504,21 @@ k_union_local(Dev d, int buf) {
     const int n = d.pcount[buf][p];
     const int idx0 = d.nbase[p];
     const uint32_t* gi = d.info[buf] + p * (size_t)d.cap;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const int idx = idx0 + j;
-      const node_t p0 = d.low0[idx] & 0x7fffffffu, p1 = d.low1[idx] & 0x7fffffffu;
-      op_edges(d, gi[j], idx, p0, p1, [&](node_t a, node_t b) {
-        if (a == b) return;   // both legs arrive from the same node (consecutive operators on one bond)
-        if (a >= lo && a < hi && b >= lo && b < hi) sm_union(s_par, a - lo, b - lo);
-        else { const int slot = atomicAdd(&s_xn, 1); if (slot < d.xcap) s_x[slot] = make_uint2(a, b); }
-      });
+    auto edge = [&](node_t a, node_t b) {
+      if (a == b) return;   // both legs arrive from the same node (consecutive operators on one bond)
+      if (a >= lo && a < hi && b >= lo && b < hi) sm_union(s_par, a - lo, b - lo);
+      else { const int slot = atomicAdd(&s_xn, 1); if (slot < d.xcap) s_x[slot] = make_uint2(a, b); }
+    };
+    // two operators per thread and round: the six loads are in flight before the first (divergent,
+    // shared-memory bound) union
+    for (int j = threadIdx.x; j < n; j += 2 * blockDim.x) {
+      const int j2 = j + blockDim.x;
+      const bool two = j2 < n;
+      const int idx = idx0 + j, idx2 = idx0 + (two ? j2 : j);
+      const node_t a0 = d.low0[idx], a1 = d.low1[idx], b0 = d.low0[idx2], b1 = d.low1[idx2];
+      const uint32_t ia = gi[j], ib = gi[two ? j2 : j];
+      op_edges(d, ia, idx, a0 & 0x7fffffffu, a1 & 0x7fffffffu, edge);
+      if (two) op_edges(d, ib, idx2, b0 & 0x7fffffffu, b1 & 0x7fffffffu, edge);
     }
   }
   __syncthreads();
@@ -521,7 +601,7 @@ __global__ void k_close(Dev d) {
 #define LQ_NPT 4  /* nodes per thread: independent pointer chases in flight */
 // SPACE: engines of the spatial cut hold ghost nodes marked NODE_JUNK (lq_space.cuh); a template parameter so
 // that the serial kernel does not carry the test
-template <bool SPACE>
+template <bool SPACE, bool COUNT>   // COUNT: hop statistics (LQ_DBG & 1, experiments only)
 __global__ void __launch_bounds__(256)
 k_compress(Dev d, size_t nwords_cap) {
   const size_t nn = (size_t)d.N + (size_t)d.npo * (size_t)(*d.d_ntotal);
@@ -544,23 +624,29 @@ k_compress(Dev d, size_t nwords_cap) {
     any = false;
 #pragma unroll
     for (int k = 0; k < LQ_NPT; ++k)
-      if (pr[k] != r[k]) { r[k] = pr[k]; pr[k] = d.parent[r[k]]; any = true; ++hops; }
+      if (pr[k] != r[k]) { r[k] = pr[k]; pr[k] = d.parent[r[k]]; any = true; if (COUNT) ++hops; }
   }
-  if (d.dbg & 1) { atomicAdd(d.dbgc + 4, (unsigned long long)LQ_NPT); atomicAdd(d.dbgc + 5, (unsigned long long)hops); }
+  if (COUNT) { atomicAdd(d.dbgc + 4, (unsigned long long)LQ_NPT); atomicAdd(d.dbgc + 5, (unsigned long long)hops); }
+  // root flags of 32 consecutive nodes = one ballot word; the LQ_NPT words of a warp are 8 words apart
+  // and stored by its first LQ_NPT lanes
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t mine = 0;
 #pragma unroll
   for (int k = 0; k < LQ_NPT; ++k) {
     const size_t x = base + (size_t)k * 256;
-    const size_t w = x >> 5;
-    if (w >= nwords_cap) continue;   // warp-uniform
     bool isroot = false;
     if (x < nn) {
       if (r[k] != (node_t)x) d.parent[x] = r[k];
       isroot = (r[k] == (node_t)x) && !(SPACE && ((junk >> k) & 1u));
     }
     const uint32_t word = __ballot_sync(0xffffffffu, isroot);
-    if ((threadIdx.x & 31) == 0) {   // words beyond the live nodes are cleared: the scan input stays clean
-      d.bitmap[w] = (w < nwords) ? word : 0u;
-      d.wcount[w] = (w < nwords) ? (uint32_t)__popc(word) : 0u;
+    if (lane == (unsigned)k) mine = word;
+  }
+  if (lane < LQ_NPT) {
+    const size_t w = ((base - lane) >> 5) + (size_t)lane * 8;   // (base - lane: node of lane 0, a multiple of 32)
+    if (w < nwords_cap) {   // words beyond the live nodes are cleared: the scan input stays clean
+      d.bitmap[w] = (w < nwords) ? mine : 0u;
+      d.wcount[w] = (w < nwords) ? (uint32_t)__popc(mine) : 0u;
     }
   }
 }
@@ -787,7 +873,7 @@ k_estimate(Dev d, int buf) {
       inf[u] = ginfo[jj];
       tt[u] = gtime[jj];
       l0[u] = d.low0[idx0 + jj];
-      l1[u] = d.low1[idx0 + jj];
+      if (NPO2) l1[u] = d.low1[idx0 + jj];   // (one node per operator: only its spin bit would be used, see below)
     }
 #pragma unroll
     for (int u = 0; u < LQ_EST_U; ++u) {
@@ -809,7 +895,10 @@ k_estimate(Dev d, int buf) {
       const long long q = d.sse ? (long long)d.spos[idx0 + j] : time_to_fx(tt[u]);
       const int lb = (int)(inf[u] >> LQ_INFO_LBSHIFT);
       const int g0 = s_gg[2 * lb], g1 = s_gg[2 * lb + 1];
-      const int c0 = (int)(l0[u] >> 31), c1 = (int)(l1[u] >> 31);   // spins below (written by the walk)
+      // spins below (written by the walk).  Without the cross graph the spin on the target side follows
+      // from the graph: graphs 0 and 2 sit on antiparallel spins, 3 on parallel ones (graph_impl.h:257) --
+      // four bytes per operator that need not be read
+      const int c0 = (int)(l0[u] >> 31), c1 = NPO2 ? (int)(l1[u] >> 31) : (c0 ^ 1 ^ (g & 1));
       const int off = (int)(inf[u] & LQ_INFO_OFFDIAG);
       const int m0 = 1 - 2 * c0, m1 = 1 - 2 * c1;              // 2(1/2-c) below
       const int n0 = 1 - 2 * (c0 ^ off), n1 = 1 - 2 * (c1 ^ off);  // above
