@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace lq {
 
@@ -54,6 +55,7 @@ struct Dev {
   int W;            // global number of windows
   int w0, Wl;       // this rank owns windows [w0, w0+Wl)
   const double* wlo;  // [W+1] window bounds: wlo[w] = window_lo(w, W), wlo[W] = 1 (two f64 divisions less per thread)
+  const double* wks;  // [W]   scale of the 32-bit window-relative time keys (k1_key): 4294967040 / (wlo[w+1] - wlo[w])
   int cap;          // page capacity (operators)
   int npo;          // nodes per operator (1: graphs {0,2,3}; 2: cross graph present)
   int ug;           // windows per union group (k_union_local / k_union_global)
@@ -87,6 +89,7 @@ struct Dev {
   const int* site_base;   // [T+1] first site of a tile (sites are tile-contiguous)
   const int* halo_off;    // [T+1]
   const int* halo_bond;   // global bond ids of the halo buckets of a tile
+  const int* halo_tl;     // bond_tl of the same buckets (owning tile << 10 | local bond index)
   const int* hsite_off;   // [T+1]
   const int* hsite;       // global ids of the halo K-sites of a tile
   const int* tile_class;  // [T]
@@ -116,7 +119,8 @@ struct Dev {
   // ---- union-find / labels ----
   node_t* parent;  // [N + npo*ncap]; after k_relabel holds the cluster id
   node_t* low0;    // [ncap] node below the operator on the source side
-  node_t* low1;    // [ncap] (npo == 2 only) node below on the target side
+  node_t* low1;    // [ncap] node below on the target side; low1 == low0 + lowstride (one allocation)
+  uint32_t lowstride;
   uint32_t* bitmap;  // root flags, one bit per node
   uint32_t* wcount;  // roots per bitmap word -> exclusive scan in wbase
   uint32_t* wbase;

@@ -456,16 +456,17 @@ struct lq_engine {
   lq::Dev d{};
   cudaStream_t stream = nullptr;
   DBuf<int> bond_s0, bond_s1, bond_base, adj_off, adj, pcount[2], nbase, d_ntotal, d_err;
-  DBuf<int> whalo_cnt, bond_tl;
-  DBuf<double> bond_emu, wlo;
+  DBuf<int> whalo_cnt, bond_tl, halo_tl;
+  DBuf<double> bond_emu, wlo, wks;
   DBuf<int> site_base, halo_off, halo_bond, hsite_off, hsite, tile_class, cls_bs, cls_sso, cls_sst, cls_nks, bs, sst_off, sst;
   int scap = 0, ccap = 0;
   size_t stage_smem = 0, walk_smem = 0;
   int tpb_walk = 32;
   typedef void (*walk_fn_t)(lq::Dev, int);
   walk_fn_t walk_fn = nullptr;
-  typedef void (*k1_fn_t)(lq::Dev, int, const lq::StepParams*, int);
+  typedef void (*k1_fn_t)(lq::Dev, int, const lq::StepParams*, int, const lq::K1Layout);
   k1_fn_t k1_fn = nullptr;
+  lq::K1Layout k1_lay = lq::K1Layout();
   int k1_fc = 12, k1_nt = 256, k1_chunk = 1, kcap = 0;
   bool k1_tma = true;
   double grow_kept = 1;
@@ -484,8 +485,9 @@ struct lq_engine {
   // world-line walk specialised on block size and coordination number
   walk_fn_t pick_walk() const {
     const int z = part.zmax;
-#define LQ_PICK(MT) (z <= 2 ? lq::k_walk<MT, 2> : z <= 4 ? lq::k_walk<MT, 4> : z <= 6 ? lq::k_walk<MT, 6> : \
-                     z <= 8 ? lq::k_walk<MT, 8> : lq::k_walk<MT, 0>)
+#define LQ_PICKZ(MT, NP) (z <= 2 ? lq::k_walk<MT, 2, NP> : z <= 4 ? lq::k_walk<MT, 4, NP> : z <= 6 ? lq::k_walk<MT, 6, NP> : \
+                          z <= 8 ? lq::k_walk<MT, 8, NP> : lq::k_walk<MT, 0, NP>)
+#define LQ_PICK(MT) (npo == 2 ? LQ_PICKZ(MT, 2) : LQ_PICKZ(MT, 1))
     if (tpb_walk <= 256) return LQ_PICK(256);
     if (tpb_walk <= 640) return LQ_PICK(640);
     return LQ_PICK(1024);
@@ -495,7 +497,7 @@ struct lq_engine {
   DBuf<float4> bond_p;
   DBuf<float> bond_q;
   DBuf<signed char> gauge;
-  DBuf<uint32_t> info[2], parent, low0, low1, bitmap, wcount, wbase, scan_tmp, d_nc, curW, firstW, labels;
+  DBuf<uint32_t> info[2], parent, low0, bitmap, wcount, wbase, scan_tmp, d_nc, curW, firstW, labels;
   DBuf<uint16_t> boff[2];
   DBuf<uint8_t> spinW;
   DBuf<uint32_t> flipw, openw;
@@ -718,6 +720,9 @@ struct lq_engine {
       std::vector<int> tl(B);
       for (int i = 0; i < B; ++i) tl[i] = (part.bond_tile[i] << 10) | (i - part.bond_base[part.bond_tile[i]]);
       bond_tl.upload(tl, &device_bytes);
+      std::vector<int> htl(part.halo_bond.size());   // the same for every halo bucket: one dependent load less per stage
+      for (size_t k = 0; k < htl.size(); ++k) htl[k] = tl[part.halo_bond[k]];
+      halo_tl.upload(htl, &device_bytes);
     }
     site_base.upload(part.site_base, &device_bytes);
     halo_off.upload(part.halo_off, &device_bytes);
@@ -830,6 +835,9 @@ struct lq_engine {
       for (int w = 0; w < W; ++w) wl[w] = lq::window_lo(w, W);
       wl[W] = 1.0;   // == window_hi(W - 1, W); window_hi(w, W) == window_lo(w + 1, W) below it
       wlo.upload(wl, nullptr);
+      std::vector<double> ks(W);
+      for (int w = 0; w < W; ++w) ks[w] = 4294967040.0 / (wl[w + 1] - wl[w]);
+      wks.upload(ks, nullptr);
     }
     const double m = opt.reserve * grow_pages * mu;
     long long c = (long long)std::ceil(m + 6.0 * std::sqrt(m) + 16.0);
@@ -882,6 +890,7 @@ struct lq_engine {
         }
       }
       stage_smem = lq::k1_smem_bytes(k1_tma, k1_fc, cap, ccap, kcap, part.nbmax, part.hmax, part.nksmax);
+      k1_lay = lq::k1_layout(k1_tma, k1_fc, cap, ccap, kcap, part.nbmax, part.hmax, part.nksmax);
       walk_smem = lq::stage_bytes(scap, part.nbmax, part.hmax, part.zmax, tpb_walk);
       if (stage_smem > (size_t)smem_optin - 2048 || walk_smem > (size_t)smem_optin - 2048 ||
           (size_t)npo * cap * sizeof(uint32_t) > (size_t)smem_optin - 2048)
@@ -931,8 +940,7 @@ struct lq_engine {
     curW.alloc((size_t)(Wl + 1) * Ns, tb);
     firstW.alloc((size_t)Wl * Ns, tb);
     parent.alloc((size_t)nodes_cap, tb);
-    low0.alloc((size_t)ncap, tb);
-    low1.alloc((size_t)ncap, tb);
+    low0.alloc(2 * (size_t)ncap, tb);   // low1 = low0 + ncap: ONE array, so the walk selects the side with an index offset
     bitmap.alloc(nwords_cap + 1, tb);
     wcount.alloc(nwords_cap + 1, tb);
     wbase.alloc(nwords_cap + 1, tb);
@@ -1065,7 +1073,7 @@ struct lq_engine {
     d.bond_s0 = bond_s0.p; d.bond_s1 = bond_s1.p; d.bond_base = bond_base.p;
     d.adj_off = adj_off.p; d.adj = adj.p; d.bond_rate = bond_rate.p; d.bond_p = bond_p.p;
     d.bond_q = bond_q.p; d.gauge = gauge.p;
-    d.whalo_cnt = whalo_cnt.p; d.bond_tl = bond_tl.p; d.bond_emu = bond_emu.p; d.wlo = wlo.p;
+    d.whalo_cnt = whalo_cnt.p; d.bond_tl = bond_tl.p; d.halo_tl = halo_tl.p; d.bond_emu = bond_emu.p; d.wlo = wlo.p; d.wks = wks.p;
     d.site_base = site_base.p; d.halo_off = halo_off.p; d.halo_bond = halo_bond.p;
     d.hsite_off = hsite_off.p; d.hsite = hsite.p; d.tile_class = tile_class.p;
     d.cls_bs = cls_bs.p; d.cls_sso = cls_sso.p; d.cls_sst = cls_sst.p; d.cls_nks = cls_nks.p;
@@ -1076,7 +1084,7 @@ struct lq_engine {
       d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
     }
     d.nbase = nbase.p; d.spinW = spinW.p; d.curW = curW.p; d.firstW = firstW.p; d.parent = parent.p; d.low0 = low0.p;
-    d.low1 = low1.p; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
+    d.low1 = low0.p + (size_t)ncap; d.lowstride = (uint32_t)ncap; d.bitmap = bitmap.p; d.wcount = wcount.p; d.wbase = wbase.p;
     d.rootw = rootw.p; d.fpack = 1; d.rootflip = opt.nranks == 1 ? 1 : 0;
     d.xedge = xedge.p; d.xcount = xcount.p;
     d.xcap = getenv("LQ_XCAP") ? std::max(0, std::min(LQ_XCAP, atoi(getenv("LQ_XCAP")))) : LQ_XCAP;
@@ -1437,7 +1445,7 @@ struct lq_engine {
     {
       Section s(this, 5);
       const unsigned nch = (unsigned)((Wl + k1_chunk - 1) / k1_chunk);
-      k1_fn<<<(unsigned)To * nch, k1_nt, stage_smem, stream>>>(d, cur, sp, k1_chunk);
+      k1_fn<<<(unsigned)To * nch, k1_nt, stage_smem, stream>>>(d, cur, sp, k1_chunk, k1_lay);
       launches += 1;
       cur ^= 1;
     }
@@ -1597,7 +1605,7 @@ struct lq_engine {
   // arenas) instead of (all old + all new).
   void release_arenas() {
     for (int k = 0; k < 2; ++k) { time_[k].release(); info[k].release(); boff[k].release(); pcount[k].release(); }
-    nbase.release(); spinW.release(); curW.release(); firstW.release(); parent.release(); low0.release(); low1.release();
+    nbase.release(); spinW.release(); curW.release(); firstW.release(); parent.release(); low0.release();
     bitmap.release(); wcount.release(); wbase.release(); rootw.release(); xedge.release(); xcount.release();
     sse_rank.release(); sse_time.release(); sse_id.release(); sse_bincnt.release(); sse_binbase.release(); sse_binfill.release();
     scan_tmp.release(); est.release(); est0.release(); flipw.release(); wind.release(); openw.release(); partial.release();

@@ -122,36 +122,62 @@ struct K1Smem {
 __host__ __device__ inline int k1_nksp(int nksmax) { return (nksmax + 31) & ~31; }
 __host__ __device__ inline int k1_capa(int cap) { return (cap + 3) & ~3; }
 
-__host__ __device__ inline size_t k1_smem_bytes(bool tma, int fc, int cap, int ccap, int kcap, int nbmax, int hmax, int nksmax) {
+// Byte offsets of the arrays above inside the dynamic shared memory, computed ONCE on the host and
+// passed as a kernel argument: the sizes are run-time values, and with the offsets derived from them
+// inside the kernel every use of a list in divergent code paid ~10 instructions of address arithmetic
+// again (8 % of the kernel's instructions, profiles/r02_k1.md); from the constant bank they are an
+// operand of the add.
+struct K1Layout {
+  uint32_t ptime, pinfo, col, ctime, ktime, kse, bs2, ksite, hpg, colcnt, wsum, klb, cmeta, cbase, noff, hlb, kspin, total;
+};
+
+inline K1Layout k1_layout(bool tma, int fc, int cap, int ccap, int kcap, int nbmax, int hmax, int nksmax) {
   const size_t nloc = (size_t)nbmax + hmax, nksp = k1_nksp(nksmax), capA = k1_capa(cap);
-  size_t b = 0;
-  if (tma) b += capA * 12;
-  b += nksp * (fc + 4) * 4 + (size_t)ccap * 8 + (((size_t)kcap * 8 + 15) & ~(size_t)15);
-  b += ((size_t)nbmax + nloc + nksp + hmax + nksp + 34) * 4;
-  b += ((size_t)kcap + ccap + 2 * ((size_t)nbmax + 1) + hmax) * 2 + nksp;
-  return b + 64;
+  K1Layout L;
+  size_t p = 0;
+  L.ptime = (uint32_t)p; if (tma) p += capA * 8;
+  L.pinfo = (uint32_t)p; if (tma) p += capA * 4;    // capA % 4 == 0: stays 16-byte aligned
+  L.col = (uint32_t)p; p += nksp * (fc + 4) * 4;    // (nksp % 32 == 0: the next array stays 16-byte aligned)
+  L.ctime = (uint32_t)p; p += (size_t)ccap * 8;
+  L.ktime = (uint32_t)p; p += ((size_t)kcap * 8 + 15) & ~(size_t)15;
+  L.kse = (uint32_t)p; p += (size_t)nbmax * 4;
+  L.bs2 = (uint32_t)p; p += nloc * 4;
+  L.ksite = (uint32_t)p; p += nksp * 4;
+  L.hpg = (uint32_t)p; p += (size_t)hmax * 4;
+  L.colcnt = (uint32_t)p; p += nksp * 4;
+  L.wsum = (uint32_t)p; p += 34 * 4;
+  L.klb = (uint32_t)p; p += (size_t)kcap * 2;
+  L.cmeta = (uint32_t)p; p += (size_t)ccap * 2;
+  L.cbase = (uint32_t)p; p += ((size_t)nbmax + 1) * 2;
+  L.noff = (uint32_t)p; p += ((size_t)nbmax + 1) * 2;
+  L.hlb = (uint32_t)p; p += (size_t)hmax * 2;
+  L.kspin = (uint32_t)p; p += nksp;
+  L.total = (uint32_t)p;
+  return L;
 }
 
-__device__ __forceinline__ void k1_carve(const Dev& d, bool tma, int fc, unsigned char* smem, K1Smem& S) {
-  const size_t nloc = (size_t)d.nbmax + d.hmax, nksp = k1_nksp(d.nksmax), capA = k1_capa(d.cap);
-  unsigned char* p = smem;
-  S.ptime = (double*)p; if (tma) p += capA * 8;
-  S.pinfo = (uint32_t*)p; if (tma) p += capA * 4;    // capA % 4 == 0: stays 16-byte aligned
-  S.col = (uint32_t*)p; p += nksp * (fc + 4) * 4;   // (nksp % 32 == 0: the next array stays 16-byte aligned)
-  S.ctime = (double*)p; p += (size_t)d.ccap * 8;
-  S.ktime = (double*)p; p += ((size_t)d.kcap * 8 + 15) & ~(size_t)15;
-  S.kse = (uint32_t*)p; p += (size_t)d.nbmax * 4;
-  S.bs2 = (uint32_t*)p; p += nloc * 4;
-  S.ksite = (int*)p; p += nksp * 4;
-  S.hpg = (int*)p; p += (size_t)d.hmax * 4;
-  S.colcnt = (int*)p; p += nksp * 4;
-  S.wsum = (int*)p; p += 34 * 4;
-  S.klb = (uint16_t*)p; p += (size_t)d.kcap * 2;
-  S.cmeta = (uint16_t*)p; p += (size_t)d.ccap * 2;
-  S.cbase = (uint16_t*)p; p += ((size_t)d.nbmax + 1) * 2;
-  S.noff = (uint16_t*)p; p += ((size_t)d.nbmax + 1) * 2;
-  S.hlb = (uint16_t*)p; p += (size_t)d.hmax * 2;
-  S.kspin = (uint8_t*)p;
+inline size_t k1_smem_bytes(bool tma, int fc, int cap, int ccap, int kcap, int nbmax, int hmax, int nksmax) {
+  return (size_t)k1_layout(tma, fc, cap, ccap, kcap, nbmax, hmax, nksmax).total + 64;
+}
+
+__device__ __forceinline__ void k1_carve(const K1Layout& L, unsigned char* smem, K1Smem& S) {
+  S.ptime = (double*)(smem + L.ptime);
+  S.pinfo = (uint32_t*)(smem + L.pinfo);
+  S.col = (uint32_t*)(smem + L.col);
+  S.ctime = (double*)(smem + L.ctime);
+  S.ktime = (double*)(smem + L.ktime);
+  S.kse = (uint32_t*)(smem + L.kse);
+  S.bs2 = (uint32_t*)(smem + L.bs2);
+  S.ksite = (int*)(smem + L.ksite);
+  S.hpg = (int*)(smem + L.hpg);
+  S.colcnt = (int*)(smem + L.colcnt);
+  S.wsum = (int*)(smem + L.wsum);
+  S.klb = (uint16_t*)(smem + L.klb);
+  S.cmeta = (uint16_t*)(smem + L.cmeta);
+  S.cbase = (uint16_t*)(smem + L.cbase);
+  S.noff = (uint16_t*)(smem + L.noff);
+  S.hlb = (uint16_t*)(smem + L.hlb);
+  S.kspin = (uint8_t*)(smem + L.kspin);
 }
 
 // parity of the off-diagonal legs before tc on a site, straight from the pages in global memory
@@ -190,14 +216,14 @@ __device__ __forceinline__ uint32_t k1_key(double t, double tlo, double kscale, 
 // TMA: pages arrive through cp.async.bulk + mbarrier (else: plain loads, no page buffer)
 template <int NT, int FC, bool TMA>
 __global__ void __launch_bounds__(NT, (NT <= 256 ? 3 : 2))
-k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) {
+k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len, const K1Layout L) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_scanb[2][2][32];   // block_exscan2_1b
   int scan_par = 0;
   __shared__ int s_misc[4];                 // [0] error word at entry
   __shared__ __align__(8) uint64_t s_mbar;
   K1Smem S;
-  k1_carve(d, TMA, FC, s_raw, S);
+  k1_carve(L, s_raw, S);
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31u;
   const int wid = tid >> 5;
@@ -260,7 +286,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len) 
     const int wg = d.w0 + wl;
     const size_t p = (size_t)t * d.Wl + wl;
     const double tlo = d.wlo[wg], thi = d.wlo[wg + 1], width = thi - tlo;   // = window_lo / window_hi (host table)
-    const double kscale = 4294967040.0 / width;
+    const double kscale = d.wks[wg];   // 4294967040 / width (host table: no f64 division per thread and window)
     const int kshift = d.k1_keyshift;
     const int n_own = d.pcount[src][p];
     uint16_t* bo_new = d.boff[dst] + p * (size_t)(d.nbmax + 1);

@@ -66,19 +66,36 @@ __device__ __forceinline__ node_t upper_node(const Dev& d, int idx, int side) {
 // instead of f64 ones; two heads whose keys agree in the 28 time bits (2^-28 of a window apart, ~60
 // pairs per step at the headline size) are ordered on their f64 times in global memory.
 // ------------------------------------------------------------------------------------------
+// shared memory through 32-bit shared-space addresses (per-thread tables in inner loops)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
 #define LQ_WKEY_END 0xfffffff0u   /* exhausted merge head (real keys stay below 2^32 - 256) */
 struct Stage {
   uint32_t* key;   // [scap+1] time key << 4 | offdiagonal << 3
   int* off;        // [nloc+1] first staged slot of each local bucket
   int* idx0;       // [nloc]   dense operator index of the first operator of the bucket
   int* gbond;      // [nloc]   global bond id (tie-break order)
-  uint16_t* head;  // [zmax*blockDim] merge heads of the generic site walk
+  uint2* head;     // [zmax*blockDim] merge heads of the site walk, [head][thread]: {staged position | end << 16,
+                   // dense index - staged position}
   int nb, nh;
 };
 
 __host__ __device__ inline size_t stage_bytes(int scap, int nbmax, int hmax, int zmax, int tpb) {
   const size_t nloc = (size_t)nbmax + hmax;
-  return ((size_t)scap + 1) * 4 + (3 * nloc + 1) * 4 + (size_t)zmax * tpb * 2 + 64;
+  return (((size_t)scap + 1) * 4 + (3 * nloc + 1) * 4 + 7) / 8 * 8 + (size_t)zmax * tpb * 8 + 64;
 }
 
 __device__ __forceinline__ uint32_t walk_key(double t, uint32_t inf, double tlo, double kscale, int shift) {
@@ -92,7 +109,7 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   S.off = (int*)(S.key + d.scap + 1);
   S.idx0 = S.off + nloc_max + 1;
   S.gbond = S.idx0 + nloc_max;
-  S.head = (uint16_t*)(S.gbond + nloc_max);
+  S.head = (uint2*)(((uintptr_t)(S.gbond + nloc_max) + 7) & ~(uintptr_t)7);
   const size_t p = (size_t)t * d.Wl + wl;
   const int b0 = d.bond_base[t];
   S.nb = d.bond_base[t + 1] - b0;
@@ -103,8 +120,21 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
   const uint16_t* bo = d.boff[buf] + p * (size_t)(d.nbmax + 1);
   const int tid = threadIdx.x;
   const int wg = d.w0 + wl;
-  const double tlo = d.wlo[wg], kscale = 4294967040.0 / (d.wlo[wg + 1] - tlo);
+  const double tlo = d.wlo[wg], kscale = d.wks[wg];
   const int kshift = d.k1_keyshift;
+  // halo buckets: their extents are two dependent loads away (halo_tl -> bucket offsets and operator base).
+  // The loads are issued HERE and first used after the own page has been copied, so that the chain runs
+  // under that copy instead of behind it.
+  int b2 = 0, h_o0 = 0, h_o1 = 0, h_nb = 0;
+  size_t h_p2 = 0;
+  if (tid < S.nh) {
+    b2 = d.halo_bond[h0 + tid];
+    const int tl = d.halo_tl[h0 + tid];
+    h_p2 = (size_t)(tl >> 10) * d.Wl + wl;
+    const uint16_t* bo2 = d.boff[buf] + h_p2 * (size_t)(d.nbmax + 1) + (tl & 1023);
+    h_o0 = bo2[0]; h_o1 = bo2[1];
+    h_nb = d.nbase[h_p2];
+  }
   for (int i = tid; i < S.nb; i += blockDim.x) {
     const int o = bo[i];
     S.off[i] = o;
@@ -131,10 +161,10 @@ __device__ __forceinline__ bool stage_page(const Dev& d, int buf, int t, int wl,
       }
     }
   }
-  // halo buckets
-  BucketRef r; r.base = 0; r.n = 0; r.idx0 = 0;
-  int b2 = 0;
-  if (tid < S.nh) { b2 = d.halo_bond[h0 + tid]; r = bucket_of(d, buf, b2, wl); }
+  BucketRef r;
+  r.base = h_p2 * (size_t)d.cap + h_o0;
+  r.n = h_o1 - h_o0;
+  r.idx0 = h_nb + h_o0;
   int total;
   const int hoff = block_exscan(r.n, &total, s_scan);
   const bool ok = (n_own + total <= d.scap);
@@ -280,9 +310,10 @@ __global__ void k_carry_scan(Dev d) {
 // memory.  Heads that agree in the 28 time bits of the key are ordered on the f64 times (then by bond
 // id: two operators of one site at exactly the same time keep the order lq_get_state exports).
 #ifndef LQ_WALK_MINB
-#define LQ_WALK_MINB 6   /* resident 256-thread CTAs per SM the square-lattice walk is compiled for (40 registers) */
+#define LQ_WALK_MINB 5   /* resident 256-thread CTAs per SM the square-lattice walk is compiled for (48 registers;
+                            6 = 40 registers spills in the prologue and measured 3 % slower) */
 #endif
-template <int MAXT, int Z>
+template <int MAXT, int Z, int NPO>   // NPO: graph nodes per operator (Dev::npo)
 __global__ void __launch_bounds__(MAXT, (MAXT <= 256 && Z > 2 && Z <= 4) ? LQ_WALK_MINB : 1)
 k_walk(Dev d, int buf) {
   extern __shared__ __align__(16) unsigned char s_stage[];
@@ -307,29 +338,33 @@ k_walk(Dev d, int buf) {
   node_t cur = 0;          // the node entering from below is patched in by k_carry_scan
   bool have = false;       // a leg of this site has been seen in this window
   uint32_t spin = d.spinW[(size_t)wl * d.N + s];
-  const node_t nmul = (node_t)d.npo, nside = (node_t)(d.npo >> 1);   // nodes per operator: 1 or 2
+  // the merge heads of this thread: [head][thread] in shared memory, addressed by 32-bit shared offsets
+  // (through generic pointers every access recomputed the shared window: 6 instructions per load)
+  const int hs = blockDim.x;
+  uint2* const hx = S.head + tid;
+  const uint32_t hx_s = smem_u32(hx), key_s = smem_u32(S.key), hstep = (uint32_t)hs * 8u;
   if (Z > 0) {
     constexpr int ZZ = Z > 0 ? Z : 1;
-    uint32_t tk[ZZ], he[ZZ];   // key | head number; staged position | end << 16
-    int ix[ZZ];                // dense index = ix + staged position
+    uint32_t tk[ZZ];           // key | head number of the next unread operator of every head
     uint32_t sdm = 0;          // side of the site on the bond of head k, one bit each
 #pragma unroll
     for (int k = 0; k < Z; ++k) {
-      tk[k] = LQ_WKEY_END | (uint32_t)k; he[k] = 0; ix[k] = 0;
+      tk[k] = LQ_WKEY_END | (uint32_t)k;
       if (k < z) {
         const int ent = sse[k], lid = ent >> 1;
         const int h = S.off[lid], e = S.off[lid + 1];
-        he[k] = (uint32_t)h | ((uint32_t)e << 16);
-        ix[k] = S.idx0[lid] - h;
+        sts64(hx_s + (uint32_t)k * hstep, (uint32_t)h | ((uint32_t)e << 16), (uint32_t)(S.idx0[lid] - h));
         sdm |= (uint32_t)(ent & 1) << k;
         if (h < e) tk[k] = S.key[h] | (uint32_t)k;
       }
     }
-    for (;;) {
+    // one leg: FIRST = the first leg of the site in this window (its lower end stays open for
+    // k_carry_scan); peeled so that the loop below carries no test for it.  Returns false at the end.
+    auto step = [&](auto first) -> bool {
       uint32_t m = tk[0];
 #pragma unroll
       for (int k = 1; k < Z; ++k) m = min(m, tk[k]);
-      if (m >= LQ_WKEY_END) break;
+      if (m >= LQ_WKEY_END) return false;
       // another head within 16 of the minimum shares its time key (or sits on the next one): rare
       uint32_t dmin = 0xffffffffu;
       const uint32_t nm = ~m;   // tk - m - 1: the winner itself wraps to 0xffffffff
@@ -344,41 +379,33 @@ k_walk(Dev d, int buf) {
           if ((tk[k] >> 4) == mh) {
             const int lid = sse[k] >> 1, gb = S.gbond[lid];
             const double t2 = walk_exact_time(d.bond_tl, d.boff[buf], d.time[buf], d.Wl, d.nbmax, d.cap, gb, wl,
-                                              (int)(he[k] & 0xffffu) - S.off[lid]);
+                                              (int)(lds32(hx_s + (uint32_t)k * hstep) & 0xffffu) - S.off[lid]);
             if (t2 < bt || (t2 == bt && gb < bb)) { bt = t2; bb = gb; m = tk[k]; }
           }
       }
-      const int best = (int)(m & 7u);
-      // branch-free head update: select the winner's registers, ONE shared-memory load for the
-      // whole warp, then predicated write-back
-      uint32_t bhe = 0;
-      int bix = 0;
+      const uint32_t best = m & 7u;
+      // the winner's state: one 64-bit shared-memory load, its position goes back incremented
+      const uint32_t ha = hx_s + best * hstep;
+      const uint2 st = lds64(ha);
+      const uint32_t bh = st.x & 0xffffu, ben = st.x >> 16;
+      const uint32_t kn = lds32(key_s + 4u * bh + 4u);   // (the stage has one spare word behind the last operator)
+      sts32(ha, st.x + 1u);
+      const uint32_t tn = ((bh + 1u < ben) ? kn : LQ_WKEY_END) | best;
 #pragma unroll
-      for (int k = 0; k < Z; ++k) {
-        const bool w = (k == best);
-        bhe = w ? he[k] : bhe; bix = w ? ix[k] : bix;
-      }
-      const int bh = (int)(bhe & 0xffffu), ben = (int)(bhe >> 16);
-      const uint32_t kn = S.key[bh + 1];   // (the stage has one spare word behind the last operator)
-      const uint32_t tn = ((bh + 1 < ben) ? kn : LQ_WKEY_END) | (uint32_t)best;
-#pragma unroll
-      for (int k = 0; k < Z; ++k) {
-        const bool w = (k == best);
-        he[k] = w ? bhe + 1u : he[k];
-        tk[k] = w ? tn : tk[k];
-      }
-      const int bsd = (int)((sdm >> best) & 1u);
-      const int idx = bix + bh;
-      if (have) (bsd ? d.low1 : d.low0)[idx] = cur | (spin << 31);
-      else d.firstW[(size_t)wl * d.N + s] = (uint32_t)idx | ((uint32_t)bsd << 31);
-      have = true;
+      for (int k = 0; k < Z; ++k) tk[k] = ((uint32_t)k == best) ? tn : tk[k];
+      const uint32_t bsd = (sdm >> best) & 1u;
+      const uint32_t idx = st.y + bh;
+      if (decltype(first)::value) d.firstW[(size_t)wl * d.N + s] = idx | (bsd << 31);
+      else d.low0[idx + bsd * d.lowstride] = cur | (spin << 31);   // (one array: low1[i] = low0[lowstride + i])
       spin ^= (m >> 3) & 1u;
-      cur = (node_t)d.N + (node_t)idx * nmul + ((node_t)bsd & nside);   // = upper_node(d, idx, bsd)
-    }
+      cur = (node_t)d.N + (NPO == 2 ? 2u * idx + bsd : idx);   // = upper_node(d, idx, bsd)
+      return true;
+    };
+    have = step(std::true_type());
+    if (have)
+      while (step(std::false_type())) {}
   } else {
-    uint16_t* head = S.head + tid;
-    const int hs = blockDim.x;
-    for (int k = 0; k < z; ++k) head[k * hs] = (uint16_t)S.off[sse[k] >> 1];
+    for (int k = 0; k < z; ++k) hx[k * hs].x = (uint32_t)S.off[sse[k] >> 1];
     for (;;) {
       int best = -1, bh = 0, bent = 0;
       uint32_t bk = 0;
@@ -386,7 +413,7 @@ k_walk(Dev d, int buf) {
       for (int k = 0; k < z; ++k) {
         const int ent = sse[k];
         const int lid = ent >> 1;
-        const int h = head[k * hs];
+        const int h = (int)hx[k * hs].x;
         if (h < S.off[lid + 1]) {
           const uint32_t k2 = S.key[h];
           if (best < 0 || (k2 >> 4) < (bk >> 4)) { best = k; bk = k2; bh = h; bent = ent; tie = false; }
@@ -401,7 +428,7 @@ k_walk(Dev d, int buf) {
         for (int k = 0; k < z; ++k) {
           const int ent = sse[k];
           const int lid = ent >> 1;
-          const int h = head[k * hs];
+          const int h = (int)hx[k * hs].x;
           if (h < S.off[lid + 1] && (S.key[h] >> 4) == mh) {
             const int gb = S.gbond[lid];
             const double t2 = walk_exact_time(d.bond_tl, d.boff[buf], d.time[buf], d.Wl, d.nbmax, d.cap, gb, wl, h - S.off[lid]);
@@ -409,7 +436,7 @@ k_walk(Dev d, int buf) {
           }
         }
       }
-      head[best * hs] = (uint16_t)(bh + 1);
+      hx[best * hs].x = (uint32_t)(bh + 1);
       const int lid = bent >> 1, side = bent & 1;
       const int idx = S.idx0[lid] + (bh - S.off[lid]);
       if (have) (side ? d.low1 : d.low0)[idx] = cur | (spin << 31);

@@ -34,7 +34,16 @@ CASES = [
     ("square12x20_b6", lambda lq: lq.hypercubic_lattice((12, 20)), 6.0, 60),
     ("cubic8_b2", lambda lq: lq.hypercubic_lattice((8, 8, 8)), 2.0, 40),
     ("ladder2x16_b8", lambda lq: lq.hypercubic_lattice((16, 2)), 8.0, 100),
+    # coordination number 9 (> 8): the generic world-line walk, merge heads in shared memory; a general graph
+    # without lattice dimensions (tiles cut by site index, one of them owns no bond)
+    ("complete_bipartite_9x9_b3", lambda lq: _complete_bipartite(9), 3.0, 100),
 ]
+
+
+def _complete_bipartite(n):
+    a = np.repeat(np.arange(n), n).astype(np.int32)
+    b = (n + np.tile(np.arange(n), n)).astype(np.int32)
+    return dict(num_sites=2 * n, src=a, dst=b, gauge=np.r_[np.ones(n), -np.ones(n)], dims=(0, 0, 0))
 
 
 @pytest.mark.parametrize("name,latf,beta,therm", CASES, ids=[c[0] for c in CASES])
