@@ -15,8 +15,8 @@
  * The generic-model functions (orc_model_*: XXZ bond graphs + site graphs; orc_stiffness) restate
  * path_integral.C / graph_impl.h / transmag.h / stiffness.h, which do not compile here (ALPS) and
  * whose golden outputs depend on the ALPS generator: they are pinned to exact diagonalisation
- * (tests/golden/ed_*.json, tests/test_oracle_model.py) and, for the stiffness, to the agreement of
- * the improved with the normal estimator -- "parity unpinned" at the bit level for that part.
+ * (tests/golden/ed_*.json, tests/test_oracle_model.py; the stiffness to <W^2> = beta F''(twist = 0) of
+ * tests/golden/ed_stiffness.json, both estimators) -- "parity unpinned" at the bit level for that part.
  *
  * Every function cites the reference file:line it follows (paths relative to the
  * reference root, wistaria/alps-looper).

@@ -133,7 +133,72 @@ def ed_tfi(L, jxy, jz, gamma, T):
                 usus_density=kubo(mu) / L, ssus_density=kubo(ms) / L)
 
 
+def ed_stiffness(n, bonds, rvec, dim, jxy, jz, T):
+    """Spin stiffness as the reference reports it (looper/stiffness.h:126-129,160-167: <W^2> / (beta dim),
+    W = sum over the off-diagonal operators of +-bond_vector_relative, an integer per direction).
+    A twist phi turns the hopping term of bond b into Jxy/2 (e^{i phi r_b} S+_src S-_dst + h.c.), so that
+    Z(phi) = sum_W Z_W e^{i phi W} and <W^2> = -d^2 ln Z / d phi^2 = beta F''(0):
+      F''(0) = <d^2H/dphi^2> - sum_nm |<n|dH/dphi|m>|^2 K_nm / Z   (second-order perturbation theory,
+    K_nm = (w_m - w_n)/(E_n - E_m), beta w_n on degenerate pairs).  Returned per direction and summed;
+    `fd` is the same number from central differences of ln Z(phi) with the complex Hamiltonian."""
+    dimH = 1 << n
+    sz = lambda s, i: 0.5 - ((s >> i) & 1)
+
+    def ham(phi, k):
+        H = np.zeros((dimH, dimH), dtype=complex)
+        for s in range(dimH):
+            for b, (i, j) in enumerate(bonds):
+                H[s, s] += jz * sz(s, i) * sz(s, j)
+                bi, bj = (s >> i) & 1, (s >> j) & 1
+                if bi != bj:   # bit clear = up: S+_i S-_j moves an up spin from j to i
+                    ph = np.exp(1j * phi * rvec[b][k] * (1 if bi == 1 else -1))
+                    H[s ^ (1 << i) ^ (1 << j), s] += 0.5 * jxy * ph
+        return H
+
+    beta = 1.0 / T
+    H0 = ham(0.0, 0).real
+    E, V = np.linalg.eigh(H0)
+    w = np.exp(-beta * (E - E.min()))
+    Z = w.sum()
+    dE = E[:, None] - E[None, :]
+    wn, wm = w[:, None], w[None, :]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        K = np.where(np.abs(dE) > 1e-10, (wm - wn) / dE, beta * wn)
+    w2, fd = 0.0, 0.0
+    for k in range(dim):
+        J = np.zeros((dimH, dimH), dtype=complex)
+        T2 = np.zeros((dimH, dimH))
+        for s in range(dimH):
+            for b, (i, j) in enumerate(bonds):
+                bi, bj = (s >> i) & 1, (s >> j) & 1
+                if bi != bj:
+                    sg = 1 if bi == 1 else -1
+                    s2 = s ^ (1 << i) ^ (1 << j)
+                    J[s2, s] += 0.5 * jxy * 1j * rvec[b][k] * sg
+                    T2[s2, s] -= 0.5 * jxy * rvec[b][k] ** 2
+        M = V.T @ J @ V
+        t2 = (w * np.einsum("sn,st,tn->n", V, T2, V)).sum() / Z
+        f2 = t2 - ((np.abs(M) ** 2) * K).sum() / Z
+        w2 += beta * f2
+        h = 1e-3
+        lz = []
+        for phi in (-h, 0.0, h):
+            Ep = np.linalg.eigvalsh(ham(phi, k))
+            lz.append(np.log(np.exp(-beta * (Ep - E.min())).sum()))
+        fd += -(lz[0] - 2 * lz[1] + lz[2]) / h ** 2
+    return dict(n=n, bonds=[list(b) for b in bonds], rvec=[list(r) for r in rvec], dim=dim, jxy=jxy, jz=jz, T=T,
+                w2=w2, w2_fd=fd, stiffness=w2 / (beta * dim))
+
+
 if __name__ == "__main__":
+    chain = lambda L: ([(i, (i + 1) % L) for i in range(L)], [[1.0 / L, 0, 0]] * L)
+    n, lbonds, _ = ladder_4x2()
+    lvec = [[0.25, 0, 0]] * 8 + [[0, 0.5, 0]] * 4
+    st = [ed_stiffness(8, *chain(8), 1, 1.0, 1.0, 0.25), ed_stiffness(8, *chain(8), 1, 1.0, 0.5, 0.5),
+          ed_stiffness(6, *chain(6), 1, -1.0, -1.0, 0.5), ed_stiffness(n, lbonds, lvec, 2, 1.0, 1.0, 0.4)]
+    json.dump(st, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ed_stiffness.json"), "w"), indent=1)
+    for o in st:
+        print({k: v for k, v in o.items() if k not in ("bonds", "rvec")})
     tfi = [ed_tfi(8, 0.0, 1.0, 0.7, 0.5), ed_tfi(8, 0.0, -1.0, 0.5, 0.4), ed_tfi(8, -1.0, 0.5, 0.6, 0.4),
            ed_tfi(6, -1.0, -1.0, 1.0, 0.25)]   # Jxy <= 0 with a field: no sign problem
     json.dump(tfi, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ed_tfi.json"), "w"), indent=1)

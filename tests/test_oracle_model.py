@@ -131,6 +131,33 @@ def test_stiffness_by_hand_and_improved_vs_normal():
     assert abs(np.mean(imp) - np.mean(nrm)) < 4.5 * err, (np.mean(imp), np.mean(nrm), err)
 
 
+@pytest.mark.parametrize("row", [0, 1, 2, 3])
+def test_oracle_stiffness_vs_exact_diagonalisation(row):
+    """looper/stiffness.h:82-170 against tests/golden/ed_stiffness.json (<W^2> = beta F''(twist = 0) by
+    second-order perturbation theory, tests/golden/make_ed_golden.py): Heisenberg and XXZ rings, a
+    ferromagnetic ring, the 4 x 2 ladder (winding along the legs only).  Pins BOTH estimators of the
+    restatement -- the per-cluster winding of the improved one and the total winding of the normal one --
+    to an RNG-free number, not just to each other."""
+    from looper_lattices import hypercubic_lattice
+    ed = json.load(open(os.path.join(HERE, "golden", "ed_stiffness.json")))[row]
+    assert abs(ed["w2"] - ed["w2_fd"]) < 1e-6 * max(1.0, ed["w2"])   # the golden checks itself: finite differences of ln Z
+    lat = hypercubic_lattice((4, 2)) if ed["dim"] == 2 else chain_lattice(ed["n"])
+    assert [[int(a), int(b)] for a, b in zip(lat["src"], lat["dst"])] == ed["bonds"]
+    assert np.allclose(lat["bond_vectors"], ed["rvec"]) and lat["vector_dim"] == ed["dim"]
+    v, off, sign = xxz_weights(ed["jxy"], ed["jz"])
+    sim = orc.OracleModelSim(lat, 1 / ed["T"], weights=tuple(v), seed=7 + row)
+    imp, nrm = [], []
+    for i in range(81000):
+        sim.sweep()
+        if i >= 1000:
+            spins, ops = sim.get_state()
+            a, b = orc.stiffness(lat, spins, ops)
+            imp.append(a)
+            nrm.append(b)
+    assert abs(np.mean(imp) - ed["w2"]) < 3 * _berr(imp), (np.mean(imp), ed["w2"], _berr(imp))
+    assert abs(np.mean(nrm) - ed["w2"]) < 3 * _berr(nrm), (np.mean(nrm), ed["w2"], _berr(nrm))
+
+
 @pytest.mark.parametrize("row", [0, 1, 2])
 def test_oracle_model_vs_exact_diagonalisation_ladder(row):
     """the smallest two-dimensional case (4 x 2 ladder, tests/golden/ed_ladder.json): Heisenberg,
