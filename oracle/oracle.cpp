@@ -186,6 +186,7 @@ struct orc_sim {
   std::vector<int> built_type;  // operator types as built (pre flip)
   int nc = 0;
   bool looper_estimators = true;   // orc_set_looper_estimators
+  std::vector<sa_estimate> estimates;   // kept across sweeps like loop.C:64 (resize(0); resize(nc))
   orc_sim(int ns, int nb, const int32_t* s, const int32_t* d, const double* g, double b,
           uint32_t seed)
       : nsites(ns), nbonds(nb), src(s, s + nb), dst(d, d + nb), gauge(ns, 0.0), beta(b),
@@ -209,7 +210,8 @@ void orc_sweep(orc_sim* S, orc_collector* out) {
   std::vector<op_t>&operators = S->operators, &operators_p = S->operators_p;
   std::vector<int>&spins = S->spins, &current = S->current;
   std::vector<sa_node>& fragments = S->fragments;
-  S->spins_before = spins;
+  // (test hook for orc_get_last_graph; not a statement of loop.C -- skipped on the timed CPU legs)
+  if (S->looper_estimators) S->spins_before = spins;
 
   // loop.C:87
   std::swap(operators, operators_p);
@@ -265,7 +267,9 @@ void orc_sweep(orc_sim* S, orc_collector* out) {
   for (auto& f : fragments) f.id = fragments[sa_root_index(fragments, int(&f - &fragments[0]))].id;
   S->nc = nc;
   S->to_flip.assign(nc, 0);
-  std::vector<sa_estimate> estimates(nc);
+  std::vector<sa_estimate>& estimates = S->estimates;
+  estimates.resize(0);
+  estimates.resize(nc);
   std::vector<lp_estimate> lest(S->looper_estimators ? nc : 0);
 
   // loop.C:141-151
@@ -317,8 +321,10 @@ void orc_sweep(orc_sim* S, orc_collector* out) {
   // path_integral.C:850-851 with energy_offset = sum of bond offsets = nbonds/4 (weight_impl.h:187)
   coll.ene = 0.25 * nbonds - coll.nop / S->beta;
 
-  S->built_type.resize(operators.size());
-  for (size_t i = 0; i < operators.size(); ++i) S->built_type[i] = operators[i].type;
+  if (S->looper_estimators) {   // test hook (orc_get_last_graph), skipped on the timed CPU legs
+    S->built_type.resize(operators.size());
+    for (size_t i = 0; i < operators.size(); ++i) S->built_type[i] = operators[i].type;
+  }
 
   // loop.C:160
   for (int c = 0; c < nc; ++c) S->to_flip[c] = (S->d_uniform(S->eng) < 0.5);
@@ -358,14 +364,14 @@ void orc_get_last_graph(const orc_sim* S, int32_t* spins_before, orc_op* ops_bui
                         int32_t* lower_id, int32_t* upper_id, int32_t* site_id, int32_t* nc,
                         int32_t* flip) {
   for (int s = 0; s < S->nsites; ++s) {
-    if (spins_before) spins_before[s] = S->spins_before[s];
+    if (spins_before) spins_before[s] = S->looper_estimators ? S->spins_before[s] : -1;   // hooks are off on the timed legs
     if (site_id) site_id[s] = S->fragments[s].id;
   }
   for (size_t i = 0; i < S->operators.size(); ++i) {
     if (ops_built) {
       ops_built[i].time = S->operators[i].time;
       ops_built[i].loc = (S->operators[i].bond << 1) | 1;
-      ops_built[i].type = S->built_type[i];
+      ops_built[i].type = S->looper_estimators ? S->built_type[i] : -1;
     }
     if (lower_id) lower_id[i] = S->fragments[S->operators[i].lower_cluster].id;
     if (upper_id) upper_id[i] = S->fragments[S->operators[i].upper_cluster].id;
@@ -808,6 +814,7 @@ void orc_run_chain(int length, double temperature, unsigned sweeps, unsigned the
   }
   const double beta = 1 / temperature;
   orc_sim* S = orc_create(length, length, src.data(), dst.data(), gauge.data(), beta, 29833);
+  S->looper_estimators = false;   // loop.C's own statements only (its three sums; no looper collector, no test hooks)
   observable num_clusters, energy, usus, smag, ssus;
   for (unsigned mcs = 0; mcs < therm + sweeps; ++mcs) {
     orc_collector coll;
