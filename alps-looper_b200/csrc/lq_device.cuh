@@ -105,6 +105,9 @@ struct Dev {
   int scap;               // operators that fit the shared-memory stage (own page + halo)
   int ccap;               // candidates per page that fit the stage (K1)
   int k1_keyshift;        // LQ_K1_KEYBITS (tests): the 32-bit time keys of K1 are coarsened by this shift
+  int k1_timebits;        // LQ_K1_TIMEBITS (tests): candidate times are cut to this many bits of a window, so that
+                          // EQUAL f64 times on neighbouring bonds -- once per ~10^4 steps at full resolution -- happen
+                          // all the time (0: off)
   int kcap;               // kept (off-diagonal) operators per page that fit the kept list of K1
   // ---- pages (double buffered) ----
   double* time[2];
@@ -210,6 +213,19 @@ __host__ __device__ __forceinline__ float u24(uint32_t a) { return (float)(a >> 
 // at most extra hops, while hot roots of big clusters are served from L1.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ node_t uf_load(const node_t* p) { return *(const volatile node_t*)p; }
+
+// Two operators of ONE site with exactly the same f64 time (the continuum has no such pair; in f64 a
+// candidate meets an off-diagonal leg of a neighbouring bond at its own time about once per 10^4 steps
+// at the headline size): ordered by bond, lower key first.  The diagonal update (k1_parity_exact) and
+// the walk (its tie path) must agree on that order -- a candidate accepted against the spins "before"
+// the leg and then walked "after" it would sit on parallel spins -- and on the spatial cut two ranks
+// that hold the same site must agree as well, so the key is rank independent: the tile's id in the
+// global tiling | local bond (= the internal bond id on serial and slab engines, same order).
+__device__ __forceinline__ uint32_t bond_order_key(const uint32_t* __restrict__ tile_key, const int* __restrict__ bond_tl, int b) {
+  if (!tile_key) return (uint32_t)b;
+  const int tl = bond_tl[b];
+  return (tile_key[tl >> 10] << 10) | (uint32_t)(tl & 1023);
+}
 
 __device__ __forceinline__ node_t uf_find(node_t* parent, node_t x) {
   node_t p = uf_load(parent + x);

@@ -1080,6 +1080,7 @@ struct lq_engine {
     d.bs = bs.p; d.sst_off = sst_off.p; d.sst = sst.p;
     d.hmax = part.hmax; d.nksmax = part.nksmax; d.zmax = part.zmax; d.scap = scap; d.ccap = ccap; d.kcap = kcap;
     d.k1_keyshift = getenv("LQ_K1_KEYBITS") ? std::max(0, std::min(31, 32 - atoi(getenv("LQ_K1_KEYBITS")))) : 0;
+    d.k1_timebits = getenv("LQ_K1_TIMEBITS") ? std::max(0, std::min(30, atoi(getenv("LQ_K1_TIMEBITS")))) : 0;
     for (int k = 0; k < 2; ++k) {
       d.time[k] = time_[k].p; d.info[k] = info[k].p; d.boff[k] = boff[k].p; d.pcount[k] = pcount[k].p;
     }
@@ -1805,8 +1806,9 @@ struct lq_engine {
         idx += n;
       }
     }
+    // (equal times: by bond like the walk -- bond_order_key -- and, on one bond, in bucket order)
     std::sort(out.begin(), out.end(), [](const HostOp& a, const HostOp& b) {
-      return a.time < b.time || (a.time == b.time && a.bi < b.bi);
+      return a.time < b.time || (a.time == b.time && (a.bi < b.bi || (a.bi == b.bi && a.idx < b.idx)));
     });
   }
 

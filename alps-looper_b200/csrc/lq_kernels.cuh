@@ -307,8 +307,9 @@ __global__ void k_carry_scan(Dev d) {
 // the heads names the winner), its staged position and end packed in one word, and the offset from
 // staged position to dense operator index; every step is an integer minimum over Z registers and
 // reloads only the head that advanced.  Z == 0: generic version with the head positions in shared
-// memory.  Heads that agree in the 28 time bits of the key are ordered on the f64 times (then by bond
-// id: two operators of one site at exactly the same time keep the order lq_get_state exports).
+// memory.  Heads that agree in the 28 time bits of the key are ordered on the f64 times, then by
+// bond_order_key: two operators of one site at exactly the same time come in the order the diagonal update
+// assumed when it accepted the later one (k1_parity_exact; lq_device.cuh).
 #ifndef LQ_WALK_MINB
 #define LQ_WALK_MINB 5   /* resident 256-thread CTAs per SM the square-lattice walk is compiled for (48 registers;
                             6 = 40 registers spills in the prologue and measured 3 % slower) */
@@ -373,14 +374,15 @@ k_walk(Dev d, int buf) {
       if (dmin < 15u) {
         const uint32_t mh = m >> 4;
         double bt = 4.0;
-        int bb = 0x7fffffff;
+        uint32_t bb = 0xffffffffu;
 #pragma unroll
         for (int k = 0; k < Z; ++k)
           if ((tk[k] >> 4) == mh) {
             const int lid = sse[k] >> 1, gb = S.gbond[lid];
             const double t2 = walk_exact_time(d.bond_tl, d.boff[buf], d.time[buf], d.Wl, d.nbmax, d.cap, gb, wl,
                                               (int)(lds32(hx_s + (uint32_t)k * hstep) & 0xffffu) - S.off[lid]);
-            if (t2 < bt || (t2 == bt && gb < bb)) { bt = t2; bb = gb; m = tk[k]; }
+            const uint32_t ok = bond_order_key(d.tile_key, d.bond_tl, gb);   // equal f64 times: the order K1 assumed
+            if (t2 < bt || (t2 == bt && ok < bb)) { bt = t2; bb = ok; m = tk[k]; }
           }
       }
       const uint32_t best = m & 7u;
@@ -424,7 +426,7 @@ k_walk(Dev d, int buf) {
       if (tie) {   // heads with the same time key: f64 times, then bond ids
         const uint32_t mh = bk >> 4;
         double bt = 4.0;
-        int bb = 0x7fffffff;
+        uint32_t bb = 0xffffffffu;
         for (int k = 0; k < z; ++k) {
           const int ent = sse[k];
           const int lid = ent >> 1;
@@ -432,7 +434,8 @@ k_walk(Dev d, int buf) {
           if (h < S.off[lid + 1] && (S.key[h] >> 4) == mh) {
             const int gb = S.gbond[lid];
             const double t2 = walk_exact_time(d.bond_tl, d.boff[buf], d.time[buf], d.Wl, d.nbmax, d.cap, gb, wl, h - S.off[lid]);
-            if (t2 < bt || (t2 == bt && gb < bb)) { bt = t2; bb = gb; best = k; bk = S.key[h]; bh = h; bent = ent; }
+            const uint32_t ok = bond_order_key(d.tile_key, d.bond_tl, gb);
+            if (t2 < bt || (t2 == bt && ok < bb)) { bt = t2; bb = ok; best = k; bk = S.key[h]; bh = h; bent = ent; }
           }
         }
       }
@@ -1146,8 +1149,8 @@ k_collect_final(Dev d, const double* partial, size_t nblk_cap, double* out) {
 // and the estimators use the POSITION of an operator in it as its time (sse.C:251-283: `t`,
 // stop_top(operators.size())).  Positions come from one counting sort over (window, time bin):
 // histogram -> exclusive scan -> scatter -> rank inside the bin by comparing (time, bond) with the
-// handful of operators that share it.  Ties in time are ordered by the internal bond index, the
-// order lq_get_state exports.
+// handful of operators that share it.  Ties in time are ordered by the internal bond index, then by the
+// position inside the bucket: the order lq_get_state exports.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sse_bin(const Dev& d, int wl, double t) {
   const int wg = d.w0 + wl;
@@ -1203,7 +1206,9 @@ k_sse_rank(Dev d) {
   uint32_t r = beg;
   for (uint32_t k = beg; k < end; ++k) {
     const double tk = d.sorted_time[k];
-    r += (tk < tt || (tk == tt && d.sorted_id[k].x < me.x)) ? 1u : 0u;
+    bool before = tk < tt;
+    if (tk == tt) { const uint2 o = d.sorted_id[k]; before = o.x < me.x || (o.x == me.x && o.y < me.y); }   // then bond, then bucket order
+    r += before ? 1u : 0u;
   }
   d.spos[me.y] = r;
 }

@@ -436,3 +436,34 @@ def test_time_key_ties_take_the_exact_path(monkeypatch):
     for out, spins, ops in runs[1:]:
         assert np.array_equal(out["nop"], runs[0][0]["nop"]) and np.array_equal(out["nc"], runs[0][0]["nc"])
         assert np.array_equal(spins, runs[0][1]) and np.array_equal(ops, runs[0][2])
+
+
+def test_equal_times_on_neighbouring_bonds_are_ordered_consistently(monkeypatch):
+    """Two operators of one site at EXACTLY the same f64 time do not exist in the continuum, but a candidate
+    of the diagonal update meets an off-diagonal leg of a neighbouring bond at its own time about once per
+    10^4 steps at the headline size.  K1 (which decides the candidate against the spins before or after that
+    leg) and the world-line walk (which orders the two) must then agree, or the candidate ends up on parallel
+    spins.  LQ_K1_TIMEBITS (a test hook) cuts the candidate times to 5 bits of a window, so such pairs are
+    everywhere: the chain must stay legal, and the partition must equal the reference union-find's on the
+    exported configuration (time, then bond: csrc/lq_device.cuh bond_order_key)."""
+    lq = _lq()
+    monkeypatch.setenv("LQ_K1_TIMEBITS", "5")
+    lat = lq.hypercubic_lattice((12, 12))
+    src, dst = np.asarray(lat["src"]), np.asarray(lat["dst"])
+    eng = lq.Engine(lat, 6.0, seed=31, tile_sites=16)
+    pairs = 0
+    for rep in range(10):
+        eng.sweep_many(20, collect=False)
+        spins, ops = eng.get_state()
+        t, b, off = ops["time"], ops["loc"] >> 1, ops["type"] & 1
+        assert np.all(np.diff(t) >= 0)
+        same = np.flatnonzero(np.diff(t) == 0)
+        for k in same:   # neighbours in the list at one time: different bonds sharing a site, one of them off-diagonal
+            sa, sb = {src[b[k]], dst[b[k]]}, {src[b[k + 1]], dst[b[k + 1]]}
+            pairs += int(b[k] != b[k + 1] and bool(sa & sb) and bool(off[k] | off[k + 1]))
+        ref_labels, ref_nc, ref_coll = orc.build_clusters(lat, spins, ops)   # raises on an operator on the wrong spins
+        labels, nc, coll = eng.build_clusters()
+        assert nc == ref_nc
+        assert np.array_equal(labels, ref_labels)
+    assert pairs > 20, pairs
+    eng.close()
