@@ -469,12 +469,14 @@ struct lq_engine {
   lq::K1Layout k1_lay = lq::K1Layout();
   int k1_fc = 12, k1_nt = 256, k1_chunk = 1, kcap = 0;
   bool k1_tma = true;
+  bool k1_tq = false;   // LQ_K1_TIMEBITS: the test-hook instantiation of K1 (256 threads, 16-slot columns, plain loads)
   double grow_kept = 1;
   // diagonal update specialised on block size, on the width of the per-site columns and on how the
   // pages reach shared memory (bulk copy + mbarrier, or plain loads)
   k1_fn_t pick_k1() const {
 #define LQ_PICK2(MT, F) (k1_tma ? lq::k_diag_update<MT, F, true> : lq::k_diag_update<MT, F, false>)
 #define LQ_PICK1(MT) (k1_fc <= 8 ? LQ_PICK2(MT, 8) : k1_fc <= 12 ? LQ_PICK2(MT, 12) : LQ_PICK2(MT, 16))
+    if (k1_tq) return lq::k_diag_update<256, 16, false, true>;   // LQ_K1_TIMEBITS (tests)
     if (k1_nt <= 128) return LQ_PICK1(128);
     if (k1_nt <= 256) return LQ_PICK1(256);
     if (k1_nt <= 384) return LQ_PICK1(384);
@@ -873,10 +875,15 @@ struct lq_engine {
         while (part.nbmax > LQ_K1_QMAX * k1_nt && k1_nt < 512) k1_nt = k1_nt < 256 ? 256 : (k1_nt < 384 ? 384 : 512);
         if (part.nbmax > LQ_K1_QMAX * k1_nt) fail(LQ_E_INVALID, "tile owns too many bonds for K1: lower lq_options.tile_sites");
         k1_tma = !getenv("LQ_K1_NOTMA");
+        k1_tq = getenv("LQ_K1_TIMEBITS") && atoi(getenv("LQ_K1_TIMEBITS")) > 0;
+        if (k1_tq) {
+          if (part.nbmax > LQ_K1_QMAX * 256) fail(LQ_E_INVALID, "LQ_K1_TIMEBITS (test hook) needs tiles of at most 1280 bonds");
+          k1_nt = 256; k1_fc = 16; k1_tma = false;
+        }
         // two resident CTAs per SM matter more than wide columns or the bulk-copied page buffer
         const size_t two_ctas = (size_t)(227 * 1024) / 2 - 1200;
         auto k1_bytes = [&]() { return lq::k1_smem_bytes(k1_tma, k1_fc, cap, ccap, kcap, part.nbmax, part.hmax, part.nksmax); };
-        while (k1_fc > 8 && k1_bytes() > two_ctas && !getenv("LQ_FC")) k1_fc -= 4;
+        while (k1_fc > 8 && k1_bytes() > two_ctas && !getenv("LQ_FC") && !k1_tq) k1_fc -= 4;
         if (k1_bytes() > (size_t)smem_optin - 2048)
           k1_tma = false;   // page buffer does not fit beside the lists: stream the page with plain loads
         // windows per persistent CTA: enough CTAs for ~8 waves, at least 4 windows to amortise the tile set-up

@@ -180,29 +180,37 @@ __device__ __forceinline__ void k1_carve(const K1Layout& L, unsigned char* smem,
   S.kspin = (uint8_t*)(smem + L.kspin);
 }
 
-// parity of the off-diagonal legs before tc on a site, straight from the pages in global memory
-// (only used when a site carries more than FC legs in one window)
+// parity of the off-diagonal legs before tc on the two sites of a candidate's bond, straight from the
+// pages in global memory (only used when a leg shares the candidate's 32-bit key or a site carries more
+// than FC legs in one window).
+// A leg at exactly the candidate's f64 time counts as earlier iff its bond comes first in bond_order_key:
+// the order the walk gives such a pair (lq_device.cuh).  Legs of the candidate's own bond are seen from
+// both of its sites and cancel under any rule.
 // (plain arguments: passing the Dev struct by reference would force a copy of the kernel parameters
-// into local memory and turn every access to them into a local load)
-// A leg at exactly the candidate's time counts as earlier iff its bond comes first in bond_order_key
-// (kc = key of the candidate's bond): the order the walk gives such a pair.  (Legs of the candidate's own
-// bond are seen from both of its sites and cancel under any rule.)
+// into local memory and turn every access to them into a local load.  ONE call for both sites: with one
+// call per site the kernel around it came out 2-3 % slower -- 64 registers either way, but 8-24 bytes of
+// stack instead of none; K1 at 1024 x 1024, beta = 128: 6.19 -> 6.05 ms.)
 __device__ __noinline__ int k1_parity_exact(const int* __restrict__ adj_off, const int* __restrict__ adj,
                                             const int* __restrict__ bond_tl, const uint32_t* __restrict__ tile_key,
                                             int Wl, int nbmax, int cap,
                                             const uint16_t* __restrict__ boff, const uint32_t* __restrict__ info,
-                                            const double* __restrict__ time, int wl, int site, double tc, uint32_t kc) {
+                                            const double* __restrict__ time, int wl, int site0, int site1, double tc, int b) {
+  const uint32_t kc = bond_order_key(tile_key, bond_tl, b);
   int par = 0;
-  for (int a = adj_off[site]; a < adj_off[site + 1]; ++a) {
-    const int b2 = adj[a] >> 1;
-    const int tl = bond_tl[b2];
-    const size_t p = (size_t)(tl >> 10) * Wl + wl;
-    const uint16_t* bo = boff + p * (size_t)(nbmax + 1) + (tl & 1023);
-    const size_t base = p * (size_t)cap;
-    for (int j = bo[0]; j < bo[1]; ++j) {
-      const double t2 = time[base + j];
-      const bool before = t2 < tc || (t2 == tc && bond_order_key(tile_key, bond_tl, b2) < kc);
-      par ^= (int)(info[base + j] & LQ_INFO_OFFDIAG) & (int)before;
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const int site = side ? site1 : site0;
+    for (int a = adj_off[site]; a < adj_off[site + 1]; ++a) {
+      const int b2 = adj[a] >> 1;
+      const int tl = bond_tl[b2];
+      const size_t p = (size_t)(tl >> 10) * Wl + wl;
+      const uint16_t* bo = boff + p * (size_t)(nbmax + 1) + (tl & 1023);
+      const size_t base = p * (size_t)cap;
+      for (int j = bo[0]; j < bo[1]; ++j) {
+        const double t2 = time[base + j];
+        const bool before = t2 < tc || (t2 == tc && bond_order_key(tile_key, bond_tl, b2) < kc);
+        par ^= (int)(info[base + j] & LQ_INFO_OFFDIAG) & (int)before;
+      }
     }
   }
   return par;
@@ -221,8 +229,10 @@ __device__ __forceinline__ uint32_t k1_key(double t, double tlo, double kscale, 
 #define LQ_K1_QMAX 5   /* buckets per thread whose candidate counts travel in one packed register */
 
 // NT threads; FC (8, 12, 16) = off-diagonal legs per K-site and window held in the column table;
-// TMA: pages arrive through cp.async.bulk + mbarrier (else: plain loads, no page buffer)
-template <int NT, int FC, bool TMA>
+// TMA: pages arrive through cp.async.bulk + mbarrier (else: plain loads, no page buffer);
+// TQ: test hook LQ_K1_TIMEBITS (Dev::k1_timebits) -- candidate times cut to a few bits of a window; its own
+// instantiation, so that the production kernels carry no trace of it
+template <int NT, int FC, bool TMA, bool TQ = false>
 __global__ void __launch_bounds__(NT, (NT <= 256 ? 3 : 2))
 k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len, const K1Layout L) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -295,7 +305,7 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len, 
     const size_t p = (size_t)t * d.Wl + wl;
     const double tlo = d.wlo[wg], thi = d.wlo[wg + 1], width = thi - tlo;   // = window_lo / window_hi (host table)
     const double kscale = d.wks[wg];   // 4294967040 / width (host table: no f64 division per thread and window)
-    const int kshift = d.k1_keyshift, ktb = d.k1_timebits;
+    const int kshift = d.k1_keyshift;
     const int n_own = d.pcount[src][p];
     uint16_t* bo_new = d.boff[dst] + p * (size_t)(d.nbmax + 1);
     bool page_pending = TMA;   // a bulk copy into the page buffer is in flight / unconsumed
@@ -431,7 +441,8 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len, 
       // 53 uniform bits, (x.x << 32 | x.y) >> 11, converted in two exact 32-bit halves
       const double frac = __uint2double_rn(x.x >> 11) * (1.0 / 2097152.0) +
                           __uint2double_rn((x.x << 21) | (x.y >> 11)) * (1.0 / 9007199254740992.0);
-      double tc = tlo + (ktb ? floor(ldexp(frac, ktb)) * ldexp(1.0, -ktb) : frac) * width;   // (ktb: test hook, Dev::k1_timebits)
+      double tc = tlo + frac * width;
+      if constexpr (TQ) tc = tlo + floor(ldexp(frac, d.k1_timebits)) * ldexp(1.0, -d.k1_timebits) * width;
       if (!(tc < thi)) tc = tlo;
       const uint32_t kk = S.bs2[lb];
       const uint32_t k0 = kk & 0xffffu, k1 = kk >> 16;
@@ -450,12 +461,10 @@ k_diag_update(Dev d, int src, const StepParams* __restrict__ sp, int chunk_len, 
           tie |= (a.x == kc) | (a.y == kc) | (a.z == kc) | (a.w == kc) | (e.x == kc) | (e.y == kc) | (e.z == kc) | (e.w == kc);
         }
         // a leg within one key of the candidate, or a column that overflowed: decide on the f64 times
-        if (tie || S.colcnt[k0] > FC || S.colcnt[k1] > FC) {
-          const uint32_t bk = bond_order_key(d.tile_key, d.bond_tl, b);
+        if (tie || S.colcnt[k0] > FC || S.colcnt[k1] > FC)
           par = (S.kspin[k0] ^ S.kspin[k1]) ^
-                k1_parity_exact(d.adj_off, d.adj, d.bond_tl, d.tile_key, d.Wl, d.nbmax, d.cap, d.boff[src], d.info[src], d.time[src], wl, S.ksite[k0], tc, bk) ^
-                k1_parity_exact(d.adj_off, d.adj, d.bond_tl, d.tile_key, d.Wl, d.nbmax, d.cap, d.boff[src], d.info[src], d.time[src], wl, S.ksite[k1], tc, bk);
-        }
+                k1_parity_exact(d.adj_off, d.adj, d.bond_tl, d.tile_key, d.Wl, d.nbmax, d.cap, d.boff[src], d.info[src], d.time[src], wl,
+                                S.ksite[k0], S.ksite[k1], tc, b);
         const float4 pr = d.bond_p[b];
         const float u = u24(x.z);
         g = -1;
