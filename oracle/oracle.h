@@ -14,9 +14,16 @@
  *                                   by oracle/Makefile when the reference tree is present)
  * The generic-model functions (orc_model_*: XXZ bond graphs + site graphs; orc_stiffness) restate
  * path_integral.C / graph_impl.h / transmag.h / stiffness.h, which do not compile here (ALPS) and
- * whose golden outputs depend on the ALPS generator: they are pinned to exact diagonalisation
- * (tests/golden/ed_*.json, tests/test_oracle_model.py; the stiffness to <W^2> = beta F''(twist = 0) of
- * tests/golden/ed_stiffness.json, both estimators) -- "parity unpinned" at the bit level for that part.
+ * whose golden outputs depend on the ALPS generator: they are pinned statistically, to
+ *   - the reference's OWN Monte Carlo results for every S = 1/2 task of loop.op and extras/{transmag,gap,
+ *     corrlen,top,localsus}/*.op (tests/golden/ref_runs.json, tests/test_oracle_refruns.py): energy,
+ *     magnetisations, susceptibilities and what only the algorithm defines -- "Number of Clusters", the
+ *     generalised magnetisations, "Stiffness", "Transverse Magnetization" -- path integral and SSE,
+ *     Heisenberg / Ising (frozen graphs) / transverse field (site graphs) / simple cubic,
+ *   - exact diagonalisation (tests/golden/ed_*.json, whose generator reproduces the reference's
+ *     'diagonalization' tasks to the printed digits; tests/test_oracle_model.py; the stiffness to
+ *     <W^2> = beta F''(twist = 0), tests/golden/ed_stiffness.json, both estimators)
+ * -- "parity unpinned" at the bit level for that part (no RNG-free golden exists for it).
  *
  * Every function cites the reference file:line it follows (paths relative to the
  * reference root, wistaria/alps-looper).
