@@ -4,7 +4,6 @@
 `steps` steps with the phase timers on; prints ms per step of every phase and a checksum of the trajectory
 (operators and clusters per step: builds that only differ in code generation must agree).
 usage: k1_ab.py [--beta B] [--therm T] [--steps S] lib.so [lib.so ...]"""
-import json
 import os
 import subprocess
 import sys
