@@ -40,7 +40,14 @@ public:
     else if (name == "square lattice") ext = {L, W};
     else if (name == "simple cubic lattice") ext = {L, W, H};
     else if (name == "ladder") ext = {L, 2};
-    else throw std::invalid_argument("unknown LATTICE '" + name + "' (built-in: chain lattice, square lattice, simple cubic lattice, ladder)");
+    else if (name == "site") {   // a single site without bonds (check/site-*, extras/transmag: a spin in a field)
+      vg_ = virtual_graph();
+      vg_.nsites = 1;
+      vg_.gauge.assign(1, 1.0);
+      bipartite_ = true;
+      return;
+    }
+    else throw std::invalid_argument("unknown LATTICE '" + name + "' (built-in: chain lattice, square lattice, simple cubic lattice, ladder, site; ALPS lattice libraries are not read)");
     build_hypercubic(ext);
   }
   // periodic hypercubic lattice, site = x + L0 (y + L1 z); direction-major bond order

@@ -62,8 +62,9 @@ public:
     lq_lattice L;
     L.num_sites = num_sites(g);
     L.num_bonds = num_bonds(g);
-    L.src = g.src.data();
-    L.dst = g.dst.data();
+    static const int32_t no_bond = 0;   // LATTICE = "site": no bonds, but the C ABI wants non-null arrays
+    L.src = L.num_bonds ? g.src.data() : &no_bond;
+    L.dst = L.num_bonds ? g.dst.data() : &no_bond;
     L.gauge = lattice.is_bipartite() ? g.gauge.data() : nullptr;
     for (int k = 0; k < 3; ++k) L.dims[k] = g.dims[k];
     // MEASURE[Stiffness] (looper/stiffness.h): winding numbers need the relative bond vectors
@@ -71,7 +72,8 @@ public:
     L.vector_dim = measure_stiffness ? g.dimension : 0;
     L.bond_vectors = measure_stiffness ? g.bond_vector_relative.data() : nullptr;
     lq_model M;
-    M.bond_weights = model.bond_weights().data();
+    static const double no_weight[4] = {0, 0, 0, 0};
+    M.bond_weights = L.num_bonds ? model.bond_weights().data() : no_weight;
     for (int k = 0; k < 4; ++k) M.uniform_weights[k] = 0;
     M.energy_offset = model.energy_offset();
     M.site_weights = nullptr;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <stdexcept>
+#include <string>
 #include <vector>
 #include "lattice.h"
 #include "parameters.h"
@@ -64,19 +65,17 @@ public:
   spinmodel_helper() {}
   spinmodel_helper(const Parameters& p, const lattice_helper& lat) { init(p, lat); }
   void init(const Parameters& p, const lattice_helper& lat) {
+    check_supported(p);
     const double J = p.value_or_default<double>("J", 1.0);
     const double jxy = p.value_or_default<double>("Jxy", J), jz = p.value_or_default<double>("Jz", J);
-    if (p.value_or_default<double>("S", 0.5) != 0.5) throw std::invalid_argument("only S = 1/2 is supported");
-    if (p.value_or_default<double>("h", 0.0) != 0.0)
-      throw std::invalid_argument("longitudinal fields are outside the accelerated path");
     // transverse field Gamma (ALPS "spin" model: H -= Gamma Sx): site graphs
     site_weight_helper sw(p.value_or_default<double>("Gamma", 0.0));
     if (sw.sign < 0) throw std::invalid_argument("negative sign (Gamma < 0) is not supported");
     const double a = p.value_or_default<double>("FORCE_SCATTER", 0.0);
     const int nb = num_bonds(lat.vg());
     xxz_bond_weight_helper w(bond_parameter_xxz(0, jxy, jz), a);
-    if (w.sign < 0 && !lat.is_bipartite()) throw std::invalid_argument("negative sign (frustration) is not supported");
-    if (w.sign < 0 && sw.has_weight())
+    if (nb > 0 && w.sign < 0 && !lat.is_bipartite()) throw std::invalid_argument("negative sign (frustration) is not supported");
+    if (nb > 0 && w.sign < 0 && sw.has_weight())
       throw std::invalid_argument("negative sign (antiferromagnetic Jxy with a transverse field) is not supported");
     weights_.assign(4 * size_t(nb), 0.0);
     gw_ = 0;
@@ -91,6 +90,30 @@ public:
       const int ns = num_sites(lat.vg());
       gw_ += ns * sw.weight();
       offset_ += ns * sw.offset;
+    }
+  }
+  // A drop-in must refuse what it does not implement instead of quietly simulating something else: the
+  // parameters of the ALPS "spin" model (model_parameter.h) that change the Hamiltonian but have no
+  // counterpart on the accelerated path are errors, not ignored keys.
+  static void check_supported(const Parameters& p) {
+    const std::string model = p.value_or_default("MODEL", "spin");
+    if (model != "spin") throw std::invalid_argument("MODEL '" + model + "' is not supported (only the ALPS \"spin\" model: XXZ bonds + transverse field)");
+    for (const char* k : {"local_S", "S"})
+      if (p.value_or_default<double>(k, 0.5) != 0.5) throw std::invalid_argument(std::string(k) + " != 1/2 is outside the accelerated path");
+    if (p.value_or_default<double>("h", 0.0) != 0.0)
+      throw std::invalid_argument("longitudinal fields are outside the accelerated path");
+    if (p.value_or_default<double>("D", 0.0) != 0.0) throw std::invalid_argument("single-ion anisotropy D needs S > 1/2");
+    for (const auto& kv : p.items()) {
+      const std::string& k = kv.first;
+      if (k == "Jx" || k == "Jy") throw std::invalid_argument("parameter " + k + ": XYZ couplings are not supported");
+      // type-dependent couplings (Jz0, Jxy1, Gamma0, h1, J', ...): the C ABI takes per-bond and per-site weights
+      // (lq_model.bond_weights / site_weights), this host mirror only fills them uniformly
+      for (const char* stem : {"Jxy", "Jz", "J", "Gamma", "h", "D"}) {
+        const size_t n = std::char_traits<char>::length(stem);
+        if (k.size() > n && k.compare(0, n, stem) == 0 &&
+            k.find_first_not_of("0123456789'", n) == std::string::npos)
+          throw std::invalid_argument("parameter " + k + ": site- or bond-type dependent couplings are not supported by this host mirror");
+      }
     }
   }
   double graph_weight() const { return gw_; }       // model.h:114, graph_impl.h:694

@@ -115,6 +115,57 @@ int main() {
     CHECK(s["Transverse Magnetization"].mean() == 3.0 && s["Transverse Magnetization Density"].mean() == 3.0 / 16);
     CHECK(s["Stiffness"].mean() == 8.0 / (4.0 * 2));
   }
+  // --- ALPS parameter-file conventions the reference's own inputs use (loop.ip, check/*, extras/*/*.ip):
+  //     tasks in braces on top of the globals before them, ';' ',' and newline as separators, comments,
+  //     quoted values with ';' inside, numeric expressions over other parameters
+  {
+    std::istringstream in(
+        "LATTICE = \"chain lattice\"\nMODEL = \"spin\"\nlocal_S = 1/2; L = 4, Jxy = -1; Jz = -1  // ferromagnet\n"
+        "ALGORITHM = \"loop; path integral\"\n# a comment { with = braces }\n"
+        "{ T = 0.1 } { T = 0.2 }\n{ T = 1/L; ALGORITHM = \"loop; sse\" }\nSWEEPS = 2*512\n{ T = (1+1)/pi }\n");
+    Parameters base; base.set("SWEEPS", 64);
+    std::vector<Parameters> t = Parameters::parse_tasks(in, base);
+    CHECK(t.size() == 4);
+    CHECK(t[0].value_or_default<double>("T", 0) == 0.1 && t[1].value_or_default<double>("T", 0) == 0.2);
+    CHECK(t[2].value_or_default<double>("T", 0) == 0.25 && t[2].get("ALGORITHM") == "loop; sse");
+    CHECK(t[0].get("ALGORITHM") == "loop; path integral" && t[0].value_or_default<int>("L", 0) == 4);
+    CHECK(t[0].value_or_default<double>("local_S", 0) == 0.5 && t[0].value_or_default<double>("Jz", 0) == -1);
+    CHECK(t[0].value_or_default<int>("SWEEPS", 0) == 64 && t[3].value_or_default<int>("SWEEPS", 0) == 1024);   // globals apply to LATER tasks
+    CHECK(std::abs(t[3].value_or_default<double>("T", 0) - 2 / 3.14159265358979323846) < 1e-15);
+    CHECK(t[2].task_keys().size() == 2 && t[2].task_keys()[0] == "T");
+    CHECK(t[0].value_or_default<std::string>("LATTICE", "") == "chain lattice");
+    std::istringstream none("L = 6\nT = 0.5\n");
+    CHECK(Parameters::parse_tasks(none, base).size() == 1);
+    for (const char* bad : {"{ T = 1 ", "T = 1 }", "{ { T = 1 } }"}) {
+      std::istringstream b(bad);
+      bool threw = false;
+      try { Parameters::parse_tasks(b); } catch (const std::invalid_argument&) { threw = true; }
+      CHECK(threw);
+    }
+    Parameters q; q["T"] = "1/Lx"; q["N"] = "7/2"; q["A"] = "A+1";
+    for (const char* k : {"T", "A"}) { bool threw = false; try { q.value_or_default<double>(k, 0); } catch (const std::invalid_argument&) { threw = true; } CHECK(threw); }
+    { bool threw = false; try { q.value_or_default<int>("N", 0); } catch (const std::invalid_argument&) { threw = true; } CHECK(threw); }
+    CHECK(q.value_or_default<double>("N", 0) == 3.5);
+  }
+  // --- a drop-in refuses what it does not implement (instead of quietly simulating S = 1/2 XXZ)
+  {
+    Parameters p; p["LATTICE"] = "chain lattice"; p.set("L", 4); p.set("Jxy", -1.0);
+    lattice_helper lat(p);
+    auto refused = [&](const char* k, const char* v) {
+      Parameters q = p; q[k] = v;
+      try { spinmodel_helper m(q, lat); } catch (const std::invalid_argument&) { return true; }
+      return false;
+    };
+    CHECK(!refused("local_S", "1/2") && !refused("MODEL", "spin") && !refused("D", "0") && !refused("h", "0"));
+    CHECK(refused("local_S", "1") && refused("local_S", "3/2") && refused("MODEL", "XYZ spin") && refused("h", "0.3"));
+    CHECK(refused("D", "-0.2") && refused("Jx", "1") && refused("Jz0", "1") && refused("Gamma1", "-0.3") && refused("J'", "0.5"));
+    // LATTICE = "site" (check/site-*, extras/transmag): one spin in a transverse field, no bonds, no sign
+    Parameters s; s["LATTICE"] = "site"; s.set("Gamma", 0.7);
+    lattice_helper one(s);
+    spinmodel_helper m(s, one);
+    CHECK(num_sites(one.vg()) == 1 && num_bonds(one.vg()) == 0 && one.vg().dimension == 0);
+    CHECK(std::abs(m.graph_weight() - 0.35) < 1e-15 && std::abs(m.energy_offset() - 0.35) < 1e-15);
+  }
   std::cout << "host ok\n";
   return 0;
 }

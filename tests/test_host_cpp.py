@@ -132,3 +132,69 @@ def test_loop_driver_sse_algorithm(tmp_path):
         assert abs(mean - ex) < 5 * err + 1e-9, (name, mean, ex, err)
     bad = subprocess.run([exe, "-"], input='ALGORITHM = "loop; worm"\n', capture_output=True, text=True)
     assert bad.returncode != 0 and "unknown ALGORITHM" in bad.stderr
+
+
+def _loop_exe():
+    exe = os.path.join(ROOT, "alps-looper_b200", "looper", "loop")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)], stdout=subprocess.DEVNULL)
+    return exe
+
+
+def test_loop_driver_reads_alps_parameter_files_dry_run(tmp_path):
+    """`loop --dry-run` (no GPU): an ALPS-style parameter file -- globals, tasks in braces, expressions,
+    several statements per line -- becomes one validated task per block; what the accelerated path does not
+    implement is refused per task with a reason, the other tasks stand."""
+    f = tmp_path / "params"
+    f.write_text('LATTICE = "chain lattice"\nMODEL = "spin"\nlocal_S = 1/2; L = 4; Jxy = -1; Jz = -1\n'
+                 'ALGORITHM = "loop; path integral"\nSWEEPS = 2*512\n'
+                 '{ T = 0.1 } { T = 1/L; ALGORITHM = "loop; sse" }\n{ T = 0.5; local_S = 1 }\n'
+                 'LATTICE = "site"; Gamma = 0.7; Jxy = 0; Jz = 0\n{ T = 0.2; MEASURE[Correlations] = true }\n'
+                 '{ T = 0.2; h = 0.3 }\n{ ALGORITHM = "diagonalization" }\n')
+    out = subprocess.run([_loop_exe(), "--dry-run", str(f)], capture_output=True, text=True)
+    lines = out.stdout.splitlines()
+    assert out.returncode == 1                                   # some tasks were refused
+    assert [ln for ln in lines if ln.startswith("[task")] == [
+        "[task 1 of 6] T = 0.1;", "[task 2 of 6] T = 1/L; ALGORITHM = loop; sse;", "[task 3 of 6] T = 0.5; local_S = 1;",
+        "[task 4 of 6] T = 0.2; MEASURE[Correlations] = true;", "[task 5 of 6] T = 0.2; h = 0.3;",
+        "[task 6 of 6] ALGORITHM = diagonalization;"]
+    ok = [ln for ln in lines if ln.startswith("ok:")]
+    assert ok == ["ok: loop; path integral, 4 sites, 4 bonds, T = 0.1, graph weight 2, 128 + 1024 sweeps",
+                  "ok: loop; sse, 4 sites, 4 bonds, T = 0.25, graph weight 2, 128 + 1024 sweeps",
+                  "ok: loop; path integral, 1 sites, 0 bonds, T = 0.2, graph weight 0.35, 128 + 1024 sweeps"]
+    err = out.stderr
+    assert "error in task 3: local_S != 1/2" in err and "error in task 5: longitudinal fields" in err
+    assert "error in task 6: unknown ALGORITHM 'diagonalization'" in err
+    assert "warning: MEASURE[Correlations] is not measured" in err
+    # a single task keeps the old behaviour: the error is fatal and plain
+    out = subprocess.run([_loop_exe(), "--dry-run", "-"], input='MODEL = "XYZ spin"; Jx = 1\n', capture_output=True, text=True)
+    assert out.returncode == 1 and out.stderr.startswith("error: MODEL 'XYZ spin' is not supported")
+    out = subprocess.run([_loop_exe(), "--dry-run", "-l", "16", "-t", "0.1", "-n", "64"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok: loop; path integral, 16 sites, 16 bonds, T = 0.1")
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree absent (GPU box)")
+def test_loop_driver_dry_run_on_the_reference_input_files():
+    """The reference's own parameter files (loop.ip, check/*, extras/*/*.ip) parse into the tasks ALPS would make
+    of them: the S = 1/2 loop tasks on built-in lattices are accepted, everything else is refused with a reason --
+    nothing is 'not readable', nothing crashes."""
+    import glob
+    files = [os.path.join(REF, "loop.ip")] + sorted(glob.glob(os.path.join(REF, "extras", "*", "*.ip"))) + \
+        [p for p in sorted(glob.glob(os.path.join(REF, "check", "*-*"))) if not p.endswith((".in", ".sh"))]
+    assert len(files) > 40
+    accepted = 0
+    for path in files:
+        out = subprocess.run([_loop_exe(), "--dry-run", path], capture_output=True, text=True, timeout=60)
+        assert out.returncode in (0, 1), (path, out.returncode, out.stderr[-300:])
+        assert "not readable" not in out.stderr and "nested" not in out.stderr and "missing '}'" not in out.stderr, (path, out.stderr[-300:])
+        ntask = sum(ln.startswith("[task") for ln in out.stdout.splitlines()) or 1
+        nok = sum(ln.startswith("ok:") for ln in out.stdout.splitlines())
+        nerr = out.stderr.count("error")
+        assert nok + nerr == ntask, (path, ntask, nok, nerr)
+        accepted += nok
+    loop_ip = subprocess.run([_loop_exe(), "--dry-run", os.path.join(REF, "loop.ip")], capture_output=True, text=True)
+    assert loop_ip.stdout.count("[task") == 21 and loop_ip.stdout.count("ok:") == 5    # chain PI + SSE at T = 1/4, Ising PI + SSE, Heisenberg PI
+    assert accepted > 100
