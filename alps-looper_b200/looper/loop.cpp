@@ -72,6 +72,8 @@ static void run_task(const looper::Parameters& p, const looper::communicator& co
             << "Uniform Susceptibility    = " << beta * obs["Magnetization^2"].mean() / N << " +- " << beta * obs["Magnetization^2"].error() / N << "\n"
             << "Staggered Magnetization^2 = " << obs["Staggered Magnetization^2"].mean() << " +- " << obs["Staggered Magnetization^2"].error() << "\n"
             << "Staggered Susceptibility  = " << obs["Staggered Susceptibility"].mean() << " +- " << obs["Staggered Susceptibility"].error() << "\n";
+  looper::energy::evaluate(obs);                 // alps::parapack evaluators (loop.C:29-33: --evaluate)
+  looper::evaluate_susceptibility(obs);
   if (p.defined("VERBOSE")) obs.print(std::cout);
 }
 

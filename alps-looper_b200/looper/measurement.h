@@ -3,6 +3,7 @@
 // commit() arithmetic of the estimators the GPU fills in
 //   energy          looper/energy.h:74-83
 //   susceptibility  looper/susceptibility.h:199-254 (improved collector, path-integral and SSE forms)
+// and the evaluated observables of energy.h:89-102 (specific heat) and susceptibility.h:340-376 (Binder ratios)
 // The per-cluster sums themselves (susceptibility.h:117-155,182-198) are computed on the device
 // (csrc/lq_kernels.cuh k_estimate / k_collect); lq_collector carries the 14 collector sums.
 #pragma once
@@ -12,6 +13,7 @@
 #include <map>
 #include <ostream>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/lq.h"
 
@@ -26,6 +28,17 @@ class observable {
 public:
   void operator<<(double x) {
     ++n_; sum_ += x;
+    // jackknife bins for the evaluated observables (at most 128 bins of equal size; when they are full,
+    // neighbours are merged and the bin size doubles)
+    jcur_ += x;
+    if (++jfill_ == jsize_) {
+      jb_.push_back(jcur_); jcur_ = 0; jfill_ = 0;
+      if (jb_.size() == 128) {
+        for (size_t i = 0; i < 64; ++i) jb_[i] = jb_[2 * i] + jb_[2 * i + 1];
+        jb_.resize(64);
+        jsize_ *= 2;
+      }
+    }
     size_t l = 0;
     double v = x;
     for (;;) {
@@ -38,6 +51,8 @@ public:
   }
   unsigned long count() const { return n_; }
   double mean() const { return n_ ? sum_ / n_ : 0.0; }
+  const std::vector<double>& bin_sums() const { return jb_; }   // complete jackknife bins (sums)
+  unsigned long bin_size() const { return jsize_; }
   double naive_error() const { return lv_.empty() ? 0.0 : err(lv_[0]); }
   double error() const {
     double e = 0;
@@ -56,6 +71,10 @@ public:
       os.write(reinterpret_cast<const char*>(v), sizeof v);
       os.write(reinterpret_cast<const char*>(m), sizeof m);
     }
+    const uint64_t jh[3] = {jb_.size(), jsize_, jfill_};
+    os.write(reinterpret_cast<const char*>(jh), sizeof jh);
+    os.write(reinterpret_cast<const char*>(&jcur_), sizeof jcur_);
+    os.write(reinterpret_cast<const char*>(jb_.data()), std::streamsize(jb_.size() * sizeof(double)));
   }
   void load(std::istream& is) {
     uint64_t nl = 0;
@@ -71,6 +90,13 @@ public:
       is.read(reinterpret_cast<char*>(m), sizeof m);
       L.s = v[0]; L.s2 = v[1]; L.pend = v[2]; L.n = m[0]; L.have = m[1] != 0;
     }
+    uint64_t jh[3] = {0, 1, 0};
+    is.read(reinterpret_cast<char*>(jh), sizeof jh);
+    is.read(reinterpret_cast<char*>(&jcur_), sizeof jcur_);
+    if (!is || jh[0] > 128 || jh[1] == 0) { is.setstate(std::ios::failbit); return; }
+    jb_.assign(size_t(jh[0]), 0.0);
+    jsize_ = (unsigned long)jh[1]; jfill_ = (unsigned long)jh[2];
+    is.read(reinterpret_cast<char*>(jb_.data()), std::streamsize(jb_.size() * sizeof(double)));
   }
   double tau() const {  // integrated autocorrelation time estimate
     const double e0 = naive_error(), e = error();
@@ -86,6 +112,9 @@ private:
   unsigned long n_ = 0;
   double sum_ = 0;
   std::vector<level> lv_;
+  std::vector<double> jb_;
+  unsigned long jsize_ = 1, jfill_ = 0;
+  double jcur_ = 0;
 };
 
 class observable_set {
@@ -125,10 +154,47 @@ public:
       const observable& o = obs_.at(n);
       os << n << ": " << o.mean() << " +/- " << o.error() << "; tau = " << o.tau() << "\n";
     }
+    for (const std::string& n : eorder_) os << n << ": " << eval_.at(n).first << " +/- " << eval_.at(n).second << "\n";
   }
+  // Evaluated observables (stand-in for alps::RealObsevaluator arithmetic, energy.h:89-102,
+  // susceptibility.h:340-376): `f` of the means of the named observables, error by the jackknife over their
+  // common bins (the operands are committed together, once per sweep, so their bins line up).  Returns false
+  // -- like the reference's try/catch around every evaluation -- if an operand is missing or has < 2 bins.
+  template <class F>
+  bool evaluate(const std::string& name, const std::vector<std::string>& operands, F f) {
+    std::vector<const observable*> o;
+    for (const std::string& n : operands) {
+      if (!has(n)) return false;
+      o.push_back(&obs_.at(n));
+    }
+    const size_t nb = o[0]->bin_sums().size();
+    if (nb < 2) return false;
+    for (const observable* x : o)
+      if (x->bin_sums().size() != nb || x->bin_size() != o[0]->bin_size()) return false;
+    const double per_bin = double(o[0]->bin_size());
+    std::vector<double> tot(o.size(), 0.0), arg(o.size());
+    for (size_t k = 0; k < o.size(); ++k)
+      for (double b : o[k]->bin_sums()) tot[k] += b;
+    for (size_t k = 0; k < o.size(); ++k) arg[k] = tot[k] / (per_bin * nb);
+    const double value = f(arg);
+    double s = 0, s2 = 0;
+    for (size_t i = 0; i < nb; ++i) {
+      for (size_t k = 0; k < o.size(); ++k) arg[k] = (tot[k] - o[k]->bin_sums()[i]) / (per_bin * (nb - 1));
+      const double fi = f(arg);
+      s += fi; s2 += fi * fi;
+    }
+    const double var = s2 / nb - (s / nb) * (s / nb);
+    if (!eval_.count(name)) eorder_.push_back(name);
+    eval_[name] = std::make_pair(value, var > 0 ? std::sqrt((nb - 1) * var) : 0.0);
+    return true;
+  }
+  bool has_evaluated(const std::string& name) const { return eval_.count(name) != 0; }
+  std::pair<double, double> evaluated(const std::string& name) const { return eval_.at(name); }   // value, error
 private:
   std::map<std::string, observable> obs_;
   std::vector<std::string> order_;
+  std::map<std::string, std::pair<double, double> > eval_;
+  std::vector<std::string> eorder_;
 };
 
 struct energy {
@@ -137,6 +203,13 @@ struct energy {
     m["Energy"] << sign * c.ene;
     m["Energy Density"] << sign * c.ene / vol;
     m["Energy^2"] << sign * (power2(c.ene) - c.nop / power2(beta));
+  }
+  // energy.h:89-102: "Specific Heat" = beta^2 (<E^2> - <E>^2) / volume
+  static void evaluate(observable_set& m) {
+    if (!m.has("Inverse Temperature") || !m.has("Volume")) return;
+    const double beta = m["Inverse Temperature"].mean(), vol = m["Volume"].mean();
+    m.evaluate("Specific Heat", {"Energy", "Energy^2"},
+               [=](const std::vector<double>& x) { return beta * beta * (x[1] - x[0] * x[0]) / vol; });
   }
 };
 
@@ -179,6 +252,15 @@ struct susceptibility {
                                                       : sign * beta * c.ssize / vol);
   }
 };
+
+// susceptibility.h:340-376: the four Binder ratios <m^2>^2 / <m^4>
+inline void evaluate_susceptibility(observable_set& m) {
+  for (const char* what : {"Magnetization", "Staggered Magnetization", "Generalized Magnetization", "Generalized Staggered Magnetization"}) {
+    const std::string w(what);
+    m.evaluate("Binder Ratio of " + w, {w + "^2", w + "^4"},
+               [](const std::vector<double>& x) { return x[1] != 0 ? x[0] * x[0] / x[1] : 0.0; });
+  }
+}
 
 // stiffness.h:118-133
 struct stiffness {

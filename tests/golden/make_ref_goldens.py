@@ -16,7 +16,8 @@ FILES = ["loop.op", "extras/transmag/transmag.op", "extras/gap/gap.op", "extras/
          "extras/top/top.op", "extras/localsus/localsus.op"]
 KEEP = ["Energy", "Energy Density", "Number of Clusters", "Magnetization^2", "Magnetization^4",
         "Staggered Magnetization^2", "Staggered Magnetization^4", "Susceptibility", "Staggered Susceptibility",
-        "Generalized Magnetization^2", "Generalized Susceptibility", "Stiffness", "Transverse Magnetization"]
+        "Generalized Magnetization^2", "Generalized Susceptibility", "Stiffness", "Transverse Magnetization",
+        "Energy^2", "Specific Heat", "Binder Ratio of Magnetization", "Binder Ratio of Staggered Magnetization"]
 RES = re.compile(r"^([A-Za-z|][^:]*): (-?[0-9.eE+-]+|nan|inf) \+/- ([0-9.eE+-]+|inf|nan)(.*)$")
 PAR = re.compile(r'^([A-Za-z_][A-Za-z0-9_\[\] ]*) = (.*);$')
 

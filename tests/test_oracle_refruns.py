@@ -43,7 +43,8 @@ def _observables(c, beta, vol, sse):
             "Staggered Magnetization^2": c.smag2, "Staggered Magnetization^4": 3 * c.smag2 ** 2 - 2 * c.smag4,
             "Staggered Susceptibility": sus(c.smag, c.smag2),
             "Generalized Magnetization^2": c.usize2, "Generalized Susceptibility": sus(c.usize, c.usize2),
-            "Transverse Magnetization": 0.5 * c.tlen}
+            "Transverse Magnetization": 0.5 * c.tlen,
+            "Energy^2": c.ene ** 2 - nop / beta ** 2}      # energy.h:80
 
 
 def _lattice(r):
@@ -80,6 +81,19 @@ def test_oracle_against_the_reference_run(i):
         g = r["results"][k]
         err = np.hypot(g["error"], _berr(x))
         assert abs(np.mean(x) - g["value"]) < 4 * err + 1e-12, (r["source"], k, np.mean(x), g, _berr(x))
+    # the evaluated observables (energy.h:89-102, susceptibility.h:340-376), jackknife over 32 blocks
+    derived = {"Specific Heat": (("Energy", "Energy^2"), lambda e, e2: beta ** 2 * (e2 - e * e) / vol),
+               "Binder Ratio of Magnetization": (("Magnetization^2", "Magnetization^4"), lambda a, b: a * a / b),
+               "Binder Ratio of Staggered Magnetization": (("Staggered Magnetization^2", "Staggered Magnetization^4"), lambda a, b: a * a / b)}
+    for k, (ops, f) in derived.items():
+        if k not in r["results"] or any(o not in series for o in ops) or not np.isfinite(r["results"][k]["error"]):
+            continue
+        blocks = [np.asarray(series[o][: (len(series[o]) // 32) * 32]).reshape(32, -1).mean(axis=1) for o in ops]
+        tot = [b.sum() for b in blocks]
+        jk = np.array([f(*[(t - b[i]) / 31 for t, b in zip(tot, blocks)]) for i in range(32)])
+        val, jerr = f(*[t / 32 for t in tot]), np.sqrt(31 * jk.var())
+        g = r["results"][k]
+        assert abs(val - g["value"]) < 4 * np.hypot(g["error"], jerr) + 1e-12, (r["source"], k, val, g, jerr)
 
 
 def test_numpy_ed_reproduces_the_reference_diagonalization_blocks():
