@@ -18,6 +18,8 @@ struct virtual_graph {
   int dims[3] = {0, 0, 0};
   std::vector<double> bond_vector_relative;  // 3 per bond (lattice.h bond_vector_relative_t, stiffness.h:63)
   int dimension = 0;
+  std::vector<int> site_type, bond_type;     // ALPS vertex / edge types (all 0 on the plain lattices): the model's
+                                             // couplings may depend on them (Jz0, Jxy1, Gamma0, ...: model.h)
 };
 
 inline int num_sites(const virtual_graph& g) { return g.nsites; }
@@ -40,14 +42,24 @@ public:
     else if (name == "square lattice") ext = {L, W};
     else if (name == "simple cubic lattice") ext = {L, W, H};
     else if (name == "ladder") ext = {L, 2};
+    else if (name == "alternating chain lattice") {
+      // extras/transmag/alternating_chain.xml.in: a chain of L sites with a two-site unit cell -- vertex types
+      // 0, 1, 0, 1, ... and edge types 0 (inside a cell), 1 (between cells)
+      if (L % 2) throw std::invalid_argument("alternating chain lattice: L must be even");
+      build_hypercubic({L});
+      for (int s = 0; s < L; ++s) vg_.site_type[s] = s % 2;
+      for (int b = 0; b < num_bonds(vg_); ++b) vg_.bond_type[b] = vg_.src[b] % 2;
+      return;
+    }
     else if (name == "site") {   // a single site without bonds (check/site-*, extras/transmag: a spin in a field)
       vg_ = virtual_graph();
       vg_.nsites = 1;
       vg_.gauge.assign(1, 1.0);
+      vg_.site_type.assign(1, 0);
       bipartite_ = true;
       return;
     }
-    else throw std::invalid_argument("unknown LATTICE '" + name + "' (built-in: chain lattice, square lattice, simple cubic lattice, ladder, site; ALPS lattice libraries are not read)");
+    else throw std::invalid_argument("unknown LATTICE '" + name + "' (built-in: chain lattice, square lattice, simple cubic lattice, ladder, alternating chain lattice, site; ALPS lattice libraries are not read)");
     build_hypercubic(ext);
   }
   // periodic hypercubic lattice, site = x + L0 (y + L1 z); direction-major bond order
@@ -71,6 +83,8 @@ public:
       }
       stride *= ext[k];
     }
+    vg_.site_type.assign(n, 0);
+    vg_.bond_type.assign(vg_.src.size(), 0);
     if (bipartite_)
       for (int s = 0; s < n; ++s) {
         int par = 0, r = s;

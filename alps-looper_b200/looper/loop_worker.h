@@ -76,7 +76,8 @@ public:
     M.bond_weights = L.num_bonds ? model.bond_weights().data() : no_weight;
     for (int k = 0; k < 4; ++k) M.uniform_weights[k] = 0;
     M.energy_offset = model.energy_offset();
-    M.site_weights = nullptr;
+    // (the same |Hx|/2 on every site goes in as one number; per-site values only when they differ)
+    M.site_weights = model.uniform_site_weights() ? nullptr : model.site_weights().data();
     M.uniform_site_weight = model.site_weight();
     lq_options o = lq_options();
     o.seed = p.value_or_default<unsigned long long>("WORKER_SEED", p.value_or_default<unsigned long long>("SEED", 29833ull));
@@ -132,7 +133,7 @@ public:
     obs["Number of Clusters"] << coll.nc;
     energy::commit(obs, coll, beta_, vol);
     susceptibility::commit(obs, coll, beta_, vol, lattice.is_bipartite(), sse_);
-    if (model.site_weight() > 0) transverse_magnetization::commit(obs, coll, vol);
+    if (model.has_site_weights()) transverse_magnetization::commit(obs, coll, vol);
     if (measure_stiffness) stiffness::commit(obs, coll, beta_, lattice.vg().dimension);
     last_ = coll;
   }

@@ -199,7 +199,36 @@ int main() {
     };
     CHECK(!refused("local_S", "1/2") && !refused("MODEL", "spin") && !refused("D", "0") && !refused("h", "0"));
     CHECK(refused("local_S", "1") && refused("local_S", "3/2") && refused("MODEL", "XYZ spin") && refused("h", "0.3"));
-    CHECK(refused("D", "-0.2") && refused("Jx", "1") && refused("Jz0", "1") && refused("Gamma1", "-0.3") && refused("J'", "0.5"));
+    CHECK(refused("D", "-0.2") && refused("Jx", "1") && refused("Jz1", "1") && refused("Gamma1", "-0.3") && refused("J'", "0.5"));
+    CHECK(!refused("Jz0", "1") && refused("J0", "1") && refused("h0", "0.3") && !refused("h0", "0"));   // type 0 is every bond of a plain chain
+    // type-dependent couplings on a lattice that has the types (extras/transmag, check/transmag-3): the
+    // antiferromagnet in a STAGGERED transverse field has no sign problem, in a uniform one it has
+    Parameters a; a["LATTICE"] = "alternating chain lattice"; a.set("L", 4);
+    a.set("Jz0", 1.0); a.set("Jxy0", 1.0); a.set("Jz1", 1.0); a.set("Jxy1", 1.0); a.set("Gamma0", 0.3); a.set("Gamma1", -0.3);
+    lattice_helper alt(a);
+    CHECK(alt.vg().site_type[1] == 1 && alt.vg().site_type[2] == 0 && alt.vg().bond_type[0] == 0 && alt.vg().bond_type[1] == 1 && alt.vg().bond_type[3] == 1);
+    spinmodel_helper ma(a, alt);
+    CHECK(ma.uniform_site_weights() && std::abs(ma.site_weight() - 0.15) < 1e-15 && ma.has_site_weights());
+    CHECK(std::abs(ma.graph_weight() - (4 * 0.5 + 4 * 0.15)) < 1e-12 && std::abs(ma.energy_offset() - (4 * 0.25 + 4 * 0.15)) < 1e-12);
+    auto throws = [&](Parameters q) { try { spinmodel_helper m2(q, alt); } catch (const std::invalid_argument&) { return true; } return false; };
+    Parameters u = a; u.set("Gamma1", 0.3);            // uniform field on the antiferromagnet
+    CHECK(throws(u));
+    Parameters f = a; f.set("Jxy0", -1.0); f.set("Jxy1", -1.0);   // ferromagnetic exchange: now the STAGGERED field is the problem
+    CHECK(throws(f));
+    f.set("Gamma1", 0.3);
+    CHECK(!throws(f));
+    Parameters d = a; d.set("Jxy1", 0.5); d.set("Jz1", 2.0); d.set("Gamma1", -0.1);   // dimerised, different fields
+    spinmodel_helper md(d, alt);
+    CHECK(!md.uniform_site_weights() && md.site_weight() == 0 && md.site_weights()[0] == 0.15 && md.site_weights()[1] == 0.05);
+    CHECK(md.bond_weights()[4 * 0 + 0] == 0.5 && md.bond_weights()[4 * 1 + 0] == 0.25 && md.bond_weights()[4 * 1 + 2] == 0.75);   // Jxy = 1/2, Jz = 2: v0 = 1/4, v2 = 3/4
+    Parameters o = a; o.set("Gamma1", 0.0);            // a field on one sublattice only: no constraint from the other
+    spinmodel_helper mo(o, alt);
+    CHECK(!mo.uniform_site_weights() && mo.has_site_weights() && mo.site_weights()[1] == 0);
+    Parameters tri; tri["LATTICE"] = "chain lattice"; tri.set("L", 3);   // odd ring, antiferromagnetic exchange: frustrated
+    lattice_helper ring3(tri);
+    { bool th = false; try { spinmodel_helper m3(tri, ring3); } catch (const std::invalid_argument&) { th = true; } CHECK(th); }
+    tri.set("Jxy", -1.0);
+    { spinmodel_helper m3(tri, ring3); CHECK(std::abs(m3.graph_weight() - 1.5) < 1e-12); }
     // LATTICE = "site" (check/site-*, extras/transmag): one spin in a transverse field, no bonds, no sign
     Parameters s; s["LATTICE"] = "site"; s.set("Gamma", 0.7);
     lattice_helper one(s);
