@@ -198,3 +198,44 @@ def test_loop_driver_dry_run_on_the_reference_input_files():
     loop_ip = subprocess.run([_loop_exe(), "--dry-run", os.path.join(REF, "loop.ip")], capture_output=True, text=True)
     assert loop_ip.stdout.count("[task") == 21 and loop_ip.stdout.count("ok:") == 5    # chain PI + SSE at T = 1/4, Ising PI + SSE, Heisenberg PI
     assert accepted > 100
+
+
+def _fake_engine(tmp_path):
+    """tests/cpp/fake_lq.c: a TEST DOUBLE of the C ABI (canned collectors, no physics), preloaded in front of
+    liblq.so so that the host plumbing runs end to end without a GPU.  Never part of the product."""
+    so = os.path.join(str(tmp_path), "libfake_lq.so")
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests/cpp/fake_lq.c")])
+    return dict(os.environ, LD_PRELOAD=so)
+
+
+def test_loop_driver_plumbing_end_to_end_with_a_fake_engine(tmp_path):
+    """Driver + worker + observables + evaluators + checkpoint around a test double of the engine: several tasks
+    from one ALPS-style file, the five lines of standalone/loop.C per task, the reference's evaluated observables in
+    the VERBOSE dump, and a checkpoint that resumes where the first run stopped."""
+    env = _fake_engine(tmp_path)
+    f = tmp_path / "params"
+    f.write_text('LATTICE = "chain lattice"; L = 4; Jxy = -1; SWEEPS = 256; VERBOSE = 1\n'
+                 '{ T = 0.5 } { T = 1/L; Gamma = 0.4 }\n{ T = 0.5; local_S = 1 }\n')
+    out = subprocess.run([_loop_exe(), str(f)], capture_output=True, text=True, env=env, timeout=60)
+    assert out.returncode == 1 and "error in task 3: local_S != 1/2" in out.stderr, out.stderr
+    blocks = out.stdout.split("[task ")[1:]
+    assert len(blocks) == 3
+    for b in blocks[:2]:
+        assert "Energy Density            = " in b and "Staggered Susceptibility  = " in b
+        assert re.search(r"^Specific Heat: \S+ \+/- \S+$", b, re.M) and re.search(r"^Binder Ratio of Staggered Magnetization: \S+ \+/- \S+$", b, re.M)
+        assert "nan" not in b and "inf" not in b
+        m = re.search(r"^Number of Clusters: (\S+) \+/- ", b, re.M)
+        assert m and abs(float(m.group(1)) - 4.0) < 0.1             # the fake's 3 + step % 3
+        assert re.search(r"^Temperature: (0.5|0.25) ", b, re.M)
+    assert "Transverse Magnetization" not in blocks[0] and "Transverse Magnetization Density: " in blocks[1]
+    # checkpoint: 32 + 256 steps, then resumed into a run three times as long
+    ck = os.path.join(str(tmp_path), "run.ck")
+    first = subprocess.run([_loop_exe(), "-l", "8", "-t", "0.2", "-n", "256", "--checkpoint", ck], capture_output=True, text=True, env=env)
+    assert first.returncode == 0 and open(ck, "rb").read(8) == b"LQCKPT02", first.stderr
+    second = subprocess.run([_loop_exe(), "-l", "8", "-t", "0.2", "-n", "768", "--checkpoint", ck], capture_output=True, text=True, env=env)
+    assert second.returncode == 0 and "resumed at 0.333333" in second.stdout, (second.stdout, second.stderr)
+    third = subprocess.run([_loop_exe(), "-l", "8", "-t", "0.2", "-n", "768", "--checkpoint", ck], capture_output=True, text=True, env=env)
+    line = lambda o: re.search(r"Energy Density\s*=\s*(\S+) \+- (\S+)", o.stdout).groups()
+    assert third.returncode == 0 and "resumed at 1 " in third.stdout and line(third) == line(second)
+    bad = subprocess.run([_loop_exe(), "-l", "10", "-t", "0.2", "-n", "256", "--checkpoint", ck], capture_output=True, text=True, env=env)
+    assert bad.returncode != 0 and "lattice size differs" in bad.stderr
