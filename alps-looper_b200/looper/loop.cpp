@@ -145,10 +145,11 @@ int main(int argc, char** argv) {
         std::cerr << "error in task " << t + 1 << ": " << e.what() << "\n";   // the other tasks still run
         ++failed;
       }
-      if (nranks > 1 && comm.rank() == 0) std::remove(comm.id_file.c_str());
     }
     if (comm.rank() != 0) return failed ? 1 : 0;
     for (pid_t c : children) { int st = 0; waitpid(c, &st, 0); }
+    for (size_t t = 0; nranks > 1 && t < tasks.size(); ++t)   // (only now: every rank has read every id)
+      std::remove((id_base + (tasks.size() > 1 ? "." + std::to_string(t) : "")).c_str());
   } catch (const std::exception& e) {
     std::cerr << "error: " << e.what() << "\n";
     return 1;

@@ -77,3 +77,10 @@ int lq_get_info(lq_handle h, lq_info* out) {
   out->num_tiles = 1;
   return LQ_OK;
 }
+/* multi-rank rendezvous of the driver (--nranks P): the id is a token, the "communicator" remembers it */
+int lq_comm_unique_id(void* id_out) { memset(id_out, 0x5a, LQ_NCCL_ID_BYTES); return LQ_OK; }
+int lq_comm_init(lq_handle h, const void* id, int32_t rank, int32_t nranks) {
+  (void)h;
+  if (rank < 0 || rank >= nranks || ((const unsigned char*)id)[LQ_NCCL_ID_BYTES - 1] != 0x5a) { g_err = "fake: bad communicator id"; return -1; }
+  return LQ_OK;
+}

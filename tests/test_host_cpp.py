@@ -239,3 +239,16 @@ def test_loop_driver_plumbing_end_to_end_with_a_fake_engine(tmp_path):
     assert third.returncode == 0 and "resumed at 1 " in third.stdout and line(third) == line(second)
     bad = subprocess.run([_loop_exe(), "-l", "10", "-t", "0.2", "-n", "256", "--checkpoint", ck], capture_output=True, text=True, env=env)
     assert bad.returncode != 0 and "lattice size differs" in bad.stderr
+
+
+def test_loop_driver_two_ranks_rendezvous_with_a_fake_engine(tmp_path):
+    """`loop --nranks 2` around the test double: the process forks before it touches the engine, the ranks meet
+    through the id file of EACH task, rank 0 alone reports, the id files are gone afterwards."""
+    import glob
+    env = _fake_engine(tmp_path)
+    before = set(glob.glob("/tmp/lq_nccl_id.*"))
+    out = subprocess.run([_loop_exe(), "--nranks", "2", "-"], input='L = 4; Jxy = -1; SWEEPS = 128\n{ T = 0.5 } { T = 0.25 }\n',
+                         capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.count("[task ") == 2 and out.stdout.count("Energy Density            = ") == 2, out.stdout
+    assert set(glob.glob("/tmp/lq_nccl_id.*")) <= before
