@@ -38,14 +38,15 @@ public:
     const int W = p.value_or_default<int>("W", L);
     const int H = p.value_or_default<int>("H", W);
     std::vector<int> ext;
+    bool open_rung = false;
     if (name == "chain lattice") ext = {L};
     else if (name == "square lattice") ext = {L, W};
     else if (name == "simple cubic lattice") ext = {L, W, H};
-    else if (name == "ladder") ext = {L, 2};
+    else if (name == "ladder") { ext = {L, 2}; open_rung = true; }
     else if (name == "alternating chain lattice") {
       // extras/transmag/alternating_chain.xml.in: a chain of L sites with a two-site unit cell -- vertex types
       // 0, 1, 0, 1, ... and edge types 0 (inside a cell), 1 (between cells)
-      if (L % 2) throw std::invalid_argument("alternating chain lattice: L must be even");
+      if (L % 2 || L < 4) throw std::invalid_argument("alternating chain lattice: L must be even and at least 4");
       build_hypercubic({L});
       for (int s = 0; s < L; ++s) vg_.site_type[s] = s % 2;
       for (int b = 0; b < num_bonds(vg_); ++b) vg_.bond_type[b] = vg_.src[b] % 2;
@@ -60,6 +61,12 @@ public:
       return;
     }
     else throw std::invalid_argument("unknown LATTICE '" + name + "' (built-in: chain lattice, square lattice, simple cubic lattice, ladder, alternating chain lattice, site; ALPS lattice libraries are not read)");
+    // A periodic direction of extent 2 is a DOUBLE bond in ALPS (test/lattice.op: "anisotropic square lattice",
+    // L = 2, W = 4 has 16 bonds); the generator below makes a single one, which is what the ladder's open rungs
+    // are.  Refused rather than simulated with half the coupling.
+    for (int e : ext)
+      if (e == 2 && !open_rung) throw std::invalid_argument("a periodic lattice direction of extent 2 (a double bond in ALPS) is not supported");
+    if (open_rung && L == 2) throw std::invalid_argument("a periodic lattice direction of extent 2 (a double bond in ALPS) is not supported");
     build_hypercubic(ext);
   }
   // periodic hypercubic lattice, site = x + L0 (y + L1 z); direction-major bond order

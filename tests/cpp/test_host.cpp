@@ -224,6 +224,14 @@ int main() {
     Parameters o = a; o.set("Gamma1", 0.0);            // a field on one sublattice only: no constraint from the other
     spinmodel_helper mo(o, alt);
     CHECK(!mo.uniform_site_weights() && mo.has_site_weights() && mo.site_weights()[1] == 0);
+    // a periodic direction of extent 2 is a double bond in ALPS (test/lattice.op: L = 2, W = 4 -> 16 bonds): refused
+    for (const char* name : {"chain lattice", "square lattice", "simple cubic lattice"}) {
+      Parameters two; two["LATTICE"] = name; two.set("L", 2); two.set("W", 4);
+      bool th = false;
+      try { lattice_helper l2(two); } catch (const std::invalid_argument&) { th = true; }
+      CHECK(th);
+    }
+    { Parameters lad; lad["LATTICE"] = "ladder"; lad.set("L", 4); lattice_helper l(lad); CHECK(num_sites(l.vg()) == 8 && num_bonds(l.vg()) == 12); }
     Parameters tri; tri["LATTICE"] = "chain lattice"; tri.set("L", 3);   // odd ring, antiferromagnetic exchange: frustrated
     lattice_helper ring3(tri);
     { bool th = false; try { spinmodel_helper m3(tri, ring3); } catch (const std::invalid_argument&) { th = true; } CHECK(th); }
