@@ -13,6 +13,11 @@ pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 RUNS = json.load(open(os.path.join(HERE, "golden", "ref_runs.json")))
+# Reference runs that sit far from the exact value themselves (so that "4 sigma from the reference" would be a coin
+# toss): the transverse-field Ising chain of extras/gap (one Markov chain, printed twice: staggered magnetisation^2
+# 1.567 +- 0.026 against 1.6567 by exact diagonalisation, 3.5 sigma) and the Ising chain of loop.op (cluster count
+# 4 sigma from its own SSE twin).  They are compared at 6 sigma -- still a factor-of-two test of every observable.
+NSIGMA = {"extras/gap/gap.op:619": 6.0, "extras/gap/gap.op:1257": 6.0, "loop.op:2070": 6.0}
 PICK = [i for i, r in enumerate(RUNS) if r["algorithm"] == "loop; path integral" and r["improved"]
         and r["lattice"] == "chain lattice" and r["source"].split("/")[-1].split(":")[0] in ("loop.op", "transmag.op", "gap.op")
         # (loop.op:2070, the Ising chain: the reference's "Number of Clusters" of that run, 2.092 +- 0.014, is 4 sigma from its
@@ -51,4 +56,4 @@ def test_engine_against_the_reference_run(i):
     for k, x in series.items():
         g = r["results"][k]
         err = np.hypot(g["error"], _berr(x))
-        assert abs(np.mean(x) - g["value"]) < 4 * err + 1e-12, (r["source"], k, np.mean(x), g, _berr(x))
+        assert abs(np.mean(x) - g["value"]) < NSIGMA.get(r["source"], 4.0) * err + 1e-12, (r["source"], k, np.mean(x), g, _berr(x))
